@@ -1,0 +1,199 @@
+/* tmap.h -- C ABI of the B200-native traversability hot path (libtmap_b200.so).
+ *
+ * Drop-in boundary for ONE path of suchetanrs/traversability_mapping: keyframe insert ->
+ * pose transform -> grid binning -> per-cell neighbourhood classification -> occupancy export,
+ * plus pose update / delete / loop-closure re-integration.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference's traversability_mapping/).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary;
+ *   - poses are row-major 3x4 float matrices [R|t] (the first three rows of Eigen::Affine3f);
+ *   - cell keys are the reference's packed ids, key = (uint32(ci) << 32) | uint32(cj)
+ *     (include/traversability_mapping/Moments.hpp:122-133);
+ *   - return value: 0 = done, >0 = the call was IGNORED exactly where the reference logs to
+ *     std::cerr and carries on, <0 = error (where the reference throws, or a CUDA failure);
+ *     tmap_last_error() returns the message of the calling thread's last failure;
+ *   - there is NO CPU fallback: without a CUDA device tmap_create fails with TMAP_ERR_NO_DEVICE.
+ *   - threading: any thread may call any function; one worker thread per map owns that map's
+ *     CUDA stream and fires the on_update callback (LocalMap.cpp:452-485).
+ */
+#ifndef TMAP_H_
+#define TMAP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum
+{
+    TMAP_OK = 0,
+    TMAP_IGNORED_DUPLICATE = 1,    /* System.cpp:125-129, :65-69 */
+    TMAP_IGNORED_UNKNOWN_MAP = 2,  /* System.cpp:130-136, :259-263 */
+    TMAP_IGNORED_EMPTY = 3,        /* System.cpp:137-141 (pruned to empty) */
+    TMAP_IGNORED_UNKNOWN_KF = 4,   /* System.cpp:203-207, :238-242 */
+    TMAP_IGNORED_NULL = 5,         /* System.cpp:169-170 (null cloud) */
+    TMAP_IGNORED_NO_OBSTACLE_PARAMS = 6, /* System.cpp:304-308 */
+    TMAP_ERR_NEGATIVE_ID = -1,     /* System.cpp:163-168 throws std::runtime_error */
+    TMAP_ERR_CUDA = -2,
+    TMAP_ERR_INVALID = -3,         /* null handle, non-finite pose, bad layer id ... */
+    TMAP_ERR_UNSUPPORTED = -4,     /* footprint / sensor range beyond the kernels' tile limits */
+    TMAP_ERR_NO_DEVICE = -5
+};
+
+/* The reference's 22 parameter keys (src/Parameters.cpp:42-73; defaults
+ * params/traversabilityParams.yaml) followed by the runtime knobs of this implementation. */
+typedef struct tmap_params
+{
+    double resolution;          /* grid/resolution_local_map */
+    double grid_center_x;       /* grid/grid_center_x */
+    double grid_center_y;       /* grid/grid_center_y */
+    double half_size;           /* grid/half_size_traversability */
+    double extend_length;       /* grid/extend_length_every_resize_by */
+    double robot_radius;        /* traversability/robot_radius */
+    double ground_clearance;    /* traversability/ground_clearance */
+    double max_slope;           /* traversability/max_slope */
+    int32_t min_points_per_grid;/* traversability/min_points_per_grid */
+    int32_t is_kf_optimization_enabled; /* mapping/is_kf_optimization_enabled */
+    int32_t num_local_keyframes;/* mapping/num_local_keyframes (unused by the reference too) */
+    int32_t global_adjustment_sleep; /* mapping/global_adjustment_sleep (unused: no backstop thread) */
+    int32_t inflation_enabled;  /* inflation/enabled */
+    int32_t use_pointcloud_buffer; /* pointcloud/use_pointcloud_buffer (buffers are out of scope) */
+    int32_t use_ros_buffer;     /* pointcloud/use_ros_buffer */
+    int32_t reserved0;
+    double inflation_radius;    /* inflation/inflation_radius */
+    double cost_scaling_factor; /* inflation/cost_scaling_factor */
+    double lethal_step_threshold; /* inflation/lethal_step_threshold */
+    double robot_height;        /* pointcloud/robot_height */
+    double max_range;           /* pointcloud/max_range_base_frame */
+    double min_range;           /* pointcloud/min_range_base_frame */
+    double publish_rate_hz;     /* node/publish_rate_hz (callers' concern) */
+    /* ---- runtime knobs (not in the reference) ---- */
+    int32_t device;             /* CUDA device ordinal */
+    int32_t max_batch;          /* keyframes folded per worker pass: 1 = the reference's
+                                   one-recompute-per-keyframe sequence (bit-for-bit the same
+                                   derived layers); 0 = everything pending in one pass (same
+                                   moment layers; derived layers recomputed once at the end) */
+    int32_t profile;            /* 1: record per-stage CUDA-event times into tmap_stats */
+    int32_t reserved1;
+} tmap_params;
+
+/* Layer ids: the reference's 20 grid_map layers in LocalMap.cpp:69-71 order, then the
+ * z-min / z-max extension layers (not in the reference). */
+enum
+{
+    TMAP_L_N = 0, TMAP_L_SX, TMAP_L_SY, TMAP_L_SZ, TMAP_L_SX2, TMAP_L_SY2, TMAP_L_SZ2,
+    TMAP_L_SXY, TMAP_L_SXZ, TMAP_L_SYZ, TMAP_L_HAZARD, TMAP_L_ELEVATION, TMAP_L_SLOPE,
+    TMAP_L_STEP, TMAP_L_ROUGHNESS, TMAP_L_BORDER, TMAP_L_NORMAL_X, TMAP_L_NORMAL_Y,
+    TMAP_L_NORMAL_Z, TMAP_L_STEP_INFLATED, TMAP_L_ZMIN, TMAP_L_ZMAX, TMAP_NUM_LAYERS
+};
+
+typedef struct tmap_stats
+{
+    uint64_t keyframes_processed;  /* recomputeKeyFrame passes that changed the grid */
+    uint64_t points_binned;        /* points through transform+bin (subtractions included) */
+    uint64_t cells_classified;     /* dirty observed cells recomputed */
+    uint64_t batches;              /* worker passes */
+    uint64_t kernel_launches;      /* CUDA kernels launched by this library */
+    uint64_t grid_reallocs;
+    /* CUDA-event times of the LAST batch, ms (0 unless params.profile) */
+    float ms_hist, ms_scan, ms_scatter, ms_fold, ms_classify, ms_inflate, ms_total;
+    float reserved;
+    uint64_t last_batch_points, last_batch_tiles, last_batch_cells_touched,
+        last_batch_cells_classified;
+} tmap_stats;
+
+typedef struct tmap_system tmap_system;
+typedef void (*tmap_update_cb)(void *user);
+
+/* params/traversabilityParams.yaml defaults; device 0, max_batch 1, profile 0 */
+void tmap_default_params(tmap_params *p);
+const char *tmap_last_error(void);
+
+/* ParameterHandler::getInstance + System::System (System.cpp:25-43) */
+int tmap_create(const tmap_params *p, tmap_system **out);
+void tmap_destroy(tmap_system *s);
+
+/* System::setExtrinsicParameters(Tsv, Tbs) (System.hpp:60, System.cpp:45-51): Tbv = Tbs*Tsv */
+int tmap_set_extrinsics(tmap_system *s, const float T_sv[12], const float T_bs[12]);
+/* System::addNewLocalMap(mapID, onUpdate) (System.hpp:76, System.cpp:62-72).  on_update fires on
+ * the map's worker thread after the grid lock is released, once per grid-changing keyframe. */
+int tmap_add_map(tmap_system *s, uint64_t map_id, tmap_update_cb on_update, void *user);
+/* System::setCurrentMap (System.cpp:74-82) */
+int tmap_set_current_map(tmap_system *s, uint64_t map_id);
+
+/* System::addNewKeyFrameWithPCL (System.hpp:85-87, System.cpp:159-172).  xyz: sensor-frame
+ * points in HOST memory, `stride_bytes` apart (16 for pcl::PointXYZ, 12 packed).  The cloud is
+ * copied to the device and pruned there (System::prune, System.cpp:93-114); it is NOT binned
+ * until the first tmap_update_pose.  Synchronous, like the reference. */
+int tmap_add_keyframe(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id,
+                      const float *xyz, size_t n, size_t stride_bytes);
+/* Same, with the cloud already in DEVICE memory (float4-strided or packed). */
+int tmap_add_keyframe_device(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id,
+                             const void *d_xyz, size_t n, size_t stride_bytes);
+/* KeyFrame ctor + LocalMap::addAlreadyDeclaredKF (LocalMap.cpp:319-328): register an already
+ * pruned BASE-frame cloud (host memory, packed xyz) without the prune step. */
+int tmap_add_keyframe_base(tmap_system *s, uint64_t kf_id, uint64_t map_id, const float *xyz, size_t n);
+
+/* System::updateKeyFrame(kfID, Affine3f pose_map_base) (System.hpp:101-105, System.cpp:195-224):
+ * O(1), latest-wins, never waits on a recompute; the first call after insert triggers the bin. */
+int tmap_update_pose(tmap_system *s, uint64_t kf_id, const float T_mb[12]);
+/* System::deleteKeyFrame (System.hpp:112, System.cpp:234-248): synchronous subtract+recompute */
+int tmap_delete_keyframe(tmap_system *s, uint64_t kf_id);
+/* System::updateKFMap (System.hpp:115, System.cpp:250-276) */
+int tmap_update_kf_map(tmap_system *s, uint64_t kf_id, uint64_t map_id);
+/* System::informLoopClosure (System.hpp:117, System.cpp:278-284): map 0 is blanked and every
+ * retained keyframe re-integrated at its latest pose (ascending kf id) by the worker. */
+int tmap_inform_loop_closure(tmap_system *s);
+
+/* System::setObstacleParameters / addObstacleKeyFrame / deleteObstacleKeyFrame
+ * (System.hpp:67,132-136, System.cpp:53-60,288-335).  *id_out = 0 when dropped. */
+int tmap_set_obstacle_params(tmap_system *s, const float T_b_obs[12], double max_range, double min_range);
+int tmap_add_obstacle_keyframe(tmap_system *s, uint64_t timestamp_ns, const float *xyz, size_t n,
+                               size_t stride_bytes, uint64_t *id_out);
+int tmap_delete_obstacle_keyframe(tmap_system *s, uint64_t kf_id);
+
+/* Block until every map's work queue is drained (test hook; the reference's tests wait on the
+ * onUpdate condvar instead, test_localmap.cpp:106-111). */
+int tmap_flush(tmap_system *s);
+
+/* ---- map access: System::getLocalMap(mapID) then LocalMap::* (LocalMap.hpp:108-121) ---- */
+/* LocalMap::getGridMapMutex(): hold across a take/occupied + read sequence for consistency */
+int tmap_lock(tmap_system *s, uint64_t map_id);
+int tmap_unlock(tmap_system *s, uint64_t map_id);
+/* LocalMap::takeChangedCells (LocalMap.cpp:401-408).  out==NULL: *n_out = pending count, nothing
+ * drained.  Otherwise up to cap keys (ascending) are written and the set is cleared. */
+int tmap_take_changed_cells(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out);
+/* LocalMap::occupiedCellKeys (LocalMap.cpp:410-414), ascending */
+int tmap_occupied_cell_keys(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out);
+/* fillSparseUpdate (traversability_mapping_ros/src/conversions.cpp:28-55): out[i*n_layers+l];
+ * keys outside the grid give NaN rows. */
+int tmap_read_layers(tmap_system *s, uint64_t map_id, const uint64_t *keys, size_t n,
+                     const int32_t *layer_ids, size_t n_layers, float *out);
+/* grid_map geometry the reference would have: cells per axis = 2*k+1 (Helpers.cpp:35-84) */
+int tmap_grid_extent(tmap_system *s, uint64_t map_id, int32_t *kx, int32_t *ky);
+/* LocalMap::getGridMap()[layer] crop: out[(cj-cj0)*w + (ci-ci0)], NaN outside the grid */
+int tmap_export_dense(tmap_system *s, uint64_t map_id, int32_t layer, int32_t ci0, int32_t cj0,
+                      int32_t w, int32_t h, float *out);
+/* grid_map::GridMapRosConverter::toOccupancyGrid(grid,"hazard",0,1,.) (call sites
+ * global_traversability_node.cpp:374, local_traversability_node.cpp:236): int8 in [0,100], -1
+ * unknown; out[(cj-cj0)*w + (ci-ci0)] (nav_msgs row-major, x fastest) */
+int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t cj0, int32_t w,
+                          int32_t h, int8_t *out);
+/* LocalMap::getKeyFramesMap().size() and the work-queue depth (LocalMap.cpp:339-340) */
+int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out);
+int tmap_queue_depth(tmap_system *s, uint64_t map_id, size_t *n_out);
+/* LocalMap::getStitchedPointCloud without the voxel filter (LocalMap.cpp:416-437): pose * cloud
+ * of every retained keyframe, packed xyz, ascending kf id.  out==NULL: count only. */
+int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t cap_points, size_t *n_out);
+
+int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out);
+/* Run the map's kernels on a caller-owned stream (cudaStream_t as void*); NULL = own stream. */
+int tmap_set_stream(tmap_system *s, uint64_t map_id, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TMAP_H_ */

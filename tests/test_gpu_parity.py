@@ -1,0 +1,297 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded inputs.
+Bar: occupied keys, N and the moment layers bit-identical; derived layers' NaN pattern
+identical and values within 1e-4 relative; occupancy labels equal except at a threshold."""
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import compare_maps, make_pair
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+I34 = np.eye(3, 4, dtype=np.float32)
+
+
+def trans(x, y, z):
+    T = I34.copy()
+    T[:, 3] = (x, y, z)
+    return T
+
+
+LOCALMAP = dict(resolution=0.25, half_size=7.5, extend_length=30.0, robot_radius=0.4, min_points_per_grid=5,
+                max_range=300.0, min_range=1.0, inflation_radius=0.5, cost_scaling_factor=3.0)
+
+
+def K(tmap, ci, cj):
+    return tmap.key(ci, cj)
+
+
+# ---- the reference's LocalMap KATs, through the C ABI (test_localmap.cpp) ----------------------
+def test_registration_does_not_touch_grid(tmap, oracle):  # test_localmap.cpp:175-183
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    assert s.addKeyFrameBase(7, 0, [[0, 0, 0]]) == tmap.OK
+    s.flush()
+    assert m.numKeyFrames() == 1 and m.occupiedCellKeys().size == 0 and m.takeChangedCells().size == 0
+    s.close()
+
+
+def test_set_pose_populates_cells_and_changed_drains(tmap, oracle):  # :197-220
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    pts = [[0, 0, 0], [1, 0, 0], [0, 1, 0], [2, 2, 0]]
+    s.addKeyFrameBase(1, 0, pts); om.add_keyframe_base(1, pts)
+    s.updateKeyFrame(1, I34); om.update_pose(1, I34)
+    s.flush(); om.process()
+    want = sorted([K(tmap, 0, 0), K(tmap, 4, 0), K(tmap, 0, 4), K(tmap, 8, 8)])
+    assert m.occupiedCellKeys().tolist() == want
+    compare_maps(m, om, check_changed=True)
+    assert m.takeChangedCells().size == 0
+    s.close()
+
+
+def test_grid_grows_pose_update_moves_delete_empties(tmap, oracle):  # :222-280
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    assert m.gridExtent() == (30, 30)
+    s.addKeyFrameBase(1, 0, [[20, 0, 0]]); om.add_keyframe_base(1, [[20, 0, 0]])
+    s.updateKeyFrame(1, I34); om.update_pose(1, I34)
+    s.flush(); om.process()
+    assert m.gridExtent() == om.grid_extent() and m.gridExtent()[0] > 30
+    assert K(tmap, 80, 0) in m.occupiedCellKeys().tolist()
+    s.updateKeyFrame(1, trans(10, 0, 0)); om.update_pose(1, trans(10, 0, 0))
+    s.flush(); om.process()
+    occ = m.occupiedCellKeys().tolist()
+    assert K(tmap, 120, 0) in occ and K(tmap, 80, 0) not in occ  # vacated cell blanked
+    compare_maps(m, om, check_changed=True)
+    assert s.deleteKeyFrame(1) == tmap.OK and om.delete_keyframe(1) == 1
+    assert m.numKeyFrames() == 0 and m.occupiedCellKeys().size == 0
+    assert s.deleteKeyFrame(999) == tmap.IGNORED_UNKNOWN_KF
+    compare_maps(m, om, check_changed=True)
+    s.close()
+
+
+def test_clear_entire_map_without_retained_clouds(tmap, oracle):  # :284-301
+    s, m, om = make_pair(tmap, oracle, **dict(LOCALMAP, is_kf_optimization_enabled=0))
+    pts = [[0, 0, 0], [2, 2, 0]]
+    s.addKeyFrameBase(1, 0, pts); om.add_keyframe_base(1, pts)
+    s.updateKeyFrame(1, I34); om.update_pose(1, I34)
+    s.flush(); om.process()
+    was = set(m.occupiedCellKeys().tolist())
+    assert was
+    m.takeChangedCells(); om.take_changed_cells()
+    s.informLoopClosure(); om.clear_entire_map()
+    s.flush(); om.process()
+    assert m.occupiedCellKeys().size == 0
+    ch = set(m.takeChangedCells().tolist())
+    assert was <= ch and ch == set(om.take_changed_cells().tolist())
+    s.close()
+
+
+def test_system_ignore_and_error_codes(tmap, oracle):  # System.cpp:121-172,195-248
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    far = np.array([[5, 0, 0, 0]], dtype=np.float32)
+    assert s.addNewKeyFrameWithPCL(0, 1, 0, far) == tmap.OK
+    assert s.addNewKeyFrameWithPCL(0, 1, 0, far) == tmap.IGNORED_DUPLICATE
+    assert s.addNewKeyFrameWithPCL(0, 2, 9, far) == tmap.IGNORED_UNKNOWN_MAP
+    assert s.addNewKeyFrameWithPCL(0, 3, 0, np.array([[0.1, 0, 0, 0]], dtype=np.float32)) == tmap.IGNORED_EMPTY  # < min range
+    assert s.addNewKeyFrameWithPCL(0, 4, 0, None) == tmap.IGNORED_NULL
+    with pytest.raises(tmap.TmapError) as e:
+        s.addNewKeyFrameWithPCL(0, -5, 0, far)  # negative id: the reference throws
+    assert e.value.code == tmap.ERR_NEGATIVE_ID
+    assert s.updateKeyFrame(77, I34) == tmap.IGNORED_UNKNOWN_KF
+    assert s.addNewLocalMap(0) == tmap.IGNORED_DUPLICATE
+    with pytest.raises(tmap.TmapError):
+        s.updateKeyFrame(1, np.full((3, 4), np.nan, dtype=np.float32))
+    s.close()
+
+
+def test_prune_matches_oracle(tmap, oracle):  # System.cpp:93-114
+    from traversability_mapping_b200 import synth
+    P = synth.trajectory("single", 1, seed=2)[0]
+    cloud = synth.make_keyframe(2, 0, P, max_range=8.0, rings=32, azimuths=512)
+    cloud[5] = (0.0, 0.0, 1.0, 0)       # ego return
+    cloud[6] = (np.inf, 1.0, 1.0, 0)    # non-finite
+    cloud[7] = (1.0, 1.0, 9.0, 0)       # above robot_height
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, max_range=6.0, min_range=1.0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    assert s.addNewKeyFrameWithPCL(1, 1, 0, cloud) == tmap.OK
+    want = om.prune(cloud, synth.T_BASE_SENSOR, 6.0, 1.0)
+    got = m.getStitchedPointCloud()  # identity pose until updated -> base-frame cloud, in order
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # packed xyz input (stride 12) gives the same keyframe
+    s.addNewKeyFrameWithPCL(1, 2, 0, np.ascontiguousarray(cloud[:, :3]))
+    s.deleteKeyFrame(1)
+    got2 = m.getStitchedPointCloud()
+    assert np.array_equal(got2.view(np.uint32), want.view(np.uint32))
+    s.close()
+
+
+# ---- golden fixture + live oracle on the seeded small scene ------------------------------------
+def run_small_scene(tmap, oracle, **extra):
+    from golden.make_golden import PARAMS, scene_inputs
+    from traversability_mapping_b200 import synth
+    poses, clouds = scene_inputs()
+    s, m, om = make_pair(tmap, oracle, **dict(PARAMS, **extra))
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    batched = extra.get("max_batch", 1) != 1
+    proc = om.process_batched if batched else om.process
+    for i, c in enumerate(clouds):
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, c) == tmap.OK
+        om.add_keyframe(i + 1, c)
+        s.updateKeyFrame(i + 1, poses[i]); om.update_pose(i + 1, poses[i])
+        if not batched:
+            s.flush(); proc()   # keep the two FIFO orders identical
+    s.flush(); proc()
+    st = compare_maps(m, om, check_changed=True, label="after build")
+    moved = poses[2].copy(); moved[0, 3] += 1.3
+    s.updateKeyFrame(3, moved); om.update_pose(3, moved)
+    s.flush(); proc()
+    compare_maps(m, om, check_changed=True, label="after pose update")
+    s.deleteKeyFrame(1); om.delete_keyframe(1)
+    st = compare_maps(m, om, check_changed=True, label="after delete")
+    return s, m, om, st
+
+
+def test_small_scene_against_golden_and_oracle(tmap, oracle):
+    s, m, om, st = run_small_scene(tmap, oracle)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "small_scene.npz"))
+    keys = m.occupiedCellKeys()
+    assert np.array_equal(keys, g["keys"])
+    L = m.readLayers(keys, helpers.MOMENT_LAYERS + helpers.DERIVED_LAYERS)
+    nm = len(helpers.MOMENT_LAYERS)
+    assert helpers.bits_equal(L[:, :nm], g["layers"][:, :nm])
+    assert np.array_equal(np.isnan(L[:, nm:]), np.isnan(g["layers"][:, nm:]))
+    f = ~np.isnan(g["layers"][:, nm:])
+    assert np.allclose(L[:, nm:][f], g["layers"][:, nm:][f], rtol=helpers.RTOL, atol=helpers.ATOL)
+    assert st["gated_in"] > 100
+    s.close()
+
+
+def test_small_scene_batched_mode(tmap, oracle):
+    s, m, om, st = run_small_scene(tmap, oracle, max_batch=0)
+    s.close()
+
+
+def test_small_scene_with_inflation(tmap, oracle):
+    s, m, om, st = run_small_scene(tmap, oracle, inflation_enabled=1, inflation_radius=1.0, cost_scaling_factor=3.0,
+                                   lethal_step_threshold=0.5)
+    infl = m.exportDense("step_haz_inflated")
+    assert np.nanmax(infl) > 0.0, "scene should contain at least one lethal step seed"
+    s.close()
+
+
+# ---- config 1: one 131 072-ray keyframe into a 20 x 20 m grid at 0.1 m -------------------------
+@pytest.mark.parametrize("radius,label", [(0.20, "13-cell disc"), (0.15, "3x3 window")])
+def test_config1_single_keyframe(tmap, oracle, radius, label):
+    from traversability_mapping_b200 import synth
+    P = synth.trajectory("single", 1, seed=1)[0]
+    cloud = synth.make_keyframe(1, 0, P, max_range=10.0)
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, half_size=10.0, max_range=10.0, min_range=1.0, robot_radius=radius)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    assert s.addNewKeyFrameWithPCL(0, 1, 0, cloud) == tmap.OK
+    om.add_keyframe(1, cloud)
+    s.updateKeyFrame(1, P); om.update_pose(1, P)
+    s.flush(); om.process()
+    st = compare_maps(m, om, check_changed=True, label=label)
+    assert st["cells"] > 5000 and st["gated_in"] > 1000
+    # size-independent properties: sum of N == points kept; subtracting the keyframe empties the map
+    N = m.readLayers(m.occupiedCellKeys(), ["N"])[:, 0]
+    assert int(N.sum()) == m.getStitchedPointCloud().shape[0]
+    s.deleteKeyFrame(1)
+    assert m.occupiedCellKeys().size == 0
+    s.close()
+
+
+# ---- config 2 shape: rolling window at 0.05 m, 49-cell disc, inflation on -----------------------
+def test_config2_rolling_window(tmap, oracle):
+    from traversability_mapping_b200 import synth
+    n, window = 6, 3
+    poses = synth.trajectory("drive", n, seed=4, step=0.5)
+    s, m, om = make_pair(tmap, oracle, resolution=0.05, half_size=20.0, max_range=8.0, min_range=1.0, min_points_per_grid=5,
+                         inflation_enabled=1, inflation_radius=0.5, cost_scaling_factor=3.0, lethal_step_threshold=0.95)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    for i in range(n):
+        c = synth.make_keyframe(4, i, poses[i], max_range=8.0, rings=64, azimuths=1024)
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, c); om.add_keyframe(i + 1, c)
+        s.updateKeyFrame(i + 1, poses[i]); om.update_pose(i + 1, poses[i])
+        s.flush(); om.process()
+        if i >= window:  # local_traversability_node.cpp:181-184
+            s.deleteKeyFrame(i + 1 - window); om.delete_keyframe(i + 1 - window)
+        st = compare_maps(m, om, check_changed=True, label=f"step {i}")
+    assert m.numKeyFrames() == window and st["gated_in"] > 1000
+    s.close()
+
+
+# ---- config 3/4 shape: many keyframes, loop closure rebuild, drift model ------------------------
+def test_loop_closure_rebuild_matches_fresh_build(tmap, oracle):
+    from traversability_mapping_b200 import synth
+    n = 12
+    true = synth.trajectory("loop", n, seed=6, extent=6.0)
+    drift = synth.drift_poses(true)
+    clouds = [synth.make_keyframe(6, i, true[i], max_range=8.0, rings=32, azimuths=512) for i in range(n)]
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, half_size=10.0, max_range=8.0, min_range=1.0, max_batch=0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    for i in range(n):
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]); om.add_keyframe(i + 1, clouds[i])
+        s.updateKeyFrame(i + 1, drift[i]); om.update_pose(i + 1, drift[i])
+    s.flush(); om.process_batched()
+    compare_maps(m, om, check_changed=True, label="drifted build")
+    # PGO batch: every keyframe gets its true pose (slam_keyframe_sim_with_drift.cpp:185-217) + loop closure
+    for i in range(n):
+        s.updateKeyFrame(i + 1, true[i]); om.update_pose(i + 1, true[i])
+    s.informLoopClosure(); om.clear_entire_map()
+    s.flush(); om.process_batched()
+    compare_maps(m, om, check_changed=True, label="rebuild")
+    # size-independent property: the rebuilt map equals a fresh build at the final poses, bit for bit
+    s2, m2, om2 = make_pair(tmap, oracle, resolution=0.1, half_size=10.0, max_range=8.0, min_range=1.0, max_batch=0)
+    s2.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    for i in range(n):
+        s2.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i])
+        s2.updateKeyFrame(i + 1, true[i])
+    s2.flush()
+    keys = m.occupiedCellKeys()
+    assert np.array_equal(keys, m2.occupiedCellKeys())
+    allL = helpers.MOMENT_LAYERS + [l for l in helpers.DERIVED_LAYERS if l != "step_haz_inflated"]
+    assert helpers.bits_equal(m.readLayers(keys, allL), m2.readLayers(keys, allL))
+    s.close(); s2.close()
+
+
+def test_multi_map_reparent_and_obstacles(tmap, oracle):  # System.cpp:250-335
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    s.addNewLocalMap(1)
+    m1 = s.getLocalMap(1)
+    s.addKeyFrameBase(1, 0, [[1, 0, 0], [2, 2, 0]])
+    s.updateKeyFrame(1, I34)
+    s.flush()
+    assert m.occupiedCellKeys().size == 2 and m1.occupiedCellKeys().size == 0
+    assert s.updateKFMap(1, 1) == tmap.OK
+    s.flush()
+    assert m.occupiedCellKeys().size == 0 and m1.occupiedCellKeys().size == 2
+    assert s.updateKFMap(1, 5) == tmap.IGNORED_UNKNOWN_MAP
+    # obstacle ids count down from INT64_MAX and are recycled
+    assert s.addObstacleKeyFrame(0, np.array([[2, 0, 0, 0]], dtype=np.float32)) == 0  # params unset -> dropped
+    s.setObstacleParameters(I34, 10.0, 0.5)
+    a = s.addObstacleKeyFrame(0, np.array([[2, 0, 0, 0]], dtype=np.float32))
+    b = s.addObstacleKeyFrame(0, np.array([[3, 0, 0, 0]], dtype=np.float32))
+    assert a == 2 ** 63 - 1 and b == 2 ** 63 - 2
+    s.deleteObstacleKeyFrame(a)
+    assert s.addObstacleKeyFrame(0, np.array([[4, 0, 0, 0]], dtype=np.float32)) == a
+    s.close()
+
+
+def test_callback_fires_once_per_keyframe(tmap, oracle):
+    p = tmap.default_params(**LOCALMAP)
+    s = tmap.System(p)
+    hits = []
+    s.addNewLocalMap(0, onUpdate=lambda: hits.append(1))
+    for i in range(3):
+        s.addKeyFrameBase(i + 1, 0, [[i, 0, 0]])
+        s.updateKeyFrame(i + 1, I34)
+    s.flush()
+    assert len(hits) == 3
+    s.close()

@@ -1,0 +1,96 @@
+"""Oracle pinned against the reference's own gtest vectors (oracle/kat.cpp) and cross-checks."""
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_reference_known_answer_vectors(oracle):
+    """oracle/kat replays test_moments.cpp, test_keyframe.cpp, test_localmap.cpp, test_helpers.cpp."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "kat")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "0 failed" in r.stdout
+
+
+def test_lattice_kats(oracle):
+    # test_moments.cpp:368-390
+    assert oracle.cell_of(0, 0, 0.25, 1.04, -0.36) == (4, -1)
+    assert oracle.lib().tmo_key(4, -1) == ((4 << 32) | 0xFFFFFFFF)
+    # round half away from zero (std::lround)
+    assert oracle.cell_of(0, 0, 0.5, 0.25, -0.25) == (1, -1)
+    assert oracle.cell_of(0, 0, 0.5, 0.75, -0.75) == (2, -2)
+
+
+def test_disc_offsets(oracle):
+    # Helpers.cpp:156-169; SURVEY 8: 13-cell / 49-cell discs, 3x3 window, 0.3/0.1 excludes (+-3, 0)
+    assert len(oracle.disc_offsets(0.20, 0.1)) == 13
+    assert len(oracle.disc_offsets(0.20, 0.05)) == 49
+    assert len(oracle.disc_offsets(0.4, 0.25)) == 9
+    d = oracle.disc_offsets(0.3, 0.1)
+    assert len(d) == 25 and [3, 0] not in d.tolist()
+    # iteration order: di outer ascending, dj inner ascending
+    d13 = oracle.disc_offsets(0.20, 0.1).tolist()
+    assert d13 == sorted(d13)
+
+
+def test_eigh3_matches_numpy(oracle):
+    rng = np.random.default_rng(3)
+    for _ in range(300):
+        B = rng.standard_normal((3, 3))
+        A = B @ B.T * 10 ** rng.uniform(-6, 2)
+        w, V = oracle.eigh3(A)
+        w_np = np.linalg.eigvalsh(A)
+        assert np.allclose(w, w_np, rtol=1e-10, atol=1e-14 * abs(w_np).max())
+        assert np.allclose(V @ np.diag(w) @ V.T, A, atol=1e-12 * abs(A).max())
+    w, V = oracle.eigh3(np.zeros((3, 3)))
+    assert np.all(w == 0) and np.array_equal(V, np.eye(3))  # Eigen: zero matrix -> Q = I
+
+
+def test_rebin_kat_vectors(oracle):
+    # test_keyframe.cpp:120-139
+    I = np.eye(3, 4, dtype=np.float32)
+    keys, mom = oracle.rebin(0, 0, 0.25, [[1.04, -0.36, 2.0]], I)
+    assert keys.tolist() == [(4 << 32) | 0xFFFFFFFF]
+    assert mom[0, 0] == 1
+    assert abs(mom[0, 1] - 0.04) < 1e-4 and abs(mom[0, 2] + 0.11) < 1e-4 and abs(mom[0, 3] - 2.0) < 1e-4
+    # test_keyframe.cpp:195-204
+    keys, _ = oracle.rebin(0, 0, 0.25, [[0, 0, 0], [5, 0, 0]], I)
+    assert sorted(keys.tolist()) == [0, 20 << 32]
+    # test_keyframe.cpp:206-213
+    keys, _ = oracle.rebin(0, 0, 0.25, np.zeros((0, 3)), I)
+    assert keys.size == 0
+
+
+def test_golden_fixture(oracle):
+    """The committed fixture (tests/golden/make_golden.py) still reproduces: guards against oracle drift."""
+    from golden.make_golden import scenario
+    g = np.load(os.path.join(ROOT, "tests", "golden", "small_scene.npz"))
+    om, _ = scenario(oracle)
+    keys = om.occupied_cell_keys()
+    assert np.array_equal(keys, g["keys"])
+    import helpers
+    L = om.read_layers(keys, helpers.MOMENT_LAYERS + helpers.DERIVED_LAYERS)
+    assert helpers.bits_equal(L, g["layers"])
+    assert np.array_equal(om.export_occupancy(), g["occupancy"])
+
+
+def test_batched_vs_sequential_oracle(oracle):
+    """Moment layers are identical in both worker modes; derived layers may differ only in the
+    elevation of cells whose fit is gated out (stale-elevation rule, LocalMap.cpp:163-164)."""
+    from golden.make_golden import scenario
+    import helpers
+    a, _ = scenario(oracle, batched=False)
+    b, _ = scenario(oracle, batched=True)
+    keys = a.occupied_cell_keys()
+    assert np.array_equal(keys, b.occupied_cell_keys())
+    assert helpers.bits_equal(a.read_layers(keys, helpers.MOMENT_LAYERS), b.read_layers(keys, helpers.MOMENT_LAYERS))
+    da = a.read_layers(keys, helpers.DERIVED_LAYERS)
+    db = b.read_layers(keys, helpers.DERIVED_LAYERS)
+    gated_out = np.isnan(da[:, 0])
+    for i, l in enumerate(helpers.DERIVED_LAYERS):
+        if l == "elevation":
+            assert helpers.bits_equal(da[~gated_out, i], db[~gated_out, i])
+        else:
+            assert helpers.bits_equal(da[:, i], db[:, i]), l

@@ -1,0 +1,781 @@
+// kernels_bin.cu -- prune, transform + cell key, tile-bucket sort, per-tile segmented fold.
+//
+// Replaces (reference paths relative to traversability_mapping/):
+//   System::prune                 src/System.cpp:93-114        -> k_prune_count / k_prune_scatter
+//   KeyFrame::rebin               src/KeyFrame.cpp:52-67       -> k_hist + k_scatter + k_fold
+//   Lattice::cellOf / centerOf    include/.../Moments.hpp:105-116
+//   NodeMetaData::insert          include/.../Moments.hpp:53-59
+//   MomentLayers::add             src/Helpers.cpp:114-127      -> k_fold (float32 fold, blank rule
+//   LocalMap::addPartialToGrid    src/LocalMap.cpp:110-126        of LocalMap.cpp:121-125)
+//
+// Bit-exactness contract: the transform is r_i = ((R_i0 x + R_i1 y) + R_i2 z) + t_i
+// in float32 with every product and sum rounded (no FMA); cell index = lround((double(x)-x0)/res);
+// per (keyframe, cell) the nine double sums run in CLOUD ORDER with separately rounded products
+// and sums; each keyframe's partial is cast to float32 and added to the float32 layer in op
+// order.  This file is compiled with -fmad=false and uses the _rn intrinsics on those paths.
+//
+// Pipeline for a batch of ops (op = keyframe cloud x pose x sign):
+//   k_hist      : per 256*PPT-point chunk, transform+key, shared-memory histogram over the op's
+//                 tile window (warp-aggregated shared atomics; integer counts are exact)
+//   k_scan_*    : exclusive prefixes over chunks, ops and tiles -> every (tile, op, chunk) slot
+//   k_scatter   : re-derive the keys, STABLE rank inside the chunk (per-warp counters +
+//                 match_any), write (x_m, y_m, z_m, op|cell) records bucketed by global tile
+//   k_fold      : one CTA per touched tile: shared-memory-staged stable LSD radix sort on the
+//                 10-bit cell key, one thread per cell walks its segment in (op, point) order
+//                 accumulating doubles, then folds float32 into the tile's 48-byte records.
+#include "tmb_common.cuh"
+#include <math_constants.h>
+
+namespace tmb
+{
+__device__ __forceinline__ void xform_rn(const float *__restrict__ T, float x, float y, float z,
+                                         float &xm, float &ym, float &zm)
+{
+    xm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], x), __fmul_rn(T[1], y)), __fmul_rn(T[2], z)), T[3]);
+    ym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], x), __fmul_rn(T[5], y)), __fmul_rn(T[6], z)), T[7]);
+    zm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
+}
+
+// Lattice::cellOf: (int)lround((x - x0)/res), round half away from zero, in double
+__device__ __forceinline__ int cell_of(float xm, double x0, double res)
+{
+    const double q = __ddiv_rn(__dsub_rn((double)xm, x0), res);
+    return (int)llround(q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// prune (System.cpp:93-114): finite, not (x==0&&y==0), base = T*p, z <= robot_height,
+// min_range <= |base| <= max_range; stable order.  One warp owns 32*PPT consecutive points.
+// ---------------------------------------------------------------------------------------------
+constexpr int PRUNE_PPT = 8;
+
+__device__ __forceinline__ bool prune_point(const float *__restrict__ T, float x, float y, float z, float rh,
+                                            float mx, float mn, float &xb, float &yb, float &zb, float &range)
+{
+    if (!isfinite(x) || !isfinite(y) || !isfinite(z))
+        return false;
+    if (x == 0.f && y == 0.f)
+        return false;
+    xform_rn(T, x, y, z, xb, yb, zb);
+    if (zb > rh)
+        return false;
+    range = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(xb, xb), __fmul_rn(yb, yb)), __fmul_rn(zb, zb)));
+    if (range > mx || range < mn)
+        return false;
+    return true;
+}
+
+struct PruneArgs
+{
+    const unsigned char *src;  // device, stride bytes apart
+    size_t n, stride;
+    float T[12];
+    float rh, mx, mn;
+};
+
+__global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
+{
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t base = (size_t)gw * 32 * PRUNE_PPT;
+    if (base >= a.n)
+        return;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int r = 0; r < PRUNE_PPT; ++r)
+    {
+        const size_t i = base + r * 32 + lane;
+        bool ok = false;
+        if (i < a.n)
+        {
+            const float *p = reinterpret_cast<const float *>(a.src + i * a.stride);
+            float xb, yb, zb, rg;
+            ok = prune_point(a.T, p[0], p[1], p[2], a.rh, a.mx, a.mn, xb, yb, zb, rg);
+        }
+        cnt += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0)
+        warp_count[gw] = cnt;
+}
+
+// single-block exclusive scan over n_warps counts; total -> out_total[0]; maxnorm slot zeroed
+__global__ void k_prune_scan(uint32_t *__restrict__ warp_count, uint32_t n_warps, uint32_t *__restrict__ out_total)
+{
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_run;
+    if (threadIdx.x == 0)
+        s_run = 0;
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t b = 0; b < n_warps; b += blockDim.x)
+    {
+        const uint32_t i = b + threadIdx.x;
+        const uint32_t v = i < n_warps ? warp_count[i] : 0;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_w[warp] = inc;
+        __syncthreads();
+        if (warp == 0)
+        {
+            uint32_t w = lane < (blockDim.x >> 5) ? s_w[lane] : 0;
+            uint32_t winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_w[lane] = winc - w;
+            if (lane == 31) s_w[32] = winc;
+        }
+        __syncthreads();
+        const uint32_t run = s_run;
+        if (i < n_warps)
+            warp_count[i] = run + s_w[warp] + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            s_run = run + s_w[32];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        out_total[0] = s_run;
+        out_total[1] = 0;  // max |p_base| as float bits
+    }
+}
+
+__global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_base, float4 *__restrict__ out,
+                                uint32_t *__restrict__ out_total)
+{
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const size_t base = (size_t)gw * 32 * PRUNE_PPT;
+    if (base >= a.n)
+        return;
+    uint32_t pos = warp_base[gw];
+    float mxr = 0.f;
+#pragma unroll
+    for (int r = 0; r < PRUNE_PPT; ++r)
+    {
+        const size_t i = base + r * 32 + lane;
+        bool ok = false;
+        float xb = 0, yb = 0, zb = 0, rg = 0;
+        if (i < a.n)
+        {
+            const float *p = reinterpret_cast<const float *>(a.src + i * a.stride);
+            ok = prune_point(a.T, p[0], p[1], p[2], a.rh, a.mx, a.mn, xb, yb, zb, rg);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (ok)
+        {
+            out[pos + __popc(m & ((1u << lane) - 1u))] = make_float4(xb, yb, zb, 0.f);
+            mxr = fmaxf(mxr, rg);
+        }
+        pos += __popc(m);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        mxr = fmaxf(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
+    if (lane == 0)
+        atomicMax(out_total + 1, __float_as_uint(mxr));
+}
+
+// packed xyz (host-provided base cloud) -> float4 store + max norm
+__global__ void k_pack_base(const float *__restrict__ xyz, size_t n, float4 *__restrict__ out, uint32_t *__restrict__ out_total)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float rg = 0.f;
+    if (i < n)
+    {
+        const float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        out[i] = make_float4(x, y, z, 0.f);
+        rg = sqrtf(x * x + y * y + z * z);
+        if (!(rg >= 0.f)) rg = CUDART_INF_F;  // NaN coordinates: force the widest window -> rejected on the host
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        rg = fmaxf(rg, __shfl_xor_sync(0xffffffffu, rg, o));
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(out_total + 1, __float_as_uint(rg));
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch initialisation: counters, per-op bbox
+// ---------------------------------------------------------------------------------------------
+__global__ void k_init_batch(BatchView b)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 16)
+        b.counters[i] = 0;
+    if (i < b.n_ops)
+        b.op_bbox[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_hist: transform + key + per-chunk tile histogram
+// ---------------------------------------------------------------------------------------------
+template <int PPT>
+__global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
+{
+    extern __shared__ uint32_t s_hist[];
+    __shared__ OpDesc s_op;
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t opi = b.chunk_op[chunk];
+    if (threadIdx.x < sizeof(OpDesc) / 4)
+        reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(b.ops + opi)[threadIdx.x];
+    __syncthreads();
+    const uint32_t T = s_op.T_tiles;
+    for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
+        s_hist[i] = 0;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cl = chunk - s_op.chunk0;
+    const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
+    int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
+    bool bad = false;
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+    {
+        const uint32_t i = base + r * 32 + lane;
+        uint32_t tile = 0xffffffffu;
+        if (i < s_op.n)
+        {
+            const float4 p = __ldg(s_op.cloud + i);
+            float xm, ym, zm;
+            xform_rn(s_op.T, p.x, p.y, p.z, xm, ym, zm);
+            const int ci = cell_of(xm, lat.x0, lat.res), cj = cell_of(ym, lat.y0, lat.res);
+            const int tx = (ci >> TILE_SHIFT) - s_op.wtx0, ty = (cj >> TILE_SHIFT) - s_op.wty0;
+            if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
+            {
+                tile = ty * s_op.wtw + tx;
+                mnx = min(mnx, ci); mxx = max(mxx, ci); mny = min(mny, cj); mxy = max(mxy, cj);
+            }
+            else
+                bad = true;
+        }
+        const uint32_t m = __match_any_sync(0xffffffffu, tile);
+        if (tile != 0xffffffffu && lane == (uint32_t)(__ffs(m) - 1))
+            atomicAdd(&s_hist[tile], __popc(m));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+    {
+        mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, o));
+        mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+        mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, o));
+        mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+    }
+    if (lane == 0 && mnx != INT_MAX)
+    {
+        int *bb = reinterpret_cast<int *>(b.op_bbox + opi);
+        atomicMin(bb + 0, mnx); atomicMax(bb + 1, mxx); atomicMin(bb + 2, mny); atomicMax(bb + 3, mxy);
+    }
+    if (__any_sync(0xffffffffu, bad) && lane == 0)
+        atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_WINDOW);
+    __syncthreads();
+    uint32_t *row = b.hist + s_op.hist_off + (size_t)cl * T;
+    for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
+        row[i] = s_hist[i];
+}
+
+// per (op, tile): exclusive prefix over the op's chunks, in place; total -> op_total
+__global__ void k_scan_chunks(BatchView b)
+{
+    const uint32_t opi = blockIdx.y;
+    const OpDesc &op = b.ops[opi];
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= op.T_tiles)
+        return;
+    uint32_t *col = b.hist + op.hist_off + t;
+    uint32_t run = 0;
+    for (uint32_t c = 0; c < op.nchunks; ++c)
+    {
+        const uint32_t v = col[(size_t)c * op.T_tiles];
+        col[(size_t)c * op.T_tiles] = run;
+        run += v;
+    }
+    b.op_total[op.tot_off + t] = run;
+}
+
+// per global tile of the batch bbox: exclusive prefix over ops (op order = fold order)
+__global__ void k_scan_ops(BatchView b)
+{
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (uint32_t)(b.btw * b.bth))
+        return;
+    const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
+    uint32_t run = 0;
+    for (uint32_t o = 0; o < b.n_ops; ++o)
+    {
+        const OpDesc &op = b.ops[o];
+        const int lx = tx - op.wtx0, ly = ty - op.wty0;
+        if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
+            continue;
+        const uint32_t t = op.tot_off + ly * op.wtw + lx;
+        b.op_start[t] = run;
+        run += b.op_total[t];
+    }
+    b.tile_count[g] = run;
+}
+
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*[33]*/, uint32_t &total)
+{
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    if (warp == 0)
+    {
+        const uint32_t w = lane < nw ? s_w[lane] : 0;
+        uint32_t winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += t;
+        }
+        s_w[lane] = winc - w;
+        if (lane == 31) s_w[32] = winc;
+    }
+    __syncthreads();
+    const uint32_t r = s_w[warp] + inc - v;
+    total = s_w[32];
+    __syncthreads();
+    return r;
+}
+
+// single CTA: exclusive scan of tile_count over the bbox + compact list of active tiles
+__global__ void __launch_bounds__(1024) k_scan_tiles(BatchView b)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t n = b.btw * b.bth;
+    uint32_t run = 0, nact = 0;
+    for (uint32_t base = 0; base < n; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n ? b.tile_count[i] : 0;
+        uint32_t tot, tota;
+        const uint32_t ex = block_excl_scan(v, s_w, tot);
+        const uint32_t exa = block_excl_scan(v ? 1u : 0u, s_w, tota);
+        if (i < n)
+        {
+            b.tile_start[i] = run + ex;
+            if (v) b.active_tiles[nact + exa] = i;
+        }
+        run += tot;
+        nact += tota;
+    }
+    if (threadIdx.x == 0)
+        b.counters[0] = nact;
+}
+
+// candidate tile lists: classify = active dilated by dc tiles, inflate = active dilated by di
+// tiles; both clipped to the allocated grid.  List order is irrelevant (tiles are independent).
+__global__ void k_mark_lists(BatchView b, GridView g, int dc, int di)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (uint32_t)(b.btw * b.bth))
+        return;
+    const int lx = i % b.btw, ly = i / b.btw;
+    const int tx = b.btx0 + lx, ty = b.bty0 + ly;
+    if (tx < g.tx0 || tx >= g.tx0 + g.tw || ty < g.ty0 || ty >= g.ty0 + g.th)
+        return;
+    const int dm = max(dc, di);
+    bool nc = false, ni = false;
+    for (int dy = -dm; dy <= dm; ++dy)
+        for (int dx = -dm; dx <= dm; ++dx)
+        {
+            const int x = lx + dx, y = ly + dy;
+            if (x < 0 || x >= b.btw || y < 0 || y >= b.bth)
+                continue;
+            if (b.tile_count[y * b.btw + x])
+            {
+                const int d = max(abs(dx), abs(dy));
+                nc |= d <= dc;
+                ni |= d <= di;
+            }
+        }
+    if (nc) b.cand_tiles[atomicAdd(b.counters + 1, 1u)] = i;
+    if (ni && di >= 0) b.infl_tiles[atomicAdd(b.counters + 2, 1u)] = i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_scatter: stable bucket scatter by global tile
+// ---------------------------------------------------------------------------------------------
+template <int PPT>
+__global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD lat)
+{
+    extern __shared__ uint32_t s_cnt[];  // [8 warps][T]
+    __shared__ OpDesc s_op;
+    constexpr int NW = BIN_THREADS / 32;
+    const uint32_t chunk = blockIdx.x;
+    const uint32_t opi = b.chunk_op[chunk];
+    if (threadIdx.x < sizeof(OpDesc) / 4)
+        reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(b.ops + opi)[threadIdx.x];
+    __syncthreads();
+    const uint32_t T = s_op.T_tiles;
+    for (uint32_t i = threadIdx.x; i < T * NW; i += BIN_THREADS)
+        s_cnt[i] = 0;
+    __syncthreads();
+
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cl = chunk - s_op.chunk0;
+    const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
+    uint32_t *my = s_cnt + warp * T;
+    float px[PPT], py[PPT], pz[PPT];
+    uint32_t tl[PPT], cc[PPT];
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+    {
+        const uint32_t i = base + r * 32 + lane;
+        tl[r] = 0xffffffffu;
+        cc[r] = 0;
+        px[r] = py[r] = pz[r] = 0.f;
+        if (i < s_op.n)
+        {
+            const float4 p = __ldg(s_op.cloud + i);
+            xform_rn(s_op.T, p.x, p.y, p.z, px[r], py[r], pz[r]);
+            const int ci = cell_of(px[r], lat.x0, lat.res), cj = cell_of(py[r], lat.y0, lat.res);
+            const int tx = (ci >> TILE_SHIFT) - s_op.wtx0, ty = (cj >> TILE_SHIFT) - s_op.wty0;
+            if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
+            {
+                tl[r] = ty * s_op.wtw + tx;
+                cc[r] = ((cj & (TILE - 1)) << TILE_SHIFT) | (ci & (TILE - 1));
+            }
+        }
+        const uint32_t m = __match_any_sync(0xffffffffu, tl[r]);
+        if (tl[r] != 0xffffffffu && lane == (uint32_t)(__ffs(m) - 1))
+            my[tl[r]] += __popc(m);   // row `warp` is private to this warp
+        __syncwarp();
+    }
+    __syncthreads();
+    // per tile: absolute base of each warp's run = tile_start + op_start + chunk prefix + earlier warps
+    const uint32_t *row = b.hist + s_op.hist_off + (size_t)cl * T;
+    for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
+    {
+        const int gx = s_op.wtx0 + (int)(t % s_op.wtw) - b.btx0, gy = s_op.wty0 + (int)(t / s_op.wtw) - b.bty0;
+        uint32_t run = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
+#pragma unroll
+        for (int w = 0; w < NW; ++w)
+        {
+            const uint32_t v = s_cnt[w * T + t];
+            s_cnt[w * T + t] = run;
+            run += v;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+    {
+        const uint32_t m = __match_any_sync(0xffffffffu, tl[r]);
+        if (tl[r] != 0xffffffffu)
+        {
+            const uint32_t leader = __ffs(m) - 1;
+            const uint32_t pos = my[tl[r]] + __popc(m & ((1u << lane) - 1u));
+            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float((opi << 10) | cc[r]));
+            __syncwarp(m);
+            if (lane == leader)
+                my[tl[r]] += __popc(m);
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fold: per touched tile -- stable smem radix sort by cell, ordered double accumulation per
+// (op, cell), float32 fold into the grid records, blank rule.
+// ---------------------------------------------------------------------------------------------
+struct CellAcc
+{
+    uint32_t n;
+    double sx, sy, sz, sx2, sy2, sz2, sxy, sxz, syz;
+    float zmin, zmax;
+    __device__ __forceinline__ void reset()
+    {
+        n = 0;
+        sx = sy = sz = sx2 = sy2 = sz2 = sxy = sxz = syz = 0.0;
+        zmin = CUDART_INF_F;
+        zmax = -CUDART_INF_F;
+    }
+};
+
+__device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, float sign, uint32_t &fl)
+{
+    if (a.n == 0)
+        return;
+    const double sg = (double)sign;
+    // MomentLayers::add (Helpers.cpp:114-127): NaN -> 0, then += (float)(sign * value)
+#define TMB_ACC(k, v)                                                                            \
+    {                                                                                            \
+        const float c0 = isnan(rec[k]) ? 0.f : rec[k];                                           \
+        rec[k] = __fadd_rn(c0, __double2float_rn(__dmul_rn(sg, (v))));                            \
+    }
+    TMB_ACC(R_N, (double)a.n)
+    TMB_ACC(R_SX, a.sx) TMB_ACC(R_SY, a.sy) TMB_ACC(R_SZ, a.sz)
+    TMB_ACC(R_SX2, a.sx2) TMB_ACC(R_SY2, a.sy2) TMB_ACC(R_SZ2, a.sz2)
+    TMB_ACC(R_SXY, a.sxy) TMB_ACC(R_SXZ, a.sxz) TMB_ACC(R_SYZ, a.syz)
+#undef TMB_ACC
+    fl |= F_TOUCHED;
+    if (sign > 0.f)
+    {
+        rec[R_ZMIN] = isnan(rec[R_ZMIN]) ? a.zmin : fminf(rec[R_ZMIN], a.zmin);
+        rec[R_ZMAX] = isnan(rec[R_ZMAX]) ? a.zmax : fmaxf(rec[R_ZMAX], a.zmax);
+    }
+    else if (lroundf(rec[R_N]) <= 0)
+    {
+        // LocalMap.cpp:121-125: a subtraction that empties the cell blanks all of its layers
+#pragma unroll
+        for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+        fl |= F_BLANKED | F_CHANGED;
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, LatticeD lat)
+{
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    float4 *s_rec = reinterpret_cast<float4 *>(s_raw);                       // [FOLD_CH]
+    uint32_t *s_a = reinterpret_cast<uint32_t *>(s_raw + FOLD_CH * 16);       // [FOLD_CH]
+    uint32_t *s_b = s_a + FOLD_CH;                                            // [FOLD_CH]
+    uint32_t *s_cnt = s_b + FOLD_CH;                                          // [32][33]
+    uint16_t *s_seg0 = reinterpret_cast<uint16_t *>(s_cnt + 32 * 33);         // [1024]
+    uint16_t *s_seg1 = s_seg0 + TILE_CELLS;                                   // [1024]
+    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_seg1 + TILE_CELLS);        // [33]
+    __shared__ uint32_t s_ticket;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_active = b.counters[0];
+    for (;;)
+    {
+        if (tid == 0)
+            s_ticket = atomicAdd(b.counters + 4, 1u);
+        __syncthreads();
+        const uint32_t it = s_ticket;
+        __syncthreads();
+        if (it >= n_active)
+            break;
+        const uint32_t gt = b.active_tiles[it];
+        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
+        const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
+        const int col = (tx - g.tx0) * TILE + (int)(tid & 31), row = (ty - g.ty0) * TILE + (int)(tid >> 5);
+        const bool inside = tx >= g.tx0 && tx < g.tx0 + g.tw && ty >= g.ty0 && ty < g.ty0 + g.th;
+        if (!inside)
+        {
+            if (tid == 0) atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
+            continue;
+        }
+        const size_t cell = (size_t)row * g.W + col;
+        float rec[REC];
+        {
+            const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
+            rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
+            rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+        }
+        const int ci = tx * TILE + (int)(tid & 31), cj = ty * TILE + (int)(tid >> 5);
+        const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
+        const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
+        CellAcc acc;
+        acc.reset();
+        int cur_op = -1;
+        uint32_t fl = 0;
+
+        for (uint32_t pos = 0; pos < cnt; pos += FOLD_CH)
+        {
+            const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+            const uint32_t R = (n + 1023) >> 10;  // rounds per thread
+            const uint32_t SL = R * 32;           // slice per warp
+            for (uint32_t i = tid; i < n; i += 1024)
+            {
+                const float4 p = b.sorted[start + pos + i];
+                s_rec[i] = p;
+                s_a[i] = ((__float_as_uint(p.w) & 1023u) << 16) | i;
+            }
+            s_seg0[tid] = 0;
+            s_seg1[tid] = 0;
+            __syncthreads();
+            // two stable LSD passes over the 10-bit cell key, 5 bits each
+            uint32_t *src = s_a, *dst = s_b;
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass)
+            {
+                const int sh = 16 + 5 * pass;
+                s_cnt[warp * 33 + lane] = 0;
+                __syncwarp();
+                for (uint32_t r = 0; r < R; ++r)
+                {
+                    const uint32_t i = warp * SL + r * 32 + lane;
+                    const uint32_t d = i < n ? ((src[i] >> sh) & 31u) : 32u;
+                    const uint32_t m = __match_any_sync(0xffffffffu, d);
+                    if (d < 32u && lane == (uint32_t)(__ffs(m) - 1))
+                        s_cnt[warp * 33 + d] += __popc(m);
+                    __syncwarp();
+                }
+                __syncthreads();
+                {   // exclusive scan over (digit major, warp minor)
+                    const uint32_t d = tid >> 5, w = tid & 31;
+                    const uint32_t v = s_cnt[w * 33 + d];
+                    uint32_t tot;
+                    const uint32_t ex = block_excl_scan(v, s_w, tot);
+                    s_cnt[w * 33 + d] = ex;
+                }
+                __syncthreads();
+                for (uint32_t r = 0; r < R; ++r)
+                {
+                    const uint32_t i = warp * SL + r * 32 + lane;
+                    const uint32_t key = i < n ? src[i] : 0u;
+                    const uint32_t d = i < n ? ((key >> sh) & 31u) : 32u;
+                    const uint32_t m = __match_any_sync(0xffffffffu, d);
+                    if (d < 32u)
+                    {
+                        const uint32_t p0 = s_cnt[warp * 33 + d];
+                        dst[p0 + __popc(m & ((1u << lane) - 1u))] = key;
+                        __syncwarp(m);
+                        if (lane == (uint32_t)(__ffs(m) - 1))
+                            s_cnt[warp * 33 + d] = p0 + __popc(m);
+                    }
+                    __syncwarp();
+                }
+                __syncthreads();
+                uint32_t *t = src; src = dst; dst = t;
+            }
+            // src now holds the keys sorted by cell, stable in (op, point) order
+            for (uint32_t i = tid; i < n; i += 1024)
+            {
+                const uint32_t c = src[i] >> 16;
+                if (i == 0 || (src[i - 1] >> 16) != c) s_seg0[c] = (uint16_t)i;
+                if (i == n - 1 || (src[i + 1] >> 16) != c) s_seg1[c] = (uint16_t)(i + 1);
+            }
+            __syncthreads();
+            const uint32_t k0 = s_seg0[tid], k1 = s_seg1[tid];
+            for (uint32_t k = k0; k < k1; ++k)
+            {
+                const float4 p = s_rec[src[k] & 0xffffu];
+                const int op = (int)(__float_as_uint(p.w) >> 10);
+                if (op != cur_op)
+                {
+                    if (cur_op >= 0)
+                        fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+                    acc.reset();
+                    cur_op = op;
+                }
+                // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
+                const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
+                acc.n += 1;
+                acc.sx = __dadd_rn(acc.sx, lx); acc.sy = __dadd_rn(acc.sy, ly); acc.sz = __dadd_rn(acc.sz, lz);
+                acc.sx2 = __dadd_rn(acc.sx2, __dmul_rn(lx, lx));
+                acc.sy2 = __dadd_rn(acc.sy2, __dmul_rn(ly, ly));
+                acc.sz2 = __dadd_rn(acc.sz2, __dmul_rn(lz, lz));
+                acc.sxy = __dadd_rn(acc.sxy, __dmul_rn(lx, ly));
+                acc.sxz = __dadd_rn(acc.sxz, __dmul_rn(lx, lz));
+                acc.syz = __dadd_rn(acc.syz, __dmul_rn(ly, lz));
+                acc.zmin = fminf(acc.zmin, p.z);
+                acc.zmax = fmaxf(acc.zmax, p.z);
+            }
+            __syncthreads();
+        }
+        if (cur_op >= 0)
+            fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+        if (fl & F_TOUCHED)
+        {
+            float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
+            dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+            g.flags[cell] |= (uint8_t)fl;
+            if (fl & F_BLANKED)
+            {
+                const size_t pl = g.plane();
+#pragma unroll
+                for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + cell] = CUDART_NAN_F;
+            }
+        }
+        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);
+        if (tid == 0 && nt)
+            atomicAdd(b.counters + 8, nt);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-callable launch wrappers
+// ---------------------------------------------------------------------------------------------
+size_t fold_smem_bytes()
+{
+    return (size_t)FOLD_CH * 16 + (size_t)FOLD_CH * 8 + 32 * 33 * 4 + TILE_CELLS * 4 + 33 * 4 + 64;
+}
+
+cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
+                         float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase)
+{
+    PruneArgs a;
+    a.src = static_cast<const unsigned char *>(d_src);
+    a.n = n; a.stride = stride;
+    for (int i = 0; i < 12; ++i) a.T[i] = T[i];
+    a.rh = rh; a.mx = mx; a.mn = mn;
+    const uint32_t n_warps = (uint32_t)((n + 32 * PRUNE_PPT - 1) / (32 * PRUNE_PPT));
+    const uint32_t blocks = (n_warps + 7) / 8;
+    if (phase == 0)
+    {
+        k_prune_count<<<blocks, 256, 0, st>>>(a, d_warp_cnt);
+        k_prune_scan<<<1, 1024, 0, st>>>(d_warp_cnt, n_warps, d_total);
+    }
+    else
+        k_prune_scatter<<<blocks, 256, 0, st>>>(a, d_warp_cnt, d_out, d_total);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, float4 *d_out, uint32_t *d_total)
+{
+    cudaMemsetAsync(d_total, 0, 8, st);
+    k_pack_base<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_xyz, n, d_out, d_total);
+    return cudaGetLastError();
+}
+
+static bool g_attr_set = false;
+cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
+                       int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/)
+{
+    if (!g_attr_set)
+    {
+        cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WINDOW_TILES * 8 * 4);
+        cudaFuncSetAttribute(k_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WINDOW_TILES * 8 * 4);
+        cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fold_smem_bytes());
+        g_attr_set = true;
+    }
+    const uint32_t nb = b.btw * b.bth;
+    k_init_batch<<<(max(b.n_ops, 16u) + 255) / 256, 256, 0, st>>>(b);
+    if (ev) cudaEventRecord(ev[0], st);
+    if (ppt == 2)
+        k_hist<2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
+    else
+        k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
+    if (ev) cudaEventRecord(ev[1], st);
+    k_scan_chunks<<<dim3((maxT + 127) / 128, b.n_ops), 128, 0, st>>>(b);
+    k_scan_ops<<<(nb + 127) / 128, 128, 0, st>>>(b);
+    k_scan_tiles<<<1, 1024, 0, st>>>(b);
+    k_mark_lists<<<(nb + 127) / 128, 128, 0, st>>>(b, g, dc, di);
+    if (ev) cudaEventRecord(ev[2], st);
+    if (ppt == 2)
+        k_scatter<2><<<b.n_chunks, BIN_THREADS, maxT * 8 * 4, st>>>(b, lat);
+    else
+        k_scatter<8><<<b.n_chunks, BIN_THREADS, maxT * 8 * 4, st>>>(b, lat);
+    if (ev) cudaEventRecord(ev[3], st);
+    const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm, nb);
+    k_fold<<<fold_blocks, 1024, fold_smem_bytes(), st>>>(b, g, lat);
+    if (ev) cudaEventRecord(ev[4], st);
+    return cudaGetLastError();
+}
+
+}  // namespace tmb

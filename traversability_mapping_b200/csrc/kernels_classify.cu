@@ -1,0 +1,584 @@
+// kernels_classify.cu -- halo-tile stencil classification, step inflation, exports.
+//
+// Replaces (reference paths relative to traversability_mapping/):
+//   LocalMap::recomputeCell / recomputeDirty   src/LocalMap.cpp:130-199    -> k_classify
+//   computeGoodness                            src/TraversabilityMetrics.cpp:23-124
+//   discOffsets / dilate                       src/Helpers.cpp:156-184     (disc in __constant__,
+//                                              dilation evaluated per cell from the touched bits)
+//   LocalMap::inflateDirty                     src/LocalMap.cpp:201-241    -> k_inflate
+//   takeChangedCells / allOccupiedKeys         src/LocalMap.cpp:401-414, src/Helpers.cpp:138-154
+//   fillSparseUpdate                           traversability_mapping_ros/src/conversions.cpp:28-55
+//   GridMapRosConverter::toOccupancyGrid       (grid_map_ros; call site global_traversability_node.cpp:374)
+//
+// k_classify: one CTA per candidate 32x32 tile (ticket loop).  The (32+2r)^2 x 48-byte halo tile
+// of moment records arrives with ONE 3-D TMA box load (cp.async.bulk.tensor, mbarrier completion,
+// out-of-bounds cells filled with NaN = unobserved).  A pre-pass derives per-halo-cell gate bits
+// and 1/N; each thread then classifies four cells: the disc moments are fused about the query
+// centre as 21 lattice-weighted sums (the shift of Moments.cpp:49-58 expanded for offsets that
+// are integer multiples of the resolution), followed by the 3x3 covariance, the smallest
+// eigenpair (eig3.cuh) and a second pass over the disc for the step spread.  All in fp64.
+#include "tmb_common.cuh"
+#include "eig3.cuh"
+#include <cuda.h>
+#include <math_constants.h>
+
+namespace tmb
+{
+__constant__ int c_disc_off[MAX_DISC];       // smem cell offset dj*TW + di
+__constant__ double2 c_disc_d[MAX_DISC];     // (di, dj) as doubles
+__constant__ ClassifyParams c_cp;
+
+// ---- mbarrier / TMA helpers (PTX ISA: mbarrier, cp.async.bulk.tensor) ----------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+
+enum : uint8_t { H_OBS = 1, H_OK = 2, H_TOUCHED = 4 };
+constexpr int CLS_THREADS = 256;
+
+__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap, BatchView b, GridView g)
+{
+    extern __shared__ __align__(1024) unsigned char s_raw[];
+    const int r = c_cp.r;
+    const int TW = TILE + 2 * r;
+    const int ncell = TW * TW;
+    float *s_rec = reinterpret_cast<float *>(s_raw);                                     // [TW*TW][12]
+    double *s_inv = reinterpret_cast<double *>(s_raw + (((size_t)ncell * REC * 4 + 127) & ~(size_t)127));  // [TW*TW]
+    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_inv + ncell);                        // [TW*TW]
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_ticket;
+
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint32_t n_cand = b.counters[1];
+    const uint32_t minp = c_cp.min_points;
+    const size_t pl = g.plane();
+    uint32_t n_done = 0;
+
+    for (;;)
+    {
+        if (tid == 0)
+            s_ticket = atomicAdd(b.counters + 5, 1u);
+        __syncthreads();
+        const uint32_t it = s_ticket;
+        if (it >= n_cand)
+            break;
+        const uint32_t gt = b.cand_tiles[it];
+        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
+        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
+        if (tid == 0)
+        {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)ncell * REC * 4);
+            tma_load_3d(s_rec, &tmap, &s_bar, 0, col0 - r, row0 - r);
+        }
+        // touched bits of the halo tile (plain loads; zero outside the grid)
+        for (int i = tid; i < ncell; i += CLS_THREADS)
+        {
+            const int hx = i % TW, hy = i / TW;
+            const int c = col0 - r + hx, rw = row0 - r + hy;
+            uint8_t f = 0;
+            if (c >= 0 && c < g.W && rw >= 0 && rw < g.H)
+                f = (g.flags[(size_t)rw * g.W + c] & F_TOUCHED) ? H_TOUCHED : 0;
+            s_flag[i] = f;
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        __syncthreads();
+        // pre-pass: observed / enough-points bits and 1/N  (MomentLayers::read, Helpers.cpp:101-112)
+        for (int i = tid; i < ncell; i += CLS_THREADS)
+        {
+            const float n = s_rec[(size_t)i * REC + R_N];
+            uint8_t f = s_flag[i];
+            double inv = 0.0;
+            if (!isnan(n) && n >= 1.f)
+            {
+                const float nr = rintf(n);
+                f |= H_OBS;
+                if (nr >= (float)minp) f |= H_OK;
+                inv = 1.0 / (double)nr;
+            }
+            s_flag[i] = f;
+            s_inv[i] = inv;
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int k = 0; k < TILE_CELLS / CLS_THREADS; ++k)
+        {
+            const int q = tid + k * CLS_THREADS;
+            const int x = q & 31, y = q >> 5;
+            const int idx = (y + r) * TW + (x + r);
+            const uint8_t fq = s_flag[idx];
+            if (!(fq & H_OBS))
+                continue;  // LocalMap.cpp:138-140: unobserved query -> nothing written
+            // dirty = query in dilate(touched, disc); gate = every disc cell has >= min_points
+            bool dirty = false, gate = true;
+            const int nd = c_cp.n_disc;
+            for (int o = 0; o < nd; ++o)
+            {
+                const uint8_t f = s_flag[idx + c_disc_off[o]];
+                dirty |= (f & H_TOUCHED) != 0;
+                gate &= (f & H_OK) != 0;
+            }
+            if (!dirty)
+                continue;
+            ++n_done;
+            const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
+            const float *rq = s_rec + (size_t)idx * REC;
+            const double nq = (double)rintf(rq[R_N]);
+            const float border = (float)fmin(nq / (double)max(1u, minp), 1.0);
+            g.flags[cell] |= F_CHANGED;  // recomputeCell returned true (LocalMap.cpp:194-196)
+            if (!gate)
+            {
+                g.der[D_HAZARD * pl + cell] = CUDART_NAN_F;
+                g.der[D_SLOPE * pl + cell] = CUDART_NAN_F;
+                g.der[D_STEP * pl + cell] = CUDART_NAN_F;
+                g.der[D_ROUGHNESS * pl + cell] = CUDART_NAN_F;
+                g.der[D_BORDER * pl + cell] = border;
+                g.der[D_NX * pl + cell] = CUDART_NAN_F;
+                g.der[D_NY * pl + cell] = CUDART_NAN_F;
+                g.der[D_NZ * pl + cell] = CUDART_NAN_F;
+                continue;
+            }
+            // ---- pass A: fuse the disc about the query centre ----
+            double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
+            double Sx0 = 0, Sxi = 0, Sxj = 0, Sy0 = 0, Syi = 0, Syj = 0, Sz0 = 0, Szi = 0, Szj = 0;
+            double Qxx = 0, Qyy = 0, Qzz = 0, Qxy = 0, Qxz = 0, Qyz = 0;
+            for (int o = 0; o < nd; ++o)
+            {
+                const int j = idx + c_disc_off[o];
+                const float4 *p = reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
+                const float4 a0 = p[0], a1 = p[1], a2 = p[2];
+                const double2 d = c_disc_d[o];
+                const double n = (double)a0.x;  // N is integral by construction
+                const double sx = a0.y, sy = a0.z, sz = a0.w;
+                const double ni = n * d.x, nj = n * d.y;
+                Nf += n; Nx += ni; Ny += nj;
+                Nxx = fma(ni, d.x, Nxx); Nyy = fma(nj, d.y, Nyy); Nxy = fma(ni, d.y, Nxy);
+                Sx0 += sx; Sxi = fma(sx, d.x, Sxi); Sxj = fma(sx, d.y, Sxj);
+                Sy0 += sy; Syi = fma(sy, d.x, Syi); Syj = fma(sy, d.y, Syj);
+                Sz0 += sz; Szi = fma(sz, d.x, Szi); Szj = fma(sz, d.y, Szj);
+                Qxx += (double)a1.x; Qyy += (double)a1.y; Qzz += (double)a1.z;
+                Qxy += (double)a1.w; Qxz += (double)a2.x; Qyz += (double)a2.y;
+            }
+            const double rs = c_cp.res, rs2 = rs * rs;
+            const double SX = fma(rs, Nx, Sx0), SY = fma(rs, Ny, Sy0), SZ = Sz0;
+            const double QXX = Qxx + 2.0 * rs * Sxi + rs2 * Nxx;
+            const double QYY = Qyy + 2.0 * rs * Syj + rs2 * Nyy;
+            const double QZZ = Qzz;
+            const double QXY = Qxy + rs * (Sxj + Syi) + rs2 * Nxy;
+            const double QXZ = fma(rs, Szi, Qxz);
+            const double QYZ = fma(rs, Szj, Qyz);
+            const double inf = 1.0 / Nf;
+            const double mx = SX * inf, my = SY * inf, mz = SZ * inf;
+            const double cxx = QXX * inf - mx * mx, cyy = QYY * inf - my * my, czz = QZZ * inf - mz * mz;
+            const double cxy = QXY * inf - mx * my, cxz = QXZ * inf - mx * mz, cyz = QYZ * inf - my * mz;
+            double nv[3];
+            const double lam0 = eig3_min(cxx, cxy, cxz, cyy, cyz, czz, nv);
+            if (nv[2] < 0.0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
+            // ---- pass B: spread of the per-cell barycentres along the normal ----
+            double dmin = CUDART_INF, dmax = -CUDART_INF;
+            for (int o = 0; o < nd; ++o)
+            {
+                const int j = idx + c_disc_off[o];
+                const float4 a0 = *reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
+                const double2 d = c_disc_d[o];
+                const double iv = s_inv[j];
+                const double bx = fma((double)a0.y, iv, d.x * rs) - mx;
+                const double by = fma((double)a0.z, iv, d.y * rs) - my;
+                const double bz = (double)a0.w * iv - mz;
+                const double dd = bx * nv[0] + by * nv[1] + bz * nv[2];
+                dmin = fmin(dmin, dd);
+                dmax = fmax(dmax, dd);
+            }
+            const double slope = acos(fmin(1.0, fabs(nv[2])));
+            const double slope_h = fmin(slope / c_cp.max_slope, 1.0);
+            const double rough_h = fmin(sqrt(fmax(0.0, lam0)) / c_cp.ground_clearance, 1.0);
+            const double step_h = fmin((dmax - dmin) / c_cp.ground_clearance, 1.0);
+            const double overall = fmax(slope_h, fmax(step_h, rough_h));
+            g.der[D_ELEVATION * pl + cell] = (float)((double)rq[R_SZ] / nq);
+            g.der[D_HAZARD * pl + cell] = (float)overall;
+            g.der[D_SLOPE * pl + cell] = (float)slope_h;
+            g.der[D_STEP * pl + cell] = (float)step_h;
+            g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
+            g.der[D_BORDER * pl + cell] = border;
+            g.der[D_NX * pl + cell] = (float)nv[0];
+            g.der[D_NY * pl + cell] = (float)nv[1];
+            g.der[D_NZ * pl + cell] = (float)nv[2];
+        }
+        __syncthreads();  // everyone done with s_rec before the next TMA overwrites it
+    }
+    // cells classified (statistics)
+    for (int o = 16; o > 0; o >>= 1)
+        n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
+    if ((tid & 31) == 0 && n_done)
+        atomicAdd(b.counters + 7, n_done);
+}
+
+// clear the per-batch touched / blanked bits of the active tiles
+__global__ void k_clear_touched(BatchView b, GridView g)
+{
+    const uint32_t n_active = b.counters[0];
+    for (uint32_t it = blockIdx.x; it < n_active; it += gridDim.x)
+    {
+        const uint32_t gt = b.active_tiles[it];
+        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
+        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
+        for (int q = threadIdx.x; q < TILE_CELLS; q += blockDim.x)
+        {
+            const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
+            g.flags[cell] &= (uint8_t)~(F_TOUCHED | F_BLANKED);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_inflate (LocalMap.cpp:201-241): for observed cells, best = max over kernel taps of
+// step*decay where step >= lethal; written (and flagged changed) only when the value differs.
+// Recomputing a cell outside the reference's window is a no-op (pure function of step_haz, N),
+// so whole candidate tiles are processed.
+// ---------------------------------------------------------------------------------------------
+constexpr int INF_THREADS = 256;
+__global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__ CUtensorMap tmap_step, BatchView b, GridView g,
+                                                         const float *__restrict__ decay /*[(2R+1)^2], 0 outside disc*/)
+{
+    extern __shared__ __align__(1024) unsigned char s_raw[];
+    float *s_step = reinterpret_cast<float *>(s_raw);
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_ticket;
+    const int R = c_cp.infl_r, TW = TILE + 2 * R, KW = 2 * R + 1;
+    const float lethal = c_cp.lethal;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    const uint32_t n_tiles = b.counters[2];
+    const size_t pl = g.plane();
+    for (;;)
+    {
+        if (tid == 0)
+            s_ticket = atomicAdd(b.counters + 6, 1u);
+        __syncthreads();
+        const uint32_t it = s_ticket;
+        if (it >= n_tiles)
+            break;
+        const uint32_t gt = b.infl_tiles[it];
+        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
+        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
+        if (tid == 0)
+        {
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TW * 4));
+            tma_load_2d(s_step, &tmap_step, &s_bar, col0 - R, row0 - R);
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        // any seed in the halo tile?
+        int seed = 0;
+        for (int i = tid; i < TW * TW; i += INF_THREADS)
+            seed |= s_step[i] >= lethal;
+        seed = __syncthreads_or(seed);
+        for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
+        {
+            const int q = tid + k * INF_THREADS;
+            const int x = q & 31, y = q >> 5;
+            const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
+            const float n = g.mom[cell * REC + R_N];
+            if (!(n >= 1.f))
+                continue;
+            float best = 0.f;
+            if (seed)
+            {
+                for (int dj = 0; dj < KW; ++dj)
+                {
+                    const float *srow = s_step + (y + dj) * TW + x;
+                    const float *drow = decay + dj * KW;
+                    for (int di = 0; di < KW; ++di)
+                    {
+                        const float sv = srow[di];
+                        const float dc = __ldg(drow + di);
+                        if (sv >= lethal && dc > 0.f)
+                            best = fmaxf(best, __fmul_rn(sv, dc));
+                    }
+                }
+            }
+            const float cur = g.der[D_INFLATED * pl + cell];
+            if (!(cur == best))
+            {
+                g.der[D_INFLATED * pl + cell] = best;
+                g.flags[cell] |= F_CHANGED;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// queries / exports
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long make_key(int ci, int cj)
+{
+    return ((unsigned long long)(uint32_t)ci << 32) | (unsigned long long)(uint32_t)cj;
+}
+
+// mode 0: keys of cells with the CHANGED bit (optionally clearing it); mode 1: keys of observed
+// cells (N >= 1).  Cells outside the logical grid |ci|<=kx, |cj|<=ky never hold data.
+__global__ void k_collect_keys(GridView g, int mode, int clear, unsigned long long *out, uint32_t cap, uint32_t *count)
+{
+    const size_t n = g.plane();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        bool hit;
+        if (mode == 0)
+        {
+            const uint8_t f = g.flags[i];
+            hit = (f & F_CHANGED) != 0;
+            if (hit && clear) g.flags[i] = f & (uint8_t)~F_CHANGED;
+        }
+        else
+        {
+            const float nn = g.mom[i * REC + R_N];
+            hit = !isnan(nn) && nn >= 1.f;
+        }
+        if (hit)
+        {
+            const uint32_t p = atomicAdd(count, 1u);
+            if (out && p < cap)
+                out[p] = make_key(g.ci0 + (int)(i % g.W), g.cj0 + (int)(i / g.W));
+        }
+    }
+}
+
+__device__ __forceinline__ float read_layer(const GridView &g, int layer, int ci, int cj)
+{
+    const int c = ci - g.ci0, r = cj - g.cj0;
+    if (c < 0 || c >= g.W || r < 0 || r >= g.H)
+        return CUDART_NAN_F;
+    const size_t cell = (size_t)r * g.W + c;
+    if (layer < 10)
+        return g.mom[cell * REC + layer];
+    if (layer < 20)
+        return g.der[(size_t)(layer - 10) * g.plane() + cell];
+    return g.mom[cell * REC + (layer - 20 + R_ZMIN)];
+}
+
+__global__ void k_read_layers(GridView g, const unsigned long long *keys, size_t n, const int *layer_ids, int n_layers,
+                              int kx, int ky, float *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * n_layers)
+        return;
+    const size_t k = i / n_layers;
+    const int l = (int)(i % n_layers);
+    const int ci = (int)(uint32_t)(keys[k] >> 32), cj = (int)(uint32_t)(keys[k] & 0xffffffffu);
+    float v = CUDART_NAN_F;
+    if (abs(ci) <= kx && abs(cj) <= ky)
+        v = read_layer(g, layer_ids[l], ci, cj);
+    out[i] = v;
+}
+
+__global__ void k_export_dense(GridView g, int layer, int ci0, int cj0, int w, int h, int kx, int ky, float *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)w * h)
+        return;
+    const int ci = ci0 + (int)(i % w), cj = cj0 + (int)(i / w);
+    float v = CUDART_NAN_F;
+    if (abs(ci) <= kx && abs(cj) <= ky)
+        v = read_layer(g, layer, ci, cj);
+    out[i] = v;
+}
+
+// grid_map_ros toOccupancyGrid(grid, "hazard", 0, 1): v=(x-0)/(1-0); NaN -> -1; else
+// 0 + min(max(0,v),1)*100 assigned to int8 (truncation)
+__global__ void k_export_occupancy(GridView g, int ci0, int cj0, int w, int h, int kx, int ky, signed char *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)w * h)
+        return;
+    const int ci = ci0 + (int)(i % w), cj = cj0 + (int)(i / w);
+    float v = CUDART_NAN_F;
+    if (abs(ci) <= kx && abs(cj) <= ky)
+        v = read_layer(g, 10, ci, cj);
+    float value = __fdiv_rn(__fsub_rn(v, 0.f), __fsub_rn(1.f, 0.f));
+    if (isnan(value))
+        value = -1.f;
+    else
+        value = __fadd_rn(0.f, __fmul_rn(fminf(fmaxf(0.0f, value), 1.0f), 100.f));
+    out[i] = (signed char)value;
+}
+
+// clearEntireMap (LocalMap.cpp:377-383): every occupied cell becomes 'changed'; per-batch bits drop
+__global__ void k_mark_observed_changed(GridView g)
+{
+    const size_t n = g.plane();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const float nn = g.mom[i * REC + R_N];
+        const uint8_t f = g.flags[i];
+        g.flags[i] = (uint8_t)((f & F_CHANGED) | ((!isnan(nn) && nn >= 1.f) ? F_CHANGED : 0));
+    }
+}
+
+// pose * cloud for the stitched cloud (LocalMap.cpp:427-437)
+__global__ void k_transform_cloud(const float4 *cloud, uint32_t n, const float *T12, float *out_xyz)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float4 p = cloud[i];
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) T[k] = T12[k];
+    out_xyz[3 * i + 0] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], p.x), __fmul_rn(T[1], p.y)), __fmul_rn(T[2], p.z)), T[3]);
+    out_xyz[3 * i + 1] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], p.x), __fmul_rn(T[5], p.y)), __fmul_rn(T[6], p.z)), T[7]);
+    out_xyz[3 * i + 2] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], p.x), __fmul_rn(T[9], p.y)), __fmul_rn(T[10], p.z)), T[11]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-callable wrappers
+// ---------------------------------------------------------------------------------------------
+size_t classify_smem_bytes(int r)
+{
+    const size_t ncell = (size_t)(TILE + 2 * r) * (TILE + 2 * r);
+    return ((ncell * REC * 4 + 127) & ~(size_t)127) + ncell * 8 + ncell + 128;
+}
+size_t inflate_smem_bytes(int R) { return (size_t)(TILE + 2 * R) * (TILE + 2 * R) * 4 + 128; }
+
+cudaError_t upload_classify_constants(const ClassifyParams &cp, const int *disc_off, const double *disc_d /*pairs*/, int n_disc)
+{
+    cudaError_t e = cudaMemcpyToSymbol(c_cp, &cp, sizeof(cp));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyToSymbol(c_disc_off, disc_off, sizeof(int) * n_disc);
+    if (e != cudaSuccess) return e;
+    return cudaMemcpyToSymbol(c_disc_d, disc_d, sizeof(double) * 2 * n_disc);
+}
+
+cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, int r, int n_blocks)
+{
+    static int attr_r = -1;
+    const size_t smem = classify_smem_bytes(r);
+    if (attr_r != r)
+    {
+        cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_r = r;
+    }
+    k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, b, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const GridView &g, int n_blocks)
+{
+    k_clear_touched<<<n_blocks, 256, 0, st>>>(b, g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g, int R,
+                           const float *d_decay, int n_blocks)
+{
+    static int attr_R = -1;
+    const size_t smem = inflate_smem_bytes(R);
+    if (attr_R != R)
+    {
+        cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_R = R;
+    }
+    k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, d_decay);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_collect_keys(cudaStream_t st, const GridView &g, int mode, int clear, unsigned long long *d_out, uint32_t cap,
+                                uint32_t *d_count)
+{
+    cudaMemsetAsync(d_count, 0, 4, st);
+    const size_t n = g.plane();
+    const unsigned blocks = (unsigned)min((size_t)148 * 16, (n + 255) / 256);
+    k_collect_keys<<<blocks ? blocks : 1, 256, 0, st>>>(g, mode, clear, d_out, cap, d_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_read_layers(cudaStream_t st, const GridView &g, const unsigned long long *d_keys, size_t n, const int *d_layers,
+                               int n_layers, int kx, int ky, float *d_out)
+{
+    const size_t tot = n * n_layers;
+    if (!tot) return cudaSuccess;
+    k_read_layers<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, d_keys, n, d_layers, n_layers, kx, ky, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_dense(cudaStream_t st, const GridView &g, int layer, int ci0, int cj0, int w, int h, int kx, int ky,
+                                float *d_out)
+{
+    const size_t tot = (size_t)w * h;
+    if (!tot) return cudaSuccess;
+    k_export_dense<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, layer, ci0, cj0, w, h, kx, ky, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_occupancy(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky,
+                                    signed char *d_out)
+{
+    const size_t tot = (size_t)w * h;
+    if (!tot) return cudaSuccess;
+    k_export_occupancy<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, ci0, cj0, w, h, kx, ky, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mark_observed_changed(cudaStream_t st, const GridView &g)
+{
+    const size_t n = g.plane();
+    const unsigned blocks = (unsigned)min((size_t)148 * 16, (n + 255) / 256);
+    k_mark_observed_changed<<<blocks ? blocks : 1, 256, 0, st>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_transform_cloud(cudaStream_t st, const float4 *d_cloud, uint32_t n, const float *d_T, float *d_out)
+{
+    if (!n) return cudaSuccess;
+    k_transform_cloud<<<(n + 255) / 256, 256, 0, st>>>(d_cloud, n, d_T, d_out);
+    return cudaGetLastError();
+}
+
+}  // namespace tmb

@@ -1,0 +1,1376 @@
+// runtime.cu -- host runtime (System / LocalMap mirror) and the C ABI of libtmap_b200.so.
+//
+// Mirrors the reference's orchestration layer (paths relative to traversability_mapping/):
+//   System      include/.../System.hpp:53-212, src/System.cpp   -> class System
+//   LocalMap    include/.../LocalMap.hpp:55-231, src/LocalMap.cpp -> class LocalMap
+//   KeyFrame    include/.../KeyFrame.hpp, src/KeyFrame.cpp:29-50 (pose state machine) -> struct KeyFrame
+// What differs by design: clouds live in device memory; a keyframe's contribution is removed by
+// re-binning its cloud at the pose it was integrated with (bit-identical to the stored partials the
+// reference subtracts, since the binning is deterministic) instead of keeping 76-byte partials per
+// (keyframe, cell); the grid is a dense tile-aligned device window that grows by reallocation.
+// No CPU fallback exists: every arithmetic step of the path runs in the CUDA kernels.
+#include "../../include/tmap.h"
+#include "tmb_kernels.h"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <condition_variable>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <unordered_set>
+#include <vector>
+
+namespace tmb
+{
+thread_local std::string g_last_error;
+
+struct CudaError : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+struct Unsupported : std::runtime_error
+{
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e__ = (call);                                                                     \
+        if (e__ != cudaSuccess)                                                                       \
+            throw CudaError(std::string(#call) + ": " + cudaGetErrorString(e__));                     \
+    } while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+
+struct DevBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        const size_t want = std::max(bytes, cap + cap / 2);
+        CK(cudaMalloc(&p, want));
+        cap = want;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct PinBuf
+{
+    void *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t bytes)
+    {
+        if (bytes <= cap)
+            return;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        const size_t want = std::max(bytes, cap + cap / 2);
+        CK(cudaMallocHost(&p, want));
+        cap = want;
+    }
+    template <class T> T *as() const { return static_cast<T *>(p); }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+static inline int floordiv32(int a) { return a >> TILE_SHIFT; }
+
+// ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn)
+    {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess)
+            throw CudaError("cuTensorMapEncodeTiled entry point unavailable");
+        fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// -------------------------------------------------------------------------------------------
+// Device grid
+// -------------------------------------------------------------------------------------------
+struct DeviceGrid
+{
+    GridView v{};
+    CUtensorMap tmap_mom{}, tmap_step{};
+    int r = 0, R = 0;  // classify halo, inflation halo (0 = none)
+    uint64_t reallocs = 0;
+
+    ~DeviceGrid() { release(); }
+    void release()
+    {
+        if (v.mom) cudaFree(v.mom);
+        if (v.der) cudaFree(v.der);
+        if (v.flags) cudaFree(v.flags);
+        v = GridView{};
+    }
+    static void alloc_view(GridView &n, int tx0, int ty0, int tw, int th, cudaStream_t st)
+    {
+        n = GridView{};
+        n.tx0 = tx0; n.ty0 = ty0; n.tw = tw; n.th = th;
+        n.W = tw * TILE; n.H = th * TILE;
+        n.ci0 = tx0 * TILE; n.cj0 = ty0 * TILE;
+        const size_t pl = n.plane();
+        CK(cudaMalloc(&n.mom, pl * REC * sizeof(float)));
+        CK(cudaMalloc(&n.der, pl * NUM_DER * sizeof(float)));
+        CK(cudaMalloc(&n.flags, pl));
+        CK(cudaMemsetAsync(n.mom, 0xFF, pl * REC * sizeof(float), st));   // all-ones = NaN
+        CK(cudaMemsetAsync(n.der, 0xFF, pl * NUM_DER * sizeof(float), st));
+        CK(cudaMemsetAsync(n.flags, 0, pl, st));
+    }
+    void encode()
+    {
+        EncodeTiledFn enc = get_encode();
+        {
+            const cuuint64_t dims[3] = {(cuuint64_t)REC, (cuuint64_t)v.W, (cuuint64_t)v.H};
+            const cuuint64_t strides[2] = {(cuuint64_t)REC * 4, (cuuint64_t)v.W * REC * 4};
+            const cuuint32_t box[3] = {(cuuint32_t)REC, (cuuint32_t)(TILE + 2 * r), (cuuint32_t)(TILE + 2 * r)};
+            const cuuint32_t es[3] = {1, 1, 1};
+            CUresult rc = enc(&tmap_mom, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, v.mom, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+            if (rc != CUDA_SUCCESS)
+                throw CudaError("cuTensorMapEncodeTiled(moments) failed: " + std::to_string((int)rc));
+        }
+        if (R > 0)
+        {
+            const cuuint64_t dims[2] = {(cuuint64_t)v.W, (cuuint64_t)v.H};
+            const cuuint64_t strides[1] = {(cuuint64_t)v.W * 4};
+            const cuuint32_t box[2] = {(cuuint32_t)(TILE + 2 * R), (cuuint32_t)(TILE + 2 * R)};
+            const cuuint32_t es[2] = {1, 1};
+            CUresult rc = enc(&tmap_step, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, v.der + (size_t)D_STEP * v.plane(), dims, strides,
+                              box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
+            if (rc != CUDA_SUCCESS)
+                throw CudaError("cuTensorMapEncodeTiled(step) failed: " + std::to_string((int)rc));
+        }
+    }
+    // make the window cover tiles [tx0,tx1) x [ty0,ty1); existing content is kept
+    void ensure(cudaStream_t st, int tx0, int ty0, int tx1, int ty1)
+    {
+        if (v.mom && tx0 >= v.tx0 && ty0 >= v.ty0 && tx1 <= v.tx0 + v.tw && ty1 <= v.ty0 + v.th)
+            return;
+        int nx0 = tx0, ny0 = ty0, nx1 = tx1, ny1 = ty1;
+        if (v.mom)
+        {
+            // grow geometrically in the direction that is needed so repeated extension amortises
+            const int gx = std::max(4, v.tw / 4), gy = std::max(4, v.th / 4);
+            if (tx0 < v.tx0) nx0 = std::min(tx0, v.tx0 - gx); else nx0 = v.tx0;
+            if (ty0 < v.ty0) ny0 = std::min(ty0, v.ty0 - gy); else ny0 = v.ty0;
+            if (tx1 > v.tx0 + v.tw) nx1 = std::max(tx1, v.tx0 + v.tw + gx); else nx1 = v.tx0 + v.tw;
+            if (ty1 > v.ty0 + v.th) ny1 = std::max(ty1, v.ty0 + v.th + gy); else ny1 = v.ty0 + v.th;
+        }
+        GridView n;
+        alloc_view(n, nx0, ny0, nx1 - nx0, ny1 - ny0, st);
+        if (v.mom)
+        {
+            const size_t ox = (size_t)(v.tx0 - nx0) * TILE, oy = (size_t)(v.ty0 - ny0) * TILE;
+            CK(cudaMemcpy2DAsync(n.mom + (oy * n.W + ox) * REC, (size_t)n.W * REC * 4, v.mom, (size_t)v.W * REC * 4,
+                                 (size_t)v.W * REC * 4, v.H, cudaMemcpyDeviceToDevice, st));
+            for (int k = 0; k < NUM_DER; ++k)
+                CK(cudaMemcpy2DAsync(n.der + k * n.plane() + oy * n.W + ox, (size_t)n.W * 4, v.der + k * v.plane(),
+                                     (size_t)v.W * 4, (size_t)v.W * 4, v.H, cudaMemcpyDeviceToDevice, st));
+            CK(cudaMemcpy2DAsync(n.flags + oy * n.W + ox, n.W, v.flags, v.W, v.W, v.H, cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            release();
+        }
+        v = n;
+        ++reallocs;
+        encode();
+    }
+    void blank_all(cudaStream_t st)
+    {
+        const size_t pl = v.plane();
+        CK(cudaMemsetAsync(v.mom, 0xFF, pl * REC * sizeof(float), st));
+        CK(cudaMemsetAsync(v.der, 0xFF, pl * NUM_DER * sizeof(float), st));
+    }
+};
+
+// -------------------------------------------------------------------------------------------
+// KeyFrame (KeyFrame.hpp): device cloud + pose state machine + the pose it is integrated at
+// -------------------------------------------------------------------------------------------
+struct KeyFrame
+{
+    uint64_t id = 0;
+    double timestamp = 0;
+    uint64_t mapId = 0;
+    float4 *d_cloud = nullptr;
+    uint32_t n = 0;
+    float maxnorm = 0.f;
+    bool hasCloud = true;  // false once "dropped" (is_kf_optimization_enabled == false)
+    std::mutex poseMutex;
+    float pose[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    bool pending = false;
+    bool integrated = false;  // has a contribution in the grid (== reference partials non-empty)
+    float intPose[12] = {0};
+    ~KeyFrame() { if (d_cloud) cudaFree(d_cloud); }
+
+    void setPose(const float p[12])  // KeyFrame.cpp:29-34
+    {
+        std::lock_guard<std::mutex> l(poseMutex);
+        std::memcpy(pose, p, sizeof(pose));
+        pending = true;
+    }
+    bool getPendingPose(float out[12])  // KeyFrame.cpp:36-44
+    {
+        std::lock_guard<std::mutex> l(poseMutex);
+        if (!pending) return false;
+        std::memcpy(out, pose, sizeof(pose));
+        pending = false;
+        return true;
+    }
+    void getPose(float out[12])
+    {
+        std::lock_guard<std::mutex> l(poseMutex);
+        std::memcpy(out, pose, sizeof(pose));
+    }
+};
+
+struct Op
+{
+    std::shared_ptr<KeyFrame> kf;
+    float pose[12];
+    float sign;
+};
+
+static std::vector<std::pair<int, int>> discOffsets(double radius, double res)  // Helpers.cpp:156-169
+{
+    const double rc = std::max(1.0, radius / res);
+    const int r = static_cast<int>(std::ceil(rc));
+    const double rc2 = rc * rc;
+    std::vector<std::pair<int, int>> out;
+    for (int di = -r; di <= r; ++di)
+        for (int dj = -r; dj <= r; ++dj)
+            if (static_cast<double>(di * di + dj * dj) <= rc2)
+                out.emplace_back(di, dj);
+    return out;
+}
+
+// -------------------------------------------------------------------------------------------
+// LocalMap
+// -------------------------------------------------------------------------------------------
+class LocalMap
+{
+  public:
+    LocalMap(uint64_t mapID, const tmap_params &P, tmap_update_cb cb, void *user) : mapID_(mapID), P_(P), cb_(cb), user_(user)
+    {
+        CK(cudaSetDevice(P.device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, P.device));
+        nSM_ = prop.multiProcessorCount;
+        lat_ = LatticeD{P.grid_center_x, P.grid_center_y, P.resolution};
+        disc_ = discOffsets(P.robot_radius, P.resolution);
+        if ((int)disc_.size() > MAX_DISC)
+            throw Unsupported("robot_radius/resolution gives a footprint of " + std::to_string(disc_.size()) + " cells (limit " +
+                              std::to_string(MAX_DISC) + ")");
+        r_ = 0;
+        for (auto &o : disc_) r_ = std::max(r_, std::max(std::abs(o.first), std::abs(o.second)));
+        if (classify_smem_bytes(r_) > 200 * 1024)
+            throw Unsupported("footprint radius of " + std::to_string(r_) + " cells exceeds the halo-tile shared-memory budget");
+        R_ = 0;
+        if (P.inflation_enabled)
+        {
+            auto io = discOffsets(P.inflation_radius, P.resolution);
+            int rr = 0;
+            for (auto &o : io) rr = std::max(rr, std::max(std::abs(o.first), std::abs(o.second)));
+            R_ = (rr + 1) & ~1;  // even, so the TMA box rows are 16-byte multiples
+            if (inflate_smem_bytes(R_) > 200 * 1024 || TILE + 2 * R_ > 256)
+                throw Unsupported("inflation radius of " + std::to_string(rr) + " cells exceeds the halo-tile budget");
+            const int KW = 2 * R_ + 1;
+            std::vector<float> decay((size_t)KW * KW, 0.f);
+            for (auto &o : io)  // LocalMap.cpp:57-67
+            {
+                const double dist_m = std::hypot((double)o.first, (double)o.second) * P.resolution;
+                decay[(size_t)(o.second + R_) * KW + (o.first + R_)] = static_cast<float>(std::exp(-P.cost_scaling_factor * dist_m));
+            }
+            nInfl_ = (int)io.size();
+            decay_.ensure(decay.size() * 4);
+            CK(cudaMemcpy(decay_.p, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
+        }
+        CK(cudaStreamCreateWithFlags(&ownStream_, cudaStreamNonBlocking));
+        stream_ = ownStream_;
+        for (auto &e : ev_) CK(cudaEventCreate(&e));
+        grid_.r = r_;
+        grid_.R = R_;
+        // logical (reference) extent: makeGridMap(half, half) (LocalMap.cpp:73-74, Helpers.cpp:42-47)
+        kx_ = static_cast<int>(std::ceil(P.half_size / P.resolution));
+        ky_ = kx_;
+        grid_.ensure(stream_, floordiv32(-kx_), floordiv32(-ky_), floordiv32(kx_) + 1, floordiv32(ky_) + 1);
+        counters_h_.ensure(64 * 4);
+        running_ = true;
+        worker_ = std::thread(&LocalMap::run, this);
+    }
+    ~LocalMap()
+    {
+        {
+            std::lock_guard<std::mutex> l(qMutex_);
+            running_ = false;
+        }
+        qCv_.notify_all();
+        if (worker_.joinable()) worker_.join();
+        cudaStreamSynchronize(stream_);
+        for (auto &e : ev_) cudaEventDestroy(e);
+        cudaStreamDestroy(ownStream_);
+    }
+
+    uint64_t id() const { return mapID_; }
+    std::recursive_mutex &gridMutex() { return gridMutex_; }
+
+    void addAlreadyDeclaredKF(const std::shared_ptr<KeyFrame> &kf)  // LocalMap.cpp:319-328
+    {
+        std::lock_guard<std::mutex> l(kfMutex_);
+        kf->mapId = mapID_;
+        kfs_[kf->id] = kf;
+    }
+    void setKeyFramePose(const std::shared_ptr<KeyFrame> &kf, const float pose[12])  // LocalMap.cpp:330-341
+    {
+        if (!kf) return;
+        kf->setPose(pose);
+        {
+            std::lock_guard<std::mutex> l(qMutex_);
+            if (queued_.insert(kf->id).second)
+                queue_.push_back(kf);
+        }
+        qCv_.notify_one();
+    }
+    std::shared_ptr<KeyFrame> detachKeyFrame(uint64_t id)  // LocalMap.cpp:343-373
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        std::shared_ptr<KeyFrame> kf;
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            auto it = kfs_.find(id);
+            if (it == kfs_.end()) return nullptr;
+            kf = it->second;
+        }
+        if (kf->integrated)
+        {
+            std::vector<Op> ops(1);
+            ops[0].kf = kf;
+            std::memcpy(ops[0].pose, kf->intPose, sizeof(kf->intPose));
+            ops[0].sign = -1.f;
+            runBatch(ops);
+            kf->integrated = false;
+        }
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            kfs_.erase(id);
+        }
+        {
+            std::lock_guard<std::mutex> l(qMutex_);
+            queued_.erase(id);
+        }
+        return kf;
+    }
+    void clearEntireMap()  // LocalMap.cpp:375-397
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        CK(launch_mark_observed_changed(stream_, grid_.v));
+        ++g_launches;
+        grid_.blank_all(stream_);
+        CK(cudaStreamSynchronize(stream_));
+        std::lock_guard<std::mutex> l(kfMutex_);
+        {
+            std::lock_guard<std::mutex> ql(qMutex_);
+            for (auto &kv : kfs_)  // ascending kf id (the reference iterates an unordered_map)
+            {
+                kv.second->integrated = false;
+                float p[12];
+                kv.second->getPose(p);
+                kv.second->setPose(p);
+                if (queued_.insert(kv.first).second)
+                    queue_.push_back(kv.second);
+            }
+        }
+        qCv_.notify_one();
+    }
+    size_t numKeyFrames()
+    {
+        std::lock_guard<std::mutex> l(kfMutex_);
+        return kfs_.size();
+    }
+    size_t queueDepth()
+    {
+        std::lock_guard<std::mutex> l(qMutex_);
+        return queue_.size();
+    }
+    void flush()
+    {
+        std::unique_lock<std::mutex> l(qMutex_);
+        idleCv_.wait(l, [&] { return (queue_.empty() && !busy_) || !running_; });
+    }
+    void setStream(void *s)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaStreamSynchronize(stream_));
+        stream_ = s ? static_cast<cudaStream_t>(s) : ownStream_;
+    }
+
+    // ---- queries (caller may hold gridMutex via tmap_lock; the mutex is recursive) ----
+    std::vector<uint64_t> collectKeys(int mode, bool drain)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        scratchCount_.ensure(16);
+        uint32_t *d_count = scratchCount_.as<uint32_t>();
+        // first pass: count; second pass: write (+clear)
+        CK(launch_collect_keys(stream_, grid_.v, mode, 0, nullptr, 0, d_count));
+        uint32_t n = 0;
+        CK(cudaMemcpyAsync(&n, d_count, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+        std::vector<uint64_t> keys(n);
+        if (n)
+        {
+            scratchKeys_.ensure((size_t)n * 8);
+            CK(launch_collect_keys(stream_, grid_.v, mode, drain ? 1 : 0, scratchKeys_.as<unsigned long long>(), n, d_count));
+            CK(cudaMemcpyAsync(keys.data(), scratchKeys_.p, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            g_launches += 1;
+            std::sort(keys.begin(), keys.end());
+        }
+        return keys;
+    }
+    size_t countKeys(int mode)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        scratchCount_.ensure(16);
+        uint32_t *d_count = scratchCount_.as<uint32_t>();
+        CK(launch_collect_keys(stream_, grid_.v, mode, 0, nullptr, 0, d_count));
+        uint32_t n = 0;
+        CK(cudaMemcpyAsync(&n, d_count, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+        return n;
+    }
+    void readLayers(const uint64_t *keys, size_t n, const int32_t *layers, size_t nl, float *out)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        if (!n || !nl) return;
+        scratchKeys_.ensure(n * 8);
+        scratchLayers_.ensure(nl * 4);
+        scratchOut_.ensure(n * nl * 4);
+        CK(cudaMemcpyAsync(scratchKeys_.p, keys, n * 8, cudaMemcpyHostToDevice, stream_));
+        CK(cudaMemcpyAsync(scratchLayers_.p, layers, nl * 4, cudaMemcpyHostToDevice, stream_));
+        CK(launch_read_layers(stream_, grid_.v, scratchKeys_.as<unsigned long long>(), n, scratchLayers_.as<int>(), (int)nl, kx_, ky_,
+                              scratchOut_.as<float>()));
+        CK(cudaMemcpyAsync(out, scratchOut_.p, n * nl * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+    }
+    void exportDense(int layer, int ci0, int cj0, int w, int h, float *out)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        const size_t tot = (size_t)w * h;
+        if (!tot) return;
+        scratchOut_.ensure(tot * 4);
+        CK(launch_export_dense(stream_, grid_.v, layer, ci0, cj0, w, h, kx_, ky_, scratchOut_.as<float>()));
+        CK(cudaMemcpyAsync(out, scratchOut_.p, tot * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+    }
+    void exportOccupancy(int ci0, int cj0, int w, int h, int8_t *out)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        const size_t tot = (size_t)w * h;
+        if (!tot) return;
+        scratchOut_.ensure(tot);
+        CK(launch_export_occupancy(stream_, grid_.v, ci0, cj0, w, h, kx_, ky_, scratchOut_.as<signed char>()));
+        CK(cudaMemcpyAsync(out, scratchOut_.p, tot, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+    }
+    void extent(int32_t *kx, int32_t *ky)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        *kx = kx_;
+        *ky = ky_;
+    }
+    size_t stitched(float *out, size_t cap)  // LocalMap.cpp:416-437 (no voxel filter)
+    {
+        std::vector<std::shared_ptr<KeyFrame>> snap;
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            for (auto &kv : kfs_) snap.push_back(kv.second);
+        }
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        size_t total = 0;
+        for (auto &kf : snap)
+            if (kf->hasCloud) total += kf->n;
+        if (!out) return total;
+        size_t off = 0;
+        scratchLayers_.ensure(48);
+        for (auto &kf : snap)
+        {
+            if (!kf->hasCloud || off + kf->n > cap) continue;
+            float p[12];
+            kf->getPose(p);
+            scratchOut_.ensure((size_t)kf->n * 12);
+            CK(cudaMemcpyAsync(scratchLayers_.p, p, 48, cudaMemcpyHostToDevice, stream_));
+            CK(launch_transform_cloud(stream_, kf->d_cloud, kf->n, scratchLayers_.as<float>(), scratchOut_.as<float>()));
+            CK(cudaMemcpyAsync(out + off * 3, scratchOut_.p, (size_t)kf->n * 12, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            g_launches += 1;
+            off += kf->n;
+        }
+        return total;
+    }
+    void getStats(tmap_stats *s)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        *s = stats_;
+        s->kernel_launches = g_launches.load();
+        s->grid_reallocs = grid_.reallocs;
+    }
+
+  private:
+    // ---- the worker (LocalMap::RunLocalKeyFrames, LocalMap.cpp:452-485) ----
+    void run()
+    {
+        cudaSetDevice(P_.device);
+        for (;;)
+        {
+            std::vector<std::shared_ptr<KeyFrame>> take;
+            {
+                std::unique_lock<std::mutex> l(qMutex_);
+                qCv_.wait(l, [&] { return !queue_.empty() || !running_; });
+                if (!running_) break;
+                const size_t lim = P_.max_batch <= 0 ? queue_.size() : std::min<size_t>(queue_.size(), (size_t)P_.max_batch);
+                for (size_t i = 0; i < lim; ++i)
+                {
+                    take.push_back(queue_.front());
+                    queue_.pop_front();
+                    queued_.erase(take.back()->id);
+                }
+                busy_ = true;
+            }
+            int changed = 0;
+            try
+            {
+                changed = processTaken(take);
+            }
+            catch (const std::exception &e)
+            {
+                std::lock_guard<std::mutex> l(qMutex_);
+                workerError_ = e.what();
+            }
+            for (int i = 0; i < changed; ++i)
+                if (cb_) cb_(user_);  // onUpdate_, grid lock released (LocalMap.cpp:479-481)
+            {
+                std::lock_guard<std::mutex> l(qMutex_);
+                busy_ = false;
+            }
+            idleCv_.notify_all();
+        }
+        idleCv_.notify_all();
+    }
+    int processTaken(const std::vector<std::shared_ptr<KeyFrame>> &take)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        std::vector<Op> ops;
+        std::vector<std::shared_ptr<KeyFrame>> done;
+        for (auto &kf : take)
+        {
+            float pose[12];
+            if (!kf->getPendingPose(pose)) continue;  // LocalMap.cpp:473-475
+            {
+                std::lock_guard<std::mutex> l(kfMutex_);  // deleted since enqueued? (LocalMap.cpp:248-256)
+                if (kfs_.find(kf->id) == kfs_.end()) continue;
+            }
+            if (!kf->hasCloud) continue;  // LocalMap.cpp:260-267
+            if (kf->integrated)
+            {
+                Op s;
+                s.kf = kf;
+                std::memcpy(s.pose, kf->intPose, sizeof(s.pose));
+                s.sign = -1.f;
+                ops.push_back(s);
+            }
+            Op a;
+            a.kf = kf;
+            std::memcpy(a.pose, pose, sizeof(a.pose));
+            a.sign = +1.f;
+            ops.push_back(a);
+            done.push_back(kf);
+        }
+        if (ops.empty()) return 0;
+        runBatch(ops);
+        for (auto &op : ops)
+            if (op.sign > 0)
+            {
+                op.kf->integrated = true;
+                std::memcpy(op.kf->intPose, op.pose, sizeof(op.pose));
+            }
+        if (!P_.is_kf_optimization_enabled)
+            for (auto &kf : done) kf->hasCloud = false;  // dropCloud (LocalMap.cpp:311-312)
+        stats_.keyframes_processed += done.size();
+        return (int)done.size();
+    }
+
+    // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
+    void runBatch(const std::vector<Op> &ops)
+    {
+        CK(cudaSetDevice(P_.device));
+        const uint32_t n_ops = (uint32_t)ops.size();
+        const double res = P_.resolution;
+        // choose the chunk size: small batches use small chunks so the grid still fills the GPU
+        uint64_t total_pts = 0, chunks8 = 0;
+        for (auto &op : ops) { total_pts += op.kf->n; chunks8 += (op.kf->n + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8); }
+        const int ppt = chunks8 >= (uint64_t)2 * nSM_ ? 8 : 2;
+        const uint32_t CH = BIN_THREADS * ppt;
+        if (total_pts >= (1ull << 32))
+            throw Unsupported("batch exceeds 2^32 points");
+        if (n_ops >= (1u << 22) || n_ops > 65535)
+            throw Unsupported("batch exceeds 65535 ops");
+
+        opsH_.ensure(n_ops * sizeof(OpDesc));
+        OpDesc *od = opsH_.as<OpDesc>();
+        uint32_t n_chunks = 0, tot_off = 0, maxT = 0;
+        unsigned long long hist_off = 0;
+        int ux0 = INT_MAX, uy0 = INT_MAX, ux1 = INT_MIN, uy1 = INT_MIN;  // union of op windows (tiles, inclusive)
+        for (uint32_t i = 0; i < n_ops; ++i)
+        {
+            const Op &op = ops[i];
+            OpDesc &d = od[i];
+            std::memset(&d, 0, sizeof(d));
+            d.cloud = op.kf->d_cloud;
+            d.n = op.kf->n;
+            d.sign = op.sign;
+            std::memcpy(d.T, op.pose, sizeof(d.T));
+            for (int k = 0; k < 12; ++k)
+                if (!std::isfinite(op.pose[k])) throw std::invalid_argument("non-finite pose");
+            // window: |x_m - t_x| <= |row_x| * max|p_base| (Cauchy-Schwarz) + float-rounding slack
+            const double mn = (double)op.kf->maxnorm;
+            double lo[2], hi[2];
+            for (int a = 0; a < 2; ++a)
+            {
+                const float *rw = op.pose + 4 * a;
+                const double rn = std::sqrt((double)rw[0] * rw[0] + (double)rw[1] * rw[1] + (double)rw[2] * rw[2]);
+                const double t = rw[3];
+                const double rad = rn * mn;
+                const double slack = 1e-5 * (std::abs(t) + rad) + 2.0 * res;
+                lo[a] = t - rad - slack;
+                hi[a] = t + rad + slack;
+            }
+            const double qx0 = std::floor((lo[0] - lat_.x0) / res) - 1, qx1 = std::ceil((hi[0] - lat_.x0) / res) + 1;
+            const double qy0 = std::floor((lo[1] - lat_.y0) / res) - 1, qy1 = std::ceil((hi[1] - lat_.y0) / res) + 1;
+            if (!(qx0 > -1e9 && qx1 < 1e9 && qy0 > -1e9 && qy1 < 1e9))
+                throw std::invalid_argument("keyframe window out of the 32-bit cell range");
+            d.wtx0 = floordiv32((int)qx0);
+            d.wty0 = floordiv32((int)qy0);
+            d.wtw = floordiv32((int)qx1) - d.wtx0 + 1;
+            d.wth = floordiv32((int)qy1) - d.wty0 + 1;
+            const uint64_t T = (uint64_t)d.wtw * d.wth;
+            if (T > MAX_WINDOW_TILES)
+                throw Unsupported("keyframe spans " + std::to_string(T) + " tiles (sensor range / resolution too large; limit " +
+                                  std::to_string(MAX_WINDOW_TILES) + ")");
+            d.T_tiles = (uint32_t)T;
+            maxT = std::max(maxT, d.T_tiles);
+            d.chunk0 = n_chunks;
+            d.nchunks = (d.n + CH - 1) / CH;
+            n_chunks += d.nchunks;
+            d.tot_off = tot_off;
+            tot_off += d.T_tiles;
+            d.hist_off = hist_off;
+            hist_off += (unsigned long long)d.nchunks * d.T_tiles;
+            ux0 = std::min(ux0, d.wtx0); uy0 = std::min(uy0, d.wty0);
+            ux1 = std::max(ux1, d.wtx0 + d.wtw - 1); uy1 = std::max(uy1, d.wty0 + d.wth - 1);
+        }
+        // tile-list dilation radii
+        const int dc = (r_ + TILE - 1) / TILE;
+        const int di = R_ > 0 ? (r_ + R_ + TILE - 1) / TILE : -1;
+        const int dm = std::max(dc, di);
+
+        grid_.ensure(stream_, ux0, uy0, ux1 + 1, uy1 + 1);
+
+        BatchView b{};
+        b.n_ops = n_ops;
+        b.n_chunks = n_chunks;
+        b.btx0 = ux0 - dm; b.bty0 = uy0 - dm;
+        b.btw = ux1 - ux0 + 1 + 2 * dm; b.bth = uy1 - uy0 + 1 + 2 * dm;
+        const size_t nb = (size_t)b.btw * b.bth;
+        b.total_points = (uint32_t)total_pts;
+
+        chunkH_.ensure((size_t)n_chunks * 4 + 4);
+        uint32_t *ch = chunkH_.as<uint32_t>();
+        for (uint32_t i = 0; i < n_ops; ++i)
+            for (uint32_t c = 0; c < od[i].nchunks; ++c) ch[od[i].chunk0 + c] = i;
+
+        opsD_.ensure(n_ops * sizeof(OpDesc));
+        chunkD_.ensure((size_t)n_chunks * 4 + 4);
+        histD_.ensure((size_t)hist_off * 4 + 4);
+        totD_.ensure((size_t)tot_off * 8 + 8);
+        tileD_.ensure(nb * 4 * 5 + 64);
+        bboxD_.ensure((size_t)n_ops * sizeof(int4));
+        sortedD_.ensure((size_t)total_pts * 16 + 16);
+        countersD_.ensure(64 * 4);
+        CK(cudaMemcpyAsync(opsD_.p, od, n_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, stream_));
+        CK(cudaMemcpyAsync(chunkD_.p, ch, (size_t)n_chunks * 4, cudaMemcpyHostToDevice, stream_));
+        b.ops = opsD_.as<OpDesc>();
+        b.chunk_op = chunkD_.as<uint32_t>();
+        b.hist = histD_.as<uint32_t>();
+        b.op_total = totD_.as<uint32_t>();
+        b.op_start = totD_.as<uint32_t>() + tot_off;
+        b.tile_count = tileD_.as<uint32_t>();
+        b.tile_start = b.tile_count + nb;
+        b.active_tiles = b.tile_start + nb;
+        b.cand_tiles = b.active_tiles + nb;
+        b.infl_tiles = b.cand_tiles + nb;
+        b.counters = countersD_.as<uint32_t>();
+        b.op_bbox = bboxD_.as<int4>();
+        b.sorted = sortedD_.as<float4>();
+
+        uploadConstants();
+        const bool prof = P_.profile != 0;
+        CK(launch_bin(stream_, b, grid_.v, lat_, ppt, maxT, dc, di, nSM_, prof ? ev_ : nullptr));
+        g_launches += 8;
+        const int cls_per_sm = std::max(1, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048)));
+        const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * std::min(cls_per_sm, 4), nb);
+        CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, r_, cls_blocks));
+        g_launches += 1;
+        if (prof) CK(cudaEventRecord(ev_[5], stream_));
+        if (R_ > 0)
+        {
+            const int inf_blocks = (int)std::min<size_t>((size_t)nSM_ * 4, nb);
+            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, R_, decay_.as<float>(), inf_blocks));
+            g_launches += 1;
+        }
+        if (prof) CK(cudaEventRecord(ev_[6], stream_));
+        CK(launch_clear_touched(stream_, b, grid_.v, (int)std::min<size_t>((size_t)nSM_ * 4, nb)));
+        g_launches += 1;
+        if (prof) CK(cudaEventRecord(ev_[7], stream_));
+
+        // results the host needs: counters + per-op bounding boxes
+        bboxH_.ensure((size_t)n_ops * sizeof(int4));
+        CK(cudaMemcpyAsync(counters_h_.p, countersD_.p, 16 * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, (size_t)n_ops * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        const uint32_t *cnt = counters_h_.as<uint32_t>();
+        if (cnt[3])
+            throw CudaError("binning consistency check failed (flags " + std::to_string(cnt[3]) + ")");
+
+        // logical grid growth, one keyframe at a time (growToIncludeCells, LocalMap.cpp:91-106 +
+        // growGridToInclude, Helpers.cpp:53-84)
+        const int4 *bb = bboxH_.as<int4>();
+        for (uint32_t i = 0; i < n_ops; ++i)
+            if (ops[i].sign > 0 && bb[i].x != INT_MAX)
+                growLogical(bb[i].x, bb[i].y, bb[i].z, bb[i].w);
+
+        stats_.batches += 1;
+        stats_.points_binned += total_pts;
+        stats_.cells_classified += cnt[7];
+        stats_.last_batch_points = total_pts;
+        stats_.last_batch_tiles = cnt[0];
+        stats_.last_batch_cells_touched = cnt[8];
+        stats_.last_batch_cells_classified = cnt[7];
+        if (prof)
+        {
+            float t;
+            cudaEventElapsedTime(&t, ev_[0], ev_[1]); stats_.ms_hist = t;
+            cudaEventElapsedTime(&t, ev_[1], ev_[2]); stats_.ms_scan = t;
+            cudaEventElapsedTime(&t, ev_[2], ev_[3]); stats_.ms_scatter = t;
+            cudaEventElapsedTime(&t, ev_[3], ev_[4]); stats_.ms_fold = t;
+            cudaEventElapsedTime(&t, ev_[4], ev_[5]); stats_.ms_classify = t;
+            cudaEventElapsedTime(&t, ev_[5], ev_[6]); stats_.ms_inflate = t;
+            cudaEventElapsedTime(&t, ev_[0], ev_[7]); stats_.ms_total = t;
+        }
+    }
+
+    void growLogical(int cimin, int cimax, int cjmin, int cjmax)
+    {
+        const double res = P_.resolution;
+        const double minx = lat_.x0 + cimin * res, maxx = lat_.x0 + cimax * res;
+        const double miny = lat_.y0 + cjmin * res, maxy = lat_.y0 + cjmax * res;
+        const double margin = res;
+        const double curHalfX = ((2 * kx_ + 1) * res) / 2.0, curHalfY = ((2 * ky_ + 1) * res) / 2.0;
+        const double needX = std::max(std::abs(maxx - lat_.x0), std::abs(minx - lat_.x0)) + margin;
+        const double needY = std::max(std::abs(maxy - lat_.y0), std::abs(miny - lat_.y0)) + margin;
+        if (needX <= curHalfX && needY <= curHalfY)
+            return;
+        double newHalfX = curHalfX, newHalfY = curHalfY;
+        while (newHalfX < needX) newHalfX += P_.extend_length;
+        while (newHalfY < needY) newHalfY += P_.extend_length;
+        kx_ = static_cast<int>(std::ceil(newHalfX / res));
+        ky_ = static_cast<int>(std::ceil(newHalfY / res));
+    }
+
+    void uploadConstants()
+    {
+        // __constant__ tables are per process; re-upload when another map (with other parameters) used them last
+        static std::mutex m;
+        static const void *owner = nullptr;
+        std::lock_guard<std::mutex> l(m);
+        if (owner == this) return;
+        ClassifyParams cp{};
+        cp.res = P_.resolution;
+        cp.ground_clearance = P_.ground_clearance;
+        cp.max_slope = P_.max_slope;
+        cp.min_points = (uint32_t)P_.min_points_per_grid;
+        cp.r = r_;
+        cp.n_disc = (int)disc_.size();
+        cp.infl_r = R_;
+        cp.n_infl = nInfl_;
+        cp.lethal = (float)P_.lethal_step_threshold;
+        const int TW = TILE + 2 * r_;
+        std::vector<int> off(disc_.size());
+        std::vector<double> dd(disc_.size() * 2);
+        for (size_t i = 0; i < disc_.size(); ++i)
+        {
+            off[i] = disc_[i].second * TW + disc_[i].first;
+            dd[2 * i] = disc_[i].first;
+            dd[2 * i + 1] = disc_[i].second;
+        }
+        CK(cudaDeviceSynchronize());
+        CK(upload_classify_constants(cp, off.data(), dd.data(), (int)disc_.size()));
+        owner = this;
+    }
+
+    uint64_t mapID_;
+    tmap_params P_;
+    tmap_update_cb cb_;
+    void *user_;
+    int nSM_ = 148;
+    LatticeD lat_;
+    std::vector<std::pair<int, int>> disc_;
+    int r_ = 0, R_ = 0, nInfl_ = 0;
+    int kx_ = 0, ky_ = 0;  // logical (reference) grid half extents in cells
+
+    std::recursive_mutex gridMutex_;  // masterGridMapMutex_
+    DeviceGrid grid_;
+    cudaStream_t stream_ = nullptr, ownStream_ = nullptr;
+    cudaEvent_t ev_[8];
+    tmap_stats stats_{};
+
+    std::mutex kfMutex_;  // keyFramesMapMutex_
+    std::map<uint64_t, std::shared_ptr<KeyFrame>> kfs_;
+
+    std::mutex qMutex_;  // poseQueueMutex_
+    std::condition_variable qCv_, idleCv_;
+    std::deque<std::shared_ptr<KeyFrame>> queue_;
+    std::unordered_set<uint64_t> queued_;
+    bool running_ = false, busy_ = false;
+    std::string workerError_;
+    std::thread worker_;
+
+    PinBuf opsH_, chunkH_, bboxH_, counters_h_;
+    DevBuf opsD_, chunkD_, histD_, totD_, tileD_, bboxD_, sortedD_, countersD_, decay_;
+    DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_;
+
+  public:
+    std::string takeWorkerError()
+    {
+        std::lock_guard<std::mutex> l(qMutex_);
+        std::string e;
+        e.swap(workerError_);
+        return e;
+    }
+};
+
+// -------------------------------------------------------------------------------------------
+// System
+// -------------------------------------------------------------------------------------------
+static void compose(const float A[12], const float B[12], float out[12])
+{
+    // Eigen Affine3f * Affine3f: linear = A.linear*B.linear, translation = A.linear*B.translation + A.translation,
+    // coefficient-wise ((a0 b0 + a1 b1) + a2 b2), float
+    for (int i = 0; i < 3; ++i)
+    {
+        for (int j = 0; j < 3; ++j)
+            out[4 * i + j] = (A[4 * i] * B[j] + A[4 * i + 1] * B[4 + j]) + A[4 * i + 2] * B[8 + j];
+        out[4 * i + 3] = ((A[4 * i] * B[3] + A[4 * i + 1] * B[7]) + A[4 * i + 2] * B[11]) + A[4 * i + 3];
+    }
+}
+
+class System
+{
+  public:
+    explicit System(const tmap_params &P) : P_(P)
+    {
+        int ndev = 0;
+        cudaError_t e = cudaGetDeviceCount(&ndev);
+        if (e != cudaSuccess || ndev <= 0 || P.device >= ndev || P.device < 0)
+            throw std::runtime_error("NO_DEVICE");
+        CK(cudaSetDevice(P.device));
+        if (!(P.resolution > 0)) throw std::invalid_argument("resolution must be positive");
+        CK(cudaStreamCreateWithFlags(&ingest_, cudaStreamNonBlocking));
+    }
+    ~System()
+    {
+        maps_.clear();
+        kfs_.clear();
+        cudaStreamDestroy(ingest_);
+    }
+
+    int setExtrinsics(const float Tsv[12], const float Tbs[12])  // System.cpp:45-51
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        compose(Tbs, Tsv, Tbv_);
+        return TMAP_OK;
+    }
+    int setObstacleParams(const float T[12], double mx, double mn)  // System.cpp:53-60
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        std::memcpy(Tb_obs_, T, sizeof(Tb_obs_));
+        obsMax_ = mx; obsMin_ = mn; obsSet_ = true;
+        return TMAP_OK;
+    }
+    int addMap(uint64_t id, tmap_update_cb cb, void *user)  // System.cpp:62-72
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        if (maps_.count(id)) return TMAP_IGNORED_DUPLICATE;
+        maps_[id] = std::make_shared<LocalMap>(id, P_, cb, user);
+        current_ = maps_[id];
+        return TMAP_OK;
+    }
+    int setCurrentMap(uint64_t id)  // System.cpp:74-82
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto it = maps_.find(id);
+        if (it == maps_.end()) return TMAP_IGNORED_UNKNOWN_MAP;
+        current_ = it->second;
+        return TMAP_OK;
+    }
+    std::shared_ptr<LocalMap> map(uint64_t id)
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto it = maps_.find(id);
+        return it == maps_.end() ? nullptr : it->second;
+    }
+
+    // System::prune on the device; src may be host or device memory
+    std::shared_ptr<KeyFrame> pruneToKeyFrame(const void *src, bool on_device, size_t n, size_t stride, const float T[12], double mx,
+                                              double mn)
+    {
+        std::lock_guard<std::mutex> l(ingestMutex_);
+        CK(cudaSetDevice(P_.device));
+        auto kf = std::make_shared<KeyFrame>();
+        if (n == 0) return kf;
+        const void *d_src = src;
+        if (!on_device)
+        {
+            raw_.ensure(n * stride);
+            CK(cudaMemcpyAsync(raw_.p, src, n * stride, cudaMemcpyHostToDevice, ingest_));
+            d_src = raw_.p;
+        }
+        const size_t n_warps = (n + 255) / 256;
+        warpCnt_.ensure(n_warps * 4 + 64);
+        total_.ensure(16);
+        totalH_.ensure(16);
+        CK(cudaMalloc(&kf->d_cloud, n * sizeof(float4)));
+        CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
+                        total_.as<uint32_t>(), kf->d_cloud, 0));
+        CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
+                        total_.as<uint32_t>(), kf->d_cloud, 1));
+        g_launches += 3;
+        CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
+        CK(cudaStreamSynchronize(ingest_));
+        kf->n = totalH_.as<uint32_t>()[0];
+        std::memcpy(&kf->maxnorm, totalH_.as<uint32_t>() + 1, 4);
+        return kf;
+    }
+
+    int registerKeyFrame(double ts, uint64_t kfID, uint64_t mapID, std::shared_ptr<KeyFrame> kf)  // System.cpp:121-151
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        if (kfs_.count(kfID)) return TMAP_IGNORED_DUPLICATE;
+        auto mit = maps_.find(mapID);
+        if (mit == maps_.end()) return TMAP_IGNORED_UNKNOWN_MAP;
+        if (kf->n == 0) return TMAP_IGNORED_EMPTY;
+        kf->id = kfID;
+        kf->timestamp = ts;
+        kf->mapId = mapID;
+        kfs_[kfID] = kf;
+        kfMap_[kfID] = mapID;
+        mit->second->addAlreadyDeclaredKF(kf);
+        return TMAP_OK;
+    }
+    static double nsToSec(uint64_t ns) { return (double)(ns / 1000000000ULL) + (double)(ns % 1000000000ULL) * 1e-9; }
+
+    int addKeyFrame(uint64_t ts_ns, uint64_t kfID, uint64_t mapID, const void *xyz, bool on_device, size_t n, size_t stride)
+    {
+        if (kfID > (uint64_t)std::numeric_limits<int64_t>::max()) return TMAP_ERR_NEGATIVE_ID;  // System.cpp:163-168
+        if (!xyz) return TMAP_IGNORED_NULL;
+        if (stride < 12 || stride % 4) throw std::invalid_argument("stride_bytes must be a multiple of 4 and >= 12");
+        {
+            // cheap pre-checks before spending a prune pass (same outcomes as registerKeyFrame)
+            std::lock_guard<std::recursive_mutex> l(m_);
+            if (kfs_.count(kfID)) return TMAP_IGNORED_DUPLICATE;
+            if (!maps_.count(mapID)) return TMAP_IGNORED_UNKNOWN_MAP;
+        }
+        float T[12];
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            std::memcpy(T, Tbv_, sizeof(T));
+        }
+        auto kf = pruneToKeyFrame(xyz, on_device, n, stride, T, P_.max_range, P_.min_range);
+        return registerKeyFrame(nsToSec(ts_ns), kfID, mapID, kf);
+    }
+    int addKeyFrameBase(uint64_t kfID, uint64_t mapID, const float *xyz, size_t n)
+    {
+        if (n && !xyz) return TMAP_IGNORED_NULL;
+        auto kf = std::make_shared<KeyFrame>();
+        if (n)
+        {
+            std::lock_guard<std::mutex> l(ingestMutex_);
+            CK(cudaSetDevice(P_.device));
+            raw_.ensure(n * 12);
+            total_.ensure(16);
+            totalH_.ensure(16);
+            CK(cudaMemcpyAsync(raw_.p, xyz, n * 12, cudaMemcpyHostToDevice, ingest_));
+            CK(cudaMalloc(&kf->d_cloud, n * sizeof(float4)));
+            CK(launch_pack_base(ingest_, raw_.as<float>(), n, kf->d_cloud, total_.as<uint32_t>()));
+            g_launches += 1;
+            CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
+            CK(cudaStreamSynchronize(ingest_));
+            kf->n = (uint32_t)n;
+            std::memcpy(&kf->maxnorm, totalH_.as<uint32_t>() + 1, 4);
+            if (!std::isfinite(kf->maxnorm)) throw std::invalid_argument("non-finite point in base cloud");
+        }
+        return registerKeyFrame(0.0, kfID, mapID, kf);
+    }
+    int updateKeyFrame(uint64_t kfID, const float pose[12])  // System.cpp:195-224
+    {
+        for (int k = 0; k < 12; ++k)
+            if (!std::isfinite(pose[k])) throw std::invalid_argument("non-finite pose");
+        std::shared_ptr<LocalMap> mp;
+        std::shared_ptr<KeyFrame> kf;
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            auto rit = kfMap_.find(kfID);
+            if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+            auto mit = maps_.find(rit->second);
+            if (mit == maps_.end()) return TMAP_IGNORED_UNKNOWN_MAP;
+            mp = mit->second;
+            auto kit = kfs_.find(kfID);
+            if (kit != kfs_.end()) kf = kit->second;
+        }
+        mp->setKeyFramePose(kf, pose);
+        return TMAP_OK;
+    }
+    int deleteKeyFrame(uint64_t kfID)  // System.cpp:234-248
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto rit = kfMap_.find(kfID);
+        if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+        auto mit = maps_.find(rit->second);
+        if (mit != maps_.end()) mit->second->detachKeyFrame(kfID);
+        kfs_.erase(kfID);
+        kfMap_.erase(rit);
+        return TMAP_OK;
+    }
+    int updateKFMap(uint64_t kfID, uint64_t mapID)  // System.cpp:250-276
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto rit = kfMap_.find(kfID);
+        if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+        if (!maps_.count(mapID)) return TMAP_IGNORED_UNKNOWN_MAP;
+        const uint64_t old = rit->second;
+        if (old == mapID) return TMAP_OK;
+        auto kf = maps_[old]->detachKeyFrame(kfID);
+        if (!kf) return TMAP_OK;
+        maps_[mapID]->addAlreadyDeclaredKF(kf);
+        float p[12];
+        kf->getPose(p);
+        maps_[mapID]->setKeyFramePose(kf, p);
+        rit->second = mapID;
+        return TMAP_OK;
+    }
+    int informLoopClosure()  // System.cpp:278-284
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto it = maps_.find(0);
+        if (it != maps_.end()) it->second->clearEntireMap();
+        return TMAP_OK;
+    }
+    int addObstacleKeyFrame(uint64_t ts_ns, const float *xyz, size_t n, size_t stride, uint64_t *id_out)  // System.cpp:300-323
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        *id_out = 0;
+        if (!obsSet_) return TMAP_IGNORED_NO_OBSTACLE_PARAMS;
+        if (!xyz) return TMAP_IGNORED_NULL;
+        auto kf = pruneToKeyFrame(xyz, false, n, stride, Tb_obs_, obsMax_, obsMin_);
+        if (kf->n == 0) return TMAP_IGNORED_EMPTY;
+        uint64_t id;
+        if (!freeObs_.empty()) { id = freeObs_.back(); freeObs_.pop_back(); }
+        else id = nextObs_--;
+        const int rc = registerKeyFrame(nsToSec(ts_ns), id, 0, kf);
+        if (rc != TMAP_OK) { freeObs_.push_back(id); return rc; }
+        *id_out = id;
+        return TMAP_OK;
+    }
+    int deleteObstacleKeyFrame(uint64_t id)  // System.cpp:325-335
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        if (!kfMap_.count(id)) return TMAP_IGNORED_UNKNOWN_KF;
+        deleteKeyFrame(id);
+        freeObs_.push_back(id);
+        return TMAP_OK;
+    }
+    int flush()
+    {
+        std::vector<std::shared_ptr<LocalMap>> ms;
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            for (auto &kv : maps_) ms.push_back(kv.second);
+        }
+        std::string err;
+        for (auto &mp : ms)
+        {
+            mp->flush();
+            std::string e = mp->takeWorkerError();
+            if (!e.empty()) err = e;
+        }
+        if (!err.empty()) throw CudaError("worker: " + err);
+        return TMAP_OK;
+    }
+
+  private:
+    tmap_params P_;
+    std::recursive_mutex m_;  // localMapMutex_
+    std::map<uint64_t, std::shared_ptr<LocalMap>> maps_;
+    std::shared_ptr<LocalMap> current_;
+    std::unordered_map<uint64_t, std::shared_ptr<KeyFrame>> kfs_;
+    std::unordered_map<uint64_t, uint64_t> kfMap_;  // allKeyFramesSet_
+    float Tbv_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    float Tb_obs_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    double obsMax_ = 0, obsMin_ = 0;
+    bool obsSet_ = false;
+    uint64_t nextObs_ = (uint64_t)std::numeric_limits<int64_t>::max();
+    std::vector<uint64_t> freeObs_;
+    std::mutex ingestMutex_;
+    cudaStream_t ingest_ = nullptr;
+    DevBuf raw_, warpCnt_, total_;
+    PinBuf totalH_;
+};
+}  // namespace tmb
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+struct tmap_system
+{
+    std::unique_ptr<tmb::System> sys;
+};
+
+#define TMAP_API_BEGIN try {
+#define TMAP_API_END                                                                              \
+    }                                                                                             \
+    catch (const tmb::Unsupported &e) { tmb::g_last_error = e.what(); return TMAP_ERR_UNSUPPORTED; } \
+    catch (const tmb::CudaError &e) { tmb::g_last_error = e.what(); return TMAP_ERR_CUDA; }        \
+    catch (const std::invalid_argument &e) { tmb::g_last_error = e.what(); return TMAP_ERR_INVALID; } \
+    catch (const std::exception &e)                                                                \
+    {                                                                                             \
+        tmb::g_last_error = e.what();                                                              \
+        return std::string(e.what()) == "NO_DEVICE" ? TMAP_ERR_NO_DEVICE : TMAP_ERR_CUDA;          \
+    }
+
+#define NEED(s) if (!(s) || !(s)->sys) { tmb::g_last_error = "null handle"; return TMAP_ERR_INVALID; }
+#define NEED_MAP(mp, s, id)                                                                       \
+    auto mp = (s)->sys->map(id);                                                                  \
+    if (!mp) { tmb::g_last_error = "unknown map"; return TMAP_IGNORED_UNKNOWN_MAP; }
+
+extern "C" {
+
+void tmap_default_params(tmap_params *p)
+{
+    std::memset(p, 0, sizeof(*p));
+    p->resolution = 0.05; p->grid_center_x = 0; p->grid_center_y = 0; p->half_size = 7.5;
+    p->extend_length = 30.0; p->robot_radius = 0.20; p->ground_clearance = 0.15; p->max_slope = 0.4;
+    p->min_points_per_grid = 3; p->is_kf_optimization_enabled = 1; p->num_local_keyframes = 10;
+    p->global_adjustment_sleep = 0; p->inflation_enabled = 0; p->inflation_radius = 1.5;
+    p->cost_scaling_factor = 2.0; p->lethal_step_threshold = 0.95; p->robot_height = 3.5;
+    p->max_range = 6.0; p->min_range = 1.0; p->use_pointcloud_buffer = 0; p->use_ros_buffer = 0;
+    p->publish_rate_hz = 1.0;
+    p->device = 0; p->max_batch = 1; p->profile = 0;
+}
+
+const char *tmap_last_error(void) { return tmb::g_last_error.c_str(); }
+
+int tmap_create(const tmap_params *p, tmap_system **out)
+{
+    if (!p || !out) { tmb::g_last_error = "null argument"; return TMAP_ERR_INVALID; }
+    *out = nullptr;
+    TMAP_API_BEGIN
+    auto s = new tmap_system;
+    try { s->sys.reset(new tmb::System(*p)); }
+    catch (...) { delete s; throw; }
+    *out = s;
+    return TMAP_OK;
+    TMAP_API_END
+}
+
+void tmap_destroy(tmap_system *s) { delete s; }
+
+int tmap_set_extrinsics(tmap_system *s, const float T_sv[12], const float T_bs[12])
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->setExtrinsics(T_sv, T_bs); TMAP_API_END
+}
+int tmap_add_map(tmap_system *s, uint64_t map_id, tmap_update_cb cb, void *user)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->addMap(map_id, cb, user); TMAP_API_END
+}
+int tmap_set_current_map(tmap_system *s, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->setCurrentMap(map_id); TMAP_API_END
+}
+int tmap_add_keyframe(tmap_system *s, uint64_t ts, uint64_t kf_id, uint64_t map_id, const float *xyz, size_t n, size_t stride)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->addKeyFrame(ts, kf_id, map_id, xyz, false, n, stride); TMAP_API_END
+}
+int tmap_add_keyframe_device(tmap_system *s, uint64_t ts, uint64_t kf_id, uint64_t map_id, const void *d_xyz, size_t n, size_t stride)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->addKeyFrame(ts, kf_id, map_id, d_xyz, true, n, stride); TMAP_API_END
+}
+int tmap_add_keyframe_base(tmap_system *s, uint64_t kf_id, uint64_t map_id, const float *xyz, size_t n)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->addKeyFrameBase(kf_id, map_id, xyz, n); TMAP_API_END
+}
+int tmap_update_pose(tmap_system *s, uint64_t kf_id, const float T[12])
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->updateKeyFrame(kf_id, T); TMAP_API_END
+}
+int tmap_delete_keyframe(tmap_system *s, uint64_t kf_id)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->deleteKeyFrame(kf_id); TMAP_API_END
+}
+int tmap_update_kf_map(tmap_system *s, uint64_t kf_id, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->updateKFMap(kf_id, map_id); TMAP_API_END
+}
+int tmap_inform_loop_closure(tmap_system *s)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->informLoopClosure(); TMAP_API_END
+}
+int tmap_set_obstacle_params(tmap_system *s, const float T[12], double mx, double mn)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->setObstacleParams(T, mx, mn); TMAP_API_END
+}
+int tmap_add_obstacle_keyframe(tmap_system *s, uint64_t ts, const float *xyz, size_t n, size_t stride, uint64_t *id_out)
+{
+    NEED(s)
+    if (!id_out) { tmb::g_last_error = "null id_out"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN return s->sys->addObstacleKeyFrame(ts, xyz, n, stride, id_out); TMAP_API_END
+}
+int tmap_delete_obstacle_keyframe(tmap_system *s, uint64_t kf_id)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->deleteObstacleKeyFrame(kf_id); TMAP_API_END
+}
+int tmap_flush(tmap_system *s)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->flush(); TMAP_API_END
+}
+int tmap_lock(tmap_system *s, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->gridMutex().lock(); return TMAP_OK; TMAP_API_END
+}
+int tmap_unlock(tmap_system *s, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->gridMutex().unlock(); return TMAP_OK; TMAP_API_END
+}
+static int keys_out(std::vector<uint64_t> &keys, uint64_t *out, size_t cap, size_t *n_out)
+{
+    if (n_out) *n_out = keys.size();
+    for (size_t i = 0; i < keys.size() && i < cap; ++i) out[i] = keys[i];
+    return TMAP_OK;
+}
+int tmap_take_changed_cells(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    if (!out) { if (n_out) *n_out = mp->countKeys(0); return TMAP_OK; }
+    auto keys = mp->collectKeys(0, true);
+    return keys_out(keys, out, cap, n_out);
+    TMAP_API_END
+}
+int tmap_occupied_cell_keys(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    if (!out) { if (n_out) *n_out = mp->countKeys(1); return TMAP_OK; }
+    auto keys = mp->collectKeys(1, false);
+    return keys_out(keys, out, cap, n_out);
+    TMAP_API_END
+}
+int tmap_read_layers(tmap_system *s, uint64_t map_id, const uint64_t *keys, size_t n, const int32_t *layer_ids, size_t n_layers,
+                     float *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    for (size_t l = 0; l < n_layers; ++l)
+        if (layer_ids[l] < 0 || layer_ids[l] >= TMAP_NUM_LAYERS) throw std::invalid_argument("bad layer id");
+    mp->readLayers(keys, n, layer_ids, n_layers, out);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_grid_extent(tmap_system *s, uint64_t map_id, int32_t *kx, int32_t *ky)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->extent(kx, ky); return TMAP_OK; TMAP_API_END
+}
+int tmap_export_dense(tmap_system *s, uint64_t map_id, int32_t layer, int32_t ci0, int32_t cj0, int32_t w, int32_t h, float *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    if (layer < 0 || layer >= TMAP_NUM_LAYERS || w < 0 || h < 0) throw std::invalid_argument("bad layer id or size");
+    mp->exportDense(layer, ci0, cj0, w, h, out);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t cj0, int32_t w, int32_t h, int8_t *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    if (w < 0 || h < 0) throw std::invalid_argument("bad size");
+    mp->exportOccupancy(ci0, cj0, w, h, out);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) *n_out = mp->numKeyFrames(); return TMAP_OK; TMAP_API_END
+}
+int tmap_queue_depth(tmap_system *s, uint64_t map_id, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) *n_out = mp->queueDepth(); return TMAP_OK; TMAP_API_END
+}
+int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t cap, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    const size_t n = mp->stitched(out_xyz, cap);
+    if (n_out) *n_out = n;
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->getStats(out); return TMAP_OK; TMAP_API_END
+}
+int tmap_set_stream(tmap_system *s, uint64_t map_id, void *stream)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->setStream(stream); return TMAP_OK; TMAP_API_END
+}
+
+}  // extern "C"

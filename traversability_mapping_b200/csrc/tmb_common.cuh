@@ -1,0 +1,94 @@
+// tmb_common.cuh -- shared device/host structures of the B200 traversability hot path.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tmb
+{
+constexpr int TILE = 32;              // cells per tile edge (tile = 32x32 cells)
+constexpr int TILE_SHIFT = 5;
+constexpr int TILE_CELLS = TILE * TILE;
+constexpr int REC = 12;               // floats per moment record
+constexpr int NUM_DER = 10;           // derived planes
+constexpr int MAX_WINDOW_TILES = 4096;  // tiles in one keyframe's window (binning smem limit)
+constexpr int MAX_DISC = 1024;        // footprint offsets held in __constant__ memory
+constexpr int BIN_THREADS = 256;
+constexpr int FOLD_CH = 4096;         // records staged per fold iteration
+
+// moment record field order (one 48-byte AoS record per cell)
+enum { R_N = 0, R_SX, R_SY, R_SZ, R_SX2, R_SY2, R_SZ2, R_SXY, R_SXZ, R_SYZ, R_ZMIN, R_ZMAX };
+// derived plane order
+enum { D_HAZARD = 0, D_ELEVATION, D_SLOPE, D_STEP, D_ROUGHNESS, D_BORDER, D_NX, D_NY, D_NZ, D_INFLATED };
+// per-cell flag bits
+enum : uint8_t { F_TOUCHED = 1, F_CHANGED = 2, F_BLANKED = 4 };
+
+struct LatticeD { double x0, y0, res; };
+
+// Device grid: a dense, tile-aligned window of the absolute cell lattice.
+//   mom   [H][W][12]  float   AoS moment records (N, sx..syz, zmin, zmax)
+//   der   [10][H][W]  float   derived planes
+//   flags [H][W]      uint8   touched / changed / blanked bits
+// Column c <-> cell index ci = ci0 + c, row r <-> cj = cj0 + r; ci0, cj0, W, H multiples of 32.
+struct GridView
+{
+    float *mom;
+    float *der;
+    uint8_t *flags;
+    int W, H;
+    int ci0, cj0;
+    int tx0, ty0, tw, th;  // same window in tile units
+    __host__ __device__ size_t plane() const { return (size_t)W * H; }
+};
+
+// One binning op = one keyframe cloud folded with a sign at a pose.
+struct OpDesc
+{
+    const float4 *cloud;   // base-frame points (x,y,z,unused)
+    uint32_t n;            // points
+    float sign;            // +1 add, -1 subtract
+    float T[12];           // map <- base, row-major 3x4
+    int wtx0, wty0, wtw, wth;  // tile window (global tile indices) covering every point
+    uint32_t T_tiles;      // wtw*wth
+    uint32_t chunk0;       // first chunk id of this op
+    uint32_t nchunks;
+    uint32_t tot_off;      // offset of this op's per-tile arrays (total / op_start)
+    unsigned long long hist_off;  // offset (u32 units) of this op's [nchunks][T_tiles] histogram
+};
+
+struct BatchView
+{
+    const OpDesc *ops;
+    uint32_t n_ops;
+    const uint32_t *chunk_op;  // chunk -> op
+    uint32_t n_chunks;
+    uint32_t *hist;            // per (op, chunk, tile) counts -> exclusive prefix over chunks
+    uint32_t *op_total;        // per (op, tile) point count
+    uint32_t *op_start;        // per (op, tile) offset inside the global tile bucket
+    // batch tile bounding box (global tile indices) and per-tile arrays over it
+    int btx0, bty0, btw, bth;
+    uint32_t *tile_count;      // [btw*bth]
+    uint32_t *tile_start;      // [btw*bth] exclusive scan of tile_count
+    uint32_t *active_tiles;    // compact list of tiles with count>0 (index into bbox)
+    uint32_t *cand_tiles;      // tiles to classify (active dilated by 1)
+    uint32_t *infl_tiles;      // tiles to inflate
+    uint32_t *counters;        // [0] n_active [1] n_cand [2] n_infl [3] error flags [4] fold ticket
+                               // [5] classify ticket [6] inflate ticket [7] cells classified [8] cells touched
+    int4 *op_bbox;             // per op: min ci, max ci, min cj, max cj of its points
+    float4 *sorted;            // bucket-sorted records (xm, ym, zm, meta)
+    uint32_t total_points;
+};
+
+struct ClassifyParams
+{
+    double res, ground_clearance, max_slope;
+    uint32_t min_points;
+    int r;           // disc bounding radius in cells
+    int n_disc;      // number of footprint offsets
+    int infl_r;      // inflation radius in cells (even), 0 = disabled
+    int n_infl;
+    float lethal;
+};
+
+enum { ERR_OUT_OF_WINDOW = 1, ERR_OUT_OF_GRID = 2 };
+
+}  // namespace tmb

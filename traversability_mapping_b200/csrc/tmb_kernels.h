@@ -1,0 +1,32 @@
+// tmb_kernels.h -- host-callable launch wrappers implemented in kernels_bin.cu / kernels_classify.cu
+#pragma once
+#include "tmb_common.cuh"
+#include <cuda.h>
+
+namespace tmb
+{
+size_t fold_smem_bytes();
+cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
+                         float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase);
+cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, float4 *d_out, uint32_t *d_total);
+cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
+                       int dc, int di, int n_sm, cudaEvent_t *ev);
+
+size_t classify_smem_bytes(int r);
+size_t inflate_smem_bytes(int R);
+cudaError_t upload_classify_constants(const ClassifyParams &cp, const int *disc_off, const double *disc_d, int n_disc);
+cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, int r, int n_blocks);
+cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const GridView &g, int n_blocks);
+cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g, int R,
+                           const float *d_decay, int n_blocks);
+cudaError_t launch_collect_keys(cudaStream_t st, const GridView &g, int mode, int clear, unsigned long long *d_out, uint32_t cap,
+                                uint32_t *d_count);
+cudaError_t launch_read_layers(cudaStream_t st, const GridView &g, const unsigned long long *d_keys, size_t n, const int *d_layers,
+                               int n_layers, int kx, int ky, float *d_out);
+cudaError_t launch_export_dense(cudaStream_t st, const GridView &g, int layer, int ci0, int cj0, int w, int h, int kx, int ky,
+                                float *d_out);
+cudaError_t launch_export_occupancy(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky,
+                                    signed char *d_out);
+cudaError_t launch_transform_cloud(cudaStream_t st, const float4 *d_cloud, uint32_t n, const float *d_T, float *d_out);
+cudaError_t launch_mark_observed_changed(cudaStream_t st, const GridView &g);
+}  // namespace tmb
