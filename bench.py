@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- points/s binned+classified on BASELINE.json config[1]: the local traversability map,
+a 10 Hz stream of 131 072-ray keyframes into a 40 x 40 m rolling grid at 0.05 m (49-cell footprint
+disc, step inflation on, rolling window of 15 keyframes; params/traversabilityParamsLocal.yaml with
+the grid half-size and sensor range set to 20 m).
+
+One "step" = one stream tick exactly as local_traversability_node.cpp:153-185 drives the library:
+keyframe insert -> pose update (first bin + classify + inflate) -> eviction of keyframe id-15
+(subtract + reclassify).  `value` counts the points binned for the NEW keyframe only (the evicted
+keyframe's points are re-binned too, but not counted) with the clouds already resident in HBM;
+`e2e` is the same tick through the C ABI with the cloud in pinned host memory (H2D + prune inside)
+plus the D2H of the robot-centred 40 x 40 m occupancy grid.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+N>1: launched by torchrun, one replica map per GPU ("replicas only" for this config: a 40 m local
+map has nothing to shard), value = sum over ranks / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WINDOW = 15
+RAYS = 131072
+C2 = dict(resolution=0.05, half_size=20.0, extend_length=30.0, robot_radius=0.20, ground_clearance=0.15,
+          max_slope=0.4, min_points_per_grid=5, inflation_enabled=1, inflation_radius=0.5,
+          cost_scaling_factor=3.0, lethal_step_threshold=0.95, robot_height=3.5, max_range=20.0, min_range=1.0)
+CROP = 801  # 40 m / 0.05 m + 1 cells, robot-centred
+SEED = 2
+
+
+def workload(n_kf):
+    from traversability_mapping_b200 import synth
+    poses = synth.trajectory("drive", n_kf, seed=SEED, step=0.1, curvature=0.02)  # 1 m/s sampled at 10 Hz
+    clouds = [synth.make_keyframe(SEED, i, poses[i], max_range=20.0) for i in range(n_kf)]
+    return poses, clouds
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def oracle_steps(poses, clouds, first, count, window=WINDOW):
+    """The CPU oracle on the same ticks.  Returns (seconds, points binned for the new keyframes)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle as po
+    from traversability_mapping_b200 import synth
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    om = po.OracleMap(po.default_params(**C2))
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    pts = 0
+    t_total = 0.0
+    for i in range(first + count):
+        timed = i >= first
+        t0 = time.perf_counter()
+        om.add_keyframe(i + 1, clouds[i])
+        om.update_pose(i + 1, poses[i])
+        om.process()
+        if i >= window:
+            om.delete_keyframe(i + 1 - window)
+        dt = time.perf_counter() - t0
+        if timed:
+            t_total += dt
+            pts += om.prune(clouds[i], synth.T_BASE_SENSOR, C2["max_range"], C2["min_range"]).shape[0]
+    om.close()
+    return t_total, pts
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference cannot be built
+    here (Eigen/PCL/grid_map absent), so this times the oracle port -- single worker thread, which is
+    how the reference runs a map (LocalMap.cpp:76-77)."""
+    if rank != 0:
+        return
+    steps = min(args.steps, 4)
+    warm = min(args.warmup, 1)
+    n_kf = WINDOW + warm + steps
+    poses, clouds = workload(n_kf)
+    sec, pts = oracle_steps(poses, clouds, WINDOW + warm, steps)
+    v = pts / sec
+    line = {
+        "impl": "reference", "metric": "points/s binned+classified", "value": v, "unit": "points/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 moments / f32 layers", "data": "synthetic",
+        "config": {"workload": "C2 local map: 10 Hz stream of 131072-ray keyframes, 40x40 m rolling grid @0.05 m, window 15",
+                   "l2": "cpu run"},
+        "cpu_baseline": {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
+                         "sample": f"{steps} stream ticks after a {WINDOW + warm}-tick fill, oracle port (reference not buildable)"},
+        "e2e": {"value": v, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-lc", action="store_true", help="skip the loop-closure leg")
+    ap.add_argument("--lc-keyframes", type=int, default=2000)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import traversability_mapping_b200 as tm
+    from traversability_mapping_b200 import synth
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    K, Wm = args.steps, max(args.warmup, 3)
+    n_kf = WINDOW + Wm + K
+    poses, clouds = workload(n_kf)
+    pinned = [torch.from_numpy(c).pin_memory() for c in clouds]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    stream = torch.cuda.Stream()
+
+    def new_system():
+        p = tm.default_params(device=local, max_batch=1, profile=1, **C2)
+        s = tm.System(p)
+        s.addNewLocalMap(0)
+        s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+        m = s.getLocalMap(0)
+        m.setStream(stream.cuda_stream)
+        return s, m
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident arm (`value`) ----------------
+    s, m = new_system()
+    for i in range(n_kf):   # insert = H2D + prune, not timed here; keyframes are NOT binned until a pose arrives
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]) == tm.OK
+    npts = []
+    stage = {k: 0.0 for k in ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate", "ms_total")}
+    cells_classified = cells_touched = tiles = 0
+    batches0 = None
+    t_ms = 0.0
+    sampler = ClockSampler(local)
+    launches0 = 0
+    for i in range(n_kf):
+        timed = i >= WINDOW + Wm
+        if i == WINDOW + Wm:
+            barrier()
+            sampler.start()
+            launches0 = m.stats()["kernel_launches"]
+        with torch.cuda.stream(stream):
+            if timed:
+                flush_buf.fill_(i & 0xFF)  # L2 flush between timed iterations (untimed)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                stream.synchronize()
+                e0.record(stream)
+            s.updateKeyFrame(i + 1, poses[i])
+            s.flush()
+            if timed:
+                st = m.stats()
+                npts.append(st["last_batch_points"])
+                for k in stage: stage[k] += st[k]
+                cells_classified += st["last_batch_cells_classified"]; cells_touched += st["last_batch_cells_touched"]
+                tiles += st["last_batch_tiles"]
+            if i >= WINDOW:
+                s.deleteKeyFrame(i + 1 - WINDOW)
+                if timed:
+                    st = m.stats()
+                    for k in stage: stage[k] += st[k]
+                    cells_classified += st["last_batch_cells_classified"]; cells_touched += st["last_batch_cells_touched"]
+                    tiles += st["last_batch_tiles"]
+            if timed:
+                e1.record(stream)
+                e1.synchronize()
+                t_ms += e0.elapsed_time(e1)
+    barrier()
+    clocks = sampler.stop()
+    launches = m.stats()["kernel_launches"] - launches0
+    pts_total = int(sum(npts))
+    evict_pts = None
+    s.close()
+
+    # ---------------- end-to-end arm (`e2e`): host buffers through the C ABI ----------------
+    s, m = new_system()
+    occ = torch.empty((CROP, CROP), dtype=torch.int8).pin_memory()
+    occ_np = occ.numpy()
+    e2e_ms = 0.0
+    e2e_pts = 0
+    for i in range(n_kf):
+        timed = i >= WINDOW + Wm
+        if i == WINDOW + Wm:
+            barrier()
+        with torch.cuda.stream(stream):
+            if timed:
+                flush_buf.fill_(i & 0xFF)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                stream.synchronize()
+                e0.record(stream)
+            assert s.addNewKeyFrameWithPCL(i, i + 1, 0, pinned[i].numpy()) == tm.OK   # H2D + prune
+            s.updateKeyFrame(i + 1, poses[i])
+            s.flush()
+            if i >= WINDOW:
+                s.deleteKeyFrame(i + 1 - WINDOW)
+            ci = int(round(float(poses[i][0, 3]) / C2["resolution"])); cj = int(round(float(poses[i][1, 3]) / C2["resolution"]))
+            m.exportOccupancy(ci - CROP // 2, cj - CROP // 2, CROP, CROP, out=occ_np)   # D2H
+            if timed:
+                e1.record(stream)
+                e1.synchronize()
+                e2e_ms += e0.elapsed_time(e1)
+                e2e_pts += npts[i - WINDOW - Wm]
+    barrier()
+    s.close()
+
+    # ---------------- loop-closure re-integration (BASELINE metric, second half) ----------------
+    lc = None
+    if not args.no_lc:
+        nk = args.lc_keyframes
+        base = 32
+        lposes = synth.trajectory("loop", nk, seed=SEED + 1, extent=90.0)
+        lclouds = [synth.make_keyframe(SEED + 1, i, lposes[i], max_range=20.0) for i in range(base)]
+        p = tm.default_params(device=local, max_batch=0, profile=1, resolution=0.1, half_size=100.0, max_range=20.0,
+                              min_range=1.0, robot_radius=0.20)
+        s = tm.System(p)
+        s.addNewLocalMap(0)
+        s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+        m = s.getLocalMap(0)
+        m.setStream(stream.cuda_stream)
+        drift = synth.drift_poses(lposes)
+        for i in range(nk):
+            s.addNewKeyFrameWithPCL(i, i + 1, 0, lclouds[i % base])
+            s.updateKeyFrame(i + 1, drift[i])
+        s.flush()
+        times = []
+        for rep in range(3):
+            for i in range(nk):
+                s.updateKeyFrame(i + 1, lposes[i] if rep % 2 == 0 else drift[i])
+            barrier()
+            with torch.cuda.stream(stream):
+                flush_buf.fill_(rep)
+                e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                stream.synchronize()
+                e0.record(stream)
+                s.informLoopClosure()
+                s.flush()
+                e1.record(stream)
+                e1.synchronize()
+            times.append(e0.elapsed_time(e1))
+        st = m.stats()
+        lc = {"keyframes": nk, "points": int(st["last_batch_points"]), "ms": float(min(times[1:])), "ms_all": times,
+              "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]),
+              "config": "C4-shaped: 2000 stored keyframes on a 180 m loop, 0.1 m grid, drift -> true poses, informLoopClosure"}
+        s.close()
+
+    # ---------------- reduce over ranks ----------------
+    t_max, e2e_max, pts_sum, e2e_pts_sum = t_ms, e2e_ms, pts_total, e2e_pts
+    if world > 1:
+        tt = torch.tensor([t_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        pp = torch.tensor([pts_total, e2e_pts], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pp, op=dist.ReduceOp.SUM)
+        t_max, e2e_max = float(tt[0]), float(tt[1])
+        pts_sum, e2e_pts_sum = float(pp[0]), float(pp[1])
+
+    if rank == 0:
+        peak, peak_src = peaks()
+        # algorithmic bytes per stage: bin = 16 B/point (float4 store) + 80 B per touched cell;
+        # classify = 76 B per recomputed cell (+8 with inflation, booked on the inflate stage)
+        stage_bytes = {
+            "ms_hist": 16.0 * (pts_total * 2),      # new + evicted keyframe both pass through the kernels
+            "ms_scatter": 32.0 * (pts_total * 2),
+            "ms_fold": 16.0 * (pts_total * 2) + 80.0 * cells_touched,
+            "ms_classify": 76.0 * cells_classified,
+            "ms_inflate": 8.0 * tiles * 1024,
+        }
+        dom = max(("ms_hist", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate"), key=lambda k: stage[k])
+        n_launch = 2 * K - 0  # one update batch + one eviction batch per step
+        achieved = stage_bytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": dom.replace("ms_", "k_"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": stage_bytes[dom] / n_launch, "avg_launch_ms": stage[dom] / n_launch,
+                    "stages_ms_per_step": {k: v / K for k, v in stage.items()},
+                    "stages_frac_of_hbm": {k: (stage_bytes[k] / (stage[k] * 1e-3) / 1e9 / peak if stage[k] > 0 else None)
+                                           for k in stage_bytes}}
+        cpu = None
+        if not args.no_cpu:
+            sec, cpts = oracle_steps(poses, clouds, WINDOW + Wm, min(K, 3))
+            cpu = {"value": cpts / sec, "unit": "points/s", "cores": 1, "kind": "port",
+                   "sample": f"{min(K, 3)} stream ticks of the same workload after a {WINDOW + Wm}-tick fill; oracle port, "
+                             f"single worker thread as the reference runs a map; host has {os.cpu_count()} cores"}
+        line = {
+            "metric": "points/s binned+classified", "value": pts_sum / (t_max * 1e-3), "unit": "points/s",
+            "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": t_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 moments / f32 layers", "data": "synthetic",
+            "config": {"workload": "C2 local map: 10 Hz stream of 131072-ray keyframes, 40x40 m rolling grid @0.05 m, window 15, "
+                                   "49-cell disc, inflation 0.5 m",
+                       "points_binned_per_step": pts_total / K, "rays_per_keyframe": RAYS, "l2": "flushed between timed steps (256 MB write)",
+                       "parallelism": "replicas" if world > 1 else "single"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_pts_sum / (e2e_max * 1e-3), "unit": "points/s", "ms_per_step": e2e_max / K,
+                    "h2d_bytes_per_step": RAYS * 16, "d2h_bytes_per_step": CROP * CROP},
+            "gpu_launches": int(launches),
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "loop_closure": lc,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

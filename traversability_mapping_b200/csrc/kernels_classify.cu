@@ -26,7 +26,6 @@ namespace tmb
 {
 __constant__ int c_disc_off[MAX_DISC];       // smem cell offset dj*TW + di
 __constant__ double2 c_disc_d[MAX_DISC];     // (di, dj) as doubles
-__constant__ ClassifyParams c_cp;
 
 // ---- mbarrier / TMA helpers (PTX ISA: mbarrier, cp.async.bulk.tensor) ----------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -46,12 +45,21 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred P1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a transaction-count mismatch traps instead of hanging the GPU
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
-    asm volatile(
-        "{\n\t.reg .pred P1;\n\tLAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\tbra LAB_WAIT;\n\tDONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+    for (uint32_t spins = 0; !mbar_try_wait(bar, parity); ++spins)
+        if (spins > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2)
 {
@@ -69,7 +77,7 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 enum : uint8_t { H_OBS = 1, H_OK = 2, H_TOUCHED = 4 };
 constexpr int CLS_THREADS = 256;
 
-__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap, BatchView b, GridView g)
+__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap, BatchView b, GridView g, const ClassifyParams c_cp)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
     const int r = c_cp.r;
@@ -279,7 +287,8 @@ __global__ void k_clear_touched(BatchView b, GridView g)
 // ---------------------------------------------------------------------------------------------
 constexpr int INF_THREADS = 256;
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__ CUtensorMap tmap_step, BatchView b, GridView g,
-                                                         const float *__restrict__ decay /*[(2R+1)^2], 0 outside disc*/)
+                                                         const float *__restrict__ decay /*[(2R+1)^2], 0 outside disc*/,
+                                                         const ClassifyParams c_cp)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
     float *s_step = reinterpret_cast<float *>(s_raw);
@@ -487,25 +496,25 @@ size_t classify_smem_bytes(int r)
 }
 size_t inflate_smem_bytes(int R) { return (size_t)(TILE + 2 * R) * (TILE + 2 * R) * 4 + 128; }
 
-cudaError_t upload_classify_constants(const ClassifyParams &cp, const int *disc_off, const double *disc_d /*pairs*/, int n_disc)
+cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d /*pairs*/, int n_disc)
 {
-    cudaError_t e = cudaMemcpyToSymbol(c_cp, &cp, sizeof(cp));
-    if (e != cudaSuccess) return e;
-    e = cudaMemcpyToSymbol(c_disc_off, disc_off, sizeof(int) * n_disc);
+    cudaError_t e = cudaMemcpyToSymbol(c_disc_off, disc_off, sizeof(int) * n_disc);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_disc_d, disc_d, sizeof(double) * 2 * n_disc);
 }
 
-cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, int r, int n_blocks)
+cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, const ClassifyParams &cp,
+                            int n_blocks)
 {
     static int attr_r = -1;
+    const int r = cp.r;
     const size_t smem = classify_smem_bytes(r);
     if (attr_r != r)
     {
         cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_r = r;
     }
-    k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, b, g);
+    k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, b, g, cp);
     return cudaGetLastError();
 }
 
@@ -515,17 +524,18 @@ cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const Grid
     return cudaGetLastError();
 }
 
-cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g, int R,
-                           const float *d_decay, int n_blocks)
+cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
+                           const ClassifyParams &cp, const float *d_decay, int n_blocks)
 {
     static int attr_R = -1;
+    const int R = cp.infl_r;
     const size_t smem = inflate_smem_bytes(R);
     if (attr_R != R)
     {
         cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_R = R;
     }
-    k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, d_decay);
+    k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, d_decay, cp);
     return cudaGetLastError();
 }
 

@@ -310,6 +310,17 @@ class LocalMap
             decay_.ensure(decay.size() * 4);
             CK(cudaMemcpy(decay_.p, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
         }
+        static std::atomic<uint64_t> next_serial{1};
+        serial_ = next_serial.fetch_add(1);
+        cp_.res = P.resolution;
+        cp_.ground_clearance = P.ground_clearance;
+        cp_.max_slope = P.max_slope;
+        cp_.min_points = (uint32_t)P.min_points_per_grid;
+        cp_.r = r_;
+        cp_.n_disc = (int)disc_.size();
+        cp_.infl_r = R_;
+        cp_.n_infl = nInfl_;
+        cp_.lethal = (float)P.lethal_step_threshold;
         CK(cudaStreamCreateWithFlags(&ownStream_, cudaStreamNonBlocking));
         stream_ = ownStream_;
         for (auto &e : ev_) CK(cudaEventCreate(&e));
@@ -755,13 +766,13 @@ class LocalMap
         g_launches += 8;
         const int cls_per_sm = std::max(1, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048)));
         const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * std::min(cls_per_sm, 4), nb);
-        CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, r_, cls_blocks));
+        CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, cp_, cls_blocks));
         g_launches += 1;
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0)
         {
             const int inf_blocks = (int)std::min<size_t>((size_t)nSM_ * 4, nb);
-            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, R_, decay_.as<float>(), inf_blocks));
+            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.as<float>(), inf_blocks));
             g_launches += 1;
         }
         if (prof) CK(cudaEventRecord(ev_[6], stream_));
@@ -825,21 +836,12 @@ class LocalMap
 
     void uploadConstants()
     {
-        // __constant__ tables are per process; re-upload when another map (with other parameters) used them last
+        // The footprint tables live in __constant__ memory, one copy per process: re-upload whenever a
+        // different map instance (identified by a never-reused serial) used them last.
         static std::mutex m;
-        static const void *owner = nullptr;
+        static uint64_t owner = 0;
         std::lock_guard<std::mutex> l(m);
-        if (owner == this) return;
-        ClassifyParams cp{};
-        cp.res = P_.resolution;
-        cp.ground_clearance = P_.ground_clearance;
-        cp.max_slope = P_.max_slope;
-        cp.min_points = (uint32_t)P_.min_points_per_grid;
-        cp.r = r_;
-        cp.n_disc = (int)disc_.size();
-        cp.infl_r = R_;
-        cp.n_infl = nInfl_;
-        cp.lethal = (float)P_.lethal_step_threshold;
+        if (owner == serial_) return;
         const int TW = TILE + 2 * r_;
         std::vector<int> off(disc_.size());
         std::vector<double> dd(disc_.size() * 2);
@@ -850,11 +852,13 @@ class LocalMap
             dd[2 * i + 1] = disc_[i].second;
         }
         CK(cudaDeviceSynchronize());
-        CK(upload_classify_constants(cp, off.data(), dd.data(), (int)disc_.size()));
-        owner = this;
+        CK(upload_classify_constants(off.data(), dd.data(), (int)disc_.size()));
+        owner = serial_;
     }
 
     uint64_t mapID_;
+    uint64_t serial_ = 0;
+    ClassifyParams cp_{};
     tmap_params P_;
     tmap_update_cb cb_;
     void *user_;
