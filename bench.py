@@ -45,46 +45,53 @@ def workload(n_kf):
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons DURING the timed region, read in-process through NVML (spawning
+    nvidia-smi in loop mode stalls the driver for milliseconds and showed up in the step time)."""
 
-    def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
-        self.idx = gpu_index
+    def __init__(self, gpu_index, period_s=0.02):
+        self.sm, self.mx, self.reasons = [], [], set()
+        self.idx, self.period = gpu_index, period_s
+        self.stop_flag = threading.Event()
+        self.t = None
+        self.err = None
+
+    def _loop(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
+            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            while not self.stop_flag.is_set():
+                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                self.mx.append(mx)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                for k, b in bits.items():
+                    if r & b:
+                        self.reasons.add(k)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: fall back to one nvidia-smi query at stop()
+            self.err = repr(e)
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        self.t = threading.Thread(target=self._loop, daemon=True)
+        self.t.start()
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        self.stop_flag.set()
+        if self.t:
+            self.t.join(timeout=2)
+        if not self.sm:
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-                for k, nm in enumerate(names):
-                    if r[3 + k].lower().startswith("active"):
-                        reasons.add(nm)
+                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", "--query-gpu=clocks.sm,clocks.max.sm",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+                a, b = [float(x) for x in out.strip().split(",")]
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "note": f"nvml unavailable ({self.err}); sampled after the region"}
             except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 def peaks():

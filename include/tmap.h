@@ -100,7 +100,7 @@ typedef struct tmap_stats
     uint64_t grid_reallocs;
     /* CUDA-event times of the LAST batch, ms (0 unless params.profile) */
     float ms_hist, ms_scan, ms_scatter, ms_fold, ms_classify, ms_inflate, ms_total;
-    float reserved;
+    float host_ms_batch;           /* wall-clock of the last batch on the host (assembly + launches + sync) */
     uint64_t last_batch_points, last_batch_tiles, last_batch_cells_touched,
         last_batch_cells_classified;
 } tmap_stats;

@@ -49,7 +49,7 @@ class Stats(C.Structure):
         ("keyframes_processed", C.c_uint64), ("points_binned", C.c_uint64), ("cells_classified", C.c_uint64),
         ("batches", C.c_uint64), ("kernel_launches", C.c_uint64), ("grid_reallocs", C.c_uint64),
         ("ms_hist", C.c_float), ("ms_scan", C.c_float), ("ms_scatter", C.c_float), ("ms_fold", C.c_float),
-        ("ms_classify", C.c_float), ("ms_inflate", C.c_float), ("ms_total", C.c_float), ("reserved", C.c_float),
+        ("ms_classify", C.c_float), ("ms_inflate", C.c_float), ("ms_total", C.c_float), ("host_ms_batch", C.c_float),
         ("last_batch_points", C.c_uint64), ("last_batch_tiles", C.c_uint64),
         ("last_batch_cells_touched", C.c_uint64), ("last_batch_cells_classified", C.c_uint64),
     ]

@@ -294,7 +294,8 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
     float *s_step = reinterpret_cast<float *>(s_raw);
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_ticket;
-    const int R = c_cp.infl_r, TW = TILE + 2 * R, KW = 2 * R + 1;
+    const int R = c_cp.infl_r, TH = TILE + 2 * R, KW = 2 * R + 1;
+    const int TW = TH;  // R is a multiple of 4: TMA needs the box's inner start coordinate 16-byte aligned
     const float lethal = c_cp.lethal;
     const uint32_t tid = threadIdx.x;
     if (tid == 0)
@@ -319,14 +320,14 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
         if (tid == 0)
         {
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TW * 4));
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TH * 4));
             tma_load_2d(s_step, &tmap_step, &s_bar, col0 - R, row0 - R);
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1;
         // any seed in the halo tile?
         int seed = 0;
-        for (int i = tid; i < TW * TW; i += INF_THREADS)
+        for (int i = tid; i < TW * TH; i += INF_THREADS)
             seed |= s_step[i] >= lethal;
         seed = __syncthreads_or(seed);
         for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)

@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <condition_variable>
 #include <cstring>
@@ -296,7 +297,7 @@ class LocalMap
             auto io = discOffsets(P.inflation_radius, P.resolution);
             int rr = 0;
             for (auto &o : io) rr = std::max(rr, std::max(std::abs(o.first), std::abs(o.second)));
-            R_ = (rr + 1) & ~1;  // even, so the TMA box rows are 16-byte multiples
+            R_ = (rr + 3) & ~3;  // multiple of 4 cells: the TMA box must start 16-byte aligned in the inner (x) dimension
             if (inflate_smem_bytes(R_) > 200 * 1024 || TILE + 2 * R_ > 256)
                 throw Unsupported("inflation radius of " + std::to_string(rr) + " cells exceeds the halo-tile budget");
             const int KW = 2 * R_ + 1;
@@ -650,6 +651,7 @@ class LocalMap
     // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
     void runBatch(const std::vector<Op> &ops)
     {
+        const auto t_begin = std::chrono::steady_clock::now();
         CK(cudaSetDevice(P_.device));
         const uint32_t n_ops = (uint32_t)ops.size();
         const double res = P_.resolution;
@@ -796,6 +798,7 @@ class LocalMap
             if (ops[i].sign > 0 && bb[i].x != INT_MAX)
                 growLogical(bb[i].x, bb[i].y, bb[i].z, bb[i].w);
 
+        stats_.host_ms_batch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         stats_.batches += 1;
         stats_.points_binned += total_pts;
         stats_.cells_classified += cnt[7];
