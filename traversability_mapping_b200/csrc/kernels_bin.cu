@@ -284,23 +284,36 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
         row[i] = s_hist[i];
 }
 
-// per (op, tile): exclusive prefix over the op's chunks, in place; total -> op_total
+// per (op, tile): exclusive prefix over the op's chunks, in place; total -> op_total.
+// One warp per column: 32 chunk counts per step, shuffle scan, carried running total.
 __global__ void k_scan_chunks(BatchView b)
 {
     const uint32_t opi = blockIdx.y;
     const OpDesc &op = b.ops[opi];
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (t >= op.T_tiles)
         return;
     uint32_t *col = b.hist + op.hist_off + t;
+    const size_t T = op.T_tiles;
     uint32_t run = 0;
-    for (uint32_t c = 0; c < op.nchunks; ++c)
+    for (uint32_t c0 = 0; c0 < op.nchunks; c0 += 32)
     {
-        const uint32_t v = col[(size_t)c * op.T_tiles];
-        col[(size_t)c * op.T_tiles] = run;
-        run += v;
+        const uint32_t c = c0 + lane;
+        const uint32_t v = c < op.nchunks ? col[(size_t)c * T] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += u;
+        }
+        if (c < op.nchunks)
+            col[(size_t)c * T] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    b.op_total[op.tot_off + t] = run;
+    if (lane == 0)
+        b.op_total[op.tot_off + t] = run;
 }
 
 // per global tile of the batch bbox: exclusive prefix over ops (op order = fold order)
@@ -762,7 +775,7 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     else
         k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
-    k_scan_chunks<<<dim3((maxT + 127) / 128, b.n_ops), 128, 0, st>>>(b);
+    k_scan_chunks<<<dim3((maxT + 7) / 8, b.n_ops), 256, 0, st>>>(b);
     k_scan_ops<<<(nb + 127) / 128, 128, 0, st>>>(b);
     k_scan_tiles<<<1, 1024, 0, st>>>(b);
     k_mark_lists<<<(nb + 127) / 128, 128, 0, st>>>(b, g, dc, di);

@@ -294,6 +294,9 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
     float *s_step = reinterpret_cast<float *>(s_raw);
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_ticket;
+    constexpr int MAX_SEEDS = 256;
+    __shared__ int s_seed[MAX_SEEDS];
+    __shared__ int s_nseed;
     const int R = c_cp.infl_r, TH = TILE + 2 * R, KW = 2 * R + 1;
     const int TW = TH;  // R is a multiple of 4: TMA needs the box's inner start coordinate 16-byte aligned
     const float lethal = c_cp.lethal;
@@ -325,11 +328,20 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1;
-        // any seed in the halo tile?
-        int seed = 0;
+        // seeds of the halo tile -> compact list (value >= lethal); most tiles have none or a few
+        if (tid == 0) s_nseed = 0;
+        __syncthreads();
         for (int i = tid; i < TW * TH; i += INF_THREADS)
-            seed |= s_step[i] >= lethal;
-        seed = __syncthreads_or(seed);
+        {
+            const float sv = s_step[i];
+            if (sv >= lethal)
+            {
+                const int p = atomicAdd(&s_nseed, 1);
+                if (p < MAX_SEEDS) s_seed[p] = i;
+            }
+        }
+        __syncthreads();
+        const int nseed = s_nseed;
         for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
         {
             const int q = tid + k * INF_THREADS;
@@ -339,7 +351,23 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
             if (!(n >= 1.f))
                 continue;
             float best = 0.f;
-            if (seed)
+            if (nseed > 0 && nseed <= MAX_SEEDS)
+            {
+                // max over seeds inside the kernel footprint (max is order independent -> bit-exact)
+                for (int sidx = 0; sidx < nseed; ++sidx)
+                {
+                    const int i = s_seed[sidx];
+                    const int sy = i / TW, sx = i - sy * TW;
+                    const int di = sx - x, dj = sy - y;  // tap index in [0, KW) when inside the box
+                    if ((unsigned)di < (unsigned)KW && (unsigned)dj < (unsigned)KW)
+                    {
+                        const float dc = __ldg(decay + dj * KW + di);
+                        if (dc > 0.f)
+                            best = fmaxf(best, __fmul_rn(s_step[i], dc));
+                    }
+                }
+            }
+            else if (nseed > MAX_SEEDS)
             {
                 for (int dj = 0; dj < KW; ++dj)
                 {

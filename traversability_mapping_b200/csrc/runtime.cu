@@ -227,7 +227,13 @@ struct KeyFrame
     bool pending = false;
     bool integrated = false;  // has a contribution in the grid (== reference partials non-empty)
     float intPose[12] = {0};
-    ~KeyFrame() { if (d_cloud) cudaFree(d_cloud); }
+    cudaStream_t allocStream = nullptr;  // stream-ordered allocation: freed without a device-wide sync
+    ~KeyFrame()
+    {
+        if (!d_cloud) return;
+        if (allocStream) cudaFreeAsync(d_cloud, allocStream);
+        else cudaFree(d_cloud);
+    }
 
     void setPose(const float p[12])  // KeyFrame.cpp:29-34
     {
@@ -929,11 +935,17 @@ class System
         CK(cudaSetDevice(P.device));
         if (!(P.resolution > 0)) throw std::invalid_argument("resolution must be positive");
         CK(cudaStreamCreateWithFlags(&ingest_, cudaStreamNonBlocking));
+        // keep freed keyframe clouds cached in the stream-ordered pool (rolling windows recycle them)
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, P.device));
+        uint64_t thr = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     }
     ~System()
     {
         maps_.clear();
         kfs_.clear();
+        cudaStreamSynchronize(ingest_);
         cudaStreamDestroy(ingest_);
     }
 
@@ -992,7 +1004,8 @@ class System
         warpCnt_.ensure(n_warps * 4 + 64);
         total_.ensure(16);
         totalH_.ensure(16);
-        CK(cudaMalloc(&kf->d_cloud, n * sizeof(float4)));
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), n * sizeof(float4), ingest_));
+        kf->allocStream = ingest_;
         CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
                         total_.as<uint32_t>(), kf->d_cloud, 0));
         CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
@@ -1053,7 +1066,8 @@ class System
             total_.ensure(16);
             totalH_.ensure(16);
             CK(cudaMemcpyAsync(raw_.p, xyz, n * 12, cudaMemcpyHostToDevice, ingest_));
-            CK(cudaMalloc(&kf->d_cloud, n * sizeof(float4)));
+            CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), n * sizeof(float4), ingest_));
+            kf->allocStream = ingest_;
             CK(launch_pack_base(ingest_, raw_.as<float>(), n, kf->d_cloud, total_.as<uint32_t>()));
             g_launches += 1;
             CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
