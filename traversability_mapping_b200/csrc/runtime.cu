@@ -943,6 +943,7 @@ class System
     }
     ~System()
     {
+        current_.reset();  // every owner of a KeyFrame must go before the allocation stream does
         maps_.clear();
         kfs_.clear();
         cudaStreamSynchronize(ingest_);
