@@ -1,0 +1,207 @@
+// tmap_system.hpp -- header-only C++ mirror of the reference's System / LocalMap classes on top of the
+// C ABI (tmap.h).  Same method names, argument meaning and error behaviour as
+// traversability_mapping/include/traversability_mapping/System.hpp:53-212 and LocalMap.hpp:55-231, so a
+// SLAM integration that used the reference library can switch by changing the include and the link line.
+//
+// The Eigen / PCL overloads are compiled only when those headers are present (they are not in this
+// image); the plain-pointer overloads always are.
+#ifndef TMAP_SYSTEM_HPP_
+#define TMAP_SYSTEM_HPP_
+
+#include "tmap.h"
+
+#include <cstdint>
+#include <functional>
+#include <limits>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#if __has_include(<Eigen/Geometry>)
+#include <Eigen/Geometry>
+#define TMAP_HAVE_EIGEN 1
+#endif
+#if __has_include(<pcl/point_cloud.h>) && __has_include(<pcl/point_types.h>)
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#define TMAP_HAVE_PCL 1
+#endif
+
+namespace traversability_mapping_b200
+{
+/// Row-major 3x4 [R|t]: the first three rows of an Eigen::Affine3f.
+struct Pose
+{
+    float m[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    static Pose Identity() { return Pose(); }
+#ifdef TMAP_HAVE_EIGEN
+    Pose() = default;
+    Pose(const Eigen::Affine3f &T)
+    {
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 4; ++j) m[4 * i + j] = T.matrix()(i, j);
+    }
+    Pose(const Eigen::Affine3d &T) : Pose(Eigen::Affine3f(T.cast<float>())) {}  // System.cpp:229
+#endif
+};
+
+/// Lattice (Moments.hpp:99-134)
+struct Lattice
+{
+    double x0 = 0., y0 = 0., res = 0.25;
+    static inline std::uint64_t key(int ci, int cj)
+    {
+        return (static_cast<std::uint64_t>(static_cast<std::uint32_t>(ci)) << 32) |
+               static_cast<std::uint64_t>(static_cast<std::uint32_t>(cj));
+    }
+    static inline void unkey(std::uint64_t k, int &ci, int &cj)
+    {
+        ci = static_cast<int>(static_cast<std::uint32_t>(k >> 32));
+        cj = static_cast<int>(static_cast<std::uint32_t>(k & 0xffffffffu));
+    }
+};
+
+class System;
+
+/// Reader handle (LocalMap.hpp:108-121).  Hold lock()/unlock() (getGridMapMutex) across a
+/// takeChangedCells()/occupiedCellKeys() + readLayers() sequence for a consistent snapshot.
+class LocalMap
+{
+  public:
+    void lock() { tmap_lock(s_, id_); }
+    void unlock() { tmap_unlock(s_, id_); }
+    const Lattice &getLattice() const { return lat_; }
+    std::vector<std::uint64_t> takeChangedCells() { return keys(tmap_take_changed_cells); }
+    std::vector<std::uint64_t> occupiedCellKeys() { return keys(tmap_occupied_cell_keys); }
+    /// fillSparseUpdate (conversions.cpp:28-55): values[i*layers.size()+l]
+    std::vector<float> readLayers(const std::vector<std::uint64_t> &k, const std::vector<int32_t> &layers)
+    {
+        std::vector<float> out(k.size() * layers.size());
+        check(tmap_read_layers(s_, id_, k.data(), k.size(), layers.data(), layers.size(), out.data()));
+        return out;
+    }
+    void gridExtent(int32_t &kx, int32_t &ky) { check(tmap_grid_extent(s_, id_, &kx, &ky)); }
+    /// toOccupancyGrid(grid, "hazard", 0, 1, og): whole grid, nav_msgs ordering
+    std::vector<int8_t> occupancy(int32_t &width, int32_t &height)
+    {
+        int32_t kx, ky;
+        gridExtent(kx, ky);
+        width = 2 * kx + 1;
+        height = 2 * ky + 1;
+        std::vector<int8_t> out(static_cast<size_t>(width) * height);
+        check(tmap_export_occupancy(s_, id_, -kx, -ky, width, height, out.data()));
+        return out;
+    }
+    std::vector<float> layer(int32_t layer_id, int32_t ci0, int32_t cj0, int32_t w, int32_t h)
+    {
+        std::vector<float> out(static_cast<size_t>(w) * h);
+        check(tmap_export_dense(s_, id_, layer_id, ci0, cj0, w, h, out.data()));
+        return out;
+    }
+    size_t numKeyFrames() { size_t n = 0; check(tmap_num_keyframes(s_, id_, &n)); return n; }
+
+  private:
+    friend class System;
+    LocalMap(tmap_system *s, std::uint64_t id, const Lattice &l) : s_(s), id_(id), lat_(l) {}
+    static void check(int rc) { if (rc < 0) throw std::runtime_error(tmap_last_error()); }
+    template <class F> std::vector<std::uint64_t> keys(F fn)
+    {
+        size_t n = 0;
+        lock();
+        check(fn(s_, id_, nullptr, 0, &n));
+        std::vector<std::uint64_t> out(n);
+        if (n) check(fn(s_, id_, out.data(), n, &n));
+        unlock();
+        out.resize(n);
+        return out;
+    }
+    tmap_system *s_;
+    std::uint64_t id_;
+    Lattice lat_;
+};
+
+class System
+{
+  public:
+    /// ParameterHandler::getInstance(path) + System() (System.cpp:25-43): pass the 22 keys as a struct.
+    explicit System(const tmap_params &p) : params_(p)
+    {
+        if (tmap_create(&p, &s_) != TMAP_OK) throw std::runtime_error(tmap_last_error());
+    }
+    ~System() { tmap_destroy(s_); }
+    System(const System &) = delete;
+    System &operator=(const System &) = delete;
+
+    void setExtrinsicParameters(const Pose &Tsv, const Pose &Tbs) { check(tmap_set_extrinsics(s_, Tsv.m, Tbs.m)); }
+    void setObstacleParameters(const Pose &Tb_obs, double maxRange, double minRange)
+    {
+        check(tmap_set_obstacle_params(s_, Tb_obs.m, maxRange, minRange));
+    }
+    void addNewLocalMap(std::uint64_t mapID, std::function<void()> onUpdate = {})
+    {
+        auto &slot = callbacks_[mapID];
+        slot.reset(new std::function<void()>(std::move(onUpdate)));
+        check(tmap_add_map(s_, mapID, *slot ? &System::trampoline : nullptr, slot.get()));
+    }
+    void setCurrentMap(std::uint64_t mapID) { check(tmap_set_current_map(s_, mapID)); current_ = mapID; }
+
+    /// addNewKeyFrameWithPCL (System.cpp:159-172).  Throws std::runtime_error on a negative id.
+    void addNewKeyFrame(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID, const float *xyz, size_t n,
+                        size_t stride_bytes)
+    {
+        const int rc = tmap_add_keyframe(s_, timestamp_ns, kfID, mapID, xyz, n, stride_bytes);
+        if (rc == TMAP_ERR_NEGATIVE_ID)
+            throw std::runtime_error("The given KF ID was negative. Please make sure the keyFrame IDs are positive. KF ID: " +
+                                     std::to_string(static_cast<std::int64_t>(kfID)));
+        check(rc);
+    }
+#ifdef TMAP_HAVE_PCL
+    void addNewKeyFrameWithPCL(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID,
+                               std::shared_ptr<pcl::PointCloud<pcl::PointXYZ>> cloud)
+    {
+        if (!cloud) return;
+        addNewKeyFrame(timestamp_ns, kfID, mapID, reinterpret_cast<const float *>(cloud->points.data()), cloud->size(),
+                       sizeof(pcl::PointXYZ));
+    }
+#endif
+    void updateKeyFrame(std::uint64_t kfID, const Pose &pose_map_base, std::uint64_t /*numConnections*/ = 0)
+    {
+        check(tmap_update_pose(s_, kfID, pose_map_base.m));
+    }
+    void deleteKeyFrame(std::uint64_t kfID) { check(tmap_delete_keyframe(s_, kfID)); }
+    void updateKFMap(std::uint64_t kfID, std::uint64_t mapID) { check(tmap_update_kf_map(s_, kfID, mapID)); }
+    void informLoopClosure() { check(tmap_inform_loop_closure(s_)); }
+    std::uint64_t addObstacleKeyFrame(unsigned long long timestamp_ns, const float *xyz, size_t n, size_t stride_bytes)
+    {
+        std::uint64_t id = 0;
+        check(tmap_add_obstacle_keyframe(s_, timestamp_ns, xyz, n, stride_bytes, &id));
+        return id;
+    }
+    void deleteObstacleKeyFrame(std::uint64_t kfID) { check(tmap_delete_obstacle_keyframe(s_, kfID)); }
+
+    std::shared_ptr<LocalMap> getLocalMap() { return getLocalMap(current_); }
+    std::shared_ptr<LocalMap> getLocalMap(std::uint64_t mapID)
+    {
+        size_t n = 0;
+        if (tmap_num_keyframes(s_, mapID, &n) != TMAP_OK) return nullptr;  // unknown map -> nullptr (System.cpp:363-368)
+        Lattice l;
+        l.x0 = params_.grid_center_x; l.y0 = params_.grid_center_y; l.res = params_.resolution;
+        return std::shared_ptr<LocalMap>(new LocalMap(s_, mapID, l));
+    }
+    /// Blocks until the workers have drained their queues (test hook).
+    void flush() { check(tmap_flush(s_)); }
+    tmap_system *handle() { return s_; }
+
+  private:
+    static void trampoline(void *user) { (*static_cast<std::function<void()> *>(user))(); }
+    static void check(int rc) { if (rc < 0) throw std::runtime_error(tmap_last_error()); }
+    tmap_params params_;
+    tmap_system *s_ = nullptr;
+    std::uint64_t current_ = 0;
+    std::map<std::uint64_t, std::unique_ptr<std::function<void()>>> callbacks_;
+};
+}  // namespace traversability_mapping_b200
+
+#endif  // TMAP_SYSTEM_HPP_

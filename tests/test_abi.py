@@ -90,3 +90,16 @@ def test_eig3_closed_form_vs_oracle_qr():
     assert r.returncode == 0, r.stdout
     m = re.search(r"max_rel_lambda ([0-9.e+-]+).*max_1-\|dot\| ([0-9.e+-]+)", r.stdout)
     assert float(m.group(1)) < 1e-6 and float(m.group(2)) < 1e-10
+
+
+def test_cpp_mirror_header_compiles_and_fails_loudly_without_gpu(tmap):
+    """include/tmap_system.hpp (the reference-named C++ surface) builds with plain g++ against the C ABI."""
+    exe = "/tmp/tmap_cpp_mirror_check"
+    lib_dir = os.path.dirname(tmap.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp_mirror_check.cpp"),
+                    "-L" + lib_dir, "-ltmap_b200", "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    if HAS_GPU:
+        assert r.returncode == 0, r.stdout + r.stderr
+    else:
+        assert r.returncode == 42 and "failed loudly" in r.stdout

@@ -295,3 +295,14 @@ def test_callback_fires_once_per_keyframe(tmap, oracle):
     s.flush()
     assert len(hits) == 3
     s.close()
+
+
+def test_cpp_mirror_replays_localmap_kat(tmap):
+    """tests/cpp_mirror_check.cpp: test_localmap.cpp:197-207 through include/tmap_system.hpp."""
+    import subprocess
+    exe = "/tmp/tmap_cpp_mirror_check_gpu"
+    lib_dir = os.path.dirname(tmap.LIB_PATH)
+    subprocess.run(["g++", "-std=c++17", "-O1", "-o", exe, os.path.join(ROOT, "tests", "cpp_mirror_check.cpp"),
+                    "-L" + lib_dir, "-ltmap_b200", "-Wl,-rpath," + lib_dir], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr

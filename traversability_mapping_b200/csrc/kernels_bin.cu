@@ -589,14 +589,19 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
             continue;
         }
         const size_t cell = (size_t)row * g.W + col;
+        // the cell's 48-byte record is fetched only if this batch actually touches the cell
         float rec[REC];
+        bool loaded = false;
+        auto load_rec = [&]()
         {
+            if (loaded) return;
             const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
             const float4 a0 = src[0], a1 = src[1], a2 = src[2];
             rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
             rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
             rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
-        }
+            loaded = true;
+        };
         const int ci = tx * TILE + (int)(tid & 31), cj = ty * TILE + (int)(tid >> 5);
         const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
         const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
@@ -680,7 +685,10 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
                 if (op != cur_op)
                 {
                     if (cur_op >= 0)
+                    {
+                        load_rec();
                         fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+                    }
                     acc.reset();
                     cur_op = op;
                 }
@@ -700,7 +708,10 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
             __syncthreads();
         }
         if (cur_op >= 0)
+        {
+            load_rec();
             fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+        }
         if (fl & F_TOUCHED)
         {
             float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);

@@ -283,22 +283,27 @@ __global__ void k_clear_touched(BatchView b, GridView g)
 // k_inflate (LocalMap.cpp:201-241): for observed cells, best = max over kernel taps of
 // step*decay where step >= lethal; written (and flagged changed) only when the value differs.
 // Recomputing a cell outside the reference's window is a no-op (pure function of step_haz, N),
-// so whole candidate tiles are processed.
+// so whole candidate tiles are processed.  Per tile: one 2-D TMA box load of the step_haz halo
+// tile, a summed-area table of the seed mask (cells whose footprint holds no seed finish with
+// four lookups), then the taps in order of decreasing decay with an exact early exit: step <= 1,
+// so once decay_k <= best no later tap can raise the maximum.  max() is order independent, so
+// the result is bit-identical to the reference's loop.
 // ---------------------------------------------------------------------------------------------
-constexpr int INF_THREADS = 256;
+constexpr int INF_THREADS = 1024;  // one cell per thread: a seed-heavy tile is the kernel's tail, so spread it wide
+struct InflTap { int off; float decay; };
+
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__ CUtensorMap tmap_step, BatchView b, GridView g,
-                                                         const float *__restrict__ decay /*[(2R+1)^2], 0 outside disc*/,
+                                                         const InflTap *__restrict__ taps /*sorted by decay, descending*/,
                                                          const ClassifyParams c_cp)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
-    float *s_step = reinterpret_cast<float *>(s_raw);
+    const int R = c_cp.infl_r, TW = TILE + 2 * R, KW = 2 * R + 1, SW = TW + 1;
+    const int ntap = c_cp.n_infl;
+    float *s_step = reinterpret_cast<float *>(s_raw);                                   // [TW][TW]
+    uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (size_t)TW * TW * 4);         // [TW+1][TW+1]
+    InflTap *s_tap = reinterpret_cast<InflTap *>(s_raw + (((size_t)TW * TW * 4 + (size_t)SW * SW * 2 + 15) & ~(size_t)15));
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_ticket;
-    constexpr int MAX_SEEDS = 256;
-    __shared__ int s_seed[MAX_SEEDS];
-    __shared__ int s_nseed;
-    const int R = c_cp.infl_r, TH = TILE + 2 * R, KW = 2 * R + 1;
-    const int TW = TH;  // R is a multiple of 4: TMA needs the box's inner start coordinate 16-byte aligned
     const float lethal = c_cp.lethal;
     const uint32_t tid = threadIdx.x;
     if (tid == 0)
@@ -306,6 +311,8 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
+    for (int i = tid; i < ntap; i += INF_THREADS)
+        s_tap[i] = taps[i];
     __syncthreads();
     uint32_t parity = 0;
     const uint32_t n_tiles = b.counters[2];
@@ -323,68 +330,72 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
         if (tid == 0)
         {
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TH * 4));
+            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TW * 4));
             tma_load_2d(s_step, &tmap_step, &s_bar, col0 - R, row0 - R);
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        // seeds of the halo tile -> compact list (value >= lethal); most tiles have none or a few
-        if (tid == 0) s_nseed = 0;
-        __syncthreads();
-        for (int i = tid; i < TW * TH; i += INF_THREADS)
-        {
-            const float sv = s_step[i];
-            if (sv >= lethal)
-            {
-                const int p = atomicAdd(&s_nseed, 1);
-                if (p < MAX_SEEDS) s_seed[p] = i;
-            }
-        }
-        __syncthreads();
-        const int nseed = s_nseed;
+        // this thread's cells: N (observed?) and the current inflated value, in flight during the TMA
+        float nobs[TILE_CELLS / INF_THREADS], cur[TILE_CELLS / INF_THREADS];
+#pragma unroll
         for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
         {
             const int q = tid + k * INF_THREADS;
+            const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
+            nobs[k] = g.mom[cell * REC + R_N];
+            cur[k] = g.der[D_INFLATED * pl + cell];
+        }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
+        // summed-area table of the seed mask: rows, then columns
+        if ((int)tid < TW)
+        {
+            uint32_t run = 0;
+            const float *row = s_step + tid * TW;
+            uint16_t *o = s_sat + (tid + 1) * SW;
+            o[0] = 0;
+            for (int x = 0; x < TW; ++x)
+            {
+                run += row[x] >= lethal;
+                o[x + 1] = (uint16_t)run;
+            }
+        }
+        if ((int)tid <= TW) s_sat[tid] = 0;
+        __syncthreads();
+        if ((int)tid <= TW)
+        {
+            uint32_t run = 0;
+            for (int y = 1; y <= TW; ++y)
+            {
+                run += s_sat[y * SW + tid];
+                s_sat[y * SW + tid] = (uint16_t)run;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
+        {
+            if (!(nobs[k] >= 1.f))
+                continue;  // observed cells only (LocalMap.cpp:220-221)
+            const int q = tid + k * INF_THREADS;
             const int x = q & 31, y = q >> 5;
-            const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
-            const float n = g.mom[cell * REC + R_N];
-            if (!(n >= 1.f))
-                continue;
+            const int seeds = (int)s_sat[(y + KW) * SW + (x + KW)] - (int)s_sat[y * SW + (x + KW)] -
+                              (int)s_sat[(y + KW) * SW + x] + (int)s_sat[y * SW + x];
             float best = 0.f;
-            if (nseed > 0 && nseed <= MAX_SEEDS)
+            if (seeds > 0)
             {
-                // max over seeds inside the kernel footprint (max is order independent -> bit-exact)
-                for (int sidx = 0; sidx < nseed; ++sidx)
+                const int base = (y + R) * TW + (x + R);
+                for (int t = 0; t < ntap; ++t)
                 {
-                    const int i = s_seed[sidx];
-                    const int sy = i / TW, sx = i - sy * TW;
-                    const int di = sx - x, dj = sy - y;  // tap index in [0, KW) when inside the box
-                    if ((unsigned)di < (unsigned)KW && (unsigned)dj < (unsigned)KW)
-                    {
-                        const float dc = __ldg(decay + dj * KW + di);
-                        if (dc > 0.f)
-                            best = fmaxf(best, __fmul_rn(s_step[i], dc));
-                    }
+                    const InflTap tp = s_tap[t];
+                    if (tp.decay <= best)
+                        break;
+                    const float sv = s_step[base + tp.off];
+                    if (sv >= lethal)
+                        best = fmaxf(best, __fmul_rn(sv, tp.decay));
                 }
             }
-            else if (nseed > MAX_SEEDS)
+            if (!(cur[k] == best))
             {
-                for (int dj = 0; dj < KW; ++dj)
-                {
-                    const float *srow = s_step + (y + dj) * TW + x;
-                    const float *drow = decay + dj * KW;
-                    for (int di = 0; di < KW; ++di)
-                    {
-                        const float sv = srow[di];
-                        const float dc = __ldg(drow + di);
-                        if (sv >= lethal && dc > 0.f)
-                            best = fmaxf(best, __fmul_rn(sv, dc));
-                    }
-                }
-            }
-            const float cur = g.der[D_INFLATED * pl + cell];
-            if (!(cur == best))
-            {
+                const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
                 g.der[D_INFLATED * pl + cell] = best;
                 g.flags[cell] |= F_CHANGED;
             }
@@ -523,7 +534,11 @@ size_t classify_smem_bytes(int r)
     const size_t ncell = (size_t)(TILE + 2 * r) * (TILE + 2 * r);
     return ((ncell * REC * 4 + 127) & ~(size_t)127) + ncell * 8 + ncell + 128;
 }
-size_t inflate_smem_bytes(int R) { return (size_t)(TILE + 2 * R) * (TILE + 2 * R) * 4 + 128; }
+size_t inflate_smem_bytes(int R, int n_taps)
+{
+    const size_t TW = TILE + 2 * R;
+    return ((TW * TW * 4 + (TW + 1) * (TW + 1) * 2 + 15) & ~(size_t)15) + (size_t)n_taps * 8 + 128;
+}
 
 cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d /*pairs*/, int n_disc)
 {
@@ -554,17 +569,17 @@ cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const Grid
 }
 
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
-                           const ClassifyParams &cp, const float *d_decay, int n_blocks)
+                           const ClassifyParams &cp, const void *d_taps, int n_blocks)
 {
     static int attr_R = -1;
     const int R = cp.infl_r;
-    const size_t smem = inflate_smem_bytes(R);
+    const size_t smem = inflate_smem_bytes(R, cp.n_infl);
     if (attr_R != R)
     {
         cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_R = R;
     }
-    k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, d_decay, cp);
+    k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, static_cast<const InflTap *>(d_taps), cp);
     return cudaGetLastError();
 }
 

@@ -304,18 +304,21 @@ class LocalMap
             int rr = 0;
             for (auto &o : io) rr = std::max(rr, std::max(std::abs(o.first), std::abs(o.second)));
             R_ = (rr + 3) & ~3;  // multiple of 4 cells: the TMA box must start 16-byte aligned in the inner (x) dimension
-            if (inflate_smem_bytes(R_) > 200 * 1024 || TILE + 2 * R_ > 256)
+            nInfl_ = (int)io.size();
+            if (inflate_smem_bytes(R_, nInfl_) > 200 * 1024 || TILE + 2 * R_ > 248)
                 throw Unsupported("inflation radius of " + std::to_string(rr) + " cells exceeds the halo-tile budget");
-            const int KW = 2 * R_ + 1;
-            std::vector<float> decay((size_t)KW * KW, 0.f);
-            for (auto &o : io)  // LocalMap.cpp:57-67
+            // taps (LocalMap.cpp:57-67) sorted by decreasing decay for the kernel's early exit
+            struct Tap { int off; float decay; };
+            const int TWi = TILE + 2 * R_;
+            std::vector<Tap> taps;
+            for (auto &o : io)
             {
                 const double dist_m = std::hypot((double)o.first, (double)o.second) * P.resolution;
-                decay[(size_t)(o.second + R_) * KW + (o.first + R_)] = static_cast<float>(std::exp(-P.cost_scaling_factor * dist_m));
+                taps.push_back({o.second * TWi + o.first, static_cast<float>(std::exp(-P.cost_scaling_factor * dist_m))});
             }
-            nInfl_ = (int)io.size();
-            decay_.ensure(decay.size() * 4);
-            CK(cudaMemcpy(decay_.p, decay.data(), decay.size() * 4, cudaMemcpyHostToDevice));
+            std::stable_sort(taps.begin(), taps.end(), [](const Tap &a, const Tap &b) { return a.decay > b.decay; });
+            decay_.ensure(taps.size() * sizeof(Tap));
+            CK(cudaMemcpy(decay_.p, taps.data(), taps.size() * sizeof(Tap), cudaMemcpyHostToDevice));
         }
         static std::atomic<uint64_t> next_serial{1};
         serial_ = next_serial.fetch_add(1);
@@ -779,8 +782,8 @@ class LocalMap
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0)
         {
-            const int inf_blocks = (int)std::min<size_t>((size_t)nSM_ * 4, nb);
-            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.as<float>(), inf_blocks));
+            const int inf_blocks = (int)std::min<size_t>((size_t)nSM_ * 2, nb);
+            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.p, inf_blocks));
             g_launches += 1;
         }
         if (prof) CK(cudaEventRecord(ev_[6], stream_));

@@ -13,13 +13,13 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
                        int dc, int di, int n_sm, cudaEvent_t *ev);
 
 size_t classify_smem_bytes(int r);
-size_t inflate_smem_bytes(int R);
+size_t inflate_smem_bytes(int R, int n_taps);
 cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d, int n_disc);
 cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, const ClassifyParams &cp,
                             int n_blocks);
 cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const GridView &g, int n_blocks);
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
-                           const ClassifyParams &cp, const float *d_decay, int n_blocks);
+                           const ClassifyParams &cp, const void *d_taps, int n_blocks);
 cudaError_t launch_collect_keys(cudaStream_t st, const GridView &g, int mode, int clear, unsigned long long *d_out, uint32_t cap,
                                 uint32_t *d_count);
 cudaError_t launch_read_layers(cudaStream_t st, const GridView &g, const unsigned long long *d_keys, size_t n, const int *d_layers,
