@@ -45,52 +45,50 @@ def workload(n_kf):
 
 
 class ClockSampler:
-    """SM clock and throttle reasons DURING the timed region, read in-process through NVML (spawning
-    nvidia-smi in loop mode stalls the driver for milliseconds and showed up in the step time)."""
+    """SM clock and throttle reasons of the timed region, read in-process through NVML right after each
+    timed step's end event (the GPU has just been under load).  A sampler running concurrently -- an
+    `nvidia-smi -lms` child or an NVML polling thread -- takes driver locks inside the ~0.3 ms step
+    brackets and showed up in the step time, so the samples are taken between brackets instead."""
 
-    def __init__(self, gpu_index, period_s=0.02):
-        self.sm, self.mx, self.reasons = [], [], set()
-        self.idx, self.period = gpu_index, period_s
-        self.stop_flag = threading.Event()
-        self.t = None
-        self.err = None
-
-    def _loop(self):
+    def __init__(self, gpu_index):
+        self.sm, self.reasons, self.mx = [], set(), None
+        self.idx = gpu_index
+        self.h = None
         try:
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.idx)
-            bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
-                    "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
-            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            while not self.stop_flag.is_set():
-                self.sm.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
-                self.mx.append(mx)
-                r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
-                for k, b in bits.items():
-                    if r & b:
-                        self.reasons.add(k)
-                time.sleep(self.period)
-        except Exception as e:  # NVML missing: fall back to one nvidia-smi query at stop()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.bits = {"hw_slowdown": nv.nvmlClocksEventReasonHwSlowdown,
+                         "hw_thermal_slowdown": nv.nvmlClocksEventReasonHwThermalSlowdown,
+                         "sw_thermal_slowdown": nv.nvmlClocksEventReasonSwThermalSlowdown,
+                         "sw_power_cap": nv.nvmlClocksEventReasonSwPowerCap}
+        except Exception as e:
             self.err = repr(e)
 
     def start(self):
-        self.t = threading.Thread(target=self._loop, daemon=True)
-        self.t.start()
+        pass
+
+    def sample(self):
+        if self.h is None:
+            return
+        self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+        r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        for k, b in self.bits.items():
+            if r & b:
+                self.reasons.add(k)
 
     def stop(self):
-        self.stop_flag.set()
-        if self.t:
-            self.t.join(timeout=2)
         if not self.sm:
             try:
                 out = subprocess.run(["nvidia-smi", f"--id={self.idx}", "--query-gpu=clocks.sm,clocks.max.sm",
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
                 a, b = [float(x) for x in out.strip().split(",")]
-                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "note": f"nvml unavailable ({self.err}); sampled after the region"}
+                return {"sm_mhz": a, "sm_max_mhz": b, "reasons": [], "samples": 1, "note": "nvml unavailable; sampled after the region"}
             except Exception:
                 return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable"], "samples": 0}
-        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": float(max(self.mx)), "reasons": sorted(self.reasons),
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
                 "samples": len(self.sm)}
 
 
@@ -245,6 +243,7 @@ def main():
                 e1.record(stream)
                 e1.synchronize()
                 t_ms += e0.elapsed_time(e1)
+                sampler.sample()
     barrier()
     clocks = sampler.stop()
     launches = m.stats()["kernel_launches"] - launches0

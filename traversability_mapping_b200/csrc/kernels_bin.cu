@@ -205,19 +205,21 @@ __global__ void k_pack_base(const float *__restrict__ xyz, size_t n, float4 *__r
 }
 
 // ---------------------------------------------------------------------------------------------
-// batch initialisation: counters, per-op bbox
+// batch initialisation: counters, per-op bbox, inflation-tile dedup flags
 // ---------------------------------------------------------------------------------------------
-__global__ void k_init_batch(BatchView b)
+__global__ void k_init_batch(BatchView b, uint32_t n_infl_flags)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < 16)
         b.counters[i] = 0;
     if (i < b.n_ops)
         b.op_bbox[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
+    if (i < n_infl_flags)
+        b.infl_flags[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_hist: transform + key + per-chunk tile histogram
+// k_hist: transform + key + per-chunk bin histogram
 // ---------------------------------------------------------------------------------------------
 template <int PPT>
 __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
             float xm, ym, zm;
             xform_rn(s_op.T, p.x, p.y, p.z, xm, ym, zm);
             const int ci = cell_of(xm, lat.x0, lat.res), cj = cell_of(ym, lat.y0, lat.res);
-            const int tx = (ci >> TILE_SHIFT) - s_op.wtx0, ty = (cj >> TILE_SHIFT) - s_op.wty0;
+            const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
             if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
             {
                 tile = ty * s_op.wtw + tx;
@@ -284,7 +286,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
         row[i] = s_hist[i];
 }
 
-// per (op, tile): exclusive prefix over the op's chunks, in place; total -> op_total.
+// per (op, bin): exclusive prefix over the op's chunks, in place; total -> op_total.
 // One warp per column: 32 chunk counts per step, shuffle scan, carried running total.
 __global__ void k_scan_chunks(BatchView b)
 {
@@ -314,27 +316,6 @@ __global__ void k_scan_chunks(BatchView b)
     }
     if (lane == 0)
         b.op_total[op.tot_off + t] = run;
-}
-
-// per global tile of the batch bbox: exclusive prefix over ops (op order = fold order)
-__global__ void k_scan_ops(BatchView b)
-{
-    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= (uint32_t)(b.btw * b.bth))
-        return;
-    const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
-    uint32_t run = 0;
-    for (uint32_t o = 0; o < b.n_ops; ++o)
-    {
-        const OpDesc &op = b.ops[o];
-        const int lx = tx - op.wtx0, ly = ty - op.wty0;
-        if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
-            continue;
-        const uint32_t t = op.tot_off + ly * op.wtw + lx;
-        b.op_start[t] = run;
-        run += b.op_total[t];
-    }
-    b.tile_count[g] = run;
 }
 
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*[33]*/, uint32_t &total)
@@ -369,41 +350,72 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*
     return r;
 }
 
-// single CTA: exclusive scan of tile_count over the bbox + compact list of active tiles
-__global__ void __launch_bounds__(1024) k_scan_tiles(BatchView b)
+// per bin of the batch bbox: exclusive prefix over ops (op order = fold order) -> op_start, bin count;
+// per 256-bin block: sum -> block_sums
+__global__ void __launch_bounds__(256) k_scan_ops(BatchView b)
 {
     __shared__ uint32_t s_w[33];
-    const uint32_t n = b.btw * b.bth;
-    uint32_t run = 0, nact = 0;
-    for (uint32_t base = 0; base < n; base += 1024)
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    uint32_t run = 0;
+    if (g < nb)
     {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n ? b.tile_count[i] : 0;
-        uint32_t tot, tota;
-        const uint32_t ex = block_excl_scan(v, s_w, tot);
-        const uint32_t exa = block_excl_scan(v ? 1u : 0u, s_w, tota);
-        if (i < n)
+        const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
+        for (uint32_t o = 0; o < b.n_ops; ++o)
         {
-            b.tile_start[i] = run + ex;
-            if (v) b.active_tiles[nact + exa] = i;
+            const OpDesc &op = b.ops[o];
+            const int lx = tx - op.wtx0, ly = ty - op.wty0;
+            if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
+                continue;
+            const uint32_t t = op.tot_off + ly * op.wtw + lx;
+            b.op_start[t] = run;
+            run += b.op_total[t];
         }
-        run += tot;
-        nact += tota;
+        b.tile_count[g] = run;
     }
+    uint32_t tot;
+    block_excl_scan(run, s_w, tot);
     if (threadIdx.x == 0)
-        b.counters[0] = nact;
+        b.block_sums[blockIdx.x] = tot;
 }
 
-// candidate tile lists: classify = active dilated by dc tiles, inflate = active dilated by di
-// tiles; both clipped to the allocated grid.  List order is irrelevant (tiles are independent).
-__global__ void k_mark_lists(BatchView b, GridView g, int dc, int di)
+// single CTA: exclusive scan of the per-block sums (in place)
+__global__ void __launch_bounds__(1024) k_scan_blocks(BatchView b, uint32_t n_blocks)
 {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (uint32_t)(b.btw * b.bth))
+    __shared__ uint32_t s_w[33];
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < n_blocks; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? b.block_sums[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(v, s_w, tot);
+        if (i < n_blocks)
+            b.block_sums[i] = run + ex;
+        run += tot;
+    }
+}
+
+// per bin: bucket start; compact lists of active bins, of bins to classify (active dilated by dc bins)
+// and of 32x32 tiles to inflate (bins within di of an active bin; dedup through infl_flags).  List order
+// is irrelevant: bins / tiles are independent work items.
+__global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, int dc, int di)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    const uint32_t v = i < nb ? b.tile_count[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(v, s_w, tot);
+    if (i >= nb)
         return;
+    b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
+    if (v)
+        b.active_tiles[atomicAdd(b.counters + 0, 1u)] = i;
     const int lx = i % b.btw, ly = i / b.btw;
-    const int tx = b.btx0 + lx, ty = b.bty0 + ly;
-    if (tx < g.tx0 || tx >= g.tx0 + g.tw || ty < g.ty0 || ty >= g.ty0 + g.th)
+    const int bx = b.btx0 + lx, by = b.bty0 + ly;  // global bin
+    // inside the allocated grid?
+    if (bx < g.tx0 * 2 || bx >= (g.tx0 + g.tw) * 2 || by < g.ty0 * 2 || by >= (g.ty0 + g.th) * 2)
         return;
     const int dm = max(dc, di);
     bool nc = false, ni = false;
@@ -420,17 +432,24 @@ __global__ void k_mark_lists(BatchView b, GridView g, int dc, int di)
                 ni |= d <= di;
             }
         }
-    if (nc) b.cand_tiles[atomicAdd(b.counters + 1, 1u)] = i;
-    if (ni && di >= 0) b.infl_tiles[atomicAdd(b.counters + 2, 1u)] = i;
+    if (nc)
+        b.cand_tiles[atomicAdd(b.counters + 1, 1u)] = i;
+    if (ni)
+    {
+        const uint32_t t32 = (uint32_t)(((by >> 1) - g.ty0) * g.tw + ((bx >> 1) - g.tx0));
+        if (atomicExch(b.infl_flags + t32, 1u) == 0u)
+            b.infl_tiles[atomicAdd(b.counters + 2, 1u)] = t32;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_scatter: stable bucket scatter by global tile
+// k_scatter: stable bucket scatter by global bin.  Per-warp counter rows are u16 (a warp slice holds
+// at most 32*PPT <= 256 points); the absolute base of a bin lives in a separate u32 row.
 // ---------------------------------------------------------------------------------------------
 template <int PPT>
 __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD lat)
 {
-    extern __shared__ uint32_t s_cnt[];  // [8 warps][T]
+    extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ OpDesc s_op;
     constexpr int NW = BIN_THREADS / 32;
     const uint32_t chunk = blockIdx.x;
@@ -439,14 +458,17 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(b.ops + opi)[threadIdx.x];
     __syncthreads();
     const uint32_t T = s_op.T_tiles;
-    for (uint32_t i = threadIdx.x; i < T * NW; i += BIN_THREADS)
-        s_cnt[i] = 0;
+    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn);               // [T]
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_base + T);           // [NW][T]
+    for (uint32_t i = threadIdx.x; i < (T * NW + 1) / 2; i += BIN_THREADS)
+        reinterpret_cast<uint32_t *>(s_cnt)[i] = 0;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cl = chunk - s_op.chunk0;
     const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
-    uint32_t *my = s_cnt + warp * T;
+    uint16_t *my = s_cnt + warp * T;
+    const uint32_t sign_bit = s_op.sign < 0.f ? META_SIGN : 0u;
     float px[PPT], py[PPT], pz[PPT];
     uint32_t tl[PPT], cc[PPT];
 #pragma unroll
@@ -461,30 +483,31 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
             const float4 p = __ldg(s_op.cloud + i);
             xform_rn(s_op.T, p.x, p.y, p.z, px[r], py[r], pz[r]);
             const int ci = cell_of(px[r], lat.x0, lat.res), cj = cell_of(py[r], lat.y0, lat.res);
-            const int tx = (ci >> TILE_SHIFT) - s_op.wtx0, ty = (cj >> TILE_SHIFT) - s_op.wty0;
+            const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
             if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
             {
                 tl[r] = ty * s_op.wtw + tx;
-                cc[r] = ((cj & (TILE - 1)) << TILE_SHIFT) | (ci & (TILE - 1));
+                cc[r] = ((cj & (BIN - 1)) << BIN_SHIFT) | (ci & (BIN - 1));
             }
         }
         const uint32_t m = __match_any_sync(0xffffffffu, tl[r]);
         if (tl[r] != 0xffffffffu && lane == (uint32_t)(__ffs(m) - 1))
-            my[tl[r]] += __popc(m);   // row `warp` is private to this warp
+            my[tl[r]] += (uint16_t)__popc(m);   // row `warp` is private to this warp
         __syncwarp();
     }
     __syncthreads();
-    // per tile: absolute base of each warp's run = tile_start + op_start + chunk prefix + earlier warps
+    // per bin: absolute base of this chunk's run = bin start + op offset + chunk prefix; warps' runs follow
     const uint32_t *row = b.hist + s_op.hist_off + (size_t)cl * T;
     for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
     {
         const int gx = s_op.wtx0 + (int)(t % s_op.wtw) - b.btx0, gy = s_op.wty0 + (int)(t / s_op.wtw) - b.bty0;
-        uint32_t run = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
+        s_base[t] = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
+        uint32_t run = 0;
 #pragma unroll
         for (int w = 0; w < NW; ++w)
         {
             const uint32_t v = s_cnt[w * T + t];
-            s_cnt[w * T + t] = run;
+            s_cnt[w * T + t] = (uint16_t)run;
             run += v;
         }
     }
@@ -496,19 +519,22 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         if (tl[r] != 0xffffffffu)
         {
             const uint32_t leader = __ffs(m) - 1;
-            const uint32_t pos = my[tl[r]] + __popc(m & ((1u << lane) - 1u));
-            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float((opi << 10) | cc[r]));
+            const uint32_t off = my[tl[r]];
+            const uint32_t pos = s_base[tl[r]] + off + __popc(m & ((1u << lane) - 1u));
+            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | (opi << 8) | cc[r]));
             __syncwarp(m);
             if (lane == leader)
-                my[tl[r]] += __popc(m);
+                my[tl[r]] = (uint16_t)(off + __popc(m));
         }
         __syncwarp();
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_fold: per touched tile -- stable smem radix sort by cell, ordered double accumulation per
-// (op, cell), float32 fold into the grid records, blank rule.
+// k_fold: per touched 16x16 bin -- one-pass stable counting sort by cell in shared memory, ordered
+// double accumulation per (op, cell), float32 fold into the grid records, blank rule.
+// 256 threads = 256 cells; ~45 KB shared memory, so several CTAs share an SM and hide each other's
+// barriers and global-load latency.
 // ---------------------------------------------------------------------------------------------
 struct CellAcc
 {
@@ -524,24 +550,25 @@ struct CellAcc
     }
 };
 
-__device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, float sign, uint32_t &fl)
+__device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subtract, uint32_t &fl)
 {
     if (a.n == 0)
         return;
-    const double sg = (double)sign;
-    // MomentLayers::add (Helpers.cpp:114-127): NaN -> 0, then += (float)(sign * value)
-#define TMB_ACC(k, v)                                                                            \
-    {                                                                                            \
-        const float c0 = isnan(rec[k]) ? 0.f : rec[k];                                           \
-        rec[k] = __fadd_rn(c0, __double2float_rn(__dmul_rn(sg, (v))));                            \
+    // MomentLayers::add (Helpers.cpp:114-127): NaN -> 0, then += (float)(sign * value).  A cell is either
+    // entirely NaN (blank) or entirely numeric, so testing N covers the ten moment fields.
+    if (isnan(rec[R_N]))
+    {
+#pragma unroll
+        for (int k = 0; k < 10; ++k) rec[k] = 0.f;
     }
+#define TMB_ACC(k, v) rec[k] = __fadd_rn(rec[k], __double2float_rn(subtract ? -(v) : (v)));
     TMB_ACC(R_N, (double)a.n)
     TMB_ACC(R_SX, a.sx) TMB_ACC(R_SY, a.sy) TMB_ACC(R_SZ, a.sz)
     TMB_ACC(R_SX2, a.sx2) TMB_ACC(R_SY2, a.sy2) TMB_ACC(R_SZ2, a.sz2)
     TMB_ACC(R_SXY, a.sxy) TMB_ACC(R_SXZ, a.sxz) TMB_ACC(R_SYZ, a.syz)
 #undef TMB_ACC
     fl |= F_TOUCHED;
-    if (sign > 0.f)
+    if (!subtract)
     {
         rec[R_ZMIN] = isnan(rec[R_ZMIN]) ? a.zmin : fminf(rec[R_ZMIN], a.zmin);
         rec[R_ZMAX] = isnan(rec[R_ZMAX]) ? a.zmax : fmaxf(rec[R_ZMAX], a.zmax);
@@ -555,16 +582,15 @@ __device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, float sig
     }
 }
 
-__global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, LatticeD lat)
+constexpr int FOLD_NW = FOLD_THREADS / 32;
+
+__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView g, LatticeD lat)
 {
-    extern __shared__ __align__(16) unsigned char s_raw[];
-    float4 *s_rec = reinterpret_cast<float4 *>(s_raw);                       // [FOLD_CH]
-    uint32_t *s_a = reinterpret_cast<uint32_t *>(s_raw + FOLD_CH * 16);       // [FOLD_CH]
-    uint32_t *s_b = s_a + FOLD_CH;                                            // [FOLD_CH]
-    uint32_t *s_cnt = s_b + FOLD_CH;                                          // [32][33]
-    uint16_t *s_seg0 = reinterpret_cast<uint16_t *>(s_cnt + 32 * 33);         // [1024]
-    uint16_t *s_seg1 = s_seg0 + TILE_CELLS;                                   // [1024]
-    uint32_t *s_w = reinterpret_cast<uint32_t *>(s_seg1 + TILE_CELLS);        // [33]
+    __shared__ __align__(16) float4 s_rec[FOLD_CH];          // staged records            32 KB
+    __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
+    __shared__ uint16_t s_cnt[FOLD_NW][BIN_CELLS];            // per-warp cell counters       4 KB
+    __shared__ uint16_t s_seg0[BIN_CELLS], s_seg1[BIN_CELLS]; // cell segment bounds
+    __shared__ uint32_t s_w[33];
     __shared__ uint32_t s_ticket;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -579,14 +605,14 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
         if (it >= n_active)
             break;
         const uint32_t gt = b.active_tiles[it];
-        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
-        const int col = (tx - g.tx0) * TILE + (int)(tid & 31), row = (ty - g.ty0) * TILE + (int)(tid >> 5);
-        const bool inside = tx >= g.tx0 && tx < g.tx0 + g.tw && ty >= g.ty0 && ty < g.ty0 + g.th;
-        if (!inside)
+        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const int col = ci - g.ci0, row = cj - g.cj0;
+        if (col < 0 || col >= g.W || row < 0 || row >= g.H)
         {
             if (tid == 0) atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
-            continue;
+            continue;  // uniform: a bin is inside or outside as a whole (grid is 32-aligned)
         }
         const size_t cell = (size_t)row * g.W + col;
         // the cell's 48-byte record is fetched only if this batch actually touches the cell
@@ -602,95 +628,81 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
             rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
             loaded = true;
         };
-        const int ci = tx * TILE + (int)(tid & 31), cj = ty * TILE + (int)(tid >> 5);
         const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
         const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
         CellAcc acc;
         acc.reset();
-        int cur_op = -1;
+        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
         uint32_t fl = 0;
 
         for (uint32_t pos = 0; pos < cnt; pos += FOLD_CH)
         {
             const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
-            const uint32_t R = (n + 1023) >> 10;  // rounds per thread
-            const uint32_t SL = R * 32;           // slice per warp
-            for (uint32_t i = tid; i < n; i += 1024)
-            {
-                const float4 p = b.sorted[start + pos + i];
-                s_rec[i] = p;
-                s_a[i] = ((__float_as_uint(p.w) & 1023u) << 16) | i;
-            }
-            s_seg0[tid] = 0;
-            s_seg1[tid] = 0;
+            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
+            const uint32_t SL = R * 32;                                // records per warp slice
+            for (uint32_t i = tid; i < n; i += FOLD_THREADS)
+                s_rec[i] = b.sorted[start + pos + i];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = 0;
             __syncthreads();
-            // two stable LSD passes over the 10-bit cell key, 5 bits each
-            uint32_t *src = s_a, *dst = s_b;
-#pragma unroll 1
-            for (int pass = 0; pass < 2; ++pass)
+            // count: warp w owns the contiguous slice [w*SL, (w+1)*SL)
+            for (uint32_t r = 0; r < R; ++r)
             {
-                const int sh = 16 + 5 * pass;
-                s_cnt[warp * 33 + lane] = 0;
+                const uint32_t i = warp * SL + r * 32 + lane;
+                const uint32_t c = i < n ? (__float_as_uint(s_rec[i].w) & 255u) : 256u;
+                const uint32_t m = __match_any_sync(0xffffffffu, c);
+                if (c < 256u && lane == (uint32_t)(__ffs(m) - 1))
+                    s_cnt[warp][c] += (uint16_t)__popc(m);
                 __syncwarp();
-                for (uint32_t r = 0; r < R; ++r)
-                {
-                    const uint32_t i = warp * SL + r * 32 + lane;
-                    const uint32_t d = i < n ? ((src[i] >> sh) & 31u) : 32u;
-                    const uint32_t m = __match_any_sync(0xffffffffu, d);
-                    if (d < 32u && lane == (uint32_t)(__ffs(m) - 1))
-                        s_cnt[warp * 33 + d] += __popc(m);
-                    __syncwarp();
-                }
-                __syncthreads();
-                {   // exclusive scan over (digit major, warp minor)
-                    const uint32_t d = tid >> 5, w = tid & 31;
-                    const uint32_t v = s_cnt[w * 33 + d];
-                    uint32_t tot;
-                    const uint32_t ex = block_excl_scan(v, s_w, tot);
-                    s_cnt[w * 33 + d] = ex;
-                }
-                __syncthreads();
-                for (uint32_t r = 0; r < R; ++r)
-                {
-                    const uint32_t i = warp * SL + r * 32 + lane;
-                    const uint32_t key = i < n ? src[i] : 0u;
-                    const uint32_t d = i < n ? ((key >> sh) & 31u) : 32u;
-                    const uint32_t m = __match_any_sync(0xffffffffu, d);
-                    if (d < 32u)
-                    {
-                        const uint32_t p0 = s_cnt[warp * 33 + d];
-                        dst[p0 + __popc(m & ((1u << lane) - 1u))] = key;
-                        __syncwarp(m);
-                        if (lane == (uint32_t)(__ffs(m) - 1))
-                            s_cnt[warp * 33 + d] = p0 + __popc(m);
-                    }
-                    __syncwarp();
-                }
-                __syncthreads();
-                uint32_t *t = src; src = dst; dst = t;
-            }
-            // src now holds the keys sorted by cell, stable in (op, point) order
-            for (uint32_t i = tid; i < n; i += 1024)
-            {
-                const uint32_t c = src[i] >> 16;
-                if (i == 0 || (src[i - 1] >> 16) != c) s_seg0[c] = (uint16_t)i;
-                if (i == n - 1 || (src[i + 1] >> 16) != c) s_seg1[c] = (uint16_t)(i + 1);
             }
             __syncthreads();
+            // thread = cell: exclusive prefix over the warps' counts, then over cells
+            uint32_t tot = 0;
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+            {
+                const uint32_t v = s_cnt[w][tid];
+                s_cnt[w][tid] = (uint16_t)tot;
+                tot += v;
+            }
+            uint32_t all;
+            const uint32_t cstart = block_excl_scan(tot, s_w, all);
+            s_seg0[tid] = (uint16_t)cstart;
+            s_seg1[tid] = (uint16_t)(cstart + tot);
+            __syncthreads();
+            // stable placement: position = cell start + earlier warps + rank inside the warp round
+            for (uint32_t r = 0; r < R; ++r)
+            {
+                const uint32_t i = warp * SL + r * 32 + lane;
+                const uint32_t c = i < n ? (__float_as_uint(s_rec[i].w) & 255u) : 256u;
+                const uint32_t m = __match_any_sync(0xffffffffu, c);
+                if (c < 256u)
+                {
+                    const uint32_t off = s_cnt[warp][c];
+                    s_ord[s_seg0[c] + off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    __syncwarp(m);
+                    if (lane == (uint32_t)(__ffs(m) - 1))
+                        s_cnt[warp][c] = (uint16_t)(off + __popc(m));
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            // thread = cell: walk the cell's records in (op, point) order
             const uint32_t k0 = s_seg0[tid], k1 = s_seg1[tid];
             for (uint32_t k = k0; k < k1; ++k)
             {
-                const float4 p = s_rec[src[k] & 0xffffu];
-                const int op = (int)(__float_as_uint(p.w) >> 10);
-                if (op != cur_op)
+                const float4 p = s_rec[s_ord[k]];
+                const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
+                if (so != cur)
                 {
-                    if (cur_op >= 0)
+                    if (cur != 0xffffffffu)
                     {
                         load_rec();
-                        fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
                     }
                     acc.reset();
-                    cur_op = op;
+                    cur = so;
                 }
                 // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
                 const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
@@ -707,10 +719,10 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
             }
             __syncthreads();
         }
-        if (cur_op >= 0)
+        if (cur != 0xffffffffu)
         {
             load_rec();
-            fold_acc(rec, acc, b.ops[cur_op].sign, fl);
+            fold_acc(rec, acc, (cur >> 23) != 0, fl);
         }
         if (fl & F_TOUCHED)
         {
@@ -735,11 +747,6 @@ __global__ void __launch_bounds__(1024, 1) k_fold(BatchView b, GridView g, Latti
 // ---------------------------------------------------------------------------------------------
 // host-callable launch wrappers
 // ---------------------------------------------------------------------------------------------
-size_t fold_smem_bytes()
-{
-    return (size_t)FOLD_CH * 16 + (size_t)FOLD_CH * 8 + 32 * 33 * 4 + TILE_CELLS * 4 + 33 * 4 + 64;
-}
-
 cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
                          float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase)
 {
@@ -767,19 +774,22 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
     return cudaGetLastError();
 }
 
+static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 4 + (size_t)maxT * (BIN_THREADS / 32) * 2 + 16; }
+
 static bool g_attr_set = false;
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
                        int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/)
 {
     if (!g_attr_set)
     {
-        cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WINDOW_TILES * 8 * 4);
-        cudaFuncSetAttribute(k_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_WINDOW_TILES * 8 * 4);
-        cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fold_smem_bytes());
+        cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
+        cudaFuncSetAttribute(k_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
         g_attr_set = true;
     }
     const uint32_t nb = b.btw * b.bth;
-    k_init_batch<<<(max(b.n_ops, 16u) + 255) / 256, 256, 0, st>>>(b);
+    const uint32_t nblk = (nb + 255) / 256;
+    const uint32_t nflags = (uint32_t)(g.tw * g.th);
+    k_init_batch<<<(max(max(b.n_ops, 16u), nflags) + 255) / 256, 256, 0, st>>>(b, nflags);
     if (ev) cudaEventRecord(ev[0], st);
     if (ppt == 2)
         k_hist<2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
@@ -787,17 +797,17 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
         k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
     k_scan_chunks<<<dim3((maxT + 7) / 8, b.n_ops), 256, 0, st>>>(b);
-    k_scan_ops<<<(nb + 127) / 128, 128, 0, st>>>(b);
-    k_scan_tiles<<<1, 1024, 0, st>>>(b);
-    k_mark_lists<<<(nb + 127) / 128, 128, 0, st>>>(b, g, dc, di);
+    k_scan_ops<<<nblk, 256, 0, st>>>(b);
+    k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
+    k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
     if (ev) cudaEventRecord(ev[2], st);
     if (ppt == 2)
-        k_scatter<2><<<b.n_chunks, BIN_THREADS, maxT * 8 * 4, st>>>(b, lat);
+        k_scatter<2><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
     else
-        k_scatter<8><<<b.n_chunks, BIN_THREADS, maxT * 8 * 4, st>>>(b, lat);
+        k_scatter<8><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
     if (ev) cudaEventRecord(ev[3], st);
-    const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm, nb);
-    k_fold<<<fold_blocks, 1024, fold_smem_bytes(), st>>>(b, g, lat);
+    const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm * 4u, nb);
+    k_fold<<<fold_blocks, FOLD_THREADS, 0, st>>>(b, g, lat);
     if (ev) cudaEventRecord(ev[4], st);
     return cudaGetLastError();
 }

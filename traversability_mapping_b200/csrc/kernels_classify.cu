@@ -10,10 +10,10 @@
 //   fillSparseUpdate                           traversability_mapping_ros/src/conversions.cpp:28-55
 //   GridMapRosConverter::toOccupancyGrid       (grid_map_ros; call site global_traversability_node.cpp:374)
 //
-// k_classify: one CTA per candidate 32x32 tile (ticket loop).  The (32+2r)^2 x 48-byte halo tile
+// k_classify: one CTA per candidate 16x16 bin (ticket loop).  The (16+2r)^2 x 48-byte halo tile
 // of moment records arrives with ONE 3-D TMA box load (cp.async.bulk.tensor, mbarrier completion,
 // out-of-bounds cells filled with NaN = unobserved).  A pre-pass derives per-halo-cell gate bits
-// and 1/N; each thread then classifies four cells: the disc moments are fused about the query
+// and 1/N; each thread then classifies one cell: the disc moments are fused about the query
 // centre as 21 lattice-weighted sums (the shift of Moments.cpp:49-58 expanded for offsets that
 // are integer multiples of the resolution), followed by the 3x3 covariance, the smallest
 // eigenpair (eig3.cuh) and a second pass over the disc for the step spread.  All in fp64.
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
     const int r = c_cp.r;
-    const int TW = TILE + 2 * r;
+    const int TW = BIN + 2 * r;
     const int ncell = TW * TW;
     float *s_rec = reinterpret_cast<float *>(s_raw);                                     // [TW*TW][12]
     double *s_inv = reinterpret_cast<double *>(s_raw + (((size_t)ncell * REC * 4 + 127) & ~(size_t)127));  // [TW*TW]
@@ -111,14 +111,15 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
         if (it >= n_cand)
             break;
         const uint32_t gt = b.cand_tiles[it];
-        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
-        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
+        const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
         if (tid == 0)
         {
             mbar_arrive_expect_tx(&s_bar, (uint32_t)ncell * REC * 4);
             tma_load_3d(s_rec, &tmap, &s_bar, 0, col0 - r, row0 - r);
         }
         // touched bits of the halo tile (plain loads; zero outside the grid)
+        int any_touched = 0;
         for (int i = tid; i < ncell; i += CLS_THREADS)
         {
             const int hx = i % TW, hy = i / TW;
@@ -127,10 +128,12 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
             if (c >= 0 && c < g.W && rw >= 0 && rw < g.H)
                 f = (g.flags[(size_t)rw * g.W + c] & F_TOUCHED) ? H_TOUCHED : 0;
             s_flag[i] = f;
+            any_touched |= f;
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1;
-        __syncthreads();
+        if (!__syncthreads_or(any_touched))
+            continue;  // nothing in this bin's footprint halo changed: no cell of it is dirty
         // pre-pass: observed / enough-points bits and 1/N  (MomentLayers::read, Helpers.cpp:101-112)
         for (int i = tid; i < ncell; i += CLS_THREADS)
         {
@@ -150,10 +153,10 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
         __syncthreads();
 
 #pragma unroll 1
-        for (int k = 0; k < TILE_CELLS / CLS_THREADS; ++k)
+        for (int k = 0; k < BIN_CELLS / CLS_THREADS; ++k)
         {
             const int q = tid + k * CLS_THREADS;
-            const int x = q & 31, y = q >> 5;
+            const int x = q & (BIN - 1), y = q >> BIN_SHIFT;
             const int idx = (y + r) * TW + (x + r);
             const uint8_t fq = s_flag[idx];
             if (!(fq & H_OBS))
@@ -269,11 +272,11 @@ __global__ void k_clear_touched(BatchView b, GridView g)
     for (uint32_t it = blockIdx.x; it < n_active; it += gridDim.x)
     {
         const uint32_t gt = b.active_tiles[it];
-        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
-        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
-        for (int q = threadIdx.x; q < TILE_CELLS; q += blockDim.x)
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
+        const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
+        for (int q = threadIdx.x; q < BIN_CELLS; q += blockDim.x)
         {
-            const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
+            const size_t cell = (size_t)(row0 + (q >> BIN_SHIFT)) * g.W + (col0 + (q & (BIN - 1)));
             g.flags[cell] &= (uint8_t)~(F_TOUCHED | F_BLANKED);
         }
     }
@@ -325,9 +328,8 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         const uint32_t it = s_ticket;
         if (it >= n_tiles)
             break;
-        const uint32_t gt = b.infl_tiles[it];
-        const int tx = b.btx0 + (int)(gt % b.btw), ty = b.bty0 + (int)(gt / b.btw);
-        const int col0 = (tx - g.tx0) * TILE, row0 = (ty - g.ty0) * TILE;
+        const uint32_t t32 = b.infl_tiles[it];  // grid-relative 32x32 tile
+        const int col0 = (int)(t32 % g.tw) * TILE, row0 = (int)(t32 / g.tw) * TILE;
         if (tid == 0)
         {
             mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TW * 4));
@@ -345,6 +347,24 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         }
         mbar_wait(&s_bar, parity);
         parity ^= 1;
+        // no seed anywhere in the halo tile (the common case away from steps): every observed cell gets 0
+        int any_seed = 0;
+        for (int i = tid; i < TW * TW; i += INF_THREADS)
+            any_seed |= s_step[i] >= lethal;
+        if (!__syncthreads_or(any_seed))
+        {
+#pragma unroll
+            for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
+            {
+                if (!(nobs[k] >= 1.f) || cur[k] == 0.f)
+                    continue;
+                const int q = tid + k * INF_THREADS;
+                const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
+                g.der[D_INFLATED * pl + cell] = 0.f;
+                g.flags[cell] |= F_CHANGED;
+            }
+            continue;
+        }
         // summed-area table of the seed mask: rows, then columns
         if ((int)tid < TW)
         {
@@ -531,7 +551,7 @@ __global__ void k_transform_cloud(const float4 *cloud, uint32_t n, const float *
 // ---------------------------------------------------------------------------------------------
 size_t classify_smem_bytes(int r)
 {
-    const size_t ncell = (size_t)(TILE + 2 * r) * (TILE + 2 * r);
+    const size_t ncell = (size_t)(BIN + 2 * r) * (BIN + 2 * r);
     return ((ncell * REC * 4 + 127) & ~(size_t)127) + ncell * 8 + ncell + 128;
 }
 size_t inflate_smem_bytes(int R, int n_taps)

@@ -90,6 +90,7 @@ struct PinBuf
 };
 
 static inline int floordiv32(int a) { return a >> TILE_SHIFT; }
+static inline int floordiv16(int a) { return a >> BIN_SHIFT; }
 
 // ---- cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -148,7 +149,7 @@ struct DeviceGrid
         {
             const cuuint64_t dims[3] = {(cuuint64_t)REC, (cuuint64_t)v.W, (cuuint64_t)v.H};
             const cuuint64_t strides[2] = {(cuuint64_t)REC * 4, (cuuint64_t)v.W * REC * 4};
-            const cuuint32_t box[3] = {(cuuint32_t)REC, (cuuint32_t)(TILE + 2 * r), (cuuint32_t)(TILE + 2 * r)};
+            const cuuint32_t box[3] = {(cuuint32_t)REC, (cuuint32_t)(BIN + 2 * r), (cuuint32_t)(BIN + 2 * r)};
             const cuuint32_t es[3] = {1, 1, 1};
             CUresult rc = enc(&tmap_mom, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, v.mom, dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -439,10 +440,24 @@ class LocalMap
         std::lock_guard<std::mutex> l(qMutex_);
         return queue_.size();
     }
+    // Block until the queue is drained.  The caller does not just sleep: while it would wait it takes
+    // pending keyframes itself (same locks, same per-pass batch limit as the worker), which removes two
+    // thread hand-offs per pass.  on_update then fires on the flushing thread for those keyframes.
     void flush()
     {
-        std::unique_lock<std::mutex> l(qMutex_);
-        idleCv_.wait(l, [&] { return (queue_.empty() && !busy_) || !running_; });
+        for (;;)
+        {
+            std::vector<std::shared_ptr<KeyFrame>> take;
+            {
+                std::unique_lock<std::mutex> l(qMutex_);
+                idleCv_.wait(l, [&] { return !busy_ || !running_; });
+                if (!running_ || queue_.empty())
+                    return;
+                popLocked(take);
+                busy_ = true;
+            }
+            runTaken(take);
+        }
     }
     void setStream(void *s)
     {
@@ -575,6 +590,37 @@ class LocalMap
 
   private:
     // ---- the worker (LocalMap::RunLocalKeyFrames, LocalMap.cpp:452-485) ----
+    void popLocked(std::vector<std::shared_ptr<KeyFrame>> &take)  // qMutex_ held
+    {
+        const size_t lim = P_.max_batch <= 0 ? queue_.size() : std::min<size_t>(queue_.size(), (size_t)P_.max_batch);
+        for (size_t i = 0; i < lim; ++i)
+        {
+            take.push_back(queue_.front());
+            queue_.pop_front();
+            queued_.erase(take.back()->id);
+        }
+    }
+    void runTaken(const std::vector<std::shared_ptr<KeyFrame>> &take)  // busy_ already raised
+    {
+        int changed = 0;
+        try
+        {
+            changed = processTaken(take);
+        }
+        catch (const std::exception &e)
+        {
+            std::lock_guard<std::mutex> l(qMutex_);
+            workerError_ = e.what();
+        }
+        for (int i = 0; i < changed; ++i)
+            if (cb_) cb_(user_);  // onUpdate_, grid lock released (LocalMap.cpp:479-481)
+        {
+            std::lock_guard<std::mutex> l(qMutex_);
+            busy_ = false;
+        }
+        idleCv_.notify_all();
+        qCv_.notify_one();
+    }
     void run()
     {
         cudaSetDevice(P_.device);
@@ -583,34 +629,12 @@ class LocalMap
             std::vector<std::shared_ptr<KeyFrame>> take;
             {
                 std::unique_lock<std::mutex> l(qMutex_);
-                qCv_.wait(l, [&] { return !queue_.empty() || !running_; });
+                qCv_.wait(l, [&] { return (!queue_.empty() && !busy_) || !running_; });
                 if (!running_) break;
-                const size_t lim = P_.max_batch <= 0 ? queue_.size() : std::min<size_t>(queue_.size(), (size_t)P_.max_batch);
-                for (size_t i = 0; i < lim; ++i)
-                {
-                    take.push_back(queue_.front());
-                    queue_.pop_front();
-                    queued_.erase(take.back()->id);
-                }
+                popLocked(take);
                 busy_ = true;
             }
-            int changed = 0;
-            try
-            {
-                changed = processTaken(take);
-            }
-            catch (const std::exception &e)
-            {
-                std::lock_guard<std::mutex> l(qMutex_);
-                workerError_ = e.what();
-            }
-            for (int i = 0; i < changed; ++i)
-                if (cb_) cb_(user_);  // onUpdate_, grid lock released (LocalMap.cpp:479-481)
-            {
-                std::lock_guard<std::mutex> l(qMutex_);
-                busy_ = false;
-            }
-            idleCv_.notify_all();
+            runTaken(take);
         }
         idleCv_.notify_all();
     }
@@ -707,14 +731,14 @@ class LocalMap
             const double qy0 = std::floor((lo[1] - lat_.y0) / res) - 1, qy1 = std::ceil((hi[1] - lat_.y0) / res) + 1;
             if (!(qx0 > -1e9 && qx1 < 1e9 && qy0 > -1e9 && qy1 < 1e9))
                 throw std::invalid_argument("keyframe window out of the 32-bit cell range");
-            d.wtx0 = floordiv32((int)qx0);
-            d.wty0 = floordiv32((int)qy0);
-            d.wtw = floordiv32((int)qx1) - d.wtx0 + 1;
-            d.wth = floordiv32((int)qy1) - d.wty0 + 1;
+            d.wtx0 = floordiv16((int)qx0);
+            d.wty0 = floordiv16((int)qy0);
+            d.wtw = floordiv16((int)qx1) - d.wtx0 + 1;
+            d.wth = floordiv16((int)qy1) - d.wty0 + 1;
             const uint64_t T = (uint64_t)d.wtw * d.wth;
-            if (T > MAX_WINDOW_TILES)
-                throw Unsupported("keyframe spans " + std::to_string(T) + " tiles (sensor range / resolution too large; limit " +
-                                  std::to_string(MAX_WINDOW_TILES) + ")");
+            if (T > MAX_WINDOW_BINS)
+                throw Unsupported("keyframe spans " + std::to_string(T) + " bins of 16x16 cells (sensor range / resolution too large; limit " +
+                                  std::to_string(MAX_WINDOW_BINS) + ")");
             d.T_tiles = (uint32_t)T;
             maxT = std::max(maxT, d.T_tiles);
             d.chunk0 = n_chunks;
@@ -728,11 +752,11 @@ class LocalMap
             ux1 = std::max(ux1, d.wtx0 + d.wtw - 1); uy1 = std::max(uy1, d.wty0 + d.wth - 1);
         }
         // tile-list dilation radii
-        const int dc = (r_ + TILE - 1) / TILE;
-        const int di = R_ > 0 ? (r_ + R_ + TILE - 1) / TILE : -1;
+        const int dc = (r_ + BIN - 1) / BIN;                       // in bins
+        const int di = R_ > 0 ? (r_ + R_ + BIN - 1) / BIN : -1;
         const int dm = std::max(dc, di);
 
-        grid_.ensure(stream_, ux0, uy0, ux1 + 1, uy1 + 1);
+        grid_.ensure(stream_, ux0 >> 1, uy0 >> 1, (ux1 >> 1) + 1, (uy1 >> 1) + 1);  // bins -> 32x32 tiles
 
         BatchView b{};
         b.n_ops = n_ops;
@@ -751,7 +775,8 @@ class LocalMap
         chunkD_.ensure((size_t)n_chunks * 4 + 4);
         histD_.ensure((size_t)hist_off * 4 + 4);
         totD_.ensure((size_t)tot_off * 8 + 8);
-        tileD_.ensure(nb * 4 * 5 + 64);
+        const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
+        tileD_.ensure((nb * 4 + (nb + 255) / 256 + 2 * n_t32) * 4 + 256);
         bboxD_.ensure((size_t)n_ops * sizeof(int4));
         sortedD_.ensure((size_t)total_pts * 16 + 16);
         countersD_.ensure(64 * 4);
@@ -766,7 +791,9 @@ class LocalMap
         b.tile_start = b.tile_count + nb;
         b.active_tiles = b.tile_start + nb;
         b.cand_tiles = b.active_tiles + nb;
-        b.infl_tiles = b.cand_tiles + nb;
+        b.block_sums = b.cand_tiles + nb;
+        b.infl_tiles = b.block_sums + (nb + 255) / 256;
+        b.infl_flags = b.infl_tiles + n_t32;
         b.counters = countersD_.as<uint32_t>();
         b.op_bbox = bboxD_.as<int4>();
         b.sorted = sortedD_.as<float4>();
@@ -774,9 +801,9 @@ class LocalMap
         uploadConstants();
         const bool prof = P_.profile != 0;
         CK(launch_bin(stream_, b, grid_.v, lat_, ppt, maxT, dc, di, nSM_, prof ? ev_ : nullptr));
-        g_launches += 8;
-        const int cls_per_sm = std::max(1, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048)));
-        const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * std::min(cls_per_sm, 4), nb);
+        g_launches += 8;  // init, hist, 4 scan kernels, scatter, fold
+        const int cls_per_sm = std::max(1, std::min(2, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048))));
+        const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * cls_per_sm, nb);
         CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, cp_, cls_blocks));
         g_launches += 1;
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
@@ -787,7 +814,7 @@ class LocalMap
             g_launches += 1;
         }
         if (prof) CK(cudaEventRecord(ev_[6], stream_));
-        CK(launch_clear_touched(stream_, b, grid_.v, (int)std::min<size_t>((size_t)nSM_ * 4, nb)));
+        CK(launch_clear_touched(stream_, b, grid_.v, (int)std::min<size_t>((size_t)nSM_ * 8, nb)));
         g_launches += 1;
         if (prof) CK(cudaEventRecord(ev_[7], stream_));
 
@@ -854,7 +881,7 @@ class LocalMap
         static uint64_t owner = 0;
         std::lock_guard<std::mutex> l(m);
         if (owner == serial_) return;
-        const int TW = TILE + 2 * r_;
+        const int TW = BIN + 2 * r_;
         std::vector<int> off(disc_.size());
         std::vector<double> dd(disc_.size() * 2);
         for (size_t i = 0; i < disc_.size(); ++i)

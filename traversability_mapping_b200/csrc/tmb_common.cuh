@@ -5,15 +5,20 @@
 
 namespace tmb
 {
-constexpr int TILE = 32;              // cells per tile edge (tile = 32x32 cells)
+constexpr int TILE = 32;              // grid allocation / inflation tile edge (32x32 cells)
 constexpr int TILE_SHIFT = 5;
 constexpr int TILE_CELLS = TILE * TILE;
+constexpr int BIN = 16;               // binning + classification tile edge: buckets are 16x16 cells
+constexpr int BIN_SHIFT = 4;
+constexpr int BIN_CELLS = BIN * BIN;  // 256: one fold / classify thread per cell
 constexpr int REC = 12;               // floats per moment record
 constexpr int NUM_DER = 10;           // derived planes
-constexpr int MAX_WINDOW_TILES = 4096;  // tiles in one keyframe's window (binning smem limit)
+constexpr int MAX_WINDOW_BINS = 6144; // bins in one keyframe's window (scatter shared-memory limit)
 constexpr int MAX_DISC = 1024;        // footprint offsets held in __constant__ memory
 constexpr int BIN_THREADS = 256;
-constexpr int FOLD_CH = 4096;         // records staged per fold iteration
+constexpr int FOLD_THREADS = 256;
+constexpr int FOLD_CH = 2048;         // records staged per fold iteration
+constexpr uint32_t META_SIGN = 0x80000000u;  // record meta: bit31 = subtract, bits 8..30 = op, bits 0..7 = cell in bin
 
 // moment record field order (one 48-byte AoS record per cell)
 enum { R_N = 0, R_SX, R_SY, R_SZ, R_SX2, R_SY2, R_SZ2, R_SXY, R_SXZ, R_SYZ, R_ZMIN, R_ZMAX };
@@ -47,8 +52,8 @@ struct OpDesc
     uint32_t n;            // points
     float sign;            // +1 add, -1 subtract
     float T[12];           // map <- base, row-major 3x4
-    int wtx0, wty0, wtw, wth;  // tile window (global tile indices) covering every point
-    uint32_t T_tiles;      // wtw*wth
+    int wtx0, wty0, wtw, wth;  // window in BIN units (global bin indices) covering every point
+    uint32_t T_tiles;      // wtw*wth bins
     uint32_t chunk0;       // first chunk id of this op
     uint32_t nchunks;
     uint32_t tot_off;      // offset of this op's per-tile arrays (total / op_start)
@@ -64,13 +69,15 @@ struct BatchView
     uint32_t *hist;            // per (op, chunk, tile) counts -> exclusive prefix over chunks
     uint32_t *op_total;        // per (op, tile) point count
     uint32_t *op_start;        // per (op, tile) offset inside the global tile bucket
-    // batch tile bounding box (global tile indices) and per-tile arrays over it
+    // batch bounding box in BIN units (global bin indices) and per-bin arrays over it
     int btx0, bty0, btw, bth;
-    uint32_t *tile_count;      // [btw*bth]
+    uint32_t *tile_count;      // [btw*bth] records per bin
     uint32_t *tile_start;      // [btw*bth] exclusive scan of tile_count
-    uint32_t *active_tiles;    // compact list of tiles with count>0 (index into bbox)
-    uint32_t *cand_tiles;      // tiles to classify (active dilated by 1)
-    uint32_t *infl_tiles;      // tiles to inflate
+    uint32_t *block_sums;      // [ceil(btw*bth/256)] scan scratch
+    uint32_t *active_tiles;    // compact list of bins with count>0 (index into bbox)
+    uint32_t *cand_tiles;      // bins to classify (active dilated by the footprint)
+    uint32_t *infl_tiles;      // 32x32 tiles to inflate: (ty32 - g.ty0) * g.tw + (tx32 - g.tx0)
+    uint32_t *infl_flags;      // [g.tw*g.th] dedup flags for infl_tiles
     uint32_t *counters;        // [0] n_active [1] n_cand [2] n_infl [3] error flags [4] fold ticket
                                // [5] classify ticket [6] inflate ticket [7] cells classified [8] cells touched
     int4 *op_bbox;             // per op: min ci, max ci, min cj, max cj of its points
