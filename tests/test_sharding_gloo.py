@@ -1,0 +1,85 @@
+"""N>1 host logic of the sharded rebuild on CPU: slab planning, the all-to-all routing plan and the
+per-bin merge order, exercised with world_size 2 over gloo (no GPU, no CUDA library calls)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from traversability_mapping_b200 import sharding  # noqa: E402
+
+
+def test_slab_boundaries_balanced_and_tile_aligned():
+    rng = np.random.default_rng(0)
+    for world in (2, 4, 8):
+        for first in (0, -7, 5):
+            rows = rng.integers(0, 1000, size=64).astype(float)
+            rows[:5] = 0
+            slabs = sharding.slab_boundaries(rows, world, first_global_row=first)
+            assert slabs[0][0] == 0 and slabs[-1][1] == 64
+            for (a, b), (c, d) in zip(slabs[:-1], slabs[1:]):
+                assert b == c and b > a + 1
+                assert (first + b) % 2 == 0, "interior boundaries sit on 32-cell tile rows"
+            tot = [rows[a:b].sum() for a, b in slabs]
+            assert max(tot) <= rows.sum() / world + 2 * rows.max() + 1
+
+
+def test_exchange_plan_and_merge_reference_single_process():
+    rng = np.random.default_rng(1)
+    world, btw, bth = 3, 5, 12
+    nb = btw * bth
+    counts = rng.integers(0, 4, size=(world, nb))
+    starts = np.concatenate([np.zeros((world, 1), int), np.cumsum(counts, 1)[:, :-1]], 1)
+    # record = (bin, source, running index): sources' arrays are sorted by bin
+    recs = [np.array([(b, s, k) for b in range(nb) for k in range(counts[s, b])], dtype=np.int64).reshape(-1, 3) for s in range(world)]
+    slabs = sharding.slab_boundaries(counts.sum(0).reshape(bth, btw).sum(1), world)
+    for rank in range(world):
+        y0, y1 = slabs[rank]
+        recv = np.concatenate([recs[s][starts[s, y0 * btw]: starts[s, y0 * btw] + counts[s, y0 * btw:y1 * btw].sum()] for s in range(world)])
+        send, rcv, src_base = sharding.exchange_plan(counts, btw, slabs, rank)
+        assert sum(rcv) == len(recv) and send[rank] == rcv[rank]
+        merged, cnt, st = sharding.merge_reference(recv, counts, starts, src_base, btw, (y0, y1))
+        # merged must be ordered by (bin, source, index) -- the single-GPU fold order
+        key = merged[:, 0] * 10 ** 6 + merged[:, 1] * 10 ** 3 + merged[:, 2]
+        assert np.all(np.diff(key) > 0)
+        assert np.array_equal(cnt, counts[:, y0 * btw:y1 * btw].sum(0))
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from traversability_mapping_b200 import sharding
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(7)          # same stream on both ranks: everybody knows everybody's counts
+btw, bth = 6, 20
+nb = btw * bth
+counts = rng.integers(0, 5, size=(world, nb))
+starts = np.concatenate([np.zeros((world, 1), int), np.cumsum(counts, 1)[:, :-1]], 1)
+mine = np.array([(b, rank, k, 0) for b in range(nb) for k in range(counts[rank, b])], dtype=np.float32).reshape(-1, 4)
+# all-gather of the counts as the GPU path does it
+ca = [torch.zeros(nb, dtype=torch.int32) for _ in range(world)]
+dist.all_gather(ca, torch.from_numpy(counts[rank].astype(np.int32)))
+counts_all = torch.stack(ca).numpy()
+assert np.array_equal(counts_all, counts)
+slabs = sharding.slab_boundaries(counts_all.astype(np.int64).sum(0).reshape(bth, btw).sum(1), world)
+recv, send_s, recv_s, src_base = sharding.exchange_records(torch.from_numpy(mine).reshape(-1), counts_all, btw, slabs, rank, dist)
+recv = recv.numpy().reshape(-1, 4)
+merged, cnt, st = sharding.merge_reference(recv, counts_all, starts, src_base, btw, slabs[rank])
+y0, y1 = slabs[rank]
+want = np.array([(b, s, k, 0) for b in range(y0 * btw, y1 * btw) for s in range(world) for k in range(counts[s, b])], dtype=np.float32).reshape(-1, 4)
+assert np.array_equal(merged, want), (rank, merged.shape, want.shape)
+sys.stdout.write(f"[rank{rank}-ok:{len(merged)}]\n"); sys.stdout.flush()
+dist.destroy_process_group()
+'''
+
+
+def test_all_to_all_routing_world2_gloo(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("-ok:") == 2

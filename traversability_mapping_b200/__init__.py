@@ -55,6 +55,12 @@ class Stats(C.Structure):
     ]
 
 
+class ShardBuffers(C.Structure):
+    _fields_ = [("d_records", C.c_void_p), ("n_records", C.c_uint64), ("d_bin_count", C.c_void_p), ("d_bin_start", C.c_void_p),
+                ("n_bins", C.c_uint32), ("btx0", C.c_int32), ("bty0", C.c_int32), ("btw", C.c_int32), ("bth", C.c_int32),
+                ("cell_bbox", C.c_int32 * 4)]
+
+
 UPDATE_CB = C.CFUNCTYPE(None, C.c_void_p)
 
 # every symbol include/tmap.h declares: name -> (restype, argtypes)
@@ -91,6 +97,15 @@ _SIG = {
     "tmap_stitched_cloud": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tmap_get_stats": (C.c_int, [_P, C.c_uint64, C.POINTER(Stats)]),
     "tmap_set_stream": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
+    "tmap_shard_window": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
+    "tmap_shard_blank": (C.c_int, [_P, C.c_uint64]),
+    "tmap_shard_bin": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32),
+                                 C.POINTER(ShardBuffers)]),
+    "tmap_shard_fold": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
+                                  C.c_int32, C.c_int32]),
+    "tmap_shard_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "tmap_shard_classify": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
+    "tmap_shard_clear_flag_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
 }
 
 _lib = None

@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
     // inside the allocated grid?
     if (bx < g.tx0 * 2 || bx >= (g.tx0 + g.tw) * 2 || by < g.ty0 * 2 || by >= (g.ty0 + g.th) * 2)
         return;
+    if (ly < b.cand_y0 || ly >= b.cand_y1)
+        return;
     const int dm = max(dc, di);
     bool nc = false, ni = false;
     for (int dy = -dm; dy <= dm; ++dy)
@@ -425,7 +427,7 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
             const int x = lx + dx, y = ly + dy;
             if (x < 0 || x >= b.btw || y < 0 || y >= b.bth)
                 continue;
-            if (b.tile_count[y * b.btw + x])
+            if (b.nbr_count[y * b.btw + x])
             {
                 const int d = max(abs(dx), abs(dy));
                 nc |= d <= dc;
@@ -521,7 +523,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
             const uint32_t leader = __ffs(m) - 1;
             const uint32_t off = my[tl[r]];
             const uint32_t pos = s_base[tl[r]] + off + __popc(m & ((1u << lane) - 1u));
-            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | (opi << 8) | cc[r]));
+            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | ((opi + b.op_base) << 8) | cc[r]));
             __syncwarp(m);
             if (lane == leader)
                 my[tl[r]] = (uint16_t)(off + __popc(m));
@@ -745,6 +747,61 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
 }
 
 // ---------------------------------------------------------------------------------------------
+// sharded rebuild (one process per GPU; bins are owned in slabs of bin rows)
+//   counts_all / starts_all : [world][nb] every rank's per-bin record count and exclusive start
+//   k_shard_counts : my bins' merged count (sum over sources inside my slab, 0 outside), the global
+//                    total per bin (candidate-list neighbour test) and the 256-bin block sums
+//   k_shard_merge  : warp per (source, bin of my slab): copy that source's segment behind the earlier
+//                    sources' segments -> per-bin buckets ordered (source rank, op, point) = global op
+//                    order, because ranks hold contiguous keyframe-id blocks
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_shard_counts(BatchView b, const uint32_t *__restrict__ counts_all, int world, int y0, int y1,
+                                                      uint32_t *__restrict__ glob)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    uint32_t mine = 0;
+    if (i < nb)
+    {
+        uint32_t tot = 0;
+        for (int s = 0; s < world; ++s)
+            tot += counts_all[(size_t)s * nb + i];
+        glob[i] = tot;
+        const int ly = i / b.btw;
+        mine = (ly >= y0 && ly < y1) ? tot : 0;
+        b.tile_count[i] = mine;
+    }
+    uint32_t tot;
+    block_excl_scan(mine, s_w, tot);
+    if (threadIdx.x == 0)
+        b.block_sums[blockIdx.x] = tot;
+}
+
+__global__ void k_shard_merge(BatchView b, const float4 *__restrict__ recv, const uint32_t *__restrict__ counts_all,
+                              const uint32_t *__restrict__ starts_all, const unsigned long long *__restrict__ src_base, int world,
+                              int y0, int y1)
+{
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    const uint32_t nslab = (uint32_t)((y1 - y0) * b.btw);
+    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= nslab * (uint32_t)world)
+        return;
+    const int s = warp / nslab;
+    const uint32_t bin = (uint32_t)y0 * b.btw + warp % nslab;
+    const uint32_t cnt = counts_all[(size_t)s * nb + bin];
+    if (!cnt)
+        return;
+    const uint32_t first = (uint32_t)y0 * b.btw;
+    const unsigned long long src = src_base[s] + (starts_all[(size_t)s * nb + bin] - starts_all[(size_t)s * nb + first]);
+    uint32_t dst = b.tile_start[bin];
+    for (int q = 0; q < s; ++q)
+        dst += counts_all[(size_t)q * nb + bin];
+    for (uint32_t k = lane; k < cnt; k += 32)
+        b.sorted[dst + k] = recv[src + k];
+}
+
+// ---------------------------------------------------------------------------------------------
 // host-callable launch wrappers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
@@ -778,8 +835,9 @@ static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 4 + (size_t)ma
 
 static bool g_attr_set = false;
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
-                       int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/)
+                       int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/, int phases)
 {
+    // phases: bit0 = init + hist + scans + scatter, bit1 = fold
     if (!g_attr_set)
     {
         cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
@@ -789,6 +847,8 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     const uint32_t nb = b.btw * b.bth;
     const uint32_t nblk = (nb + 255) / 256;
     const uint32_t nflags = (uint32_t)(g.tw * g.th);
+    if (phases & 1)
+    {
     k_init_batch<<<(max(max(b.n_ops, 16u), nflags) + 255) / 256, 256, 0, st>>>(b, nflags);
     if (ev) cudaEventRecord(ev[0], st);
     if (ppt == 2)
@@ -806,9 +866,29 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     else
         k_scatter<8><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
     if (ev) cudaEventRecord(ev[3], st);
+    }
+    if (!(phases & 2))
+        return cudaGetLastError();
     const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm * 4u, nb);
     k_fold<<<fold_blocks, FOLD_THREADS, 0, st>>>(b, g, lat);
     if (ev) cudaEventRecord(ev[4], st);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridView &g, const float4 *d_recv, const uint32_t *d_counts_all,
+                               const uint32_t *d_starts_all, const unsigned long long *d_src_base, int world, int y0, int y1,
+                               uint32_t *d_glob, int dc, int di)
+{
+    const uint32_t nb = b.btw * b.bth;
+    const uint32_t nblk = (nb + 255) / 256;
+    const uint32_t nflags = (uint32_t)(g.tw * g.th);
+    k_init_batch<<<(max(16u, nflags) + 255) / 256, 256, 0, st>>>(b, nflags);   // b.n_ops == 0 here: bboxes untouched
+    k_shard_counts<<<nblk, 256, 0, st>>>(b, d_counts_all, world, y0, y1, d_glob);
+    k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
+    k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
+    const uint32_t nwarps = (uint32_t)((y1 - y0) * b.btw) * (uint32_t)world;
+    if (nwarps)
+        k_shard_merge<<<(nwarps + 7) / 8, 256, 0, st>>>(b, d_recv, d_counts_all, d_starts_all, d_src_base, world, y0, y1);
     return cudaGetLastError();
 }
 

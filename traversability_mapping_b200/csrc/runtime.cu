@@ -682,27 +682,63 @@ class LocalMap
     }
 
     // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
-    void runBatch(const std::vector<Op> &ops)
+    struct Plan
     {
-        const auto t_begin = std::chrono::steady_clock::now();
-        CK(cudaSetDevice(P_.device));
-        const uint32_t n_ops = (uint32_t)ops.size();
+        BatchView b{};
+        uint32_t n_ops = 0, maxT = 0;
+        int ppt = 2, dc = 0, di = -1, dm = 0;
+        uint64_t total_pts = 0;
+        int ux0 = 0, uy0 = 0, ux1 = 0, uy1 = 0;  // union of op windows, bins, inclusive
+    };
+
+    // op windows: |x_m - t_x| <= |row_x| * max|p_base| (Cauchy-Schwarz) + float-rounding slack, in bins
+    void opWindow(const Op &op, int &bx0, int &by0, int &bx1, int &by1) const
+    {
         const double res = P_.resolution;
-        // choose the chunk size: small batches use small chunks so the grid still fills the GPU
+        for (int k = 0; k < 12; ++k)
+            if (!std::isfinite(op.pose[k])) throw std::invalid_argument("non-finite pose");
+        const double mn = (double)op.kf->maxnorm;
+        double lo[2], hi[2];
+        for (int a = 0; a < 2; ++a)
+        {
+            const float *rw = op.pose + 4 * a;
+            const double rn = std::sqrt((double)rw[0] * rw[0] + (double)rw[1] * rw[1] + (double)rw[2] * rw[2]);
+            const double t = rw[3];
+            const double rad = rn * mn;
+            const double slack = 1e-5 * (std::abs(t) + rad) + 2.0 * res;
+            lo[a] = t - rad - slack;
+            hi[a] = t + rad + slack;
+        }
+        const double qx0 = std::floor((lo[0] - lat_.x0) / res) - 1, qx1 = std::ceil((hi[0] - lat_.x0) / res) + 1;
+        const double qy0 = std::floor((lo[1] - lat_.y0) / res) - 1, qy1 = std::ceil((hi[1] - lat_.y0) / res) + 1;
+        if (!(qx0 > -1e9 && qx1 < 1e9 && qy0 > -1e9 && qy1 < 1e9))
+            throw std::invalid_argument("keyframe window out of the 32-bit cell range");
+        bx0 = floordiv16((int)qx0); by0 = floordiv16((int)qy0);
+        bx1 = floordiv16((int)qx1); by1 = floordiv16((int)qy1);
+    }
+
+    // host side of a pass: op descriptors, chunk table, scratch buffers, uploads.  `forced` (bins, inclusive,
+    // already including the candidate margin) pins the per-bin arrays to a bbox shared by all ranks.
+    Plan planBatch(const std::vector<Op> &ops, const int *forced, uint32_t op_base)
+    {
+        Plan pl;
+        const uint32_t n_ops = (uint32_t)ops.size();
+        pl.n_ops = n_ops;
         uint64_t total_pts = 0, chunks8 = 0;
         for (auto &op : ops) { total_pts += op.kf->n; chunks8 += (op.kf->n + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8); }
-        const int ppt = chunks8 >= (uint64_t)2 * nSM_ ? 8 : 2;
-        const uint32_t CH = BIN_THREADS * ppt;
+        pl.total_pts = total_pts;
+        pl.ppt = chunks8 >= (uint64_t)2 * nSM_ ? 8 : 2;  // small batches use small chunks so the grid still fills the GPU
+        const uint32_t CH = BIN_THREADS * pl.ppt;
         if (total_pts >= (1ull << 32))
             throw Unsupported("batch exceeds 2^32 points");
-        if (n_ops >= (1u << 22) || n_ops > 65535)
+        if (n_ops > 65535 || (uint64_t)n_ops + op_base >= (1u << 23))
             throw Unsupported("batch exceeds 65535 ops");
 
-        opsH_.ensure(n_ops * sizeof(OpDesc));
+        opsH_.ensure((size_t)std::max(n_ops, 1u) * sizeof(OpDesc));
         OpDesc *od = opsH_.as<OpDesc>();
         uint32_t n_chunks = 0, tot_off = 0, maxT = 0;
         unsigned long long hist_off = 0;
-        int ux0 = INT_MAX, uy0 = INT_MAX, ux1 = INT_MIN, uy1 = INT_MIN;  // union of op windows (tiles, inclusive)
+        int ux0 = INT_MAX, uy0 = INT_MAX, ux1 = INT_MIN, uy1 = INT_MIN;
         for (uint32_t i = 0; i < n_ops; ++i)
         {
             const Op &op = ops[i];
@@ -712,29 +748,10 @@ class LocalMap
             d.n = op.kf->n;
             d.sign = op.sign;
             std::memcpy(d.T, op.pose, sizeof(d.T));
-            for (int k = 0; k < 12; ++k)
-                if (!std::isfinite(op.pose[k])) throw std::invalid_argument("non-finite pose");
-            // window: |x_m - t_x| <= |row_x| * max|p_base| (Cauchy-Schwarz) + float-rounding slack
-            const double mn = (double)op.kf->maxnorm;
-            double lo[2], hi[2];
-            for (int a = 0; a < 2; ++a)
-            {
-                const float *rw = op.pose + 4 * a;
-                const double rn = std::sqrt((double)rw[0] * rw[0] + (double)rw[1] * rw[1] + (double)rw[2] * rw[2]);
-                const double t = rw[3];
-                const double rad = rn * mn;
-                const double slack = 1e-5 * (std::abs(t) + rad) + 2.0 * res;
-                lo[a] = t - rad - slack;
-                hi[a] = t + rad + slack;
-            }
-            const double qx0 = std::floor((lo[0] - lat_.x0) / res) - 1, qx1 = std::ceil((hi[0] - lat_.x0) / res) + 1;
-            const double qy0 = std::floor((lo[1] - lat_.y0) / res) - 1, qy1 = std::ceil((hi[1] - lat_.y0) / res) + 1;
-            if (!(qx0 > -1e9 && qx1 < 1e9 && qy0 > -1e9 && qy1 < 1e9))
-                throw std::invalid_argument("keyframe window out of the 32-bit cell range");
-            d.wtx0 = floordiv16((int)qx0);
-            d.wty0 = floordiv16((int)qy0);
-            d.wtw = floordiv16((int)qx1) - d.wtx0 + 1;
-            d.wth = floordiv16((int)qy1) - d.wty0 + 1;
+            int bx0, by0, bx1, by1;
+            opWindow(op, bx0, by0, bx1, by1);
+            d.wtx0 = bx0; d.wty0 = by0;
+            d.wtw = bx1 - bx0 + 1; d.wth = by1 - by0 + 1;
             const uint64_t T = (uint64_t)d.wtw * d.wth;
             if (T > MAX_WINDOW_BINS)
                 throw Unsupported("keyframe spans " + std::to_string(T) + " bins of 16x16 cells (sensor range / resolution too large; limit " +
@@ -748,40 +765,56 @@ class LocalMap
             tot_off += d.T_tiles;
             d.hist_off = hist_off;
             hist_off += (unsigned long long)d.nchunks * d.T_tiles;
-            ux0 = std::min(ux0, d.wtx0); uy0 = std::min(uy0, d.wty0);
-            ux1 = std::max(ux1, d.wtx0 + d.wtw - 1); uy1 = std::max(uy1, d.wty0 + d.wth - 1);
+            ux0 = std::min(ux0, bx0); uy0 = std::min(uy0, by0);
+            ux1 = std::max(ux1, bx1); uy1 = std::max(uy1, by1);
         }
-        // tile-list dilation radii
-        const int dc = (r_ + BIN - 1) / BIN;                       // in bins
-        const int di = R_ > 0 ? (r_ + R_ + BIN - 1) / BIN : -1;
-        const int dm = std::max(dc, di);
-
+        pl.maxT = maxT;
+        pl.dc = (r_ + BIN - 1) / BIN;                       // candidate dilation, in bins
+        pl.di = R_ > 0 ? (r_ + R_ + BIN - 1) / BIN : -1;
+        pl.dm = std::max(pl.dc, pl.di);
+        BatchView &b = pl.b;
+        if (forced)
+        {
+            if (n_ops && (ux0 < forced[0] || uy0 < forced[1] || ux1 > forced[2] || uy1 > forced[3]))
+                throw std::invalid_argument("shard bbox does not cover this rank's keyframe windows");
+            b.btx0 = forced[0]; b.bty0 = forced[1];
+            b.btw = forced[2] - forced[0] + 1; b.bth = forced[3] - forced[1] + 1;
+            ux0 = forced[0]; uy0 = forced[1]; ux1 = forced[2]; uy1 = forced[3];
+        }
+        else
+        {
+            b.btx0 = ux0 - pl.dm; b.bty0 = uy0 - pl.dm;
+            b.btw = ux1 - ux0 + 1 + 2 * pl.dm; b.bth = uy1 - uy0 + 1 + 2 * pl.dm;
+        }
+        pl.ux0 = ux0; pl.uy0 = uy0; pl.ux1 = ux1; pl.uy1 = uy1;
         grid_.ensure(stream_, ux0 >> 1, uy0 >> 1, (ux1 >> 1) + 1, (uy1 >> 1) + 1);  // bins -> 32x32 tiles
 
-        BatchView b{};
         b.n_ops = n_ops;
         b.n_chunks = n_chunks;
-        b.btx0 = ux0 - dm; b.bty0 = uy0 - dm;
-        b.btw = ux1 - ux0 + 1 + 2 * dm; b.bth = uy1 - uy0 + 1 + 2 * dm;
+        b.op_base = op_base;
         const size_t nb = (size_t)b.btw * b.bth;
         b.total_points = (uint32_t)total_pts;
+        b.cand_y0 = 0; b.cand_y1 = b.bth;
 
         chunkH_.ensure((size_t)n_chunks * 4 + 4);
         uint32_t *ch = chunkH_.as<uint32_t>();
         for (uint32_t i = 0; i < n_ops; ++i)
             for (uint32_t c = 0; c < od[i].nchunks; ++c) ch[od[i].chunk0 + c] = i;
 
-        opsD_.ensure(n_ops * sizeof(OpDesc));
+        opsD_.ensure((size_t)std::max(n_ops, 1u) * sizeof(OpDesc));
         chunkD_.ensure((size_t)n_chunks * 4 + 4);
         histD_.ensure((size_t)hist_off * 4 + 4);
         totD_.ensure((size_t)tot_off * 8 + 8);
         const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
-        tileD_.ensure((nb * 4 + (nb + 255) / 256 + 2 * n_t32) * 4 + 256);
-        bboxD_.ensure((size_t)n_ops * sizeof(int4));
+        tileD_.ensure((nb * 5 + (nb + 255) / 256 + 2 * n_t32) * 4 + 256);
+        bboxD_.ensure((size_t)std::max(n_ops, 1u) * sizeof(int4));
         sortedD_.ensure((size_t)total_pts * 16 + 16);
         countersD_.ensure(64 * 4);
-        CK(cudaMemcpyAsync(opsD_.p, od, n_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, stream_));
-        CK(cudaMemcpyAsync(chunkD_.p, ch, (size_t)n_chunks * 4, cudaMemcpyHostToDevice, stream_));
+        if (n_ops)
+        {
+            CK(cudaMemcpyAsync(opsD_.p, od, n_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, stream_));
+            CK(cudaMemcpyAsync(chunkD_.p, ch, (size_t)n_chunks * 4, cudaMemcpyHostToDevice, stream_));
+        }
         b.ops = opsD_.as<OpDesc>();
         b.chunk_op = chunkD_.as<uint32_t>();
         b.hist = histD_.as<uint32_t>();
@@ -791,17 +824,23 @@ class LocalMap
         b.tile_start = b.tile_count + nb;
         b.active_tiles = b.tile_start + nb;
         b.cand_tiles = b.active_tiles + nb;
-        b.block_sums = b.cand_tiles + nb;
+        globD_ = b.cand_tiles + nb;                 // sharded runs: global per-bin totals
+        b.block_sums = globD_ + nb;
         b.infl_tiles = b.block_sums + (nb + 255) / 256;
         b.infl_flags = b.infl_tiles + n_t32;
+        b.nbr_count = b.tile_count;
         b.counters = countersD_.as<uint32_t>();
         b.op_bbox = bboxD_.as<int4>();
         b.sorted = sortedD_.as<float4>();
+        return pl;
+    }
 
-        uploadConstants();
+    // classify + inflate + clear of the bins listed by the bin phase, statistics, logical growth
+    void finishBatch(const Plan &pl, const std::vector<Op> &ops, const std::chrono::steady_clock::time_point &t_begin)
+    {
+        const BatchView &b = pl.b;
+        const size_t nb = (size_t)b.btw * b.bth;
         const bool prof = P_.profile != 0;
-        CK(launch_bin(stream_, b, grid_.v, lat_, ppt, maxT, dc, di, nSM_, prof ? ev_ : nullptr));
-        g_launches += 8;  // init, hist, 4 scan kernels, scatter, fold
         const int cls_per_sm = std::max(1, std::min(2, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048))));
         const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * cls_per_sm, nb);
         CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, cp_, cls_blocks));
@@ -819,9 +858,11 @@ class LocalMap
         if (prof) CK(cudaEventRecord(ev_[7], stream_));
 
         // results the host needs: counters + per-op bounding boxes
-        bboxH_.ensure((size_t)n_ops * sizeof(int4));
+        const uint32_t n_ops = pl.n_ops;
+        bboxH_.ensure((size_t)std::max(n_ops, 1u) * sizeof(int4));
         CK(cudaMemcpyAsync(counters_h_.p, countersD_.p, 16 * 4, cudaMemcpyDeviceToHost, stream_));
-        CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, (size_t)n_ops * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
+        if (n_ops)
+            CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, (size_t)n_ops * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
         const uint32_t *cnt = counters_h_.as<uint32_t>();
         if (cnt[3])
@@ -830,15 +871,15 @@ class LocalMap
         // logical grid growth, one keyframe at a time (growToIncludeCells, LocalMap.cpp:91-106 +
         // growGridToInclude, Helpers.cpp:53-84)
         const int4 *bb = bboxH_.as<int4>();
-        for (uint32_t i = 0; i < n_ops; ++i)
+        for (uint32_t i = 0; i < n_ops && i < ops.size(); ++i)
             if (ops[i].sign > 0 && bb[i].x != INT_MAX)
                 growLogical(bb[i].x, bb[i].y, bb[i].z, bb[i].w);
 
         stats_.host_ms_batch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
         stats_.batches += 1;
-        stats_.points_binned += total_pts;
+        stats_.points_binned += pl.total_pts;
         stats_.cells_classified += cnt[7];
-        stats_.last_batch_points = total_pts;
+        stats_.last_batch_points = pl.total_pts;
         stats_.last_batch_tiles = cnt[0];
         stats_.last_batch_cells_touched = cnt[8];
         stats_.last_batch_cells_classified = cnt[7];
@@ -855,6 +896,156 @@ class LocalMap
         }
     }
 
+    // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
+    void runBatch(const std::vector<Op> &ops)
+    {
+        const auto t_begin = std::chrono::steady_clock::now();
+        CK(cudaSetDevice(P_.device));
+        Plan pl = planBatch(ops, nullptr, 0);
+        uploadConstants();
+        CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
+        g_launches += 8;  // init, hist, 4 scan kernels, scatter, fold
+        finishBatch(pl, ops, t_begin);
+    }
+
+  public:
+    // ---- sharded rebuild: this process owns a slab of bin rows of a global map -------------
+    struct ShardBuffers
+    {
+        void *d_records; uint64_t n_records; void *d_bin_count; void *d_bin_start;
+        uint32_t n_bins; int32_t btx0, bty0, btw, bth; int32_t cell_bbox[4];
+    };
+    std::vector<Op> shardOps(const uint64_t *ids, size_t n, const float *poses)
+    {
+        std::vector<Op> ops(n);
+        std::lock_guard<std::mutex> l(kfMutex_);
+        for (size_t i = 0; i < n; ++i)
+        {
+            auto it = kfs_.find(ids[i]);
+            if (it == kfs_.end()) throw std::invalid_argument("unknown keyframe id in shard op list");
+            ops[i].kf = it->second;
+            std::memcpy(ops[i].pose, poses + 12 * i, sizeof(ops[i].pose));
+            ops[i].sign = +1.f;
+        }
+        return ops;
+    }
+    void shardWindow(const uint64_t *ids, size_t n, const float *poses, int32_t out[4])
+    {
+        auto ops = shardOps(ids, n, poses);
+        int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
+        for (auto &op : ops)
+        {
+            int a, b, c, d;
+            opWindow(op, a, b, c, d);
+            x0 = std::min(x0, a); y0 = std::min(y0, b); x1 = std::max(x1, c); y1 = std::max(y1, d);
+        }
+        out[0] = x0; out[1] = y0; out[2] = x1; out[3] = y1;
+    }
+    void shardBlank()
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        grid_.blank_all(stream_);
+        CK(cudaMemsetAsync(grid_.v.flags, 0, grid_.v.plane(), stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
+    // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
+    void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        shardOps_ = shardOps(ids, n, poses);
+        const int forced[4] = {bbox[0], bbox[1], bbox[2], bbox[3]};
+        shardPlan_ = planBatch(shardOps_, forced, op_base);
+        uploadConstants();
+        CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
+                      nSM_, nullptr, 1));
+        g_launches += 7;
+        bboxH_.ensure((size_t)std::max<size_t>(n, 1) * sizeof(int4));
+        if (n)
+            CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, n * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaMemcpyAsync(counters_h_.p, countersD_.p, 16 * 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (counters_h_.as<uint32_t>()[3])
+            throw CudaError("binning consistency check failed");
+        const BatchView &b = shardPlan_.b;
+        out->d_records = b.sorted; out->n_records = shardPlan_.total_pts;
+        out->d_bin_count = b.tile_count; out->d_bin_start = b.tile_start;
+        out->n_bins = (uint32_t)(b.btw * b.bth);
+        out->btx0 = b.btx0; out->bty0 = b.bty0; out->btw = b.btw; out->bth = b.bth;
+        int bb4[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        const int4 *bb = bboxH_.as<int4>();
+        for (size_t i = 0; i < n; ++i)
+            if (bb[i].x != INT_MAX)
+            {
+                bb4[0] = std::min(bb4[0], bb[i].x); bb4[1] = std::max(bb4[1], bb[i].y);
+                bb4[2] = std::min(bb4[2], bb[i].z); bb4[3] = std::max(bb4[3], bb[i].w);
+            }
+        for (int k = 0; k < 4; ++k) out->cell_bbox[k] = bb4[k];
+    }
+    // merge the records received from every rank for bin rows [y0, y1) (bbox-local) and fold them
+    void shardFold(const void *d_recv, uint64_t n_recv, const void *d_counts_all, const void *d_starts_all, const uint64_t *src_base,
+                   int world, int y0, int y1)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        BatchView &b = shardPlan_.b;
+        if (y0 < 0 || y1 > b.bth || y0 > y1) throw std::invalid_argument("bad slab rows");
+        mergedD_.ensure((size_t)n_recv * 16 + 16);
+        srcBaseD_.ensure((size_t)world * 8);
+        CK(cudaMemcpyAsync(srcBaseD_.p, src_base, (size_t)world * 8, cudaMemcpyHostToDevice, stream_));
+        b.sorted = mergedD_.as<float4>();
+        b.n_ops = 0;  // per-op bboxes were consumed by shardBin
+        b.nbr_count = globD_;
+        b.cand_y0 = y0; b.cand_y1 = y1;
+        CK(launch_shard_merge(stream_, b, grid_.v, static_cast<const float4 *>(d_recv), static_cast<const uint32_t *>(d_counts_all),
+                              static_cast<const uint32_t *>(d_starts_all), srcBaseD_.as<unsigned long long>(), world, y0, y1, globD_,
+                              shardPlan_.dc, shardPlan_.di));
+        CK(launch_bin(stream_, b, grid_.v, lat_, shardPlan_.ppt, 1, shardPlan_.dc, shardPlan_.di, nSM_, nullptr, 2));
+        g_launches += 6;
+        CK(cudaStreamSynchronize(stream_));
+    }
+    // pointer into the grid for an in-place halo exchange: `nrows` cell rows starting at absolute row cj
+    void shardRows(int kind, int32_t cj, int32_t nrows, void **ptr, size_t *bytes)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        const int row = cj - grid_.v.cj0;
+        if (row < 0 || row + nrows > grid_.v.H) throw std::invalid_argument("halo rows outside the allocated grid");
+        if (kind == 0)
+        {
+            *ptr = grid_.v.mom + (size_t)row * grid_.v.W * REC;
+            *bytes = (size_t)nrows * grid_.v.W * REC * 4;
+        }
+        else
+        {
+            *ptr = grid_.v.flags + (size_t)row * grid_.v.W;
+            *bytes = (size_t)nrows * grid_.v.W;
+        }
+    }
+    void shardClassify(const int32_t cell_bbox[4])
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        if (R_ > 0) throw Unsupported("step inflation is not available on a sharded map yet");
+        const auto t_begin = std::chrono::steady_clock::now();
+        if (cell_bbox[0] != INT_MAX)
+            growLogical(cell_bbox[0], cell_bbox[1], cell_bbox[2], cell_bbox[3]);
+        std::vector<Op> none;
+        Plan pl = shardPlan_;
+        pl.n_ops = 0;
+        finishBatch(pl, none, t_begin);
+    }
+    void shardClearFlagsRows(int32_t cj, int32_t nrows)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        void *p; size_t bytes;
+        shardRows(1, cj, nrows, &p, &bytes);
+        CK(cudaMemsetAsync(p, 0, bytes, stream_));
+        CK(cudaStreamSynchronize(stream_));
+    }
+    int rOf() const { return r_; }
+
+  private:
     void growLogical(int cimin, int cimax, int cjmin, int cjmax)
     {
         const double res = P_.resolution;
@@ -926,7 +1117,10 @@ class LocalMap
 
     PinBuf opsH_, chunkH_, bboxH_, counters_h_;
     DevBuf opsD_, chunkD_, histD_, totD_, tileD_, bboxD_, sortedD_, countersD_, decay_;
-    DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_;
+    DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_, mergedD_, srcBaseD_;
+    uint32_t *globD_ = nullptr;
+    Plan shardPlan_;
+    std::vector<Op> shardOps_;
 
   public:
     std::string takeWorkerError()
@@ -1423,6 +1617,45 @@ int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out)
 int tmap_set_stream(tmap_system *s, uint64_t map_id, void *stream)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->setStream(stream); return TMAP_OK; TMAP_API_END
+}
+
+/* ---- sharded global map ---- */
+int tmap_shard_window(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, int32_t out_bins[4])
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardWindow(kf_ids, n, poses, out_bins); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_blank(tmap_system *s, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardBlank(); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_bin(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, uint32_t op_base,
+                   const int32_t bbox_bins[4], tmap_shard_buffers *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    static_assert(sizeof(tmap_shard_buffers) == sizeof(tmb::LocalMap::ShardBuffers), "layout");
+    mp->shardBin(kf_ids, n, poses, op_base, bbox_bins, reinterpret_cast<tmb::LocalMap::ShardBuffers *>(out));
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_shard_fold(tmap_system *s, uint64_t map_id, const void *d_recv, uint64_t n_recv, const void *d_counts_all,
+                    const void *d_starts_all, const uint64_t *src_base, int32_t world, int32_t y0, int32_t y1)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    mp->shardFold(d_recv, n_recv, d_counts_all, d_starts_all, src_base, world, y0, y1);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_shard_rows(tmap_system *s, uint64_t map_id, int32_t kind, int32_t cj, int32_t nrows, void **d_ptr, size_t *bytes)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardRows(kind, cj, nrows, d_ptr, bytes); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_classify(tmap_system *s, uint64_t map_id, const int32_t cell_bbox[4])
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardClassify(cell_bbox); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_clear_flag_rows(tmap_system *s, uint64_t map_id, int32_t cj, int32_t nrows)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardClearFlagsRows(cj, nrows); return TMAP_OK; TMAP_API_END
 }
 
 }  // extern "C"

@@ -83,6 +83,9 @@ struct BatchView
     int4 *op_bbox;             // per op: min ci, max ci, min cj, max cj of its points
     float4 *sorted;            // bucket-sorted records (xm, ym, zm, meta)
     uint32_t total_points;
+    uint32_t op_base;          // added to the op index written into record meta (sharded runs: globally unique ops)
+    const uint32_t *nbr_count; // per-bin counts used for the candidate-list neighbour test (sharded: global totals)
+    int cand_y0, cand_y1;      // bbox-local bin rows [y0, y1) this process classifies / inflates (sharded: its slab)
 };
 
 struct ClassifyParams
