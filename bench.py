@@ -288,39 +288,76 @@ def main():
         nk = args.lc_keyframes
         base = 32
         lposes = synth.trajectory("loop", nk, seed=SEED + 1, extent=90.0)
-        lclouds = [synth.make_keyframe(SEED + 1, i, lposes[i], max_range=20.0) for i in range(base)]
-        p = tm.default_params(device=local, max_batch=0, profile=1, resolution=0.1, half_size=100.0, max_range=20.0,
-                              min_range=1.0, robot_radius=0.20)
-        s = tm.System(p)
-        s.addNewLocalMap(0)
-        s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
-        m = s.getLocalMap(0)
-        m.setStream(stream.cuda_stream)
         drift = synth.drift_poses(lposes)
-        for i in range(nk):
-            s.addNewKeyFrameWithPCL(i, i + 1, 0, lclouds[i % base])
-            s.updateKeyFrame(i + 1, drift[i])
-        s.flush()
-        times = []
-        for rep in range(3):
+        LCP = dict(resolution=0.1, half_size=100.0, max_range=20.0, min_range=1.0, robot_radius=0.20)
+        cfg = "C4-shaped: %d stored keyframes on a 180 m loop, 0.1 m grid, 13-cell disc, drifted -> true poses" % nk
+        if world == 1:
+            lclouds = [synth.make_keyframe(SEED + 1, i, lposes[i], max_range=20.0) for i in range(base)]
+            p = tm.default_params(device=local, max_batch=0, profile=1, **LCP)
+            s = tm.System(p)
+            s.addNewLocalMap(0)
+            s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+            m = s.getLocalMap(0)
+            m.setStream(stream.cuda_stream)
             for i in range(nk):
-                s.updateKeyFrame(i + 1, lposes[i] if rep % 2 == 0 else drift[i])
-            barrier()
-            with torch.cuda.stream(stream):
+                s.addNewKeyFrameWithPCL(i, i + 1, 0, lclouds[i % base])
+                s.updateKeyFrame(i + 1, drift[i])
+            s.flush()
+            times = []
+            for rep in range(3):
+                for i in range(nk):
+                    s.updateKeyFrame(i + 1, lposes[i] if rep % 2 == 0 else drift[i])
+                barrier()
+                with torch.cuda.stream(stream):
+                    flush_buf.fill_(rep)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    stream.synchronize()
+                    e0.record(stream)
+                    s.informLoopClosure()
+                    s.flush()
+                    e1.record(stream)
+                    e1.synchronize()
+                times.append(e0.elapsed_time(e1))
+            st = m.stats()
+            lc = {"keyframes": nk, "points": int(st["last_batch_points"]), "ms": float(min(times[1:])), "ms_all": times, "n_gpus": 1,
+                  "mode": "informLoopClosure + batched worker pass (max_batch=0)",
+                  "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]), "config": cfg}
+            s.close()
+        else:
+            # the global map sharded over the ranks: contiguous keyframe-id blocks per rank, all-to-all point
+            # routing + halo exchange over NVLink (traversability_mapping_b200/sharding.py)
+            from traversability_mapping_b200 import sharding
+            per = (nk + world - 1) // world
+            mine = [i for i in range(nk) if i // per == rank]
+            lclouds = {i % base: None for i in mine}
+            for k in lclouds:
+                lclouds[k] = synth.make_keyframe(SEED + 1, k, lposes[k], max_range=20.0)
+            sm = sharding.ShardedMap(tm.default_params(device=local, max_batch=0, **LCP))
+            sm.sys.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+            for i in mine:
+                sm.add_keyframe(i + 1, lclouds[i % base])
+            times, info, tim = [], None, {}
+            for rep in range(3):
+                for i in mine:
+                    sm.set_pose(i + 1, lposes[i] if rep % 2 == 0 else drift[i])
+                barrier()
                 flush_buf.fill_(rep)
+                torch.cuda.synchronize()
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                stream.synchronize()
-                e0.record(stream)
-                s.informLoopClosure()
-                s.flush()
-                e1.record(stream)
+                e0.record()
+                tim = {}
+                info = sm.rebuild(tim)
+                e1.record()
                 e1.synchronize()
-            times.append(e0.elapsed_time(e1))
-        st = m.stats()
-        lc = {"keyframes": nk, "points": int(st["last_batch_points"]), "ms": float(min(times[1:])), "ms_all": times,
-              "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]),
-              "config": "C4-shaped: 2000 stored keyframes on a 180 m loop, 0.1 m grid, drift -> true poses, informLoopClosure"}
-        s.close()
+                t = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                times.append(float(t))
+            pts = torch.tensor([float(info["local_records"]), float(info["sent_records"])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(pts)
+            lc = {"keyframes": nk, "points": int(pts[0]), "ms": float(min(times[1:])), "ms_all": times, "n_gpus": world,
+                  "mode": "sharded rebuild: slabs of bin rows, all-to-all point routing, halo exchange",
+                  "routed_points": int(pts[1]), "stages_ms_rank0": tim, "slabs": info["slabs"], "config": cfg}
+            sm.close()
 
     # ---------------- reduce over ranks ----------------
     t_max, e2e_max, pts_sum, e2e_pts_sum = t_ms, e2e_ms, pts_total, e2e_pts

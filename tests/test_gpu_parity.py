@@ -306,3 +306,25 @@ def test_cpp_mirror_replays_localmap_kat(tmap):
                     "-L" + lib_dir, "-ltmap_b200", "-Wl,-rpath," + lib_dir], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def _run_shard_check(nproc, n_kf, port):
+    import subprocess, sys
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_gpu_check.py"), str(n_kf)],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "bit-identical=True" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_sharded_rebuild_world1_matches_plain_rebuild(tmap):
+    """The tmap_shard_* path (bin -> exchange -> merge -> fold -> halo -> classify) on one rank equals the
+    ordinary informLoopClosure rebuild bit for bit on every layer."""
+    _run_shard_check(1, 12, 29561)
+
+
+def test_sharded_rebuild_world2_bit_identical(tmap):
+    """Two ranks / two GPUs: all-to-all point routing + halo exchange; gathered slabs == 1-GPU rebuild."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_shard_check(2, 24, 29562)
