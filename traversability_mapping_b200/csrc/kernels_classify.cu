@@ -21,6 +21,7 @@
 #include "eig3.cuh"
 #include <cuda.h>
 #include <math_constants.h>
+#include <cstdlib>
 
 namespace tmb
 {
@@ -76,187 +77,236 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, u
 
 enum : uint8_t { H_OBS = 1, H_OK = 2, H_TOUCHED = 4 };
 constexpr int CLS_THREADS = 256;
+constexpr int FLAG_BOX_W = BIN + 32;  // flag-byte box: starts 16 columns left of the bin (TMA needs a 16-byte aligned start)
 
-__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap, BatchView b, GridView g, const ClassifyParams c_cp)
+struct ClsSmem
+{
+    size_t rec_bytes, flag_bytes, stage_bytes, inv_off, flag_off, total;
+    __host__ __device__ explicit ClsSmem(int r)
+    {
+        const size_t TW = BIN + 2 * r, ncell = TW * TW;
+        rec_bytes = ncell * REC * 4;
+        flag_bytes = TW * FLAG_BOX_W;
+        stage_bytes = ((rec_bytes + 127) & ~(size_t)127) + ((flag_bytes + 127) & ~(size_t)127);
+        inv_off = 2 * stage_bytes;
+        flag_off = inv_off + ncell * 8;
+        total = flag_off + ((ncell + 127) & ~(size_t)127);
+    }
+};
+
+// Double-buffered: while bin i is classified, the halo tile (moment records, 3-D box) and flag bytes
+// (2-D box) of bin i+1 are already in flight on the other stage's mbarrier.
+__global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap,
+                                                             const __grid_constant__ CUtensorMap tmap_flags, BatchView b, GridView g,
+                                                          const ClassifyParams c_cp)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
     const int r = c_cp.r;
     const int TW = BIN + 2 * r;
     const int ncell = TW * TW;
-    float *s_rec = reinterpret_cast<float *>(s_raw);                                     // [TW*TW][12]
-    double *s_inv = reinterpret_cast<double *>(s_raw + (((size_t)ncell * REC * 4 + 127) & ~(size_t)127));  // [TW*TW]
-    uint8_t *s_flag = reinterpret_cast<uint8_t *>(s_inv + ncell);                        // [TW*TW]
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_ticket;
+    // shared-memory layout (same arithmetic as ClsSmem on the host)
+    const uint32_t rec_bytes = (uint32_t)ncell * REC * 4, flag_bytes = (uint32_t)TW * FLAG_BOX_W;
+    const uint32_t rec_pad = (rec_bytes + 127u) & ~127u;
+    const uint32_t stage_bytes = rec_pad + ((flag_bytes + 127u) & ~127u);
+    double *s_inv = reinterpret_cast<double *>(s_raw + 2 * stage_bytes);           // [TW*TW]
+    uint8_t *s_flag = s_raw + 2 * stage_bytes + (size_t)ncell * 8;                 // [TW*TW]
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_tmask[32], s_okmask[32];  // per halo row: touched / enough-points bits
 
     const uint32_t tid = threadIdx.x;
-    if (tid == 0)
-    {
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    uint32_t parity = 0;
     const uint32_t n_cand = b.counters[1];
     const uint32_t minp = c_cp.min_points;
     const size_t pl = g.plane();
     uint32_t n_done = 0;
 
-    for (;;)
+    auto issue = [&](int stage, uint32_t it)  // thread 0 only
     {
-        if (tid == 0)
-            s_ticket = atomicAdd(b.counters + 5, 1u);
-        __syncthreads();
-        const uint32_t it = s_ticket;
-        if (it >= n_cand)
-            break;
         const uint32_t gt = b.cand_tiles[it];
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
+        const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
+        unsigned char *base = s_raw + (size_t)stage * stage_bytes;
+        mbar_arrive_expect_tx(&s_bar[stage], rec_bytes + flag_bytes);
+        tma_load_3d(base, &tmap, &s_bar[stage], 0, col0 - r, row0 - r);
+        tma_load_2d(base + rec_pad, &tmap_flags, &s_bar[stage], col0 - 16, row0 - r);
+    };
+
+    if (tid == 0)
+    {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // static round-robin over the candidate list (its order is already arbitrary): no ticket atomics and no
+    // barrier on them in the loop; the next bin's boxes are issued one iteration ahead
+    const uint32_t stride = gridDim.x;
+    uint32_t cur = blockIdx.x;
+    if (tid == 0 && cur < n_cand)
+        issue(0, cur);
+    int stage = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+
+    while (cur < n_cand)
+    {
+        const uint32_t nxt = cur + stride;
+        __syncthreads();  // previous bin fully consumed: the other stage may be refilled
+        if (tid == 0 && nxt < n_cand)
+            issue(stage ^ 1, nxt);
+
+        const uint32_t gt = b.cand_tiles[cur];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
-        if (tid == 0)
-        {
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)ncell * REC * 4);
-            tma_load_3d(s_rec, &tmap, &s_bar, 0, col0 - r, row0 - r);
-        }
-        // touched bits of the halo tile (plain loads; zero outside the grid)
-        int any_touched = 0;
-        for (int i = tid; i < ncell; i += CLS_THREADS)
-        {
-            const int hx = i % TW, hy = i / TW;
-            const int c = col0 - r + hx, rw = row0 - r + hy;
-            uint8_t f = 0;
-            if (c >= 0 && c < g.W && rw >= 0 && rw < g.H)
-                f = (g.flags[(size_t)rw * g.W + c] & F_TOUCHED) ? H_TOUCHED : 0;
-            s_flag[i] = f;
-            any_touched |= f;
-        }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        if (!__syncthreads_or(any_touched))
-            continue;  // nothing in this bin's footprint halo changed: no cell of it is dirty
-        // pre-pass: observed / enough-points bits and 1/N  (MomentLayers::read, Helpers.cpp:101-112)
-        for (int i = tid; i < ncell; i += CLS_THREADS)
-        {
-            const float n = s_rec[(size_t)i * REC + R_N];
-            uint8_t f = s_flag[i];
-            double inv = 0.0;
-            if (!isnan(n) && n >= 1.f)
-            {
-                const float nr = rintf(n);
-                f |= H_OBS;
-                if (nr >= (float)minp) f |= H_OK;
-                inv = 1.0 / (double)nr;
-            }
-            s_flag[i] = f;
-            s_inv[i] = inv;
-        }
-        __syncthreads();
+        const float *s_rec = reinterpret_cast<const float *>(s_raw + (size_t)stage * stage_bytes);
+        const uint8_t *s_fraw = s_raw + (size_t)stage * stage_bytes + rec_pad;
+        if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
 
-#pragma unroll 1
-        for (int k = 0; k < BIN_CELLS / CLS_THREADS; ++k)
+        // pre-pass: touched / observed / enough-points bits and 1/N  (MomentLayers::read, Helpers.cpp:101-112).
+        // One warp per halo row (TW <= 32 lanes): the row's bits also land in 32-bit row masks, so the
+        // per-cell dirty / gate tests below are a few shifts per footprint row instead of a loop over taps.
+        int any_touched = 0;
+        const uint32_t lane = tid & 31, warp = tid >> 5;
+        for (int hy = warp; hy < TW; hy += CLS_THREADS / 32)
         {
-            const int q = tid + k * CLS_THREADS;
-            const int x = q & (BIN - 1), y = q >> BIN_SHIFT;
+            uint8_t f = 0;
+            double inv = 0.0;
+            if ((int)lane < TW)
+            {
+                const int i = hy * TW + lane;
+                f = (s_fraw[hy * FLAG_BOX_W + ((int)lane - r + 16)] & F_TOUCHED) ? H_TOUCHED : 0;
+                const float n = s_rec[(size_t)i * REC + R_N];
+                if (!isnan(n) && n >= 1.f)
+                {
+                    const float nr = rintf(n);
+                    f |= H_OBS;
+                    if (nr >= (float)minp) f |= H_OK;
+                    inv = 1.0 / (double)nr;
+                }
+                s_flag[i] = f;
+                s_inv[i] = inv;
+            }
+            const uint32_t mt = __ballot_sync(0xffffffffu, (f & H_TOUCHED) != 0);
+            const uint32_t mo = __ballot_sync(0xffffffffu, (f & H_OK) != 0);
+            any_touched |= mt != 0;
+            if (lane == 0)
+            {
+                s_tmask[hy] = mt;
+                s_okmask[hy] = mo;
+            }
+        }
+        if (__syncthreads_or(any_touched))  // else: nothing in this bin's footprint halo changed, no cell is dirty
+        {
+            const int x = tid & (BIN - 1), y = tid >> BIN_SHIFT;
             const int idx = (y + r) * TW + (x + r);
             const uint8_t fq = s_flag[idx];
-            if (!(fq & H_OBS))
-                continue;  // LocalMap.cpp:138-140: unobserved query -> nothing written
-            // dirty = query in dilate(touched, disc); gate = every disc cell has >= min_points
+            // LocalMap.cpp:138-140: an unobserved query cell is skipped, nothing written
             bool dirty = false, gate = true;
             const int nd = c_cp.n_disc;
-            for (int o = 0; o < nd; ++o)
+            if (fq & H_OBS)
             {
-                const uint8_t f = s_flag[idx + c_disc_off[o]];
-                dirty |= (f & H_TOUCHED) != 0;
-                gate &= (f & H_OK) != 0;
+                // dirty = query in dilate(touched, disc); gate = every disc cell has >= min_points:
+                // per footprint row, a contiguous run of 2w+1 bits of the row masks
+                for (int dj = -r; dj <= r; ++dj)
+                {
+                    const int w = c_cp.row_w[dj + r];
+                    if (w < 0) continue;
+                    const uint32_t wm = (2u << (2 * w)) - 1u;
+                    const int sh = x + r - w;
+                    dirty |= ((s_tmask[y + r + dj] >> sh) & wm) != 0u;
+                    gate &= ((s_okmask[y + r + dj] >> sh) & wm) == wm;
+                }
             }
-            if (!dirty)
-                continue;
-            ++n_done;
-            const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
-            const float *rq = s_rec + (size_t)idx * REC;
-            const double nq = (double)rintf(rq[R_N]);
-            const float border = (float)fmin(nq / (double)max(1u, minp), 1.0);
-            g.flags[cell] |= F_CHANGED;  // recomputeCell returned true (LocalMap.cpp:194-196)
-            if (!gate)
+            if (dirty)
             {
-                g.der[D_HAZARD * pl + cell] = CUDART_NAN_F;
-                g.der[D_SLOPE * pl + cell] = CUDART_NAN_F;
-                g.der[D_STEP * pl + cell] = CUDART_NAN_F;
-                g.der[D_ROUGHNESS * pl + cell] = CUDART_NAN_F;
-                g.der[D_BORDER * pl + cell] = border;
-                g.der[D_NX * pl + cell] = CUDART_NAN_F;
-                g.der[D_NY * pl + cell] = CUDART_NAN_F;
-                g.der[D_NZ * pl + cell] = CUDART_NAN_F;
-                continue;
+                ++n_done;
+                const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
+                const float *rq = s_rec + (size_t)idx * REC;
+                const double nq = (double)rintf(rq[R_N]);
+                const float border = (float)fmin(nq / (double)max(1u, minp), 1.0);
+                g.flags[cell] |= F_CHANGED;  // recomputeCell returned true (LocalMap.cpp:194-196)
+                if (!gate)
+                {
+                    g.der[D_HAZARD * pl + cell] = CUDART_NAN_F;
+                    g.der[D_SLOPE * pl + cell] = CUDART_NAN_F;
+                    g.der[D_STEP * pl + cell] = CUDART_NAN_F;
+                    g.der[D_ROUGHNESS * pl + cell] = CUDART_NAN_F;
+                    g.der[D_BORDER * pl + cell] = border;
+                    g.der[D_NX * pl + cell] = CUDART_NAN_F;
+                    g.der[D_NY * pl + cell] = CUDART_NAN_F;
+                    g.der[D_NZ * pl + cell] = CUDART_NAN_F;
+                }
+                else
+                {
+                    // ---- pass A: fuse the disc about the query centre ----
+                    double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
+                    double Sx0 = 0, Sxi = 0, Sxj = 0, Sy0 = 0, Syi = 0, Syj = 0, Sz0 = 0, Szi = 0, Szj = 0;
+                    double Qxx = 0, Qyy = 0, Qzz = 0, Qxy = 0, Qxz = 0, Qyz = 0;
+                    for (int o = 0; o < nd; ++o)
+                    {
+                        const int j = idx + c_disc_off[o];
+                        const float4 *p = reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
+                        const float4 a0 = p[0], a1 = p[1], a2 = p[2];
+                        const double2 d = c_disc_d[o];
+                        const double n = (double)a0.x;  // N is integral by construction
+                        const double sx = a0.y, sy = a0.z, sz = a0.w;
+                        const double ni = n * d.x, nj = n * d.y;
+                        Nf += n; Nx += ni; Ny += nj;
+                        Nxx = fma(ni, d.x, Nxx); Nyy = fma(nj, d.y, Nyy); Nxy = fma(ni, d.y, Nxy);
+                        Sx0 += sx; Sxi = fma(sx, d.x, Sxi); Sxj = fma(sx, d.y, Sxj);
+                        Sy0 += sy; Syi = fma(sy, d.x, Syi); Syj = fma(sy, d.y, Syj);
+                        Sz0 += sz; Szi = fma(sz, d.x, Szi); Szj = fma(sz, d.y, Szj);
+                        Qxx += (double)a1.x; Qyy += (double)a1.y; Qzz += (double)a1.z;
+                        Qxy += (double)a1.w; Qxz += (double)a2.x; Qyz += (double)a2.y;
+                    }
+                    const double rs = c_cp.res, rs2 = rs * rs;
+                    const double SX = fma(rs, Nx, Sx0), SY = fma(rs, Ny, Sy0), SZ = Sz0;
+                    const double QXX = Qxx + 2.0 * rs * Sxi + rs2 * Nxx;
+                    const double QYY = Qyy + 2.0 * rs * Syj + rs2 * Nyy;
+                    const double QZZ = Qzz;
+                    const double QXY = Qxy + rs * (Sxj + Syi) + rs2 * Nxy;
+                    const double QXZ = fma(rs, Szi, Qxz);
+                    const double QYZ = fma(rs, Szj, Qyz);
+                    const double inf = 1.0 / Nf;
+                    const double mx = SX * inf, my = SY * inf, mz = SZ * inf;
+                    const double cxx = QXX * inf - mx * mx, cyy = QYY * inf - my * my, czz = QZZ * inf - mz * mz;
+                    const double cxy = QXY * inf - mx * my, cxz = QXZ * inf - mx * mz, cyz = QYZ * inf - my * mz;
+                    double nv[3];
+                    const double lam0 = eig3_min(cxx, cxy, cxz, cyy, cyz, czz, nv);
+                    if (nv[2] < 0.0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
+                    // ---- pass B: spread of the per-cell barycentres along the normal ----
+                    double dmin = CUDART_INF, dmax = -CUDART_INF;
+                    for (int o = 0; o < nd; ++o)
+                    {
+                        const int j = idx + c_disc_off[o];
+                        const float4 a0 = *reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
+                        const double2 d = c_disc_d[o];
+                        const double iv = s_inv[j];
+                        const double bx_ = fma((double)a0.y, iv, d.x * rs) - mx;
+                        const double by_ = fma((double)a0.z, iv, d.y * rs) - my;
+                        const double bz_ = (double)a0.w * iv - mz;
+                        const double dd = bx_ * nv[0] + by_ * nv[1] + bz_ * nv[2];
+                        dmin = fmin(dmin, dd);
+                        dmax = fmax(dmax, dd);
+                    }
+                    const double slope = acos(fmin(1.0, fabs(nv[2])));
+                    const double slope_h = fmin(slope / c_cp.max_slope, 1.0);
+                    const double rough_h = fmin(sqrt(fmax(0.0, lam0)) / c_cp.ground_clearance, 1.0);
+                    const double step_h = fmin((dmax - dmin) / c_cp.ground_clearance, 1.0);
+                    const double overall = fmax(slope_h, fmax(step_h, rough_h));
+                    g.der[D_ELEVATION * pl + cell] = (float)((double)rq[R_SZ] / nq);
+                    g.der[D_HAZARD * pl + cell] = (float)overall;
+                    g.der[D_SLOPE * pl + cell] = (float)slope_h;
+                    g.der[D_STEP * pl + cell] = (float)step_h;
+                    g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
+                    g.der[D_BORDER * pl + cell] = border;
+                    g.der[D_NX * pl + cell] = (float)nv[0];
+                    g.der[D_NY * pl + cell] = (float)nv[1];
+                    g.der[D_NZ * pl + cell] = (float)nv[2];
+                }
             }
-            // ---- pass A: fuse the disc about the query centre ----
-            double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
-            double Sx0 = 0, Sxi = 0, Sxj = 0, Sy0 = 0, Syi = 0, Syj = 0, Sz0 = 0, Szi = 0, Szj = 0;
-            double Qxx = 0, Qyy = 0, Qzz = 0, Qxy = 0, Qxz = 0, Qyz = 0;
-            for (int o = 0; o < nd; ++o)
-            {
-                const int j = idx + c_disc_off[o];
-                const float4 *p = reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
-                const float4 a0 = p[0], a1 = p[1], a2 = p[2];
-                const double2 d = c_disc_d[o];
-                const double n = (double)a0.x;  // N is integral by construction
-                const double sx = a0.y, sy = a0.z, sz = a0.w;
-                const double ni = n * d.x, nj = n * d.y;
-                Nf += n; Nx += ni; Ny += nj;
-                Nxx = fma(ni, d.x, Nxx); Nyy = fma(nj, d.y, Nyy); Nxy = fma(ni, d.y, Nxy);
-                Sx0 += sx; Sxi = fma(sx, d.x, Sxi); Sxj = fma(sx, d.y, Sxj);
-                Sy0 += sy; Syi = fma(sy, d.x, Syi); Syj = fma(sy, d.y, Syj);
-                Sz0 += sz; Szi = fma(sz, d.x, Szi); Szj = fma(sz, d.y, Szj);
-                Qxx += (double)a1.x; Qyy += (double)a1.y; Qzz += (double)a1.z;
-                Qxy += (double)a1.w; Qxz += (double)a2.x; Qyz += (double)a2.y;
-            }
-            const double rs = c_cp.res, rs2 = rs * rs;
-            const double SX = fma(rs, Nx, Sx0), SY = fma(rs, Ny, Sy0), SZ = Sz0;
-            const double QXX = Qxx + 2.0 * rs * Sxi + rs2 * Nxx;
-            const double QYY = Qyy + 2.0 * rs * Syj + rs2 * Nyy;
-            const double QZZ = Qzz;
-            const double QXY = Qxy + rs * (Sxj + Syi) + rs2 * Nxy;
-            const double QXZ = fma(rs, Szi, Qxz);
-            const double QYZ = fma(rs, Szj, Qyz);
-            const double inf = 1.0 / Nf;
-            const double mx = SX * inf, my = SY * inf, mz = SZ * inf;
-            const double cxx = QXX * inf - mx * mx, cyy = QYY * inf - my * my, czz = QZZ * inf - mz * mz;
-            const double cxy = QXY * inf - mx * my, cxz = QXZ * inf - mx * mz, cyz = QYZ * inf - my * mz;
-            double nv[3];
-            const double lam0 = eig3_min(cxx, cxy, cxz, cyy, cyz, czz, nv);
-            if (nv[2] < 0.0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
-            // ---- pass B: spread of the per-cell barycentres along the normal ----
-            double dmin = CUDART_INF, dmax = -CUDART_INF;
-            for (int o = 0; o < nd; ++o)
-            {
-                const int j = idx + c_disc_off[o];
-                const float4 a0 = *reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
-                const double2 d = c_disc_d[o];
-                const double iv = s_inv[j];
-                const double bx = fma((double)a0.y, iv, d.x * rs) - mx;
-                const double by = fma((double)a0.z, iv, d.y * rs) - my;
-                const double bz = (double)a0.w * iv - mz;
-                const double dd = bx * nv[0] + by * nv[1] + bz * nv[2];
-                dmin = fmin(dmin, dd);
-                dmax = fmax(dmax, dd);
-            }
-            const double slope = acos(fmin(1.0, fabs(nv[2])));
-            const double slope_h = fmin(slope / c_cp.max_slope, 1.0);
-            const double rough_h = fmin(sqrt(fmax(0.0, lam0)) / c_cp.ground_clearance, 1.0);
-            const double step_h = fmin((dmax - dmin) / c_cp.ground_clearance, 1.0);
-            const double overall = fmax(slope_h, fmax(step_h, rough_h));
-            g.der[D_ELEVATION * pl + cell] = (float)((double)rq[R_SZ] / nq);
-            g.der[D_HAZARD * pl + cell] = (float)overall;
-            g.der[D_SLOPE * pl + cell] = (float)slope_h;
-            g.der[D_STEP * pl + cell] = (float)step_h;
-            g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
-            g.der[D_BORDER * pl + cell] = border;
-            g.der[D_NX * pl + cell] = (float)nv[0];
-            g.der[D_NY * pl + cell] = (float)nv[1];
-            g.der[D_NZ * pl + cell] = (float)nv[2];
         }
-        __syncthreads();  // everyone done with s_rec before the next TMA overwrites it
+        cur = nxt;
+        stage ^= 1;
     }
     // cells classified (statistics)
     for (int o = 16; o > 0; o >>= 1)
@@ -292,7 +342,7 @@ __global__ void k_clear_touched(BatchView b, GridView g)
 // so once decay_k <= best no later tap can raise the maximum.  max() is order independent, so
 // the result is bit-identical to the reference's loop.
 // ---------------------------------------------------------------------------------------------
-constexpr int INF_THREADS = 1024;  // one cell per thread: a seed-heavy tile is the kernel's tail, so spread it wide
+constexpr int INF_THREADS = 1024;  // one cell per thread
 struct InflTap { int off; float decay; };
 
 __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__ CUtensorMap tmap_step, BatchView b, GridView g,
@@ -300,41 +350,50 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
                                                          const ClassifyParams c_cp)
 {
     extern __shared__ __align__(1024) unsigned char s_raw[];
-    const int R = c_cp.infl_r, TW = TILE + 2 * R, KW = 2 * R + 1, SW = TW + 1;
+    const int R = c_cp.infl_r, TW = TILE + 2 * R, KW = 2 * R + 1;
     const int ntap = c_cp.n_infl;
-    float *s_step = reinterpret_cast<float *>(s_raw);                                   // [TW][TW]
-    uint16_t *s_sat = reinterpret_cast<uint16_t *>(s_raw + (size_t)TW * TW * 4);         // [TW+1][TW+1]
-    InflTap *s_tap = reinterpret_cast<InflTap *>(s_raw + (((size_t)TW * TW * 4 + (size_t)SW * SW * 2 + 15) & ~(size_t)15));
-    __shared__ __align__(8) uint64_t s_bar;
-    __shared__ uint32_t s_ticket;
+    const size_t stage_bytes = ((size_t)TW * TW * 4 + 127) & ~(size_t)127;
+    unsigned long long *s_seedrow = reinterpret_cast<unsigned long long *>(s_raw + 2 * stage_bytes);  // [TW] seed bit per column
+    InflTap *s_tap = reinterpret_cast<InflTap *>(s_raw + 2 * stage_bytes + (((size_t)(TW <= 64 ? TW : 0) * 8 + 15) & ~(size_t)15));
+    __shared__ __align__(8) uint64_t s_bar[2];
     const float lethal = c_cp.lethal;
     const uint32_t tid = threadIdx.x;
+    const uint32_t n_tiles = b.counters[2];
+    const size_t pl = g.plane();
+
+    auto issue = [&](int stage, uint32_t it)  // thread 0 only
+    {
+        const uint32_t t32 = b.infl_tiles[it];  // grid-relative 32x32 tile
+        const int col0 = (int)(t32 % g.tw) * TILE, row0 = (int)(t32 / g.tw) * TILE;
+        mbar_arrive_expect_tx(&s_bar[stage], (uint32_t)(TW * TW * 4));
+        tma_load_2d(s_raw + (size_t)stage * stage_bytes, &tmap_step, &s_bar[stage], col0 - R, row0 - R);
+    };
+
     if (tid == 0)
     {
-        mbar_init(&s_bar, 1);
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
         fence_mbar_init();
     }
     for (int i = tid; i < ntap; i += INF_THREADS)
         s_tap[i] = taps[i];
     __syncthreads();
-    uint32_t parity = 0;
-    const uint32_t n_tiles = b.counters[2];
-    const size_t pl = g.plane();
-    for (;;)
+    // static round-robin over the tile list, next tile's box issued one iteration ahead
+    const uint32_t stride = gridDim.x;
+    uint32_t curt = blockIdx.x;
+    if (tid == 0 && curt < n_tiles)
+        issue(0, curt);
+    int stage = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+    while (curt < n_tiles)
     {
-        if (tid == 0)
-            s_ticket = atomicAdd(b.counters + 6, 1u);
-        __syncthreads();
-        const uint32_t it = s_ticket;
-        if (it >= n_tiles)
-            break;
-        const uint32_t t32 = b.infl_tiles[it];  // grid-relative 32x32 tile
+        const uint32_t nxt = curt + stride;
+        __syncthreads();  // previous tile consumed
+        if (tid == 0 && nxt < n_tiles)
+            issue(stage ^ 1, nxt);
+        const uint32_t t32 = b.infl_tiles[curt];
         const int col0 = (int)(t32 % g.tw) * TILE, row0 = (int)(t32 / g.tw) * TILE;
-        if (tid == 0)
-        {
-            mbar_arrive_expect_tx(&s_bar, (uint32_t)(TW * TW * 4));
-            tma_load_2d(s_step, &tmap_step, &s_bar, col0 - R, row0 - R);
-        }
+        const float *s_step = reinterpret_cast<const float *>(s_raw + (size_t)stage * stage_bytes);
         // this thread's cells: N (observed?) and the current inflated value, in flight during the TMA
         float nobs[TILE_CELLS / INF_THREADS], cur[TILE_CELLS / INF_THREADS];
 #pragma unroll
@@ -345,51 +404,31 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
             nobs[k] = g.mom[cell * REC + R_N];
             cur[k] = g.der[D_INFLATED * pl + cell];
         }
-        mbar_wait(&s_bar, parity);
-        parity ^= 1;
-        // no seed anywhere in the halo tile (the common case away from steps): every observed cell gets 0
+        if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        // seed mask per halo row (64-bit, when the halo tile is at most 64 columns wide): one warp per row,
+        // two ballots.  Wider kernels skip the per-cell box pre-test and rely on the taps' early exit.
         int any_seed = 0;
-        for (int i = tid; i < TW * TW; i += INF_THREADS)
-            any_seed |= s_step[i] >= lethal;
-        if (!__syncthreads_or(any_seed))
+        const bool use_masks = TW <= 64;
+        if (use_masks)
         {
-#pragma unroll
-            for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
+            const uint32_t lane = tid & 31, warp = tid >> 5;
+            for (int hy = warp; hy < TW; hy += INF_THREADS / 32)
             {
-                if (!(nobs[k] >= 1.f) || cur[k] == 0.f)
-                    continue;
-                const int q = tid + k * INF_THREADS;
-                const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
-                g.der[D_INFLATED * pl + cell] = 0.f;
-                g.flags[cell] |= F_CHANGED;
-            }
-            continue;
-        }
-        // summed-area table of the seed mask: rows, then columns
-        if ((int)tid < TW)
-        {
-            uint32_t run = 0;
-            const float *row = s_step + tid * TW;
-            uint16_t *o = s_sat + (tid + 1) * SW;
-            o[0] = 0;
-            for (int x = 0; x < TW; ++x)
-            {
-                run += row[x] >= lethal;
-                o[x + 1] = (uint16_t)run;
+                const float *row = s_step + hy * TW;
+                const uint32_t lo = __ballot_sync(0xffffffffu, (int)lane < TW && row[lane] >= lethal);
+                const uint32_t hi = __ballot_sync(0xffffffffu, (int)lane + 32 < TW && row[min((int)lane + 32, TW - 1)] >= lethal);
+                any_seed |= (lo | hi) != 0u;
+                if (lane == 0)
+                    s_seedrow[hy] = ((unsigned long long)hi << 32) | lo;
             }
         }
-        if ((int)tid <= TW) s_sat[tid] = 0;
-        __syncthreads();
-        if ((int)tid <= TW)
+        else
         {
-            uint32_t run = 0;
-            for (int y = 1; y <= TW; ++y)
-            {
-                run += s_sat[y * SW + tid];
-                s_sat[y * SW + tid] = (uint16_t)run;
-            }
+            for (int i = tid; i < TW * TW; i += INF_THREADS)
+                any_seed |= s_step[i] >= lethal;
         }
-        __syncthreads();
+        const int have_seed = __syncthreads_or(any_seed);
 #pragma unroll
         for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
         {
@@ -397,20 +436,29 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
                 continue;  // observed cells only (LocalMap.cpp:220-221)
             const int q = tid + k * INF_THREADS;
             const int x = q & 31, y = q >> 5;
-            const int seeds = (int)s_sat[(y + KW) * SW + (x + KW)] - (int)s_sat[y * SW + (x + KW)] -
-                              (int)s_sat[(y + KW) * SW + x] + (int)s_sat[y * SW + x];
             float best = 0.f;
-            if (seeds > 0)
+            if (have_seed)
             {
-                const int base = (y + R) * TW + (x + R);
-                for (int t = 0; t < ntap; ++t)
+                // any seed inside the (2R+1)^2 box of this cell?  KW bits of each of the KW row masks
+                unsigned long long seeds = use_masks ? 0ull : ~0ull;
+                if (use_masks)
                 {
-                    const InflTap tp = s_tap[t];
-                    if (tp.decay <= best)
-                        break;
-                    const float sv = s_step[base + tp.off];
-                    if (sv >= lethal)
-                        best = fmaxf(best, __fmul_rn(sv, tp.decay));
+                    const unsigned long long km = (1ull << KW) - 1ull;  // KW <= 33 here
+                    for (int dj = 0; dj < KW; ++dj)
+                        seeds |= (s_seedrow[y + dj] >> x) & km;
+                }
+                if (seeds != 0ull)
+                {
+                    const int base = (y + R) * TW + (x + R);
+                    for (int t = 0; t < ntap; ++t)
+                    {
+                        const InflTap tp = s_tap[t];
+                        if (tp.decay <= best)
+                            break;
+                        const float sv = s_step[base + tp.off];
+                        if (sv >= lethal)
+                            best = fmaxf(best, __fmul_rn(sv, tp.decay));
+                    }
                 }
             }
             if (!(cur[k] == best))
@@ -420,7 +468,8 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
                 g.flags[cell] |= F_CHANGED;
             }
         }
-        __syncthreads();
+        curt = nxt;
+        stage ^= 1;
     }
 }
 
@@ -549,15 +598,11 @@ __global__ void k_transform_cloud(const float4 *cloud, uint32_t n, const float *
 // ---------------------------------------------------------------------------------------------
 // host-callable wrappers
 // ---------------------------------------------------------------------------------------------
-size_t classify_smem_bytes(int r)
-{
-    const size_t ncell = (size_t)(BIN + 2 * r) * (BIN + 2 * r);
-    return ((ncell * REC * 4 + 127) & ~(size_t)127) + ncell * 8 + ncell + 128;
-}
+size_t classify_smem_bytes(int r) { return ClsSmem(r).total + 128; }
 size_t inflate_smem_bytes(int R, int n_taps)
 {
     const size_t TW = TILE + 2 * R;
-    return ((TW * TW * 4 + (TW + 1) * (TW + 1) * 2 + 15) & ~(size_t)15) + (size_t)n_taps * 8 + 128;
+    return 2 * ((TW * TW * 4 + 127) & ~(size_t)127) + (((TW <= 64 ? TW : 0) * 8 + 15) & ~(size_t)15) + (size_t)n_taps * 8 + 128;
 }
 
 cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d /*pairs*/, int n_disc)
@@ -567,18 +612,32 @@ cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d 
     return cudaMemcpyToSymbol(c_disc_d, disc_d, sizeof(double) * 2 * n_disc);
 }
 
-cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const BatchView &b, const GridView &g, const ClassifyParams &cp,
-                            int n_blocks)
+// persistent one-wave grids: the kernels walk their work lists round-robin, so the grid is exactly the
+// number of CTAs that are resident at once (a second partial wave would only add a tail)
+static int resident_ctas(const void *fn, int threads, size_t smem, int n_sm)
 {
-    static int attr_r = -1;
+    int per_sm = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1)
+        per_sm = 1;
+    return per_sm * n_sm;
+}
+
+cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUtensorMap &tmap_flags, const BatchView &b, const GridView &g,
+                            const ClassifyParams &cp, int n_sm)
+{
+    static int attr_r = -1, grid = 0;
     const int r = cp.r;
     const size_t smem = classify_smem_bytes(r);
     if (attr_r != r)
     {
         cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        grid = resident_ctas((const void *)k_classify, CLS_THREADS, smem, n_sm);
         attr_r = r;
     }
-    k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, b, g, cp);
+    int gmul = 0;
+    if (const char *e = getenv("TMB_CLS_GRID")) gmul = atoi(e);
+    const int n_blocks = (int)min((size_t)(gmul > 0 ? gmul * n_sm : 3 * n_sm), (size_t)b.btw * b.bth);
+    k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, tmap_flags, b, g, cp);
     return cudaGetLastError();
 }
 
@@ -589,16 +648,20 @@ cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const Grid
 }
 
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
-                           const ClassifyParams &cp, const void *d_taps, int n_blocks)
+                           const ClassifyParams &cp, const void *d_taps, int n_sm)
 {
-    static int attr_R = -1;
+    static int attr_R = -1, grid = 0;
     const int R = cp.infl_r;
     const size_t smem = inflate_smem_bytes(R, cp.n_infl);
     if (attr_R != R)
     {
         cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        grid = resident_ctas((const void *)k_inflate, INF_THREADS, smem, n_sm);
         attr_R = R;
     }
+    int gmul = 0;
+    if (const char *e = getenv("TMB_INF_GRID")) gmul = atoi(e);
+    const int n_blocks = (int)min((size_t)(gmul > 0 ? gmul * n_sm : 2 * n_sm), (size_t)g.tw * g.th);
     k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, static_cast<const InflTap *>(d_taps), cp);
     return cudaGetLastError();
 }

@@ -117,7 +117,7 @@ static EncodeTiledFn get_encode()
 struct DeviceGrid
 {
     GridView v{};
-    CUtensorMap tmap_mom{}, tmap_step{};
+    CUtensorMap tmap_mom{}, tmap_step{}, tmap_flags{};
     int r = 0, R = 0;  // classify halo, inflation halo (0 = none)
     uint64_t reallocs = 0;
 
@@ -156,6 +156,18 @@ struct DeviceGrid
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NAN_REQUEST_ZERO_FMA);
             if (rc != CUDA_SUCCESS)
                 throw CudaError("cuTensorMapEncodeTiled(moments) failed: " + std::to_string((int)rc));
+        }
+        {
+            // flag bytes: box starts 16 columns left of the bin so the inner start stays 16-byte aligned
+            const cuuint64_t dims[2] = {(cuuint64_t)v.W, (cuuint64_t)v.H};
+            const cuuint64_t strides[1] = {(cuuint64_t)v.W};
+            const cuuint32_t box[2] = {(cuuint32_t)(BIN + 32), (cuuint32_t)(BIN + 2 * r)};
+            const cuuint32_t es[2] = {1, 1};
+            CUresult rc = enc(&tmap_flags, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, v.flags, dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (rc != CUDA_SUCCESS)
+                throw CudaError("cuTensorMapEncodeTiled(flags) failed: " + std::to_string((int)rc));
         }
         if (R > 0)
         {
@@ -296,8 +308,8 @@ class LocalMap
                               std::to_string(MAX_DISC) + ")");
         r_ = 0;
         for (auto &o : disc_) r_ = std::max(r_, std::max(std::abs(o.first), std::abs(o.second)));
-        if (classify_smem_bytes(r_) > 200 * 1024)
-            throw Unsupported("footprint radius of " + std::to_string(r_) + " cells exceeds the halo-tile shared-memory budget");
+        if (classify_smem_bytes(r_) > 200 * 1024 || r_ > 8)
+            throw Unsupported("footprint radius of " + std::to_string(r_) + " cells exceeds the classifier's 32-column halo-row limit (r <= 8)");
         R_ = 0;
         if (P.inflation_enabled)
         {
@@ -306,7 +318,7 @@ class LocalMap
             for (auto &o : io) rr = std::max(rr, std::max(std::abs(o.first), std::abs(o.second)));
             R_ = (rr + 3) & ~3;  // multiple of 4 cells: the TMA box must start 16-byte aligned in the inner (x) dimension
             nInfl_ = (int)io.size();
-            if (inflate_smem_bytes(R_, nInfl_) > 200 * 1024 || TILE + 2 * R_ > 248)
+            if (inflate_smem_bytes(R_, nInfl_) > 200 * 1024 || TILE + 2 * R_ > 256)
                 throw Unsupported("inflation radius of " + std::to_string(rr) + " cells exceeds the halo-tile budget");
             // taps (LocalMap.cpp:57-67) sorted by decreasing decay for the kernel's early exit
             struct Tap { int off; float decay; };
@@ -332,6 +344,9 @@ class LocalMap
         cp_.infl_r = R_;
         cp_.n_infl = nInfl_;
         cp_.lethal = (float)P.lethal_step_threshold;
+        for (auto &w : cp_.row_w) w = -1;
+        for (auto &o : disc_)  // rows (dj) of the footprint are contiguous runs of di: keep the half-widths
+            cp_.row_w[o.second + r_] = (signed char)std::max<int>(cp_.row_w[o.second + r_], std::abs(o.first));
         CK(cudaStreamCreateWithFlags(&ownStream_, cudaStreamNonBlocking));
         stream_ = ownStream_;
         for (auto &e : ev_) CK(cudaEventCreate(&e));
@@ -841,15 +856,12 @@ class LocalMap
         const BatchView &b = pl.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const bool prof = P_.profile != 0;
-        const int cls_per_sm = std::max(1, std::min(2, (int)((220 * 1024) / (classify_smem_bytes(r_) + 2048))));
-        const int cls_blocks = (int)std::min<size_t>((size_t)nSM_ * cls_per_sm, nb);
-        CK(launch_classify(stream_, grid_.tmap_mom, b, grid_.v, cp_, cls_blocks));
+        CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_));
         g_launches += 1;
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0)
         {
-            const int inf_blocks = (int)std::min<size_t>((size_t)nSM_ * 2, nb);
-            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.p, inf_blocks));
+            CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.p, nSM_));
             g_launches += 1;
         }
         if (prof) CK(cudaEventRecord(ev_[6], stream_));

@@ -94,9 +94,10 @@ struct ClassifyParams
     uint32_t min_points;
     int r;           // disc bounding radius in cells
     int n_disc;      // number of footprint offsets
-    int infl_r;      // inflation radius in cells (even), 0 = disabled
+    int infl_r;      // inflation radius in cells (multiple of 4), 0 = disabled
     int n_infl;
     float lethal;
+    signed char row_w[36];  // footprint half-width per row dj+r (-1: empty row); rows are contiguous runs
 };
 
 enum { ERR_OUT_OF_WINDOW = 1, ERR_OUT_OF_GRID = 2 };
