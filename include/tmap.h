@@ -103,6 +103,7 @@ typedef struct tmap_stats
     float host_ms_batch;           /* wall-clock of the last batch on the host (assembly + launches + sync) */
     uint64_t last_batch_points, last_batch_tiles, last_batch_cells_touched,
         last_batch_cells_classified;
+    uint64_t last_batch_max_bin;   /* records in the heaviest 16x16 bin of the last batch */
 } tmap_stats;
 
 typedef struct tmap_system tmap_system;

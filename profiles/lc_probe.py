@@ -23,7 +23,7 @@ s.flush()
 for rep in range(2):
     t0 = time.perf_counter(); s.informLoopClosure(); s.flush(); dt = time.perf_counter() - t0
     st = m.stats()
-    print("rebuild %d: wall %.2f ms, gpu %.2f ms, points %d, tiles %d, touched %d, classified %d | hist %.3f scan %.3f scatter %.3f fold %.3f classify %.3f" % (
-        rep, dt * 1e3, st["ms_total"], st["last_batch_points"], st["last_batch_tiles"], st["last_batch_cells_touched"],
+    print("rebuild %d: wall %.2f ms, gpu %.2f ms, points %d, bins %d (heaviest %d), touched %d, classified %d | hist %.3f scan %.3f scatter %.3f fold %.3f classify %.3f" % (
+        rep, dt * 1e3, st["ms_total"], st["last_batch_points"], st["last_batch_tiles"], st["last_batch_max_bin"], st["last_batch_cells_touched"],
         st["last_batch_cells_classified"], st["ms_hist"], st["ms_scan"], st["ms_scatter"], st["ms_fold"], st["ms_classify"]))
 s.close()

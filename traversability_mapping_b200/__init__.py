@@ -52,6 +52,7 @@ class Stats(C.Structure):
         ("ms_classify", C.c_float), ("ms_inflate", C.c_float), ("ms_total", C.c_float), ("host_ms_batch", C.c_float),
         ("last_batch_points", C.c_uint64), ("last_batch_tiles", C.c_uint64),
         ("last_batch_cells_touched", C.c_uint64), ("last_batch_cells_classified", C.c_uint64),
+        ("last_batch_max_bin", C.c_uint64),
     ]
 
 

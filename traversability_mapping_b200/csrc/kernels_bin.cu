@@ -36,10 +36,17 @@ __device__ __forceinline__ void xform_rn(const float *__restrict__ T, float x, f
     zm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], x), __fmul_rn(T[9], y)), __fmul_rn(T[10], z)), T[11]);
 }
 
-// Lattice::cellOf: (int)lround((x - x0)/res), round half away from zero, in double
-__device__ __forceinline__ int cell_of(float xm, double x0, double res)
+// Lattice::cellOf: (int)lround((x - x0)/res), round half away from zero, in double.
+// Fast path: multiply by 1/res (relative error <= 2^-52 against the true quotient) and round; that can only
+// disagree with the divided value when the quotient sits within that error of a rounding boundary k + 1/2,
+// so exactly those points (measure zero in practice) take the IEEE division.  Result == the reference's.
+__device__ __forceinline__ int cell_of(float xm, double x0, double res, double inv_res)
 {
-    const double q = __ddiv_rn(__dsub_rn((double)xm, x0), res);
+    const double d = __dsub_rn((double)xm, x0);
+    const double q = __dmul_rn(d, inv_res);
+    const double f = fabs(q) - floor(fabs(q));           // fractional part, exact
+    if (fabs(f - 0.5) <= fabs(q) * 1e-15 + 1e-300)
+        return (int)llround(__ddiv_rn(d, res));
     return (int)llround(q);
 }
 
@@ -232,6 +239,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
         reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(b.ops + opi)[threadIdx.x];
     __syncthreads();
     const uint32_t T = s_op.T_tiles;
+    const double inv_res = 1.0 / lat.res;
     for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
         s_hist[i] = 0;
     __syncthreads();
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
             const float4 p = __ldg(s_op.cloud + i);
             float xm, ym, zm;
             xform_rn(s_op.T, p.x, p.y, p.z, xm, ym, zm);
-            const int ci = cell_of(xm, lat.x0, lat.res), cj = cell_of(ym, lat.y0, lat.res);
+            const int ci = cell_of(xm, lat.x0, lat.res, inv_res), cj = cell_of(ym, lat.y0, lat.res, inv_res);
             const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
             if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
             {
@@ -318,6 +326,8 @@ __global__ void k_scan_chunks(BatchView b)
         b.op_total[op.tot_off + t] = run;
 }
 
+constexpr uint32_t HEAVY_BIN = 32768;  // records; bins at least this heavy are scheduled first
+
 __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*[33]*/, uint32_t &total)
 {
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -361,15 +371,23 @@ __global__ void __launch_bounds__(256) k_scan_ops(BatchView b)
     if (g < nb)
     {
         const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
-        for (uint32_t o = 0; o < b.n_ops; ++o)
+        // ops are visited in order; groups of 32 whose union window misses this bin are skipped whole
+        for (uint32_t o0 = 0; o0 < b.n_ops; o0 += 32)
         {
-            const OpDesc &op = b.ops[o];
-            const int lx = tx - op.wtx0, ly = ty - op.wty0;
-            if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
+            const int4 gw = b.op_groups[o0 >> 5];  // x0, y0, x1, y1 (inclusive) of the group's windows
+            if (tx < gw.x || tx > gw.z || ty < gw.y || ty > gw.w)
                 continue;
-            const uint32_t t = op.tot_off + ly * op.wtw + lx;
-            b.op_start[t] = run;
-            run += b.op_total[t];
+            const uint32_t o1 = min(o0 + 32u, b.n_ops);
+            for (uint32_t o = o0; o < o1; ++o)
+            {
+                const OpDesc &op = b.ops[o];
+                const int lx = tx - op.wtx0, ly = ty - op.wty0;
+                if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
+                    continue;
+                const uint32_t t = op.tot_off + ly * op.wtw + lx;
+                b.op_start[t] = run;
+                run += b.op_total[t];
+            }
         }
         b.tile_count[g] = run;
     }
@@ -411,7 +429,17 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
         return;
     b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
     if (v)
-        b.active_tiles[atomicAdd(b.counters + 0, 1u)] = i;
+    {
+        // heavy bins go to the front of the work list, light ones fill it from the back: the fold's ticket
+        // loop then starts the long sequential chains first (longest-processing-time-first scheduling)
+        const uint32_t k = atomicAdd(b.counters + 0, 1u);
+        (void)k;
+        if (v >= HEAVY_BIN)
+            b.active_tiles[atomicAdd(b.counters + 10, 1u)] = i;
+        else
+            b.active_tiles[nb - 1 - atomicAdd(b.counters + 11, 1u)] = i;
+        atomicMax(b.counters + 9, v);  // heaviest bin of the batch (statistics)
+    }
     const int lx = i % b.btw, ly = i / b.btw;
     const int bx = b.btx0 + lx, by = b.bty0 + ly;  // global bin
     // inside the allocated grid?
@@ -460,6 +488,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         reinterpret_cast<uint32_t *>(&s_op)[threadIdx.x] = reinterpret_cast<const uint32_t *>(b.ops + opi)[threadIdx.x];
     __syncthreads();
     const uint32_t T = s_op.T_tiles;
+    const double inv_res = 1.0 / lat.res;
     uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn);               // [T]
     uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_base + T);           // [NW][T]
     for (uint32_t i = threadIdx.x; i < (T * NW + 1) / 2; i += BIN_THREADS)
@@ -484,7 +513,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         {
             const float4 p = __ldg(s_op.cloud + i);
             xform_rn(s_op.T, p.x, p.y, p.z, px[r], py[r], pz[r]);
-            const int ci = cell_of(px[r], lat.x0, lat.res), cj = cell_of(py[r], lat.y0, lat.res);
+            const int ci = cell_of(px[r], lat.x0, lat.res, inv_res), cj = cell_of(py[r], lat.y0, lat.res, inv_res);
             const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
             if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
             {
@@ -606,7 +635,8 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
         __syncthreads();
         if (it >= n_active)
             break;
-        const uint32_t gt = b.active_tiles[it];
+        const uint32_t n_heavy = b.counters[10];
+        const uint32_t gt = it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
         const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);

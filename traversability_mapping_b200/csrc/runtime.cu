@@ -811,13 +811,27 @@ class LocalMap
         b.total_points = (uint32_t)total_pts;
         b.cand_y0 = 0; b.cand_y1 = b.bth;
 
-        chunkH_.ensure((size_t)n_chunks * 4 + 4);
+        // chunk -> op table, followed by the per-32-op union windows used by the scan over ops
+        const uint32_t n_groups = (n_ops + 31) / 32;
+        const size_t grp_off = (((size_t)n_chunks * 4 + 4) + 15) & ~(size_t)15;
+        chunkH_.ensure(grp_off + (size_t)n_groups * sizeof(int4) + 16);
         uint32_t *ch = chunkH_.as<uint32_t>();
+        int4 *grp = reinterpret_cast<int4 *>(chunkH_.as<unsigned char>() + grp_off);
+        for (uint32_t gi = 0; gi < n_groups; ++gi)
+        {
+            int4 w = make_int4(INT_MAX, INT_MAX, INT_MIN, INT_MIN);
+            for (uint32_t i = gi * 32; i < std::min(n_ops, gi * 32 + 32); ++i)
+            {
+                w.x = std::min(w.x, od[i].wtx0); w.y = std::min(w.y, od[i].wty0);
+                w.z = std::max(w.z, od[i].wtx0 + od[i].wtw - 1); w.w = std::max(w.w, od[i].wty0 + od[i].wth - 1);
+            }
+            grp[gi] = w;
+        }
         for (uint32_t i = 0; i < n_ops; ++i)
             for (uint32_t c = 0; c < od[i].nchunks; ++c) ch[od[i].chunk0 + c] = i;
 
         opsD_.ensure((size_t)std::max(n_ops, 1u) * sizeof(OpDesc));
-        chunkD_.ensure((size_t)n_chunks * 4 + 4);
+        chunkD_.ensure(grp_off + (size_t)n_groups * sizeof(int4) + 16);
         histD_.ensure((size_t)hist_off * 4 + 4);
         totD_.ensure((size_t)tot_off * 8 + 8);
         const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
@@ -828,10 +842,11 @@ class LocalMap
         if (n_ops)
         {
             CK(cudaMemcpyAsync(opsD_.p, od, n_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, stream_));
-            CK(cudaMemcpyAsync(chunkD_.p, ch, (size_t)n_chunks * 4, cudaMemcpyHostToDevice, stream_));
+            CK(cudaMemcpyAsync(chunkD_.p, ch, grp_off + (size_t)n_groups * sizeof(int4), cudaMemcpyHostToDevice, stream_));
         }
         b.ops = opsD_.as<OpDesc>();
         b.chunk_op = chunkD_.as<uint32_t>();
+        b.op_groups = reinterpret_cast<const int4 *>(chunkD_.as<unsigned char>() + grp_off);
         b.hist = histD_.as<uint32_t>();
         b.op_total = totD_.as<uint32_t>();
         b.op_start = totD_.as<uint32_t>() + tot_off;
@@ -895,6 +910,7 @@ class LocalMap
         stats_.last_batch_tiles = cnt[0];
         stats_.last_batch_cells_touched = cnt[8];
         stats_.last_batch_cells_classified = cnt[7];
+        stats_.last_batch_max_bin = cnt[9];
         if (prof)
         {
             float t;

@@ -64,6 +64,7 @@ struct BatchView
 {
     const OpDesc *ops;
     uint32_t n_ops;
+    const int4 *op_groups;     // per 32 consecutive ops: union window (x0, y0, x1, y1) in bins, inclusive
     const uint32_t *chunk_op;  // chunk -> op
     uint32_t n_chunks;
     uint32_t *hist;            // per (op, chunk, tile) counts -> exclusive prefix over chunks
