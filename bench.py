@@ -306,10 +306,25 @@ def main():
                 s.addNewKeyFrameWithPCL(i, i + 1, 0, lclouds[i % base])
                 s.updateKeyFrame(i + 1, drift[i])
             s.flush()
-            times = []
+            times, pgo = [], []
             for rep in range(3):
-                for i in range(nk):
-                    s.updateKeyFrame(i + 1, lposes[i] if rep % 2 == 0 else drift[i])
+                target = lposes if rep % 2 == 0 else drift
+                # (a) the PGO batch itself: every keyframe gets a new pose; the worker subtracts each old
+                #     contribution and adds the new one (global_traversability_node.cpp:184-188), batched
+                barrier()
+                with torch.cuda.stream(stream):
+                    flush_buf.fill_(rep)
+                    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+                    stream.synchronize()
+                    e0.record(stream)
+                    with m.locked():   # queue all 2000 updates before the worker starts: one batched pass
+                        for i in range(nk):
+                            s.updateKeyFrame(i + 1, target[i])
+                    s.flush()
+                    e1.record(stream)
+                    e1.synchronize()
+                pgo.append(e0.elapsed_time(e1))
+                # (b) informLoopClosure: blank the map and re-integrate every stored keyframe at its pose
                 barrier()
                 with torch.cuda.stream(stream):
                     flush_buf.fill_(rep)
@@ -324,6 +339,7 @@ def main():
             st = m.stats()
             lc = {"keyframes": nk, "points": int(st["last_batch_points"]), "ms": float(min(times[1:])), "ms_all": times, "n_gpus": 1,
                   "mode": "informLoopClosure + batched worker pass (max_batch=0)",
+                  "pgo_update_ms": float(min(pgo[1:])), "pgo_update_ms_all": pgo,
                   "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]), "config": cfg}
             s.close()
         else:

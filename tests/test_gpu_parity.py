@@ -328,3 +328,31 @@ def test_sharded_rebuild_world2_bit_identical(tmap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_shard_check(2, 24, 29562)
+
+
+def test_heavy_bins_split_across_ctas(tmap, oracle):
+    """Many keyframes at almost the same pose make a few 16x16 bins hold far more records than a fold
+    CTA's fair share, so they are split by cell-row group; results must still equal the oracle bit for bit."""
+    from traversability_mapping_b200 import synth
+    n = 90
+    base = synth.trajectory("single", 1, seed=21)[0]
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, half_size=10.0, max_range=10.0, min_range=1.0, max_batch=0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    clouds = [synth.make_keyframe(21, i, base, max_range=10.0, rings=64, azimuths=1024) for i in range(6)]
+    for i in range(n):
+        P = base.copy()
+        P[0, 3] += 0.003 * i
+        P[1, 3] -= 0.002 * i
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i % 6]); om.add_keyframe(i + 1, clouds[i % 6])
+        om.update_pose(i + 1, P)
+    with m.locked():
+        for i in range(n):
+            P = base.copy()
+            P[0, 3] += 0.003 * i
+            P[1, 3] -= 0.002 * i
+            s.updateKeyFrame(i + 1, P)
+    s.flush(); om.process_batched()
+    assert m.stats()["last_batch_max_bin"] > 60000, m.stats()["last_batch_max_bin"]
+    compare_maps(m, om, check_changed=True, label="heavy bins")
+    s.close()

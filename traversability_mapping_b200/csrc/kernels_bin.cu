@@ -432,12 +432,24 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
     {
         // heavy bins go to the front of the work list, light ones fill it from the back: the fold's ticket
         // loop then starts the long sequential chains first (longest-processing-time-first scheduling)
-        const uint32_t k = atomicAdd(b.counters + 0, 1u);
-        (void)k;
+        // A heavy bin is additionally split into P work items by cell-row group (rows r with r % P == part):
+        // cells are independent, so P CTAs walk the same bucket and each keeps only its rows' records.
         if (v >= HEAVY_BIN)
-            b.active_tiles[atomicAdd(b.counters + 10, 1u)] = i;
+        {
+            // split only as far as load balance needs it: each part re-streams the whole bucket
+            uint32_t lg = 0;
+            while (lg < 4 && (v >> lg) > b.split_thresh) ++lg;
+            const uint32_t P = 1u << lg;
+            atomicAdd(b.counters + 0, P);
+            const uint32_t at = atomicAdd(b.counters + 10, P);
+            for (uint32_t part = 0; part < P; ++part)
+                b.active_tiles[at + part] = i | (part << 24) | (lg << 28);
+        }
         else
+        {
+            atomicAdd(b.counters + 0, 1u);
             b.active_tiles[nb - 1 - atomicAdd(b.counters + 11, 1u)] = i;
+        }
         atomicMax(b.counters + 9, v);  // heaviest bin of the batch (statistics)
     }
     const int lx = i % b.btw, ly = i / b.btw;
@@ -636,7 +648,8 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
         if (it >= n_active)
             break;
         const uint32_t n_heavy = b.counters[10];
-        const uint32_t gt = it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)];
+        const uint32_t item = it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)];
+        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
         const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
@@ -667,13 +680,63 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
         uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
         uint32_t fl = 0;
 
-        for (uint32_t pos = 0; pos < cnt; pos += FOLD_CH)
+        for (uint32_t pos = 0; pos < cnt;)
         {
-            const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+            uint32_t n;
+            if (pmask == 0u)
+            {
+                n = min((uint32_t)FOLD_CH, cnt - pos);
+                for (uint32_t i = tid; i < n; i += FOLD_THREADS)
+                    s_rec[i] = b.sorted[start + pos + i];
+                pos += n;
+            }
+            else
+            {
+                // part of a split heavy bin: stream the bucket, keep (order-preserving) the records of my rows
+                n = 0;
+                while (n + 4 * FOLD_THREADS <= (uint32_t)FOLD_CH && pos < cnt)
+                {
+                    const uint32_t nin = min(4u * FOLD_THREADS, cnt - pos);
+                    uint32_t keep = 0, kc = 0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        const uint32_t j = 4 * tid + q;
+                        if (j < nin)
+                        {
+                            const uint32_t meta = __float_as_uint(reinterpret_cast<const float *>(b.sorted + start + pos + j)[3]);
+                            if ((((meta & 255u) >> BIN_SHIFT) & pmask) == part) { keep |= 1u << q; ++kc; }
+                        }
+                    }
+                    uint32_t inc = kc;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1)
+                    {
+                        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= (uint32_t)o) inc += u;
+                    }
+                    if (lane == 31) s_w[warp] = inc;
+                    __syncthreads();
+                    uint32_t wbase = 0, total = 0;
+#pragma unroll
+                    for (int w = 0; w < FOLD_NW; ++w)
+                    {
+                        const uint32_t v = s_w[w];
+                        if (w < (int)warp) wbase += v;
+                        total += v;
+                    }
+                    uint32_t dst = n + wbase + inc - kc;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        if (keep & (1u << q))
+                            s_rec[dst++] = b.sorted[start + pos + 4 * tid + q];
+                    __syncthreads();
+                    n += total;
+                    pos += nin;
+                }
+            }
             const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
             const uint32_t SL = R * 32;                                // records per warp slice
-            for (uint32_t i = tid; i < n; i += FOLD_THREADS)
-                s_rec[i] = b.sorted[start + pos + i];
 #pragma unroll
             for (int w = 0; w < FOLD_NW; ++w)
                 s_cnt[w][tid] = 0;

@@ -321,7 +321,7 @@ __global__ void k_clear_touched(BatchView b, GridView g)
     const uint32_t n_active = b.counters[0], n_heavy = b.counters[10];
     for (uint32_t it = blockIdx.x; it < n_active; it += gridDim.x)
     {
-        const uint32_t gt = it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)];
+        const uint32_t gt = (it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)]) & 0x00ffffffu;
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
         for (int q = threadIdx.x; q < BIN_CELLS; q += blockDim.x)

@@ -808,8 +808,12 @@ class LocalMap
         b.n_chunks = n_chunks;
         b.op_base = op_base;
         const size_t nb = (size_t)b.btw * b.bth;
+        if (nb >= (1u << 24))
+            throw Unsupported("batch spans more than 2^24 bins of 16x16 cells");
         b.total_points = (uint32_t)total_pts;
         b.cand_y0 = 0; b.cand_y1 = b.bth;
+        // a bin is split across CTAs only when it exceeds the fair share of one resident fold CTA (3 per SM)
+        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, total_pts / (uint64_t)(3 * nSM_));
 
         // chunk -> op table, followed by the per-32-op union windows used by the scan over ops
         const uint32_t n_groups = (n_ops + 31) / 32;
@@ -1023,6 +1027,7 @@ class LocalMap
         srcBaseD_.ensure((size_t)world * 8);
         CK(cudaMemcpyAsync(srcBaseD_.p, src_base, (size_t)world * 8, cudaMemcpyHostToDevice, stream_));
         b.sorted = mergedD_.as<float4>();
+        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, n_recv / (uint64_t)(3 * nSM_));
         b.n_ops = 0;  // per-op bboxes were consumed by shardBin
         b.nbr_count = globD_;
         b.cand_y0 = y0; b.cand_y1 = y1;

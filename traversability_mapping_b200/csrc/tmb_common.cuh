@@ -86,6 +86,7 @@ struct BatchView
     uint32_t total_points;
     uint32_t op_base;          // added to the op index written into record meta (sharded runs: globally unique ops)
     const uint32_t *nbr_count; // per-bin counts used for the candidate-list neighbour test (sharded: global totals)
+    uint32_t split_thresh;     // bins with more records than this are split across CTAs by cell-row group
     int cand_y0, cand_y1;      // bbox-local bin rows [y0, y1) this process classifies / inflates (sharded: its slab)
 };
 
