@@ -612,31 +612,19 @@ cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d 
     return cudaMemcpyToSymbol(c_disc_d, disc_d, sizeof(double) * 2 * n_disc);
 }
 
-// persistent one-wave grids: the kernels walk their work lists round-robin, so the grid is exactly the
-// number of CTAs that are resident at once (a second partial wave would only add a tail)
-static int resident_ctas(const void *fn, int threads, size_t smem, int n_sm)
-{
-    int per_sm = 1;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1)
-        per_sm = 1;
-    return per_sm * n_sm;
-}
-
 cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUtensorMap &tmap_flags, const BatchView &b, const GridView &g,
                             const ClassifyParams &cp, int n_sm)
 {
-    static int attr_r = -1, grid = 0;
+    static int attr_r = -1;
     const int r = cp.r;
     const size_t smem = classify_smem_bytes(r);
     if (attr_r != r)
     {
         cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = resident_ctas((const void *)k_classify, CLS_THREADS, smem, n_sm);
         attr_r = r;
     }
-    int gmul = 0;
-    if (const char *e = getenv("TMB_CLS_GRID")) gmul = atoi(e);
-    const int n_blocks = (int)min((size_t)(gmul > 0 ? gmul * n_sm : 3 * n_sm), (size_t)b.btw * b.bth);
+    // measured on B200 (C2 stream): 3 CTAs of work per SM beat an exactly-resident grid (more boxes in flight)
+    const int n_blocks = (int)min((size_t)(3 * n_sm), (size_t)b.btw * b.bth);
     k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, tmap_flags, b, g, cp);
     return cudaGetLastError();
 }
@@ -650,18 +638,15 @@ cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const Grid
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
                            const ClassifyParams &cp, const void *d_taps, int n_sm)
 {
-    static int attr_R = -1, grid = 0;
+    static int attr_R = -1;
     const int R = cp.infl_r;
     const size_t smem = inflate_smem_bytes(R, cp.n_infl);
     if (attr_R != R)
     {
         cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        grid = resident_ctas((const void *)k_inflate, INF_THREADS, smem, n_sm);
         attr_R = R;
     }
-    int gmul = 0;
-    if (const char *e = getenv("TMB_INF_GRID")) gmul = atoi(e);
-    const int n_blocks = (int)min((size_t)(gmul > 0 ? gmul * n_sm : 2 * n_sm), (size_t)g.tw * g.th);
+    const int n_blocks = (int)min((size_t)(2 * n_sm), (size_t)g.tw * g.th);
     k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, static_cast<const InflTap *>(d_taps), cp);
     return cudaGetLastError();
 }
