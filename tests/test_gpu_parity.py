@@ -356,3 +356,77 @@ def test_heavy_bins_split_across_ctas(tmap, oracle):
     assert m.stats()["last_batch_max_bin"] > 60000, m.stats()["last_batch_max_bin"]
     compare_maps(m, om, check_changed=True, label="heavy bins")
     s.close()
+
+
+def test_full_size_keyframes_against_oracle_batched(tmap, oracle):
+    """20 full 131 072-ray keyframes on a loop (config 3's shape, reduced count so the oracle finishes in
+    seconds), one batched pass: every layer against the oracle."""
+    from traversability_mapping_b200 import synth
+    n = 20
+    poses = synth.trajectory("loop", n, seed=31, extent=12.0)
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, half_size=20.0, max_range=20.0, min_range=1.0, max_batch=0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    for i in range(n):
+        c = synth.make_keyframe(31, i, poses[i], max_range=20.0)
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, c); om.add_keyframe(i + 1, c)
+        om.update_pose(i + 1, poses[i])
+    with m.locked():
+        for i in range(n):
+            s.updateKeyFrame(i + 1, poses[i])
+    s.flush(); om.process_batched()
+    st = compare_maps(m, om, check_changed=True, label="20 full keyframes")
+    assert st["cells"] > 100000 and st["gated_in"] > 50000
+    s.close()
+
+
+def test_full_size_properties_without_oracle(tmap):
+    """Size-independent properties at a size the oracle would not finish quickly (120 keyframes x 131 072
+    rays, 8.7 M points): counts are exact, rebuilds are idempotent, a PGO round trip restores the counts,
+    deleting everything empties the map."""
+    from traversability_mapping_b200 import synth
+    n, base = 120, 12
+    poses = synth.trajectory("loop", n, seed=33, extent=40.0)
+    drift = synth.drift_poses(poses)
+    clouds = [synth.make_keyframe(33, i, poses[i], max_range=20.0) for i in range(base)]
+    p = tmap.default_params(resolution=0.1, half_size=50.0, max_range=20.0, min_range=1.0, max_batch=0)
+    s = tmap.System(p); s.addNewLocalMap(0); m = s.getLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    for i in range(n):
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i % base]) == tmap.OK
+    total = m.getStitchedPointCloud().shape[0]
+
+    def update_all(P):
+        with m.locked():
+            for i in range(n):
+                s.updateKeyFrame(i + 1, P[i])
+        s.flush()
+
+    update_all(poses)
+    keys0 = m.occupiedCellKeys()
+    L0 = m.readLayers(keys0, helpers.MOMENT_LAYERS + helpers.DERIVED_LAYERS)
+    assert int(L0[:, 0].sum()) == total, "sum of per-cell counts == points binned"
+    assert np.all(L0[:, 0] == np.round(L0[:, 0])) and L0[:, 0].min() >= 1
+    # zmin <= mean z <= zmax wherever the cell is observed
+    zmean = L0[:, 3] / L0[:, 0]
+    assert np.all(L0[:, 10] <= zmean + 1e-4) and np.all(zmean <= L0[:, 11] + 1e-4)
+    # rebuild (informLoopClosure) reproduces the batched build bit for bit, twice
+    for _ in range(2):
+        s.informLoopClosure(); s.flush()
+        keys = m.occupiedCellKeys()
+        assert np.array_equal(keys, keys0)
+        assert helpers.bits_equal(m.readLayers(keys, helpers.MOMENT_LAYERS + helpers.DERIVED_LAYERS), L0)
+    # PGO round trip through drifted poses: float32 moments drift by rounding, the counts do not
+    update_all(drift)
+    update_all(poses)
+    keys = m.occupiedCellKeys()
+    assert np.array_equal(keys, keys0)
+    assert np.array_equal(m.readLayers(keys, ["N"])[:, 0], L0[:, 0])
+    # occupancy export: unknown where hazard is NaN, 0..100 elsewhere
+    occ = m.exportOccupancy()
+    haz = m.exportDense("hazard")
+    assert np.array_equal(occ == -1, np.isnan(haz)) and occ.max() <= 100 and occ[~np.isnan(haz)].min() >= 0
+    for i in range(n):
+        s.deleteKeyFrame(i + 1)
+    assert m.occupiedCellKeys().size == 0 and m.numKeyFrames() == 0
+    s.close()
