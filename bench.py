@@ -402,8 +402,18 @@ def main():
         dom = max(("ms_hist", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate"), key=lambda k: stage[k])
         n_launch = 2 * K - 0  # one update batch + one eviction batch per step
         achieved = stage_bytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
+        # measured DRAM traffic per launch of that kernel, from the committed ncu capture of this same workload
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["c2_stream"]
+            key = {"ms_hist": "k_hist<2>", "ms_scatter": "k_scatter<2>", "ms_fold": "k_fold", "ms_classify": "k_classify",
+                   "ms_inflate": "k_inflate"}[dom]
+            traffic = tj[key]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom.replace("ms_", "k_"), "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full)",
+                    "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[dom] / n_launch, "avg_launch_ms": stage[dom] / n_launch,
                     "stages_ms_per_step": {k: v / K for k, v in stage.items()},
                     "stages_frac_of_hbm": {k: (stage_bytes[k] / (stage[k] * 1e-3) / 1e9 / peak if stage[k] > 0 else None)

@@ -430,3 +430,65 @@ def test_full_size_properties_without_oracle(tmap):
         s.deleteKeyFrame(i + 1)
     assert m.occupiedCellKeys().size == 0 and m.numKeyFrames() == 0
     s.close()
+
+
+def test_growth_in_negative_directions_keeps_data(tmap, oracle):
+    """Device window reallocation (DeviceGrid::ensure) towards -x/-y and far +y keeps every stored layer;
+    the reference-visible extent follows growGridToInclude (Helpers.cpp:53-84)."""
+    from traversability_mapping_b200 import synth
+    s, m, om = make_pair(tmap, oracle, resolution=0.1, half_size=5.0, max_range=6.0, min_range=1.0, extend_length=7.0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    spots = [(0.0, 0.0), (-38.0, 3.0), (5.0, -61.0), (47.0, 90.0), (-120.0, -15.0)]
+    for i, (x, y) in enumerate(spots):
+        P = synth.pose_matrix(x, y, 0.2, 0.01, -0.02, 0.7 * i)
+        c = synth.make_keyframe(41, i, P, max_range=6.0, rings=32, azimuths=512)
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, c); om.add_keyframe(i + 1, c)
+        s.updateKeyFrame(i + 1, P); om.update_pose(i + 1, P)
+        s.flush(); om.process()
+        compare_maps(m, om, check_changed=True, label=f"spot {i}")
+    assert m.stats()["grid_reallocs"] >= 4
+    s.close()
+
+
+def test_dropped_clouds_and_queued_deletes(tmap, oracle):
+    """is_kf_optimization_enabled=false: the cloud is dropped after the first bin, later pose updates are
+    ignored (LocalMap.cpp:257-267) but delete still subtracts; a keyframe deleted while queued is skipped
+    (LocalMap.cpp:247-256)."""
+    s, m, om = make_pair(tmap, oracle, **dict(LOCALMAP, is_kf_optimization_enabled=0))
+    pts = [[1.0, 0.2, 0.1], [1.1, 0.2, 0.2], [3.0, 3.0, 0.0]]
+    s.addKeyFrameBase(1, 0, pts); om.add_keyframe_base(1, pts)
+    s.updateKeyFrame(1, I34); om.update_pose(1, I34)
+    s.flush(); om.process()
+    before = m.occupiedCellKeys().tolist()
+    s.updateKeyFrame(1, trans(5, 0, 0)); om.update_pose(1, trans(5, 0, 0))   # ignored: no retained cloud
+    s.flush(); om.process()
+    assert m.occupiedCellKeys().tolist() == before
+    compare_maps(m, om, check_changed=True)
+    s.addKeyFrameBase(2, 0, [[2.0, 2.0, 0.0]]); om.add_keyframe_base(2, [[2.0, 2.0, 0.0]])
+    with m.locked():                      # keyframe 2 is queued, then deleted before the worker gets to it
+        s.updateKeyFrame(2, I34); om.update_pose(2, I34)
+    s.deleteKeyFrame(2); om.delete_keyframe(2)
+    s.flush(); om.process()
+    s.deleteKeyFrame(1); om.delete_keyframe(1)
+    assert m.occupiedCellKeys().size == 0 and m.numKeyFrames() == 0
+    compare_maps(m, om, check_changed=True)
+    s.close()
+
+
+def test_degenerate_inputs(tmap, oracle):
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    allnan = np.full((64, 4), np.nan, dtype=np.float32)
+    assert s.addNewKeyFrameWithPCL(0, 1, 0, allnan) == tmap.IGNORED_EMPTY
+    assert s.addNewKeyFrameWithPCL(0, 2, 0, np.zeros((0, 4), dtype=np.float32)) == tmap.IGNORED_EMPTY
+    assert s.addKeyFrameBase(3, 0, np.zeros((0, 3), dtype=np.float32)) == tmap.IGNORED_EMPTY
+    one = np.array([[2.0, 0.0, 0.0, 0.0]], dtype=np.float32)
+    assert s.addNewKeyFrameWithPCL(0, 4, 0, one) == tmap.OK
+    with pytest.raises(tmap.TmapError):       # a window beyond the 32-bit cell range is refused loudly
+        s.updateKeyFrame(4, trans(1e12, 0, 0)); s.flush()
+    s.close()
+    # a footprint beyond the kernels' limits fails at map creation, not silently
+    with pytest.raises(tmap.TmapError) as e:
+        s2 = tmap.System(tmap.default_params(resolution=0.01, robot_radius=0.5))
+        s2.addNewLocalMap(0)
+    assert e.value.code == tmap.ERR_UNSUPPORTED
