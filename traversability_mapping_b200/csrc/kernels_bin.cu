@@ -212,20 +212,6 @@ __global__ void k_pack_base(const float *__restrict__ xyz, size_t n, float4 *__r
 }
 
 // ---------------------------------------------------------------------------------------------
-// batch initialisation: counters, per-op bbox, inflation-tile dedup flags
-// ---------------------------------------------------------------------------------------------
-__global__ void k_init_batch(BatchView b, uint32_t n_infl_flags)
-{
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 16)
-        b.counters[i] = 0;
-    if (i < b.n_ops)
-        b.op_bbox[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
-    if (i < n_infl_flags)
-        b.infl_flags[i] = 0;
-}
-
-// ---------------------------------------------------------------------------------------------
 // k_hist: transform + key + per-chunk bin histogram
 // ---------------------------------------------------------------------------------------------
 template <int PPT>
@@ -360,83 +346,47 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *s_w /*
     return r;
 }
 
-// per bin of the batch bbox: exclusive prefix over ops (op order = fold order) -> op_start, bin count;
-// per 256-bin block: sum -> block_sums
-__global__ void __launch_bounds__(256) k_scan_ops(BatchView b)
+// per bin of the batch bbox: exclusive prefix over ops (op order = fold order) -> op_start; returns the bin count.
+// Ops are visited in order; groups of 32 whose union window misses this bin are skipped whole.
+__device__ __forceinline__ uint32_t scan_ops_bin(const BatchView &b, uint32_t g)
 {
-    __shared__ uint32_t s_w[33];
-    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
-    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
     uint32_t run = 0;
-    if (g < nb)
+    for (uint32_t o0 = 0; o0 < b.n_ops; o0 += 32)
     {
-        const int tx = b.btx0 + (int)(g % b.btw), ty = b.bty0 + (int)(g / b.btw);
-        // ops are visited in order; groups of 32 whose union window misses this bin are skipped whole
-        for (uint32_t o0 = 0; o0 < b.n_ops; o0 += 32)
+        const int4 gw = b.op_groups[o0 >> 5];  // x0, y0, x1, y1 (inclusive) of the group's windows
+        if (tx < gw.x || tx > gw.z || ty < gw.y || ty > gw.w)
+            continue;
+        const uint32_t o1 = min(o0 + 32u, b.n_ops);
+        for (uint32_t o = o0; o < o1; ++o)
         {
-            const int4 gw = b.op_groups[o0 >> 5];  // x0, y0, x1, y1 (inclusive) of the group's windows
-            if (tx < gw.x || tx > gw.z || ty < gw.y || ty > gw.w)
+            const OpDesc &op = b.ops[o];
+            const int lx = tx - op.wtx0, ly = ty - op.wty0;
+            if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
                 continue;
-            const uint32_t o1 = min(o0 + 32u, b.n_ops);
-            for (uint32_t o = o0; o < o1; ++o)
-            {
-                const OpDesc &op = b.ops[o];
-                const int lx = tx - op.wtx0, ly = ty - op.wty0;
-                if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
-                    continue;
-                const uint32_t t = op.tot_off + ly * op.wtw + lx;
-                b.op_start[t] = run;
-                run += b.op_total[t];
-            }
+            const uint32_t t = op.tot_off + ly * op.wtw + lx;
+            b.op_start[t] = run;
+            run += b.op_total[t];
         }
-        b.tile_count[g] = run;
     }
-    uint32_t tot;
-    block_excl_scan(run, s_w, tot);
-    if (threadIdx.x == 0)
-        b.block_sums[blockIdx.x] = tot;
+    return run;
 }
 
-// single CTA: exclusive scan of the per-block sums (in place)
-__global__ void __launch_bounds__(1024) k_scan_blocks(BatchView b, uint32_t n_blocks)
+// work lists for bin i holding v records: bins to fold (heavy first / split), bins to classify (active dilated
+// by dc bins) and 32x32 tiles to inflate (within di bins of an active bin; dedup through epoch-stamped flags).
+// List order is irrelevant: bins / tiles are independent work items.
+__device__ __forceinline__ void emit_lists(const BatchView &b, const GridView &g, uint32_t i, uint32_t v, int dc, int di)
 {
-    __shared__ uint32_t s_w[33];
-    uint32_t run = 0;
-    for (uint32_t base = 0; base < n_blocks; base += 1024)
-    {
-        const uint32_t i = base + threadIdx.x;
-        const uint32_t v = i < n_blocks ? b.block_sums[i] : 0;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan(v, s_w, tot);
-        if (i < n_blocks)
-            b.block_sums[i] = run + ex;
-        run += tot;
-    }
-}
-
-// per bin: bucket start; compact lists of active bins, of bins to classify (active dilated by dc bins)
-// and of 32x32 tiles to inflate (bins within di of an active bin; dedup through infl_flags).  List order
-// is irrelevant: bins / tiles are independent work items.
-__global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, int dc, int di)
-{
-    __shared__ uint32_t s_w[33];
-    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
     const uint32_t nb = (uint32_t)(b.btw * b.bth);
-    const uint32_t v = i < nb ? b.tile_count[i] : 0;
-    uint32_t tot;
-    const uint32_t ex = block_excl_scan(v, s_w, tot);
-    if (i >= nb)
-        return;
-    b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
     if (v)
     {
         // heavy bins go to the front of the work list, light ones fill it from the back: the fold's ticket
-        // loop then starts the long sequential chains first (longest-processing-time-first scheduling)
-        // A heavy bin is additionally split into P work items by cell-row group (rows r with r % P == part):
-        // cells are independent, so P CTAs walk the same bucket and each keeps only its rows' records.
+        // loop then starts the long sequential chains first (longest-processing-time-first scheduling).
+        // A bin above a fold CTA's fair share is additionally split into P work items by cell-row group
+        // (rows r with r % P == part): cells are independent, so P CTAs walk the same bucket and each keeps
+        // only its rows' records.  Split only as far as load balance needs it: each part re-streams the bucket.
         if (v >= HEAVY_BIN)
         {
-            // split only as far as load balance needs it: each part re-streams the whole bucket
             uint32_t lg = 0;
             while (lg < 4 && (v >> lg) > b.split_thresh) ++lg;
             const uint32_t P = 1u << lg;
@@ -479,8 +429,94 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
     if (ni)
     {
         const uint32_t t32 = (uint32_t)(((by >> 1) - g.ty0) * g.tw + ((bx >> 1) - g.tx0));
-        if (atomicExch(b.infl_flags + t32, 1u) == 0u)
+        if (atomicExch(b.infl_flags + t32, b.epoch) != b.epoch)
             b.infl_tiles[atomicAdd(b.counters + 2, 1u)] = t32;
+    }
+}
+
+// per 256-bin block: bin counts + block sum
+__global__ void __launch_bounds__(256) k_scan_ops(BatchView b)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t g = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    uint32_t run = 0;
+    if (g < nb)
+    {
+        run = scan_ops_bin(b, g);
+        b.tile_count[g] = run;
+    }
+    uint32_t tot;
+    block_excl_scan(run, s_w, tot);
+    if (threadIdx.x == 0)
+        b.block_sums[blockIdx.x] = tot;
+}
+
+// single CTA: exclusive scan of the per-block sums (in place)
+__global__ void __launch_bounds__(1024) k_scan_blocks(BatchView b, uint32_t n_blocks)
+{
+    __shared__ uint32_t s_w[33];
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < n_blocks; base += 1024)
+    {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < n_blocks ? b.block_sums[i] : 0;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(v, s_w, tot);
+        if (i < n_blocks)
+            b.block_sums[i] = run + ex;
+        run += tot;
+    }
+}
+
+// per bin: bucket start + work lists
+__global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, int dc, int di)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    const uint32_t v = i < nb ? b.tile_count[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(v, s_w, tot);
+    if (i >= nb)
+        return;
+    b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
+    emit_lists(b, g, i, v, dc, di);
+}
+
+// the three kernels above in ONE single-CTA launch, for batches whose bbox has at most 4 096 bins (a
+// stream tick): saves two dependent launches on the latency-bound path
+__global__ void __launch_bounds__(1024) k_scan_small(BatchView b, GridView g, int dc, int di)
+{
+    __shared__ uint32_t s_w[33];
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    uint32_t cnt[4];
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t i = k * 1024 + threadIdx.x;
+        cnt[k] = i < nb ? scan_ops_bin(b, i) : 0u;
+        if (i < nb)
+            b.tile_count[i] = cnt[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t i = k * 1024 + threadIdx.x;
+        uint32_t tot;
+        const uint32_t ex = block_excl_scan(cnt[k], s_w, tot);
+        if (i < nb)
+            b.tile_start[i] = run + ex;
+        run += tot;
+    }
+    __syncthreads();  // every tile_count is visible to the neighbour tests below
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        const uint32_t i = k * 1024 + threadIdx.x;
+        if (i < nb)
+            emit_lists(b, g, i, cnt[k], dc, di);
     }
 }
 
@@ -825,7 +861,9 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
             dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
             dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-            g.flags[cell] |= (uint8_t)fl;
+            // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
+            const uint8_t obs = (!isnan(rec[R_N]) && rec[R_N] >= 1.f) ? F_OBSERVED : 0;
+            g.flags[cell] = (uint8_t)((g.flags[cell] & ~F_OBSERVED) | fl | obs);
             if (fl & F_BLANKED)
             {
                 const size_t pl = g.plane();
@@ -939,10 +977,9 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     }
     const uint32_t nb = b.btw * b.bth;
     const uint32_t nblk = (nb + 255) / 256;
-    const uint32_t nflags = (uint32_t)(g.tw * g.th);
     if (phases & 1)
     {
-    k_init_batch<<<(max(max(b.n_ops, 16u), nflags) + 255) / 256, 256, 0, st>>>(b, nflags);
+    // counters and per-op bboxes arrive initialised with the batch's single host-to-device copy
     if (ev) cudaEventRecord(ev[0], st);
     if (ppt == 2)
         k_hist<2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
@@ -950,9 +987,14 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
         k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
     k_scan_chunks<<<dim3((maxT + 7) / 8, b.n_ops), 256, 0, st>>>(b);
-    k_scan_ops<<<nblk, 256, 0, st>>>(b);
-    k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
-    k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
+    if (nb <= 4096)
+        k_scan_small<<<1, 1024, 0, st>>>(b, g, dc, di);
+    else
+    {
+        k_scan_ops<<<nblk, 256, 0, st>>>(b);
+        k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
+        k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
+    }
     if (ev) cudaEventRecord(ev[2], st);
     if (ppt == 2)
         k_scatter<2><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
@@ -974,8 +1016,7 @@ cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridVi
 {
     const uint32_t nb = b.btw * b.bth;
     const uint32_t nblk = (nb + 255) / 256;
-    const uint32_t nflags = (uint32_t)(g.tw * g.th);
-    k_init_batch<<<(max(16u, nflags) + 255) / 256, 256, 0, st>>>(b, nflags);   // b.n_ops == 0 here: bboxes untouched
+    cudaMemsetAsync(b.counters, 0, 64, st);
     k_shard_counts<<<nblk, 256, 0, st>>>(b, d_counts_all, world, y0, y1, d_glob);
     k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
     k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);

@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
         {
             const int q = tid + k * INF_THREADS;
             const size_t cell = (size_t)(row0 + (q >> 5)) * g.W + (col0 + (q & 31));
-            nobs[k] = g.mom[cell * REC + R_N];
+            nobs[k] = (g.flags[cell] & F_OBSERVED) ? 1.f : 0.f;  // == (N >= 1), maintained by k_fold
             cur[k] = g.der[D_INFLATED * pl + cell];
         }
         if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }

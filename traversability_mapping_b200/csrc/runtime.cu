@@ -356,7 +356,6 @@ class LocalMap
         kx_ = static_cast<int>(std::ceil(P.half_size / P.resolution));
         ky_ = kx_;
         grid_.ensure(stream_, floordiv32(-kx_), floordiv32(-ky_), floordiv32(kx_) + 1, floordiv32(ky_) + 1);
-        counters_h_.ensure(64 * 4);
         running_ = true;
         worker_ = std::thread(&LocalMap::run, this);
     }
@@ -749,8 +748,20 @@ class LocalMap
         if (n_ops > 65535 || (uint64_t)n_ops + op_base >= (1u << 23))
             throw Unsupported("batch exceeds 65535 ops");
 
-        opsH_.ensure((size_t)std::max(n_ops, 1u) * sizeof(OpDesc));
-        OpDesc *od = opsH_.as<OpDesc>();
+        // one pinned staging block per pass: [counters 64 B][per-op bbox][op descriptors][chunk table][op groups]
+        // -> ONE host-to-device copy (it also zeroes the counters and initialises the bboxes), and the first
+        //    two sections come back with ONE device-to-host copy at the end of the pass
+        uint32_t n_chunks_all = 0;
+        for (auto &op : ops) n_chunks_all += (op.kf->n + CH - 1) / CH;
+        const uint32_t n_groups = (n_ops + 31) / 32;
+        const size_t off_bbox = 64;
+        const size_t off_ops = (off_bbox + (size_t)n_ops * sizeof(int4) + 15) & ~(size_t)15;
+        const size_t ops_end = off_ops + (size_t)n_ops * sizeof(OpDesc);
+        const size_t off_chunk = (ops_end + 15) & ~(size_t)15;
+        const size_t off_grp = (off_chunk + (size_t)n_chunks_all * 4 + 15) & ~(size_t)15;
+        const size_t meta_bytes = off_grp + (size_t)n_groups * sizeof(int4);
+        metaH_.ensure(meta_bytes + 64);
+        OpDesc *od = reinterpret_cast<OpDesc *>(metaH_.as<unsigned char>() + off_ops);
         uint32_t n_chunks = 0, tot_off = 0, maxT = 0;
         unsigned long long hist_off = 0;
         int ux0 = INT_MAX, uy0 = INT_MAX, ux1 = INT_MIN, uy1 = INT_MIN;
@@ -816,11 +827,11 @@ class LocalMap
         b.split_thresh = (uint32_t)std::max<uint64_t>(32768, total_pts / (uint64_t)(3 * nSM_));
 
         // chunk -> op table, followed by the per-32-op union windows used by the scan over ops
-        const uint32_t n_groups = (n_ops + 31) / 32;
-        const size_t grp_off = (((size_t)n_chunks * 4 + 4) + 15) & ~(size_t)15;
-        chunkH_.ensure(grp_off + (size_t)n_groups * sizeof(int4) + 16);
-        uint32_t *ch = chunkH_.as<uint32_t>();
-        int4 *grp = reinterpret_cast<int4 *>(chunkH_.as<unsigned char>() + grp_off);
+        std::memset(metaH_.p, 0, 64);
+        int4 *bb0 = reinterpret_cast<int4 *>(metaH_.as<unsigned char>() + off_bbox);
+        for (uint32_t i = 0; i < n_ops; ++i) bb0[i] = make_int4(INT_MAX, INT_MIN, INT_MAX, INT_MIN);
+        uint32_t *ch = reinterpret_cast<uint32_t *>(metaH_.as<unsigned char>() + off_chunk);
+        int4 *grp = reinterpret_cast<int4 *>(metaH_.as<unsigned char>() + off_grp);
         for (uint32_t gi = 0; gi < n_groups; ++gi)
         {
             int4 w = make_int4(INT_MAX, INT_MAX, INT_MIN, INT_MIN);
@@ -834,23 +845,34 @@ class LocalMap
         for (uint32_t i = 0; i < n_ops; ++i)
             for (uint32_t c = 0; c < od[i].nchunks; ++c) ch[od[i].chunk0 + c] = i;
 
-        opsD_.ensure((size_t)std::max(n_ops, 1u) * sizeof(OpDesc));
-        chunkD_.ensure(grp_off + (size_t)n_groups * sizeof(int4) + 16);
+        metaD_.ensure(meta_bytes + 64);
         histD_.ensure((size_t)hist_off * 4 + 4);
         totD_.ensure((size_t)tot_off * 8 + 8);
         const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
-        tileD_.ensure((nb * 5 + (nb + 255) / 256 + 2 * n_t32) * 4 + 256);
-        bboxD_.ensure((size_t)std::max(n_ops, 1u) * sizeof(int4));
+        tileD_.ensure((nb * 5 + (nb + 255) / 256 + n_t32) * 4 + 256);
         sortedD_.ensure((size_t)total_pts * 16 + 16);
-        countersD_.ensure(64 * 4);
-        if (n_ops)
         {
-            CK(cudaMemcpyAsync(opsD_.p, od, n_ops * sizeof(OpDesc), cudaMemcpyHostToDevice, stream_));
-            CK(cudaMemcpyAsync(chunkD_.p, ch, grp_off + (size_t)n_groups * sizeof(int4), cudaMemcpyHostToDevice, stream_));
+            // inflation-tile dedup stamps: own buffer (persistent across passes), zeroed when it grows
+            const size_t need = n_t32 * 4 + 64;
+            if (need > inflFlagsD_.cap)
+            {
+                inflFlagsD_.ensure(need);
+                CK(cudaMemsetAsync(inflFlagsD_.p, 0, inflFlagsD_.cap, stream_));
+                epoch_ = 0;
+            }
+            if (++epoch_ == 0)
+            {
+                CK(cudaMemsetAsync(inflFlagsD_.p, 0, inflFlagsD_.cap, stream_));
+                epoch_ = 1;
+            }
         }
-        b.ops = opsD_.as<OpDesc>();
-        b.chunk_op = chunkD_.as<uint32_t>();
-        b.op_groups = reinterpret_cast<const int4 *>(chunkD_.as<unsigned char>() + grp_off);
+        {
+            CK(cudaMemcpyAsync(metaD_.p, metaH_.p, meta_bytes, cudaMemcpyHostToDevice, stream_));
+        }
+        unsigned char *md = metaD_.as<unsigned char>();
+        b.ops = reinterpret_cast<const OpDesc *>(md + off_ops);
+        b.chunk_op = reinterpret_cast<const uint32_t *>(md + off_chunk);
+        b.op_groups = reinterpret_cast<const int4 *>(md + off_grp);
         b.hist = histD_.as<uint32_t>();
         b.op_total = totD_.as<uint32_t>();
         b.op_start = totD_.as<uint32_t>() + tot_off;
@@ -861,10 +883,11 @@ class LocalMap
         globD_ = b.cand_tiles + nb;                 // sharded runs: global per-bin totals
         b.block_sums = globD_ + nb;
         b.infl_tiles = b.block_sums + (nb + 255) / 256;
-        b.infl_flags = b.infl_tiles + n_t32;
+        b.infl_flags = inflFlagsD_.as<uint32_t>();
+        b.epoch = epoch_;
         b.nbr_count = b.tile_count;
-        b.counters = countersD_.as<uint32_t>();
-        b.op_bbox = bboxD_.as<int4>();
+        b.counters = reinterpret_cast<uint32_t *>(md);
+        b.op_bbox = reinterpret_cast<int4 *>(md + off_bbox);
         b.sorted = sortedD_.as<float4>();
         return pl;
     }
@@ -890,18 +913,17 @@ class LocalMap
 
         // results the host needs: counters + per-op bounding boxes
         const uint32_t n_ops = pl.n_ops;
-        bboxH_.ensure((size_t)std::max(n_ops, 1u) * sizeof(int4));
-        CK(cudaMemcpyAsync(counters_h_.p, countersD_.p, 16 * 4, cudaMemcpyDeviceToHost, stream_));
-        if (n_ops)
-            CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, (size_t)n_ops * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
+        const size_t res_bytes = 64 + (size_t)n_ops * sizeof(int4);
+        resH_.ensure(res_bytes + 64);
+        CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
-        const uint32_t *cnt = counters_h_.as<uint32_t>();
+        const uint32_t *cnt = resH_.as<uint32_t>();
         if (cnt[3])
             throw CudaError("binning consistency check failed (flags " + std::to_string(cnt[3]) + ")");
 
         // logical grid growth, one keyframe at a time (growToIncludeCells, LocalMap.cpp:91-106 +
         // growGridToInclude, Helpers.cpp:53-84)
-        const int4 *bb = bboxH_.as<int4>();
+        const int4 *bb = reinterpret_cast<const int4 *>(resH_.as<unsigned char>() + 64);
         for (uint32_t i = 0; i < n_ops && i < ops.size(); ++i)
             if (ops[i].sign > 0 && bb[i].x != INT_MAX)
                 growLogical(bb[i].x, bb[i].y, bb[i].z, bb[i].w);
@@ -936,7 +958,7 @@ class LocalMap
         Plan pl = planBatch(ops, nullptr, 0);
         uploadConstants();
         CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
-        g_launches += 8;  // init, hist, 4 scan kernels, scatter, fold
+        g_launches += ((size_t)pl.b.btw * pl.b.bth <= 4096) ? 5 : 7;  // hist, scan kernels, scatter, fold
         finishBatch(pl, ops, t_begin);
     }
 
@@ -993,12 +1015,11 @@ class LocalMap
         CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
                       nSM_, nullptr, 1));
         g_launches += 7;
-        bboxH_.ensure((size_t)std::max<size_t>(n, 1) * sizeof(int4));
-        if (n)
-            CK(cudaMemcpyAsync(bboxH_.p, bboxD_.p, n * sizeof(int4), cudaMemcpyDeviceToHost, stream_));
-        CK(cudaMemcpyAsync(counters_h_.p, countersD_.p, 16 * 4, cudaMemcpyDeviceToHost, stream_));
+        const size_t res_bytes = 64 + n * sizeof(int4);
+        resH_.ensure(res_bytes + 64);
+        CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
-        if (counters_h_.as<uint32_t>()[3])
+        if (resH_.as<uint32_t>()[3])
             throw CudaError("binning consistency check failed");
         const BatchView &b = shardPlan_.b;
         out->d_records = b.sorted; out->n_records = shardPlan_.total_pts;
@@ -1006,7 +1027,7 @@ class LocalMap
         out->n_bins = (uint32_t)(b.btw * b.bth);
         out->btx0 = b.btx0; out->bty0 = b.bty0; out->btw = b.btw; out->bth = b.bth;
         int bb4[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
-        const int4 *bb = bboxH_.as<int4>();
+        const int4 *bb = reinterpret_cast<const int4 *>(resH_.as<unsigned char>() + 64);
         for (size_t i = 0; i < n; ++i)
             if (bb[i].x != INT_MAX)
             {
@@ -1148,8 +1169,9 @@ class LocalMap
     std::string workerError_;
     std::thread worker_;
 
-    PinBuf opsH_, chunkH_, bboxH_, counters_h_;
-    DevBuf opsD_, chunkD_, histD_, totD_, tileD_, bboxD_, sortedD_, countersD_, decay_;
+    PinBuf metaH_, resH_;
+    DevBuf metaD_, histD_, totD_, tileD_, sortedD_, inflFlagsD_, decay_;
+    uint32_t epoch_ = 0;
     DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_, mergedD_, srcBaseD_;
     uint32_t *globD_ = nullptr;
     Plan shardPlan_;
