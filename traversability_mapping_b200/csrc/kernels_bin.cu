@@ -862,8 +862,10 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
             dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
             // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
-            const uint8_t obs = (!isnan(rec[R_N]) && rec[R_N] >= 1.f) ? F_OBSERVED : 0;
-            g.flags[cell] = (uint8_t)((g.flags[cell] & ~F_OBSERVED) | fl | obs);
+            uint8_t obs = 0;
+            if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
+                obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
+            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
             if (fl & F_BLANKED)
             {
                 const size_t pl = g.plane();

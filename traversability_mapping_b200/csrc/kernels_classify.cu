@@ -79,6 +79,129 @@ enum : uint8_t { H_OBS = 1, H_OK = 2, H_TOUCHED = 4 };
 constexpr int CLS_THREADS = 256;
 constexpr int FLAG_BOX_W = BIN + 32;  // flag-byte box: starts 16 columns left of the bin (TMA needs a 16-byte aligned start)
 
+// ---------------------------------------------------------------------------------------------
+// k_gate: the cheap half of recomputeCell for every candidate bin, from the FLAG BYTES alone (1 B/cell):
+// which cells are dirty (in dilate(touched, disc)), which of those pass the footprint gate.  Gated-out dirty
+// cells get their outputs here (border value, NaN hazards); gated-in ones are marked F_FIT and their bin is
+// listed for the TMA-staged fit kernel.  Flag box via 2-D TMA (double-buffered), row masks via ballots.
+// ---------------------------------------------------------------------------------------------
+constexpr int GATE_THREADS = 256;
+__global__ void __launch_bounds__(GATE_THREADS) k_gate(const __grid_constant__ CUtensorMap tmap_flags, BatchView b, GridView g,
+                                                        const ClassifyParams c_cp)
+{
+    __shared__ __align__(128) uint8_t s_fl[2][(BIN + 16) * FLAG_BOX_W];   // r <= 8 -> at most 32 rows of 48 bytes
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ uint32_t s_t[32], s_o[32], s_e[32];
+    const int r = c_cp.r, TW = BIN + 2 * r;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_cand = b.counters[1];
+    const uint32_t minp = c_cp.min_points;
+    const size_t pl = g.plane();
+    uint32_t n_done = 0;
+
+    auto issue = [&](int stage, uint32_t it)  // thread 0 only
+    {
+        const uint32_t gt = b.cand_tiles[it];
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
+        mbar_arrive_expect_tx(&s_bar[stage], (uint32_t)(TW * FLAG_BOX_W));
+        tma_load_2d(&s_fl[stage][0], &tmap_flags, &s_bar[stage], bx * BIN - g.ci0 - 16, by * BIN - g.cj0 - r);
+    };
+    if (tid == 0)
+    {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const uint32_t stride = gridDim.x;
+    uint32_t cur = blockIdx.x;
+    if (tid == 0 && cur < n_cand)
+        issue(0, cur);
+    int stage = 0;
+    uint32_t parity0 = 0, parity1 = 0;
+    while (cur < n_cand)
+    {
+        const uint32_t nxt = cur + stride;
+        __syncthreads();  // previous bin consumed (masks and the other stage's bytes)
+        if (tid == 0 && nxt < n_cand)
+            issue(stage ^ 1, nxt);
+        const uint32_t gt = b.cand_tiles[cur];
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
+        const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
+        if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
+        else { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        const uint8_t *fl = &s_fl[stage][0];
+        // one warp per halo row: touched / observed / enough bits as 32-bit row masks
+        int any_touched = 0;
+        for (int hy = warp; hy < TW; hy += GATE_THREADS / 32)
+        {
+            const uint8_t f = (int)lane < TW ? fl[hy * FLAG_BOX_W + ((int)lane - r + 16)] : (uint8_t)0;
+            const uint32_t mt = __ballot_sync(0xffffffffu, (f & F_TOUCHED) != 0);
+            const uint32_t mo = __ballot_sync(0xffffffffu, (f & F_OBSERVED) != 0);
+            const uint32_t me = __ballot_sync(0xffffffffu, (f & F_ENOUGH) != 0);
+            any_touched |= mt != 0;
+            if (lane == 0) { s_t[hy] = mt; s_o[hy] = mo; s_e[hy] = me; }
+        }
+        int any_fit = 0;
+        if (__syncthreads_or(any_touched))  // else nothing in this bin's footprint halo changed: no cell is dirty
+        {
+            const int x = tid & (BIN - 1), y = tid >> BIN_SHIFT;
+            // LocalMap.cpp:138-140: an unobserved query cell is skipped, nothing written
+            if ((s_o[y + r] >> (x + r)) & 1u)
+            {
+                // dirty = query in dilate(touched, disc); gate = every disc cell holds >= min_points:
+                // per footprint row, a contiguous run of 2w+1 bits of the row masks
+                bool dirty = false, gate = true;
+                for (int dj = -r; dj <= r; ++dj)
+                {
+                    const int w = c_cp.row_w[dj + r];
+                    if (w < 0) continue;
+                    const uint32_t wm = (2u << (2 * w)) - 1u;
+                    const int sh = x + r - w;
+                    dirty |= ((s_t[y + r + dj] >> sh) & wm) != 0u;
+                    gate &= ((s_e[y + r + dj] >> sh) & wm) == wm;
+                }
+                if (dirty)
+                {
+                    ++n_done;
+                    const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
+                    if (gate)
+                    {
+                        g.flags[cell] |= (uint8_t)(F_CHANGED | F_FIT);  // recomputeCell returns true (LocalMap.cpp:194-196)
+                        any_fit = 1;
+                    }
+                    else
+                    {
+                        g.flags[cell] |= F_CHANGED;
+                        float border = 1.f;  // N >= min_points
+                        if (!((s_e[y + r] >> (x + r)) & 1u))
+                        {
+                            const double nq = (double)rintf(g.mom[cell * REC + R_N]);
+                            border = (float)fmin(nq / (double)max(1u, minp), 1.0);
+                        }
+                        g.der[D_HAZARD * pl + cell] = CUDART_NAN_F;
+                        g.der[D_SLOPE * pl + cell] = CUDART_NAN_F;
+                        g.der[D_STEP * pl + cell] = CUDART_NAN_F;
+                        g.der[D_ROUGHNESS * pl + cell] = CUDART_NAN_F;
+                        g.der[D_BORDER * pl + cell] = border;
+                        g.der[D_NX * pl + cell] = CUDART_NAN_F;
+                        g.der[D_NY * pl + cell] = CUDART_NAN_F;
+                        g.der[D_NZ * pl + cell] = CUDART_NAN_F;
+                    }
+                }
+            }
+        }
+        if (__syncthreads_or(any_fit) && tid == 0)
+            b.fit_tiles[atomicAdd(b.counters + 12, 1u)] = gt;
+        cur = nxt;
+        stage ^= 1;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
+    if (lane == 0 && n_done)
+        atomicAdd(b.counters + 7, n_done);
+}
+
 struct ClsSmem
 {
     size_t rec_bytes, flag_bytes, stage_bytes, inv_off, flag_off, total;
@@ -109,19 +232,15 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
     const uint32_t rec_pad = (rec_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = rec_pad + ((flag_bytes + 127u) & ~127u);
     double *s_inv = reinterpret_cast<double *>(s_raw + 2 * stage_bytes);           // [TW*TW]
-    uint8_t *s_flag = s_raw + 2 * stage_bytes + (size_t)ncell * 8;                 // [TW*TW]
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ uint32_t s_tmask[32], s_okmask[32];  // per halo row: touched / enough-points bits
 
     const uint32_t tid = threadIdx.x;
-    const uint32_t n_cand = b.counters[1];
-    const uint32_t minp = c_cp.min_points;
+    const uint32_t n_cand = b.counters[12];  // bins with at least one cell to fit (listed by k_gate)
     const size_t pl = g.plane();
-    uint32_t n_done = 0;
 
     auto issue = [&](int stage, uint32_t it)  // thread 0 only
     {
-        const uint32_t gt = b.cand_tiles[it];
+        const uint32_t gt = b.fit_tiles[it];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
         unsigned char *base = s_raw + (size_t)stage * stage_bytes;
@@ -153,7 +272,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
         if (tid == 0 && nxt < n_cand)
             issue(stage ^ 1, nxt);
 
-        const uint32_t gt = b.cand_tiles[cur];
+        const uint32_t gt = b.fit_tiles[cur];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
         const float *s_rec = reinterpret_cast<const float *>(s_raw + (size_t)stage * stage_bytes);
@@ -161,81 +280,24 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
         if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
         else { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
 
-        // pre-pass: touched / observed / enough-points bits and 1/N  (MomentLayers::read, Helpers.cpp:101-112).
-        // One warp per halo row (TW <= 32 lanes): the row's bits also land in 32-bit row masks, so the
-        // per-cell dirty / gate tests below are a few shifts per footprint row instead of a loop over taps.
-        int any_touched = 0;
-        const uint32_t lane = tid & 31, warp = tid >> 5;
-        for (int hy = warp; hy < TW; hy += CLS_THREADS / 32)
+        // pre-pass: 1/N of every observed halo cell (MomentLayers::read, Helpers.cpp:101-112)
+        for (int i = tid; i < ncell; i += CLS_THREADS)
         {
-            uint8_t f = 0;
-            double inv = 0.0;
-            if ((int)lane < TW)
-            {
-                const int i = hy * TW + lane;
-                f = (s_fraw[hy * FLAG_BOX_W + ((int)lane - r + 16)] & F_TOUCHED) ? H_TOUCHED : 0;
-                const float n = s_rec[(size_t)i * REC + R_N];
-                if (!isnan(n) && n >= 1.f)
-                {
-                    const float nr = rintf(n);
-                    f |= H_OBS;
-                    if (nr >= (float)minp) f |= H_OK;
-                    inv = 1.0 / (double)nr;
-                }
-                s_flag[i] = f;
-                s_inv[i] = inv;
-            }
-            const uint32_t mt = __ballot_sync(0xffffffffu, (f & H_TOUCHED) != 0);
-            const uint32_t mo = __ballot_sync(0xffffffffu, (f & H_OK) != 0);
-            any_touched |= mt != 0;
-            if (lane == 0)
-            {
-                s_tmask[hy] = mt;
-                s_okmask[hy] = mo;
-            }
+            const float n = s_rec[(size_t)i * REC + R_N];
+            s_inv[i] = (!isnan(n) && n >= 1.f) ? __drcp_rn((double)rintf(n)) : 0.0;
         }
-        if (__syncthreads_or(any_touched))  // else: nothing in this bin's footprint halo changed, no cell is dirty
+        __syncthreads();
         {
             const int x = tid & (BIN - 1), y = tid >> BIN_SHIFT;
             const int idx = (y + r) * TW + (x + r);
-            const uint8_t fq = s_flag[idx];
-            // LocalMap.cpp:138-140: an unobserved query cell is skipped, nothing written
-            bool dirty = false, gate = true;
             const int nd = c_cp.n_disc;
-            if (fq & H_OBS)
+            // k_gate marked the dirty cells whose whole footprint holds >= min_points (F_FIT)
+            if (s_fraw[(y + r) * FLAG_BOX_W + (x + 16)] & F_FIT)
             {
-                // dirty = query in dilate(touched, disc); gate = every disc cell has >= min_points:
-                // per footprint row, a contiguous run of 2w+1 bits of the row masks
-                for (int dj = -r; dj <= r; ++dj)
-                {
-                    const int w = c_cp.row_w[dj + r];
-                    if (w < 0) continue;
-                    const uint32_t wm = (2u << (2 * w)) - 1u;
-                    const int sh = x + r - w;
-                    dirty |= ((s_tmask[y + r + dj] >> sh) & wm) != 0u;
-                    gate &= ((s_okmask[y + r + dj] >> sh) & wm) == wm;
-                }
-            }
-            if (dirty)
-            {
-                ++n_done;
                 const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
                 const float *rq = s_rec + (size_t)idx * REC;
                 const double nq = (double)rintf(rq[R_N]);
-                const float border = (float)fmin(nq / (double)max(1u, minp), 1.0);
-                g.flags[cell] |= F_CHANGED;  // recomputeCell returned true (LocalMap.cpp:194-196)
-                if (!gate)
-                {
-                    g.der[D_HAZARD * pl + cell] = CUDART_NAN_F;
-                    g.der[D_SLOPE * pl + cell] = CUDART_NAN_F;
-                    g.der[D_STEP * pl + cell] = CUDART_NAN_F;
-                    g.der[D_ROUGHNESS * pl + cell] = CUDART_NAN_F;
-                    g.der[D_BORDER * pl + cell] = border;
-                    g.der[D_NX * pl + cell] = CUDART_NAN_F;
-                    g.der[D_NY * pl + cell] = CUDART_NAN_F;
-                    g.der[D_NZ * pl + cell] = CUDART_NAN_F;
-                }
-                else
+                g.flags[cell] &= (uint8_t)~F_FIT;
                 {
                     // ---- pass A: fuse the disc about the query centre ----
                     double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
@@ -298,7 +360,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
                     g.der[D_SLOPE * pl + cell] = (float)slope_h;
                     g.der[D_STEP * pl + cell] = (float)step_h;
                     g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
-                    g.der[D_BORDER * pl + cell] = border;
+                    g.der[D_BORDER * pl + cell] = 1.0f;  // N_q >= min_points: min(N/min_points, 1) == 1
                     g.der[D_NX * pl + cell] = (float)nv[0];
                     g.der[D_NY * pl + cell] = (float)nv[1];
                     g.der[D_NZ * pl + cell] = (float)nv[2];
@@ -308,11 +370,6 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
         cur = nxt;
         stage ^= 1;
     }
-    // cells classified (statistics)
-    for (int o = 16; o > 0; o >>= 1)
-        n_done += __shfl_xor_sync(0xffffffffu, n_done, o);
-    if ((tid & 31) == 0 && n_done)
-        atomicAdd(b.counters + 7, n_done);
 }
 
 // clear the per-batch touched / blanked bits of the active tiles
@@ -623,10 +680,12 @@ cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUte
         cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_r = r;
     }
-    // measured on B200 (C2 stream): 3 CTAs of work per SM beat an exactly-resident grid (more boxes in flight)
+    const size_t nb = (size_t)b.btw * b.bth;
+    // gate pass over every candidate bin (flag bytes only), then the TMA-staged fit over the bins it listed
+    k_gate<<<(int)min((size_t)(8 * n_sm), nb), GATE_THREADS, 0, st>>>(tmap_flags, b, g, cp);
     int gmul = 6;  // measured: 4-8 CTAs of work per SM level the per-bin imbalance best
     if (const char *e = getenv("TMB_CLS_GRID")) gmul = atoi(e);
-    const int n_blocks = (int)min((size_t)(gmul * n_sm), (size_t)b.btw * b.bth);
+    const int n_blocks = (int)min((size_t)(gmul * n_sm), nb);
     k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, tmap_flags, b, g, cp);
     return cudaGetLastError();
 }

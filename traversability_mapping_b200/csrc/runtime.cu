@@ -849,7 +849,7 @@ class LocalMap
         histD_.ensure((size_t)hist_off * 4 + 4);
         totD_.ensure((size_t)tot_off * 8 + 8);
         const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
-        tileD_.ensure((nb * 5 + (nb + 255) / 256 + n_t32) * 4 + 256);
+        tileD_.ensure((nb * 6 + (nb + 255) / 256 + n_t32) * 4 + 256);
         sortedD_.ensure((size_t)total_pts * 16 + 16);
         {
             // inflation-tile dedup stamps: own buffer (persistent across passes), zeroed when it grows
@@ -880,7 +880,9 @@ class LocalMap
         b.tile_start = b.tile_count + nb;
         b.active_tiles = b.tile_start + nb;
         b.cand_tiles = b.active_tiles + nb;
-        globD_ = b.cand_tiles + nb;                 // sharded runs: global per-bin totals
+        b.fit_tiles = b.cand_tiles + nb;
+        b.min_points = (uint32_t)std::max(0, P_.min_points_per_grid);
+        globD_ = b.fit_tiles + nb;                  // sharded runs: global per-bin totals
         b.block_sums = globD_ + nb;
         b.infl_tiles = b.block_sums + (nb + 255) / 256;
         b.infl_flags = inflFlagsD_.as<uint32_t>();
@@ -899,7 +901,7 @@ class LocalMap
         const size_t nb = (size_t)b.btw * b.bth;
         const bool prof = P_.profile != 0;
         CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_));
-        g_launches += 1;
+        g_launches += 2;  // k_gate + k_classify
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0)
         {

@@ -25,7 +25,9 @@ enum { R_N = 0, R_SX, R_SY, R_SZ, R_SX2, R_SY2, R_SZ2, R_SXY, R_SXZ, R_SYZ, R_ZM
 // derived plane order
 enum { D_HAZARD = 0, D_ELEVATION, D_SLOPE, D_STEP, D_ROUGHNESS, D_BORDER, D_NX, D_NY, D_NZ, D_INFLATED };
 // per-cell flag bits
-enum : uint8_t { F_TOUCHED = 1, F_CHANGED = 2, F_BLANKED = 4, F_OBSERVED = 8 };  // OBSERVED mirrors N >= 1 (kept by k_fold)
+// OBSERVED mirrors N >= 1 and ENOUGH mirrors N >= min_points (both kept by k_fold); FIT marks a dirty cell whose
+// footprint passed the gate (set by k_gate, consumed by k_classify)
+enum : uint8_t { F_TOUCHED = 1, F_CHANGED = 2, F_BLANKED = 4, F_OBSERVED = 8, F_ENOUGH = 16, F_FIT = 32 };
 
 struct LatticeD { double x0, y0, res; };
 
@@ -76,12 +78,15 @@ struct BatchView
     uint32_t *tile_start;      // [btw*bth] exclusive scan of tile_count
     uint32_t *block_sums;      // [ceil(btw*bth/256)] scan scratch
     uint32_t *active_tiles;    // compact list of bins with count>0 (index into bbox)
-    uint32_t *cand_tiles;      // bins to classify (active dilated by the footprint)
+    uint32_t *cand_tiles;      // bins to gate (active dilated by the footprint)
+    uint32_t *fit_tiles;       // bins holding at least one cell to fit (k_gate -> k_classify)
+    uint32_t min_points;       // traversability/min_points_per_grid (k_fold keeps the ENOUGH bit)
     uint32_t *infl_tiles;      // 32x32 tiles to inflate: (ty32 - g.ty0) * g.tw + (tx32 - g.tx0)
     uint32_t *infl_flags;      // [g.tw*g.th] dedup stamps for infl_tiles: == epoch once the tile is listed
     uint32_t epoch;            // batch serial (never 0)
     uint32_t *counters;        // [0] n_active [1] n_cand [2] n_infl [3] error flags [4] fold ticket
-                               // [5] classify ticket [6] inflate ticket [7] cells classified [8] cells touched
+                               // [7] cells classified [8] cells touched [9] heaviest bin [10] heavy items
+                               // [11] light items [12] n_fit
     int4 *op_bbox;             // per op: min ci, max ci, min cj, max cj of its points
     float4 *sorted;            // bucket-sorted records (xm, ym, zm, meta)
     uint32_t total_points;
