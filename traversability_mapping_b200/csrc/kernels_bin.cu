@@ -375,62 +375,108 @@ __device__ __forceinline__ uint32_t scan_ops_bin(const BatchView &b, uint32_t g)
 // work lists for bin i holding v records: bins to fold (heavy first / split), bins to classify (active dilated
 // by dc bins) and 32x32 tiles to inflate (within di bins of an active bin; dedup through epoch-stamped flags).
 // List order is irrelevant: bins / tiles are independent work items.
-__device__ __forceinline__ void emit_lists(const BatchView &b, const GridView &g, uint32_t i, uint32_t v, int dc, int di)
+// warp-aggregated append of `c` (0..K) slots per lane: every lane of the warp calls it; returns the lane's
+// first slot.  One atomic round trip per warp and list.
+__device__ __forceinline__ uint32_t warp_append(uint32_t *counter, uint32_t c)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t inc = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += u;
+    }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total)
+        base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - c;
+}
+
+// Work lists for the K bins i[k] (count v[k], valid[k]) held by this thread; called by every thread of the warp.
+//   bins to fold: light ones fill the list from the back, heavy ones go to the front so the fold's ticket loop
+//     starts the long sequential chains first (longest-processing-time-first).  A bin above a fold CTA's fair
+//     share is additionally split into P work items by cell-row group (rows r with r % P == part): cells are
+//     independent, so P CTAs walk the same bucket and each keeps only its rows' records.  Split only as far as
+//     load balance needs it: each part re-streams the bucket.
+//   bins to gate / classify: active bins dilated by dc bins; 32x32 tiles to inflate: within di bins of an active
+//     bin, dedup through epoch-stamped flags.  List order is irrelevant: bins / tiles are independent work items.
+template <int K>
+__device__ __forceinline__ void emit_lists(const BatchView &b, const GridView &g, const uint32_t (&i)[K], const uint32_t (&v)[K],
+                                           const bool (&valid)[K], int dc, int di)
 {
     const uint32_t nb = (uint32_t)(b.btw * b.bth);
-    if (v)
+    bool light[K], nc[K], ni[K], first[K];
+    uint32_t t32[K], n_light = 0, n_nc = 0, n_first = 0, vmax = 0;
+#pragma unroll
+    for (int k = 0; k < K; ++k)
     {
-        // heavy bins go to the front of the work list, light ones fill it from the back: the fold's ticket
-        // loop then starts the long sequential chains first (longest-processing-time-first scheduling).
-        // A bin above a fold CTA's fair share is additionally split into P work items by cell-row group
-        // (rows r with r % P == part): cells are independent, so P CTAs walk the same bucket and each keeps
-        // only its rows' records.  Split only as far as load balance needs it: each part re-streams the bucket.
-        if (v >= HEAVY_BIN)
+        const bool act = valid[k] && v[k] > 0;
+        light[k] = act && v[k] < HEAVY_BIN;
+        n_light += light[k];
+        if (act) vmax = max(vmax, v[k]);
+        if (act && !light[k])
         {
             uint32_t lg = 0;
-            while (lg < 4 && (v >> lg) > b.split_thresh) ++lg;
+            while (lg < 4 && (v[k] >> lg) > b.split_thresh) ++lg;
             const uint32_t P = 1u << lg;
-            atomicAdd(b.counters + 0, P);
             const uint32_t at = atomicAdd(b.counters + 10, P);
             for (uint32_t part = 0; part < P; ++part)
-                b.active_tiles[at + part] = i | (part << 24) | (lg << 28);
+                b.active_tiles[at + part] = i[k] | (part << 24) | (lg << 28);
         }
-        else
+        nc[k] = ni[k] = false;
+        t32[k] = 0;
+        if (valid[k])
         {
-            atomicAdd(b.counters + 0, 1u);
-            b.active_tiles[nb - 1 - atomicAdd(b.counters + 11, 1u)] = i;
-        }
-        atomicMax(b.counters + 9, v);  // heaviest bin of the batch (statistics)
-    }
-    const int lx = i % b.btw, ly = i / b.btw;
-    const int bx = b.btx0 + lx, by = b.bty0 + ly;  // global bin
-    // inside the allocated grid?
-    if (bx < g.tx0 * 2 || bx >= (g.tx0 + g.tw) * 2 || by < g.ty0 * 2 || by >= (g.ty0 + g.th) * 2)
-        return;
-    if (ly < b.cand_y0 || ly >= b.cand_y1)
-        return;
-    const int dm = max(dc, di);
-    bool nc = false, ni = false;
-    for (int dy = -dm; dy <= dm; ++dy)
-        for (int dx = -dm; dx <= dm; ++dx)
-        {
-            const int x = lx + dx, y = ly + dy;
-            if (x < 0 || x >= b.btw || y < 0 || y >= b.bth)
-                continue;
-            if (b.nbr_count[y * b.btw + x])
+            const int lx = i[k] % b.btw, ly = i[k] / b.btw;
+            const int bx = b.btx0 + lx, by = b.bty0 + ly;  // global bin
+            // inside the allocated grid, and in the rows this process owns?
+            if (bx >= g.tx0 * 2 && bx < (g.tx0 + g.tw) * 2 && by >= g.ty0 * 2 && by < (g.ty0 + g.th) * 2 && ly >= b.cand_y0 &&
+                ly < b.cand_y1)
             {
-                const int d = max(abs(dx), abs(dy));
-                nc |= d <= dc;
-                ni |= d <= di;
+                const int dm = max(dc, di);
+                for (int dy = -dm; dy <= dm; ++dy)
+                    for (int dx = -dm; dx <= dm; ++dx)
+                    {
+                        const int x = lx + dx, y = ly + dy;
+                        if (x < 0 || x >= b.btw || y < 0 || y >= b.bth)
+                            continue;
+                        if (b.nbr_count[y * b.btw + x])
+                        {
+                            const int d = max(abs(dx), abs(dy));
+                            nc[k] |= d <= dc;
+                            ni[k] |= d <= di;
+                        }
+                    }
+                t32[k] = (uint32_t)(((by >> 1) - g.ty0) * g.tw + ((bx >> 1) - g.tx0));
             }
         }
-    if (nc)
-        b.cand_tiles[atomicAdd(b.counters + 1, 1u)] = i;
-    if (ni)
+        n_nc += nc[k];
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k)
     {
-        const uint32_t t32 = (uint32_t)(((by >> 1) - g.ty0) * g.tw + ((bx >> 1) - g.tx0));
-        if (atomicExch(b.infl_flags + t32, b.epoch) != b.epoch)
-            b.infl_tiles[atomicAdd(b.counters + 2, 1u)] = t32;
+        first[k] = ni[k] && atomicExch(b.infl_flags + t32[k], b.epoch) != b.epoch;
+        n_first += first[k];
+    }
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, 16));
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, 8));
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, 4));
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, 2));
+    vmax = max(vmax, __shfl_xor_sync(0xffffffffu, vmax, 1));
+    if ((threadIdx.x & 31) == 0 && vmax)
+        atomicMax(b.counters + 9, vmax);  // heaviest bin of the batch (statistics)
+    uint32_t sl = warp_append(b.counters + 11, n_light);
+    uint32_t sc = warp_append(b.counters + 1, n_nc);
+    uint32_t sf = warp_append(b.counters + 2, n_first);
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+    {
+        if (light[k]) b.active_tiles[nb - 1 - sl++] = i[k];
+        if (nc[k]) b.cand_tiles[sc++] = i[k];
+        if (first[k]) b.infl_tiles[sf++] = t32[k];
     }
 }
 
@@ -478,10 +524,11 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
     const uint32_t v = i < nb ? b.tile_count[i] : 0;
     uint32_t tot;
     const uint32_t ex = block_excl_scan(v, s_w, tot);
-    if (i >= nb)
-        return;
-    b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
-    emit_lists(b, g, i, v, dc, di);
+    if (i < nb)
+        b.tile_start[i] = b.block_sums[blockIdx.x] + ex;
+    const uint32_t ii[1] = {i}, vv[1] = {v};
+    const bool ok[1] = {i < nb};
+    emit_lists<1>(b, g, ii, vv, ok, dc, di);
 }
 
 // the three kernels above in ONE single-CTA launch, for batches whose bbox has at most 4 096 bins (a
@@ -511,13 +558,15 @@ __global__ void __launch_bounds__(1024) k_scan_small(BatchView b, GridView g, in
         run += tot;
     }
     __syncthreads();  // every tile_count is visible to the neighbour tests below
+    uint32_t ii[4];
+    bool ok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {
-        const uint32_t i = k * 1024 + threadIdx.x;
-        if (i < nb)
-            emit_lists(b, g, i, cnt[k], dc, di);
+        ii[k] = k * 1024 + threadIdx.x;
+        ok[k] = ii[k] < nb;
     }
+    emit_lists<4>(b, g, ii, cnt, ok, dc, di);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -673,7 +722,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
     __shared__ uint32_t s_ticket;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_active = b.counters[0];
+    const uint32_t n_active = b.counters[10] + b.counters[11];  // heavy items (front) + light bins (back)
     for (;;)
     {
         if (tid == 0)

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
 // clear the per-batch touched / blanked bits of the active tiles
 __global__ void k_clear_touched(BatchView b, GridView g)
 {
-    const uint32_t n_active = b.counters[0], n_heavy = b.counters[10];
+    const uint32_t n_heavy = b.counters[10], n_active = n_heavy + b.counters[11];
     for (uint32_t it = blockIdx.x; it < n_active; it += gridDim.x)
     {
         const uint32_t gt = (it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)]) & 0x00ffffffu;

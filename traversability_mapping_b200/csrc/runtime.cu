@@ -935,7 +935,7 @@ class LocalMap
         stats_.points_binned += pl.total_pts;
         stats_.cells_classified += cnt[7];
         stats_.last_batch_points = pl.total_pts;
-        stats_.last_batch_tiles = cnt[0];
+        stats_.last_batch_tiles = cnt[10] + cnt[11];
         stats_.last_batch_cells_touched = cnt[8];
         stats_.last_batch_cells_classified = cnt[7];
         stats_.last_batch_max_bin = cnt[9];

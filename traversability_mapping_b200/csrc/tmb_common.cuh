@@ -84,7 +84,7 @@ struct BatchView
     uint32_t *infl_tiles;      // 32x32 tiles to inflate: (ty32 - g.ty0) * g.tw + (tx32 - g.tx0)
     uint32_t *infl_flags;      // [g.tw*g.th] dedup stamps for infl_tiles: == epoch once the tile is listed
     uint32_t epoch;            // batch serial (never 0)
-    uint32_t *counters;        // [0] n_active [1] n_cand [2] n_infl [3] error flags [4] fold ticket
+    uint32_t *counters;        // [0] unused [1] n_cand [2] n_infl [3] error flags [4] fold ticket
                                // [7] cells classified [8] cells touched [9] heaviest bin [10] heavy items
                                // [11] light items [12] n_fit
     int4 *op_bbox;             // per op: min ci, max ci, min cj, max cj of its points
