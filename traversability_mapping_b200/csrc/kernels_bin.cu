@@ -929,6 +929,67 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
 }
 
 // ---------------------------------------------------------------------------------------------
+// EXPERIMENT (not on the product path; enabled by TMB_EXPERIMENT_ATOMIC_FOLD=1, see profiles/README.md):
+// the alternative the north_star asks the sort to be "chosen against" -- privatised shared-memory atomic
+// accumulation.  One CTA per bin streams the bin's records in bucket order and atomicAdd()s the ten sums per
+// cell in shared memory (fp64 atomics), then casts once to float32.  It needs no sort, but (i) the order of
+// the fp64 additions is whatever the hardware serialises, and (ii) all keyframes of a batch are summed before
+// the single float32 cast, whereas the reference rounds each keyframe's partial to float32 and adds those
+// (Helpers.cpp:114-127) -- so its moment layers are not the reference's.  The kernel writes to a scratch
+// record array; `mismatch` counts cells whose ten float32 moments differ from the sorted fold's.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(FOLD_THREADS) k_fold_atomic_experiment(BatchView b, GridView g, LatticeD lat, float *scratch /*[H][W][12]*/,
+                                                                         uint32_t *mismatch)
+{
+    __shared__ double s_acc[BIN_CELLS][10];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t nb = (uint32_t)(b.btw * b.bth);
+    for (uint32_t gt = blockIdx.x; gt < nb; gt += gridDim.x)
+    {
+        const uint32_t cnt = b.tile_count[gt];
+        if (!cnt)
+            continue;
+        const uint32_t start = b.tile_start[gt];
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
+#pragma unroll
+        for (int k = 0; k < 10; ++k) s_acc[tid][k] = 0.0;
+        __syncthreads();
+        for (uint32_t i = tid; i < cnt; i += FOLD_THREADS)
+        {
+            const float4 p = b.sorted[start + i];
+            const uint32_t meta = __float_as_uint(p.w);
+            const uint32_t c = meta & 255u;
+            const double sg = (meta & META_SIGN) ? -1.0 : 1.0;
+            const int ci = bx * BIN + (int)(c & (BIN - 1)), cj = by * BIN + (int)(c >> BIN_SHIFT);
+            const double lx = (double)p.x - (lat.x0 + ci * lat.res), ly = (double)p.y - (lat.y0 + cj * lat.res), lz = (double)p.z;
+            double *a = s_acc[c];
+            atomicAdd(a + 0, sg);
+            atomicAdd(a + 1, sg * lx); atomicAdd(a + 2, sg * ly); atomicAdd(a + 3, sg * lz);
+            atomicAdd(a + 4, sg * lx * lx); atomicAdd(a + 5, sg * ly * ly); atomicAdd(a + 6, sg * lz * lz);
+            atomicAdd(a + 7, sg * lx * ly); atomicAdd(a + 8, sg * lx * lz); atomicAdd(a + 9, sg * ly * lz);
+        }
+        __syncthreads();
+        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const int col = ci - g.ci0, row = cj - g.cj0;
+        uint32_t bad = 0;
+        if (col >= 0 && col < g.W && row >= 0 && row < g.H && s_acc[tid][0] != 0.0)
+        {
+            const size_t cell = (size_t)row * g.W + col;
+            for (int k = 0; k < 10; ++k)
+            {
+                const float v = (float)s_acc[tid][k];
+                scratch[cell * REC + k] = v;
+                bad |= (v != g.mom[cell * REC + k]);
+            }
+        }
+        bad = __syncthreads_count(bad);
+        if (tid == 0 && bad)
+            atomicAdd(mismatch, bad);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // sharded rebuild (one process per GPU; bins are owned in slabs of bin rows)
 //   counts_all / starts_all : [world][nb] every rank's per-bin record count and exclusive start
 //   k_shard_counts : my bins' merged count (sum over sources inside my slab, 0 outside), the global
@@ -1074,6 +1135,14 @@ cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridVi
     const uint32_t nwarps = (uint32_t)((y1 - y0) * b.btw) * (uint32_t)world;
     if (nwarps)
         k_shard_merge<<<(nwarps + 7) / 8, 256, 0, st>>>(b, d_recv, d_counts_all, d_starts_all, d_src_base, world, y0, y1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fold_atomic_experiment(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, float *d_scratch,
+                                          uint32_t *d_mismatch, int n_sm)
+{
+    const uint32_t nb = b.btw * b.bth;
+    k_fold_atomic_experiment<<<min((uint32_t)n_sm * 6u, nb), FOLD_THREADS, 0, st>>>(b, g, lat, d_scratch, d_mismatch);
     return cudaGetLastError();
 }
 

@@ -17,6 +17,8 @@
 #include <chrono>
 #include <cmath>
 #include <condition_variable>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <functional>
@@ -961,7 +963,33 @@ class LocalMap
         uploadConstants();
         CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
         g_launches += ((size_t)pl.b.btw * pl.b.bth <= 4096) ? 5 : 7;  // hist, scan kernels, scatter, fold
+        if (std::getenv("TMB_EXPERIMENT_ATOMIC_FOLD"))
+            runAtomicExperiment(pl);
         finishBatch(pl, ops, t_begin);
+    }
+
+    // profiles/README.md "sort vs shared atomics": times the atomic alternative on the batch just folded and counts
+    // the cells whose float32 moments differ from the product's (meaningful after a rebuild from a blank map)
+    void runAtomicExperiment(const Plan &pl)
+    {
+        expScratch_.ensure(grid_.v.plane() * REC * 4 + 64);
+        expCount_.ensure(64);
+        cudaEvent_t e0, e1;
+        CK(cudaEventCreate(&e0));
+        CK(cudaEventCreate(&e1));
+        CK(cudaMemsetAsync(expCount_.p, 0, 4, stream_));
+        CK(cudaEventRecord(e0, stream_));
+        CK(launch_fold_atomic_experiment(stream_, pl.b, grid_.v, lat_, expScratch_.as<float>(), expCount_.as<uint32_t>(), nSM_));
+        CK(cudaEventRecord(e1, stream_));
+        uint32_t bad = 0;
+        CK(cudaMemcpyAsync(&bad, expCount_.p, 4, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        std::fprintf(stderr, "[tmap experiment] atomic fold: %.3f ms for %llu records, %u cells differ from the sorted fold\n", ms,
+                     (unsigned long long)pl.total_pts, bad);
     }
 
   public:
@@ -1174,7 +1202,7 @@ class LocalMap
     PinBuf metaH_, resH_;
     DevBuf metaD_, histD_, totD_, tileD_, sortedD_, inflFlagsD_, decay_;
     uint32_t epoch_ = 0;
-    DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_, mergedD_, srcBaseD_;
+    DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_, mergedD_, srcBaseD_, expScratch_, expCount_;
     uint32_t *globD_ = nullptr;
     Plan shardPlan_;
     std::vector<Op> shardOps_;

@@ -11,6 +11,8 @@ cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t st
 cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, float4 *d_out, uint32_t *d_total);
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
                        int dc, int di, int n_sm, cudaEvent_t *ev, int phases);
+cudaError_t launch_fold_atomic_experiment(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, float *d_scratch,
+                                          uint32_t *d_mismatch, int n_sm);
 cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridView &g, const float4 *d_recv, const uint32_t *d_counts_all,
                                const uint32_t *d_starts_all, const unsigned long long *d_src_base, int world, int y0, int y1,
                                uint32_t *d_glob, int dc, int di);
