@@ -44,10 +44,11 @@ __device__ __forceinline__ int cell_of(float xm, double x0, double res, double i
 {
     const double d = __dsub_rn((double)xm, x0);
     const double q = __dmul_rn(d, inv_res);
-    const double f = fabs(q) - floor(fabs(q));           // fractional part, exact
-    if (fabs(f - 0.5) <= fabs(q) * 1e-15 + 1e-300)
-        return (int)llround(__ddiv_rn(d, res));
-    return (int)llround(q);
+    const double r = rint(q);                      // nearest integer (ties to even): one instruction
+    const double f = fabs(__dsub_rn(q, r));        // distance to it, exact, <= 0.5
+    if (f >= 0.5 - (fabs(q) * 1e-15 + 1e-300))     // within the multiply's error of a k + 1/2 boundary (or a tie)
+        return (int)llround(__ddiv_rn(d, res));    // the reference's own arithmetic, half away from zero
+    return __double2int_rn(r);                     // away from boundaries every rounding rule agrees
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -235,6 +236,14 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
     const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
     bool bad = false;
+    // all of the thread's points are requested before any is used: PPT independent 16-byte loads in flight
+    float4 pts[PPT];
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+    {
+        const uint32_t i = base + r * 32 + lane;
+        pts[r] = i < s_op.n ? __ldg(s_op.cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
         uint32_t tile = 0xffffffffu;
         if (i < s_op.n)
         {
-            const float4 p = __ldg(s_op.cloud + i);
+            const float4 p = pts[r];
             float xm, ym, zm;
             xform_rn(s_op.T, p.x, p.y, p.z, xm, ym, zm);
             const int ci = cell_of(xm, lat.x0, lat.res, inv_res), cj = cell_of(ym, lat.y0, lat.res, inv_res);
@@ -599,6 +608,13 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
     const uint32_t sign_bit = s_op.sign < 0.f ? META_SIGN : 0u;
     float px[PPT], py[PPT], pz[PPT];
     uint32_t tl[PPT], cc[PPT];
+    float4 pts[PPT];
+#pragma unroll
+    for (int r = 0; r < PPT; ++r)
+    {
+        const uint32_t i = base + r * 32 + lane;
+        pts[r] = i < s_op.n ? __ldg(s_op.cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
@@ -608,7 +624,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         px[r] = py[r] = pz[r] = 0.f;
         if (i < s_op.n)
         {
-            const float4 p = __ldg(s_op.cloud + i);
+            const float4 p = pts[r];
             xform_rn(s_op.T, p.x, p.y, p.z, px[r], py[r], pz[r]);
             const int ci = cell_of(px[r], lat.x0, lat.res, inv_res), cj = cell_of(py[r], lat.y0, lat.res, inv_res);
             const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
