@@ -696,33 +696,43 @@ struct CellAcc
 
 __device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subtract, uint32_t &fl)
 {
-    if (a.n == 0)
-        return;
     // MomentLayers::add (Helpers.cpp:114-127): NaN -> 0, then += (float)(sign * value).  A cell is either
-    // entirely NaN (blank) or entirely numeric, so testing N covers the ten moment fields.
+    // entirely NaN (blank) or entirely numeric, so testing N covers all twelve fields.  (float)(-v) == -(float)v,
+    // so the sign is applied to the rounded float (a free negate on the add).
     if (isnan(rec[R_N]))
     {
 #pragma unroll
         for (int k = 0; k < 10; ++k) rec[k] = 0.f;
+        rec[R_ZMIN] = CUDART_INF_F;
+        rec[R_ZMAX] = -CUDART_INF_F;
     }
-#define TMB_ACC(k, v) rec[k] = __fadd_rn(rec[k], __double2float_rn(subtract ? -(v) : (v)));
-    TMB_ACC(R_N, (double)a.n)
-    TMB_ACC(R_SX, a.sx) TMB_ACC(R_SY, a.sy) TMB_ACC(R_SZ, a.sz)
-    TMB_ACC(R_SX2, a.sx2) TMB_ACC(R_SY2, a.sy2) TMB_ACC(R_SZ2, a.sz2)
-    TMB_ACC(R_SXY, a.sxy) TMB_ACC(R_SXZ, a.sxz) TMB_ACC(R_SYZ, a.syz)
-#undef TMB_ACC
+    const float f0 = __double2float_rn((double)a.n), f1 = __double2float_rn(a.sx), f2 = __double2float_rn(a.sy),
+                f3 = __double2float_rn(a.sz), f4 = __double2float_rn(a.sx2), f5 = __double2float_rn(a.sy2),
+                f6 = __double2float_rn(a.sz2), f7 = __double2float_rn(a.sxy), f8 = __double2float_rn(a.sxz),
+                f9 = __double2float_rn(a.syz);
     fl |= F_TOUCHED;
     if (!subtract)
     {
-        rec[R_ZMIN] = isnan(rec[R_ZMIN]) ? a.zmin : fminf(rec[R_ZMIN], a.zmin);
-        rec[R_ZMAX] = isnan(rec[R_ZMAX]) ? a.zmax : fmaxf(rec[R_ZMAX], a.zmax);
+        rec[0] = __fadd_rn(rec[0], f0); rec[1] = __fadd_rn(rec[1], f1); rec[2] = __fadd_rn(rec[2], f2);
+        rec[3] = __fadd_rn(rec[3], f3); rec[4] = __fadd_rn(rec[4], f4); rec[5] = __fadd_rn(rec[5], f5);
+        rec[6] = __fadd_rn(rec[6], f6); rec[7] = __fadd_rn(rec[7], f7); rec[8] = __fadd_rn(rec[8], f8);
+        rec[9] = __fadd_rn(rec[9], f9);
+        rec[R_ZMIN] = fminf(rec[R_ZMIN], a.zmin);
+        rec[R_ZMAX] = fmaxf(rec[R_ZMAX], a.zmax);
     }
-    else if (lroundf(rec[R_N]) <= 0)
+    else
     {
-        // LocalMap.cpp:121-125: a subtraction that empties the cell blanks all of its layers
+        rec[0] = __fsub_rn(rec[0], f0); rec[1] = __fsub_rn(rec[1], f1); rec[2] = __fsub_rn(rec[2], f2);
+        rec[3] = __fsub_rn(rec[3], f3); rec[4] = __fsub_rn(rec[4], f4); rec[5] = __fsub_rn(rec[5], f5);
+        rec[6] = __fsub_rn(rec[6], f6); rec[7] = __fsub_rn(rec[7], f7); rec[8] = __fsub_rn(rec[8], f8);
+        rec[9] = __fsub_rn(rec[9], f9);
+        if (rec[R_N] < 0.5f)
+        {
+            // LocalMap.cpp:121-125: a subtraction that empties the cell (lround(N) <= 0) blanks all of its layers
 #pragma unroll
-        for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
-        fl |= F_BLANKED | F_CHANGED;
+            for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+            fl |= F_BLANKED | F_CHANGED;
+        }
     }
 }
 
@@ -733,7 +743,6 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
     __shared__ __align__(16) float4 s_rec[FOLD_CH];          // staged records            32 KB
     __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
     __shared__ uint16_t s_cnt[FOLD_NW][BIN_CELLS];            // per-warp cell counters       4 KB
-    __shared__ uint16_t s_seg0[BIN_CELLS], s_seg1[BIN_CELLS]; // cell segment bounds
     __shared__ uint32_t s_w[33];
     __shared__ uint32_t s_ticket;
 
@@ -854,18 +863,18 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             }
             __syncthreads();
             // thread = cell: exclusive prefix over the warps' counts, then over cells
-            uint32_t tot = 0;
+            uint32_t tot = 0, wc[FOLD_NW];
 #pragma unroll
             for (int w = 0; w < FOLD_NW; ++w)
             {
-                const uint32_t v = s_cnt[w][tid];
-                s_cnt[w][tid] = (uint16_t)tot;
-                tot += v;
+                wc[w] = tot;
+                tot += s_cnt[w][tid];
             }
             uint32_t all;
             const uint32_t cstart = block_excl_scan(tot, s_w, all);
-            s_seg0[tid] = (uint16_t)cstart;
-            s_seg1[tid] = (uint16_t)(cstart + tot);
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
             __syncthreads();
             // stable placement: position = cell start + earlier warps + rank inside the warp round
             for (uint32_t r = 0; r < R; ++r)
@@ -876,7 +885,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 if (c < 256u)
                 {
                     const uint32_t off = s_cnt[warp][c];
-                    s_ord[s_seg0[c] + off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
+                    s_ord[off + __popc(m & ((1u << lane) - 1u))] = (uint16_t)i;
                     __syncwarp(m);
                     if (lane == (uint32_t)(__ffs(m) - 1))
                         s_cnt[warp][c] = (uint16_t)(off + __popc(m));
@@ -885,7 +894,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             }
             __syncthreads();
             // thread = cell: walk the cell's records in (op, point) order
-            const uint32_t k0 = s_seg0[tid], k1 = s_seg1[tid];
+            const uint32_t k0 = cstart, k1 = cstart + tot;
             for (uint32_t k = k0; k < k1; ++k)
             {
                 const float4 p = s_rec[s_ord[k]];
