@@ -236,29 +236,36 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
     const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
     bool bad = false;
+    // op constants live in registers (the shared copy would be re-read around every shared atomic)
+    const uint32_t n_pts = s_op.n;
+    const float4 *cloud = s_op.cloud;
+    const int wtx0 = s_op.wtx0, wty0 = s_op.wty0, wtw = s_op.wtw, wth = s_op.wth;
+    float Tm[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) Tm[k] = s_op.T[k];
     // all of the thread's points are requested before any is used: PPT independent 16-byte loads in flight
     float4 pts[PPT];
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
         const uint32_t i = base + r * 32 + lane;
-        pts[r] = i < s_op.n ? __ldg(s_op.cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pts[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
         const uint32_t i = base + r * 32 + lane;
         uint32_t tile = 0xffffffffu;
-        if (i < s_op.n)
+        if (i < n_pts)
         {
             const float4 p = pts[r];
-            float xm, ym, zm;
-            xform_rn(s_op.T, p.x, p.y, p.z, xm, ym, zm);
+            const float xm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[0], p.x), __fmul_rn(Tm[1], p.y)), __fmul_rn(Tm[2], p.z)), Tm[3]);
+            const float ym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[4], p.x), __fmul_rn(Tm[5], p.y)), __fmul_rn(Tm[6], p.z)), Tm[7]);
             const int ci = cell_of(xm, lat.x0, lat.res, inv_res), cj = cell_of(ym, lat.y0, lat.res, inv_res);
-            const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
-            if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
+            const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
+            if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
             {
-                tile = ty * s_op.wtw + tx;
+                tile = ty * wtw + tx;
                 mnx = min(mnx, ci); mxx = max(mxx, ci); mny = min(mny, cj); mxy = max(mxy, cj);
             }
             else
@@ -290,35 +297,66 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
 }
 
 // per (op, bin): exclusive prefix over the op's chunks, in place; total -> op_total.
-// One warp per column: 32 chunk counts per step, shuffle scan, carried running total.
-__global__ void k_scan_chunks(BatchView b)
+// A CTA owns 32 adjacent columns (bins): a warp reads the 32 counters of a chunk row as one 128-byte line.
+// The chunk rows are split into 8 contiguous ranges, one per warp; each warp sums its range (loads issued
+// SCAN_U at a time), the range sums are exchanged through shared memory, then the range is re-read (L1/L2
+// hits) and replaced by the running prefix.
+constexpr int SCAN_U = 8;
+__global__ void __launch_bounds__(256) k_scan_chunks(BatchView b)
 {
+    __shared__ uint32_t s_sum[8][32];
     const uint32_t opi = blockIdx.y;
-    const OpDesc &op = b.ops[opi];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (t >= op.T_tiles)
+    const OpDesc *op = b.ops + opi;
+    const uint32_t T = __ldg(&op->T_tiles);
+    if (blockIdx.x * 32 >= T)
         return;
-    uint32_t *col = b.hist + op.hist_off + t;
-    const size_t T = op.T_tiles;
-    uint32_t run = 0;
-    for (uint32_t c0 = 0; c0 < op.nchunks; c0 += 32)
-    {
-        const uint32_t c = c0 + lane;
-        const uint32_t v = c < op.nchunks ? col[(size_t)c * T] : 0u;
-        uint32_t inc = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1)
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t t = blockIdx.x * 32 + lane;
+    const bool ok = t < T;
+    const uint32_t nch = __ldg(&op->nchunks);
+    const uint32_t L = (nch + 7) / 8;
+    const uint32_t c_begin = min(warp * L, nch), c_end = min(c_begin + L, nch);
+    uint32_t *col = b.hist + __ldg(&op->hist_off) + t;
+    uint32_t sum = 0;
+    if (ok)
+        for (uint32_t c0 = c_begin; c0 < c_end; c0 += SCAN_U)
         {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= (uint32_t)o) inc += u;
+            uint32_t v[SCAN_U];
+#pragma unroll
+            for (int k = 0; k < SCAN_U; ++k)
+                v[k] = c0 + k < c_end ? col[(size_t)(c0 + k) * T] : 0u;
+#pragma unroll
+            for (int k = 0; k < SCAN_U; ++k)
+                sum += v[k];
         }
-        if (c < op.nchunks)
-            col[(size_t)c * T] = run + inc - v;
-        run += __shfl_sync(0xffffffffu, inc, 31);
+    s_sum[warp][lane] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+    {
+        const uint32_t v = s_sum[w][lane];
+        if (w < (int)warp) run += v;
+        total += v;
     }
-    if (lane == 0)
-        b.op_total[op.tot_off + t] = run;
+    if (!ok)
+        return;
+    for (uint32_t c0 = c_begin; c0 < c_end; c0 += SCAN_U)
+    {
+        uint32_t v[SCAN_U];
+#pragma unroll
+        for (int k = 0; k < SCAN_U; ++k)
+            v[k] = c0 + k < c_end ? col[(size_t)(c0 + k) * T] : 0u;
+#pragma unroll
+        for (int k = 0; k < SCAN_U; ++k)
+        {
+            if (c0 + k < c_end)
+                col[(size_t)(c0 + k) * T] = run;
+            run += v[k];
+        }
+    }
+    if (warp == 0)
+        b.op_total[__ldg(&op->tot_off) + t] = total;
 }
 
 constexpr uint32_t HEAVY_BIN = 32768;  // records; bins at least this heavy are scheduled first
@@ -363,19 +401,39 @@ __device__ __forceinline__ uint32_t scan_ops_bin(const BatchView &b, uint32_t g)
     uint32_t run = 0;
     for (uint32_t o0 = 0; o0 < b.n_ops; o0 += 32)
     {
-        const int4 gw = b.op_groups[o0 >> 5];  // x0, y0, x1, y1 (inclusive) of the group's windows
+        const int4 gw = __ldg(b.op_groups + (o0 >> 5));  // x0, y0, x1, y1 (inclusive) of the group's windows
         if (tx < gw.x || tx > gw.z || ty < gw.y || ty > gw.w)
             continue;
         const uint32_t o1 = min(o0 + 32u, b.n_ops);
-        for (uint32_t o = o0; o < o1; ++o)
+        // 8 ops at a time: their descriptors and totals are requested together (read-only path, so the loads
+        // are not ordered behind the op_start stores), then the running prefix is applied in op order
+        for (uint32_t ob = o0; ob < o1; ob += 8)
         {
-            const OpDesc &op = b.ops[o];
-            const int lx = tx - op.wtx0, ly = ty - op.wty0;
-            if (lx < 0 || lx >= op.wtw || ly < 0 || ly >= op.wth)
-                continue;
-            const uint32_t t = op.tot_off + ly * op.wtw + lx;
-            b.op_start[t] = run;
-            run += b.op_total[t];
+            uint32_t t[8], v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+            {
+                t[k] = 0xffffffffu;
+                v[k] = 0;
+                if (ob + k < o1)
+                {
+                    const OpDesc *op = b.ops + ob + k;
+                    const int4 w = __ldg(reinterpret_cast<const int4 *>(&op->wtx0));  // wtx0, wty0, wtw, wth
+                    const int lx = tx - w.x, ly = ty - w.y;
+                    if (lx >= 0 && lx < w.z && ly >= 0 && ly < w.w)
+                    {
+                        t[k] = __ldg(&op->tot_off) + (uint32_t)(ly * w.z + lx);
+                        v[k] = __ldg(b.op_total + t[k]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (t[k] != 0xffffffffu)
+                {
+                    b.op_start[t[k]] = run;
+                    run += v[k];
+                }
         }
     }
     return run;
@@ -546,35 +604,56 @@ __global__ void __launch_bounds__(1024) k_scan_small(BatchView b, GridView g, in
 {
     __shared__ uint32_t s_w[33];
     const uint32_t nb = (uint32_t)(b.btw * b.bth);
-    uint32_t cnt[4];
-    uint32_t run = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        const uint32_t i = k * 1024 + threadIdx.x;
-        cnt[k] = i < nb ? scan_ops_bin(b, i) : 0u;
-        if (i < nb)
-            b.tile_count[i] = cnt[k];
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-    {
-        const uint32_t i = k * 1024 + threadIdx.x;
-        uint32_t tot;
-        const uint32_t ex = block_excl_scan(cnt[k], s_w, tot);
-        if (i < nb)
-            b.tile_start[i] = run + ex;
-        run += tot;
-    }
-    __syncthreads();  // every tile_count is visible to the neighbour tests below
-    uint32_t ii[4];
+    // a thread owns 4 consecutive bins, so one block scan of the threads' sums orders all of them
+    uint32_t cnt[4], ii[4];
     bool ok[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k)
     {
-        ii[k] = k * 1024 + threadIdx.x;
+        ii[k] = threadIdx.x * 4 + k;
         ok[k] = ii[k] < nb;
+        cnt[k] = 0;
     }
+    if (b.n_ops == 1)
+    {
+        // a stream tick: the bin count is the single op's total; the four lookups are independent loads
+        const OpDesc *op = b.ops;
+        const int4 w = __ldg(reinterpret_cast<const int4 *>(&op->wtx0));
+        const uint32_t tot_off = __ldg(&op->tot_off);
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+        {
+            const int lx = b.btx0 + (int)(ii[k] % b.btw) - w.x, ly = b.bty0 + (int)(ii[k] / b.btw) - w.y;
+            t[k] = (ok[k] && lx >= 0 && lx < w.z && ly >= 0 && ly < w.w) ? tot_off + (uint32_t)(ly * w.z + lx) : 0xffffffffu;
+            if (t[k] != 0xffffffffu)
+                cnt[k] = __ldg(b.op_total + t[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (t[k] != 0xffffffffu)
+                b.op_start[t[k]] = 0;
+    }
+    else
+    {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (ok[k])
+                cnt[k] = scan_ops_bin(b, ii[k]);
+    }
+    uint32_t tot;
+    uint32_t ex = block_excl_scan(cnt[0] + cnt[1] + cnt[2] + cnt[3], s_w, tot);
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+    {
+        if (ok[k])
+        {
+            b.tile_count[ii[k]] = cnt[k];
+            b.tile_start[ii[k]] = ex;
+        }
+        ex += cnt[k];
+    }
+    __syncthreads();  // every tile_count is visible to the neighbour tests below
     emit_lists<4>(b, g, ii, cnt, ok, dc, di);
 }
 
@@ -606,6 +685,12 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
     const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
     uint16_t *my = s_cnt + warp * T;
     const uint32_t sign_bit = s_op.sign < 0.f ? META_SIGN : 0u;
+    const uint32_t n_pts = s_op.n;
+    const float4 *cloud = s_op.cloud;
+    const int wtx0 = s_op.wtx0, wty0 = s_op.wty0, wtw = s_op.wtw, wth = s_op.wth;
+    float Tm[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) Tm[k] = s_op.T[k];
     float px[PPT], py[PPT], pz[PPT];
     uint32_t tl[PPT], cc[PPT];
     float4 pts[PPT];
@@ -613,7 +698,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
     for (int r = 0; r < PPT; ++r)
     {
         const uint32_t i = base + r * 32 + lane;
-        pts[r] = i < s_op.n ? __ldg(s_op.cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        pts[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
@@ -622,15 +707,15 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
         tl[r] = 0xffffffffu;
         cc[r] = 0;
         px[r] = py[r] = pz[r] = 0.f;
-        if (i < s_op.n)
+        if (i < n_pts)
         {
             const float4 p = pts[r];
-            xform_rn(s_op.T, p.x, p.y, p.z, px[r], py[r], pz[r]);
+            xform_rn(Tm, p.x, p.y, p.z, px[r], py[r], pz[r]);
             const int ci = cell_of(px[r], lat.x0, lat.res, inv_res), cj = cell_of(py[r], lat.y0, lat.res, inv_res);
-            const int tx = (ci >> BIN_SHIFT) - s_op.wtx0, ty = (cj >> BIN_SHIFT) - s_op.wty0;
-            if (tx >= 0 && tx < s_op.wtw && ty >= 0 && ty < s_op.wth)
+            const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
+            if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
             {
-                tl[r] = ty * s_op.wtw + tx;
+                tl[r] = ty * wtw + tx;
                 cc[r] = ((cj & (BIN - 1)) << BIN_SHIFT) | (ci & (BIN - 1));
             }
         }
@@ -1123,7 +1208,7 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     else
         k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
-    k_scan_chunks<<<dim3((maxT + 7) / 8, b.n_ops), 256, 0, st>>>(b);
+    k_scan_chunks<<<dim3((maxT + 31) / 32, b.n_ops), 256, 0, st>>>(b);
     if (nb <= 4096)
         k_scan_small<<<1, 1024, 0, st>>>(b, g, dc, di);
     else

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 
 namespace tmb
 {
@@ -48,7 +49,7 @@ struct GridView
 };
 
 // One binning op = one keyframe cloud folded with a sign at a pose.
-struct OpDesc
+struct alignas(16) OpDesc
 {
     const float4 *cloud;   // base-frame points (x,y,z,unused)
     uint32_t n;            // points
@@ -61,6 +62,7 @@ struct OpDesc
     uint32_t tot_off;      // offset of this op's per-tile arrays (total / op_start)
     unsigned long long hist_off;  // offset (u32 units) of this op's [nchunks][T_tiles] histogram
 };
+static_assert(sizeof(OpDesc) == 112 && offsetof(OpDesc, wtx0) == 64, "window fields are read as one aligned int4");
 
 struct BatchView
 {
