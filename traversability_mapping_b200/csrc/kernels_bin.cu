@@ -779,18 +779,24 @@ struct CellAcc
     }
 };
 
-__device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subtract, uint32_t &fl)
+// Inside k_fold a cell's record is held in "zero form": a blank cell (all NaN in memory) is N = 0, sums = 0,
+// zmin = +inf, zmax = -inf.  That is MomentLayers::add's NaN -> 0 (Helpers.cpp:114-127) done once at load
+// instead of at every fold; N is a sum of integers, so N == 0 identifies a blank cell exactly and the store
+// turns it back into NaNs.
+__device__ __forceinline__ void rec_to_zero_form(float *rec)
 {
-    // MomentLayers::add (Helpers.cpp:114-127): NaN -> 0, then += (float)(sign * value).  A cell is either
-    // entirely NaN (blank) or entirely numeric, so testing N covers all twelve fields.  (float)(-v) == -(float)v,
-    // so the sign is applied to the rounded float (a free negate on the add).
-    if (isnan(rec[R_N]))
+    if (isnan(rec[R_N]))  // a cell is either entirely NaN or entirely numeric
     {
 #pragma unroll
         for (int k = 0; k < 10; ++k) rec[k] = 0.f;
         rec[R_ZMIN] = CUDART_INF_F;
         rec[R_ZMAX] = -CUDART_INF_F;
     }
+}
+
+__device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subtract, uint32_t &fl)
+{
+    // rec += (float)(sign * partial); (float)(-v) == -(float)v, so the sign is applied to the rounded float
     const float f0 = __double2float_rn((double)a.n), f1 = __double2float_rn(a.sx), f2 = __double2float_rn(a.sy),
                 f3 = __double2float_rn(a.sz), f4 = __double2float_rn(a.sx2), f5 = __double2float_rn(a.sy2),
                 f6 = __double2float_rn(a.sz2), f7 = __double2float_rn(a.sxy), f8 = __double2float_rn(a.sxz),
@@ -815,10 +821,25 @@ __device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subt
         {
             // LocalMap.cpp:121-125: a subtraction that empties the cell (lround(N) <= 0) blanks all of its layers
 #pragma unroll
-            for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+            for (int k = 0; k < 10; ++k) rec[k] = 0.f;
+            rec[R_ZMIN] = CUDART_INF_F;
+            rec[R_ZMAX] = -CUDART_INF_F;
             fl |= F_BLANKED | F_CHANGED;
         }
     }
+}
+
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
+{
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t addr)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
 }
 
 constexpr int FOLD_NW = FOLD_THREADS / 32;
@@ -866,6 +887,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
             rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
             rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+            rec_to_zero_form(rec);
             loaded = true;
         };
         const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
@@ -978,34 +1000,38 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 __syncwarp();
             }
             __syncthreads();
-            // thread = cell: walk the cell's records in (op, point) order
+            // thread = cell: walk the cell's records in (op, point) order.  A new (op, cell) segment restarts the
+            // sums through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly), so the
+            // accumulators are updated in place and only the fold itself is a divergent block.
             const uint32_t k0 = cstart, k1 = cstart + tot;
+            const uint32_t ord_base = (uint32_t)__cvta_generic_to_shared(s_ord), rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
             for (uint32_t k = k0; k < k1; ++k)
             {
-                const float4 p = s_rec[s_ord[k]];
+                const float4 p = lds_f4(rec_base + 16u * lds_u16(ord_base + 2u * k));
                 const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
-                if (so != cur)
+                const bool fresh = so != cur;
+                if (fresh)
                 {
                     if (cur != 0xffffffffu)
                     {
                         load_rec();
                         fold_acc(rec, acc, (cur >> 23) != 0, fl);
                     }
-                    acc.reset();
                     cur = so;
                 }
+                const double keep = fresh ? 0.0 : 1.0;
                 // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
                 const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
-                acc.n += 1;
-                acc.sx = __dadd_rn(acc.sx, lx); acc.sy = __dadd_rn(acc.sy, ly); acc.sz = __dadd_rn(acc.sz, lz);
-                acc.sx2 = __dadd_rn(acc.sx2, __dmul_rn(lx, lx));
-                acc.sy2 = __dadd_rn(acc.sy2, __dmul_rn(ly, ly));
-                acc.sz2 = __dadd_rn(acc.sz2, __dmul_rn(lz, lz));
-                acc.sxy = __dadd_rn(acc.sxy, __dmul_rn(lx, ly));
-                acc.sxz = __dadd_rn(acc.sxz, __dmul_rn(lx, lz));
-                acc.syz = __dadd_rn(acc.syz, __dmul_rn(ly, lz));
-                acc.zmin = fminf(acc.zmin, p.z);
-                acc.zmax = fmaxf(acc.zmax, p.z);
+                acc.n = fresh ? 1u : acc.n + 1u;
+                acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
+                acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
+                acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
+                acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
+                acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
+                acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
+                acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
+                acc.zmin = fminf(fresh ? CUDART_INF_F : acc.zmin, p.z);
+                acc.zmax = fmaxf(fresh ? -CUDART_INF_F : acc.zmax, p.z);
             }
             __syncthreads();
         }
@@ -1017,6 +1043,11 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
         if (fl & F_TOUCHED)
         {
             float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
+            if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
+            {
+#pragma unroll
+                for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+            }
             dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
             dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
             dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
