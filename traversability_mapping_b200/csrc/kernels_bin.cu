@@ -842,66 +842,24 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
     return v;
 }
 
-// Peer mask of the lanes holding the same 9-bit key.  match.any costs ~8 cycles per DISTINCT value on sm_100
-// (profiles/ubench/pipes.cu: 257 cycles for 32 distinct keys), and the records of a bin spread over many cells;
-// nine ballots are a fixed ~70 cycles.
-__device__ __forceinline__ uint32_t match_any_9bit(uint32_t key)
-{
-    uint32_t m = 0xffffffffu;
-#pragma unroll
-    for (int bit = 0; bit < 9; ++bit)
-    {
-        const bool on = (key >> bit) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, on);
-        m &= on ? bal : ~bal;
-    }
-    return m;
-}
-
 constexpr int FOLD_NW = FOLD_THREADS / 32;
-constexpr int FOLD_KEYS = 64;          // per-chunk record counts are ranked through min(count, 63)
-constexpr uint32_t F_LOADED = 0x80u;   // shared flag byte only: the cell's record is in FoldSmem::cell
 
-struct FoldSmem
-{
-    float4 rec[FOLD_CH];                   // staged records                                   32 KB
-    float cell[BIN_CELLS][REC];            // zero-form moment records of the bin's cells       12 KB
-    uint16_t ord[FOLD_CH];                 // staged record indices sorted by cell               4 KB
-    uint16_t cnt[FOLD_NW][BIN_CELLS];      // per-warp cell counters -> next sorted slot         4 KB
-    uint16_t k0[BIN_CELLS], k1[BIN_CELLS]; // sorted range of each cell
-    uint16_t perm[BIN_CELLS];              // thread -> cell for this chunk's walk
-    uint32_t kh[FOLD_KEYS];                // histogram of the count keys
-    uint8_t fl[BIN_CELLS];                 // per-cell flag bits gathered over the chunks
-    uint32_t w[33];
-    uint32_t ticket;
-};
-
-// k_fold work item = one 16x16 bin (or one row group of a split heavy bin).  The bin's bucket is consumed in
-// chunks of up to FOLD_CH records; every chunk is counting-sorted by cell in shared memory and then walked, one
-// thread per cell, in (op, point) order: doubles are accumulated per (op, cell) segment and every finished
-// segment is folded, as float32, into the cell's record (KeyFrame::rebin + MomentLayers::add).
-//
-// Walk balance: the walk's cost per warp is its LONGEST cell, and LiDAR density varies a lot inside a bin, so the
-// cells are handed to the threads in descending order of their record count in this chunk (a counting sort of
-// the 256 counts): the 32 cells of a warp then have similar lengths.  The mapping changes from chunk to chunk, so
-// the cell records live in shared memory between chunks, and a chunk is cut at an op boundary (the bucket is
-// op-major) so that no (op, cell) segment is left open across two chunks.  When that is impossible -- one op's run
-// is longer than a chunk, or the item is a row group of a split bin, whose records are compacted on the fly --
-// the chunk uses the identity mapping and the open segment simply stays in the thread's registers.
 __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView g, LatticeD lat)
 {
-    extern __shared__ __align__(16) unsigned char s_fold_raw[];
-    FoldSmem &s = *reinterpret_cast<FoldSmem *>(s_fold_raw);
+    __shared__ __align__(16) float4 s_rec[FOLD_CH];          // staged records            32 KB
+    __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
+    __shared__ uint16_t s_cnt[FOLD_NW][BIN_CELLS];            // per-warp cell counters       4 KB
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_ticket;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_active = b.counters[10] + b.counters[11];  // heavy items (front) + light bins (back)
-    const uint32_t ord_base = (uint32_t)__cvta_generic_to_shared(s.ord), rec_base = (uint32_t)__cvta_generic_to_shared(s.rec);
     for (;;)
     {
         if (tid == 0)
-            s.ticket = atomicAdd(b.counters + 4, 1u);
+            s_ticket = atomicAdd(b.counters + 4, 1u);
         __syncthreads();
-        const uint32_t it = s.ticket;
+        const uint32_t it = s_ticket;
         __syncthreads();
         if (it >= n_active)
             break;
@@ -910,47 +868,43 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
         const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
-        const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
-        if (col0 < 0 || col0 + BIN > g.W || row0 < 0 || row0 + BIN > g.H)
+        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const int col = ci - g.ci0, row = cj - g.cj0;
+        if (col < 0 || col >= g.W || row < 0 || row >= g.H)
         {
             if (tid == 0) atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
             continue;  // uniform: a bin is inside or outside as a whole (grid is 32-aligned)
         }
-        s.fl[tid] = 0;  // ordered before its first use by the barriers of the first chunk
+        const size_t cell = (size_t)row * g.W + col;
+        // the cell's 48-byte record is fetched only if this batch actually touches the cell
+        float rec[REC];
+        bool loaded = false;
+        auto load_rec = [&]()
+        {
+            if (loaded) return;
+            const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
+            rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
+            rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+            rec_to_zero_form(rec);
+            loaded = true;
+        };
+        const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
+        const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
         CellAcc acc;
         acc.reset();
-        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment open in this thread's registers
-        bool carry_in = false;
+        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
+        uint32_t fl = 0;
 
         for (uint32_t pos = 0; pos < cnt;)
         {
             uint32_t n;
-            bool carry_out;
             if (pmask == 0u)
             {
                 n = min((uint32_t)FOLD_CH, cnt - pos);
                 for (uint32_t i = tid; i < n; i += FOLD_THREADS)
-                    s.rec[i] = b.sorted[start + pos + i];
-#pragma unroll
-                for (int w = 0; w < FOLD_NW; ++w)
-                    s.cnt[w][tid] = 0;
-                if (tid < FOLD_KEYS)
-                    s.kh[tid] = 0;
-                __syncthreads();
-                carry_out = false;
-                if (pos + n < cnt)
-                {
-                    // cut the chunk where the op of the first record beyond it begins (its records are a suffix)
-                    const uint32_t so_next = __float_as_uint(reinterpret_cast<const float *>(b.sorted + start + pos + n)[3]) >> 8;
-                    uint32_t lo = 0, hi = n;
-                    while (lo < hi)
-                    {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if ((__float_as_uint(s.rec[mid].w) >> 8) == so_next) hi = mid; else lo = mid + 1;
-                    }
-                    if (lo == 0) carry_out = true;  // a single op fills the chunk: its segments stay open
-                    else n = lo;
-                }
+                    s_rec[i] = b.sorted[start + pos + i];
                 pos += n;
             }
             else
@@ -978,13 +932,13 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                         const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
                         if (lane >= (uint32_t)o) inc += u;
                     }
-                    if (lane == 31) s.w[warp] = inc;
+                    if (lane == 31) s_w[warp] = inc;
                     __syncthreads();
                     uint32_t wbase = 0, total = 0;
 #pragma unroll
                     for (int w = 0; w < FOLD_NW; ++w)
                     {
-                        const uint32_t v = s.w[w];
+                        const uint32_t v = s_w[w];
                         if (w < (int)warp) wbase += v;
                         total += v;
                     }
@@ -992,23 +946,20 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
 #pragma unroll
                     for (int q = 0; q < 4; ++q)
                         if (keep & (1u << q))
-                            s.rec[dst++] = b.sorted[start + pos + 4 * tid + q];
+                            s_rec[dst++] = b.sorted[start + pos + 4 * tid + q];
                     __syncthreads();
                     n += total;
                     pos += nin;
                 }
-#pragma unroll
-                for (int w = 0; w < FOLD_NW; ++w)
-                    s.cnt[w][tid] = 0;
-                __syncthreads();
-                carry_out = pos < cnt;
             }
-            const bool ident = pmask != 0u || carry_in || carry_out;  // uniform over the CTA
-
             const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
             const uint32_t SL = R * 32;                                // records per warp slice
-            // count: warp w owns the contiguous slice [w*SL, (w+1)*SL).  The peer masks are kept for the placement
-            // pass (match.any is the slow instruction of this kernel)
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = 0;
+            __syncthreads();
+            // count: warp w owns the contiguous slice [w*SL, (w+1)*SL).  The peer masks are kept in registers for
+            // the placement pass: match.any costs ~8 cycles per distinct value (profiles/ubench/pipes.cu)
             constexpr int MAX_R = FOLD_CH / FOLD_THREADS;
             uint32_t cm[MAX_R], mm[MAX_R];
 #pragma unroll
@@ -1019,11 +970,11 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 if ((uint32_t)r < R)
                 {
                     const uint32_t i = warp * SL + r * 32 + lane;
-                    cm[r] = i < n ? (__float_as_uint(s.rec[i].w) & 255u) : 256u;
-                    mm[r] = match_any_9bit(cm[r]);
-                    // the group's highest lane adds the group size (its rank + 1): no leader search
+                    cm[r] = i < n ? (__float_as_uint(s_rec[i].w) & 255u) : 256u;
+                    mm[r] = __match_any_sync(0xffffffffu, cm[r]);
+                    // the group's highest lane adds the group size: no leader search
                     if (cm[r] < 256u && (mm[r] >> lane) == 1u)
-                        s.cnt[warp][cm[r]] += (uint16_t)__popc(mm[r]);
+                        s_cnt[warp][cm[r]] += (uint16_t)__popc(mm[r]);
                     __syncwarp();
                 }
             }
@@ -1034,12 +985,8 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             for (int w = 0; w < FOLD_NW; ++w)
             {
                 wc[w] = tot;
-                tot += s.cnt[w][tid];
+                tot += s_cnt[w][tid];
             }
-            const uint32_t key = min(tot, (uint32_t)FOLD_KEYS - 1u);
-            uint32_t kidx = 0;
-            if (!ident)
-                kidx = atomicAdd(&s.kh[key], 1u);  // complete at the barrier below
             // exclusive prefix of the cell counts: warp scan, one barrier, then the earlier warps' totals
             uint32_t inc = tot;
 #pragma unroll
@@ -1048,35 +995,15 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= (uint32_t)o) inc += u;
             }
-            if (lane == 31) s.w[warp] = inc;
+            if (lane == 31) s_w[warp] = inc;
             __syncthreads();
             uint32_t cstart = inc - tot;
 #pragma unroll
             for (int w = 0; w < FOLD_NW; ++w)
-                if (w < (int)warp) cstart += s.w[w];
+                if (w < (int)warp) cstart += s_w[w];
 #pragma unroll
             for (int w = 0; w < FOLD_NW; ++w)
-                s.cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
-            s.k0[tid] = (uint16_t)cstart;
-            s.k1[tid] = (uint16_t)(cstart + tot);
-            if (!ident)
-            {
-                // every warp ranks the keys itself: exclusive prefix of the key histogram in DESCENDING key
-                // order, two keys per lane (lane L: keys 63-2L and 62-2L), looked up with a shuffle
-                const uint32_t v0 = s.kh[FOLD_KEYS - 1 - 2 * lane], v1 = s.kh[FOLD_KEYS - 2 - 2 * lane];
-                uint32_t kin = v0 + v1;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1)
-                {
-                    const uint32_t u = __shfl_up_sync(0xffffffffu, kin, o);
-                    if (lane >= (uint32_t)o) kin += u;
-                }
-                const uint32_t ex0 = kin - (v0 + v1), ex1 = ex0 + v0;
-                const uint32_t src = (FOLD_KEYS - 1 - key) >> 1;
-                const uint32_t b0 = __shfl_sync(0xffffffffu, ex0, src), b1 = __shfl_sync(0xffffffffu, ex1, src);
-                const uint32_t kbase = ((FOLD_KEYS - 1 - key) & 1u) ? b1 : b0;
-                s.perm[kbase + kidx] = (uint16_t)tid;  // order inside a key is irrelevant
-            }
+                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
             __syncthreads();
             // stable placement: position = next slot of (warp, cell) + rank inside the warp round
 #pragma unroll
@@ -1088,110 +1015,72 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                     const uint32_t c = cm[r], m = mm[r];
                     if (c < 256u)
                     {
-                        const uint32_t off = s.cnt[warp][c];
-                        const uint32_t slot = off + __popc(m & ((1u << lane) - 1u));
-                        s.ord[slot] = (uint16_t)i;
+                        const uint32_t slot = s_cnt[warp][c] + __popc(m & ((1u << lane) - 1u));
+                        s_ord[slot] = (uint16_t)i;
                         __syncwarp(m);
                         if ((m >> lane) == 1u)  // highest lane of the group: its slot + 1 is the group's end
-                            s.cnt[warp][c] = (uint16_t)(slot + 1u);
+                            s_cnt[warp][c] = (uint16_t)(slot + 1u);
                     }
                     __syncwarp();
                 }
             }
             __syncthreads();
-
-            // walk: this thread's cell of the chunk, its records in (op, point) order.  A new (op, cell) segment
-            // restarts the sums through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both
-            // exactly), so the accumulators are updated in place and only the fold itself is a divergent block.
-            const uint32_t c = ident ? tid : (uint32_t)s.perm[tid];
-            const uint32_t k0 = s.k0[c], k1 = s.k1[c];
-            const bool close = !carry_out;
-            if (k1 > k0 || (close && cur != 0xffffffffu))
+            // thread = cell: walk the cell's records in (op, point) order.  A new (op, cell) segment restarts the
+            // sums through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly), so the
+            // accumulators are updated in place and only the fold itself is a divergent block.
+            const uint32_t k0 = cstart, k1 = cstart + tot;
+            const uint32_t ord_base = (uint32_t)__cvta_generic_to_shared(s_ord), rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
+            for (uint32_t k = k0; k < k1; ++k)
             {
-                const int ci = bx * BIN + (int)(c & (BIN - 1)), cj = by * BIN + (int)(c >> BIN_SHIFT);
-                const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
-                const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
-                float rec[REC];
-                uint32_t fl = s.fl[c];
-                if (fl & F_LOADED)
+                const float4 p = lds_f4(rec_base + 16u * lds_u16(ord_base + 2u * k));
+                const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
+                const bool fresh = so != cur;
+                if (fresh)
                 {
-                    const float4 *src = reinterpret_cast<const float4 *>(s.cell[c]);
-                    const float4 a0 = src[0], a1 = src[1], a2 = src[2];
-                    rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
-                    rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
-                    rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
-                }
-                else
-                {
-                    const size_t cell = (size_t)(row0 + (int)(c >> BIN_SHIFT)) * g.W + (size_t)(col0 + (int)(c & (BIN - 1)));
-                    const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
-                    const float4 a0 = src[0], a1 = src[1], a2 = src[2];
-                    rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
-                    rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
-                    rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
-                    rec_to_zero_form(rec);
-                    fl |= F_LOADED;
-                }
-                for (uint32_t k = k0; k < k1; ++k)
-                {
-                    const float4 p = lds_f4(rec_base + 16u * lds_u16(ord_base + 2u * k));
-                    const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
-                    const bool fresh = so != cur;
-                    if (fresh)
+                    if (cur != 0xffffffffu)
                     {
-                        if (cur != 0xffffffffu)
-                            fold_acc(rec, acc, (cur >> 23) != 0, fl);
-                        cur = so;
+                        load_rec();
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
                     }
-                    const double keep = fresh ? 0.0 : 1.0;
-                    // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
-                    const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
-                    acc.n = fresh ? 1u : acc.n + 1u;
-                    acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
-                    acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
-                    acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
-                    acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
-                    acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
-                    acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
-                    acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
-                    acc.zmin = fminf(fresh ? CUDART_INF_F : acc.zmin, p.z);
-                    acc.zmax = fmaxf(fresh ? -CUDART_INF_F : acc.zmax, p.z);
+                    cur = so;
                 }
-                if (close && cur != 0xffffffffu)
-                {
-                    fold_acc(rec, acc, (cur >> 23) != 0, fl);
-                    cur = 0xffffffffu;
-                }
-                float4 *dst = reinterpret_cast<float4 *>(s.cell[c]);
-                dst[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-                dst[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-                dst[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-                s.fl[c] = (uint8_t)fl;
+                const double keep = fresh ? 0.0 : 1.0;
+                // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
+                const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
+                acc.n = fresh ? 1u : acc.n + 1u;
+                acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
+                acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
+                acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
+                acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
+                acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
+                acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
+                acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
+                acc.zmin = fminf(fresh ? CUDART_INF_F : acc.zmin, p.z);
+                acc.zmax = fmaxf(fresh ? -CUDART_INF_F : acc.zmax, p.z);
             }
             __syncthreads();
-            carry_in = carry_out;
         }
-
-        // thread = cell: write back what the batch changed
-        const uint32_t fl = s.fl[tid];
+        if (cur != 0xffffffffu)
+        {
+            load_rec();
+            fold_acc(rec, acc, (cur >> 23) != 0, fl);
+        }
         if (fl & F_TOUCHED)
         {
-            const size_t cell = (size_t)(row0 + (int)(tid >> BIN_SHIFT)) * g.W + (size_t)(col0 + (int)(tid & (BIN - 1)));
-            float4 a0, a1, a2;
-            {
-                const float4 *src = reinterpret_cast<const float4 *>(s.cell[tid]);
-                a0 = src[0]; a1 = src[1]; a2 = src[2];
-            }
-            const float nrec = a0.x;
-            if (nrec == 0.f)  // zero form of a blank cell -> NaN layers
-                a0 = a1 = a2 = make_float4(CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F, CUDART_NAN_F);
             float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
-            dstp[0] = a0; dstp[1] = a1; dstp[2] = a2;
+            if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
+            {
+#pragma unroll
+                for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+            }
+            dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
             // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
             uint8_t obs = 0;
-            if (nrec >= 1.f)
-                obs = (uint8_t)(F_OBSERVED | (lroundf(nrec) >= (long)b.min_points ? F_ENOUGH : 0));
-            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | (fl & (F_TOUCHED | F_CHANGED | F_BLANKED)) | obs);
+            if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
+                obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
+            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
             if (fl & F_BLANKED)
             {
                 const size_t pl = g.plane();
@@ -1362,7 +1251,6 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     {
         cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
         cudaFuncSetAttribute(k_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        cudaFuncSetAttribute(k_fold, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(FoldSmem));
         g_attr_set = true;
     }
     const uint32_t nb = b.btw * b.bth;
@@ -1395,7 +1283,7 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     if (!(phases & 2))
         return cudaGetLastError();
     const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm * 4u, nb);
-    k_fold<<<fold_blocks, FOLD_THREADS, sizeof(FoldSmem), st>>>(b, g, lat);
+    k_fold<<<fold_blocks, FOLD_THREADS, 0, st>>>(b, g, lat);
     if (ev) cudaEventRecord(ev[4], st);
     return cudaGetLastError();
 }
