@@ -208,19 +208,17 @@ def main():
     s, m = new_system()
     for i in range(n_kf):   # insert = H2D + prune, not timed here; keyframes are NOT binned until a pose arrives
         assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]) == tm.OK
-    npts = []
-    stage = {k: 0.0 for k in ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate", "ms_total")}
-    cells_classified = cells_touched = tiles = 0
-    batches0 = None
+    STAGES = ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate", "ms_total")
+    npts = [s.keyFramePoints(i + 1) for i in range(WINDOW + Wm, n_kf)]   # points of each timed step's new keyframe
     t_ms = 0.0
     sampler = ClockSampler(local)
-    launches0 = 0
+    st0 = None
     for i in range(n_kf):
         timed = i >= WINDOW + Wm
         if i == WINDOW + Wm:
             barrier()
             sampler.start()
-            launches0 = m.stats()["kernel_launches"]
+            st0 = m.stats()   # the library keeps running sums; they are read once before / after the timed steps
         with torch.cuda.stream(stream):
             if timed:
                 flush_buf.fill_(i & 0xFF)  # L2 flush between timed iterations (untimed)
@@ -229,24 +227,21 @@ def main():
                 e0.record(stream)
             s.updateKeyFrame(i + 1, poses[i])
             s.flush()
-            if timed:
-                st = m.stats()
-                npts.append(st["last_batch_points"])
-                for k in stage: stage[k] += st[k]
-                cells_classified += st["last_batch_cells_classified"]; cells_touched += st["last_batch_cells_touched"]
-                tiles += st["last_batch_tiles"]
             if i >= WINDOW:
-                s.deleteKeyFrame(i + 1 - WINDOW)
-                if timed:
-                    st = m.stats()
-                    for k in stage: stage[k] += st[k]
-                    cells_classified += st["last_batch_cells_classified"]; cells_touched += st["last_batch_cells_touched"]
-                    tiles += st["last_batch_tiles"]
+                s.deleteKeyFrame(i + 1 - WINDOW)   # synchronous: subtracts the evicted keyframe before returning
             if timed:
                 e1.record(stream)
                 e1.synchronize()
                 t_ms += e0.elapsed_time(e1)
                 sampler.sample()
+    st1 = m.stats()
+    stage = {k: st1["sum_" + k] - st0["sum_" + k] for k in STAGES}
+    cells_classified = st1["cells_classified"] - st0["cells_classified"]
+    cells_touched = st1["sum_cells_touched"] - st0["sum_cells_touched"]
+    tiles = st1["sum_tiles"] - st0["sum_tiles"]
+    launches0 = st0["kernel_launches"]
+    host = {k: (st1["sum_host_ms_" + k] - st0["sum_host_ms_" + k]) / K for k in ("plan", "launch", "wait", "batch")}
+    host["grid_reallocs_in_timed_steps"] = st1["grid_reallocs"] - st0["grid_reallocs"]
     barrier()
     clocks = sampler.stop()
     launches = m.stats()["kernel_launches"] - launches0
@@ -416,6 +411,7 @@ def main():
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[dom] / n_launch, "avg_launch_ms": stage[dom] / n_launch,
                     "stages_ms_per_step": {k: v / K for k, v in stage.items()},
+                    "host_ms_per_step": host,
                     "stages_frac_of_hbm": {k: (stage_bytes[k] / (stage[k] * 1e-3) / 1e9 / peak if stage[k] > 0 else None)
                                            for k in stage_bytes}}
         cpu = None

@@ -104,6 +104,12 @@ typedef struct tmap_stats
     uint64_t last_batch_points, last_batch_tiles, last_batch_cells_touched,
         last_batch_cells_classified;
     uint64_t last_batch_max_bin;   /* records in the heaviest 16x16 bin of the last batch */
+    /* running sums over all batches (same CUDA-event times; 0 unless params.profile) */
+    double sum_ms_hist, sum_ms_scan, sum_ms_scatter, sum_ms_fold, sum_ms_classify, sum_ms_inflate, sum_ms_total;
+    uint64_t sum_tiles, sum_cells_touched;
+    /* host wall-clock per batch, summed: op descriptors + buffers + the meta upload / kernel launches /
+     * waiting for the device (result copy + stream synchronize) / the whole batch */
+    double sum_host_ms_plan, sum_host_ms_launch, sum_host_ms_wait, sum_host_ms_batch;
 } tmap_stats;
 
 typedef struct tmap_system tmap_system;
@@ -186,6 +192,9 @@ int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t 
 /* LocalMap::getKeyFramesMap().size() and the work-queue depth (LocalMap.cpp:339-340) */
 int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out);
 int tmap_queue_depth(tmap_system *s, uint64_t map_id, size_t *n_out);
+/* KeyFrame::cloudBase().size() (KeyFrame.hpp:85): points of a keyframe's retained, pruned base-frame cloud
+ * (0 once dropped); TMAP_IGNORED_UNKNOWN_KF for an unknown id */
+int tmap_keyframe_points(tmap_system *s, uint64_t kf_id, size_t *n_out);
 /* LocalMap::getStitchedPointCloud without the voxel filter (LocalMap.cpp:416-437): pose * cloud
  * of every retained keyframe, packed xyz, ascending kf id.  out==NULL: count only. */
 int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t cap_points, size_t *n_out);

@@ -53,6 +53,11 @@ class Stats(C.Structure):
         ("last_batch_points", C.c_uint64), ("last_batch_tiles", C.c_uint64),
         ("last_batch_cells_touched", C.c_uint64), ("last_batch_cells_classified", C.c_uint64),
         ("last_batch_max_bin", C.c_uint64),
+        ("sum_ms_hist", C.c_double), ("sum_ms_scan", C.c_double), ("sum_ms_scatter", C.c_double), ("sum_ms_fold", C.c_double),
+        ("sum_ms_classify", C.c_double), ("sum_ms_inflate", C.c_double), ("sum_ms_total", C.c_double),
+        ("sum_tiles", C.c_uint64), ("sum_cells_touched", C.c_uint64),
+        ("sum_host_ms_plan", C.c_double), ("sum_host_ms_launch", C.c_double), ("sum_host_ms_wait", C.c_double),
+        ("sum_host_ms_batch", C.c_double),
     ]
 
 
@@ -95,6 +100,7 @@ _SIG = {
     "tmap_export_occupancy": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tmap_num_keyframes": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_queue_depth": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
+    "tmap_keyframe_points": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_stitched_cloud": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tmap_get_stats": (C.c_int, [_P, C.c_uint64, C.POINTER(Stats)]),
     "tmap_set_stream": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
@@ -347,6 +353,12 @@ class System:
 
     def deleteKeyFrame(self, kf_id):
         return _check(self._lib.tmap_delete_keyframe(self._h, int(kf_id)))
+
+    def keyFramePoints(self, kf_id):
+        """Points of the keyframe's retained, pruned base-frame cloud (KeyFrame::cloudBase().size())."""
+        n = C.c_size_t(0)
+        _check(self._lib.tmap_keyframe_points(self._h, int(kf_id), C.byref(n)))
+        return int(n.value)
 
     def updateKFMap(self, kf_id, map_id):
         return _check(self._lib.tmap_update_kf_map(self._h, int(kf_id), int(map_id)))

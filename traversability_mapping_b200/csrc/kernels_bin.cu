@@ -37,18 +37,22 @@ __device__ __forceinline__ void xform_rn(const float *__restrict__ T, float x, f
 }
 
 // Lattice::cellOf: (int)lround((x - x0)/res), round half away from zero, in double.
-// Fast path: multiply by 1/res (relative error <= 2^-52 against the true quotient) and round; that can only
-// disagree with the divided value when the quotient sits within that error of a rounding boundary k + 1/2,
-// so exactly those points (measure zero in practice) take the IEEE division.  Result == the reference's.
+// Fast path: multiply by 1/res (relative error <= 2^-52 against the true quotient) and round to nearest with the
+// 2^52 + 2^51 add/subtract (two FP64-pipe adds; the result's low word is the integer, so no conversion unit
+// is involved).  That can only disagree with the divided value when the quotient sits within the multiply's error
+// (< 5e-7 cells for |q| < 1e9) of a rounding boundary k + 1/2, so exactly those points -- and anything outside
+// the +-1e9 range, including NaN -- take the IEEE division.  Result == the reference's.
 __device__ __forceinline__ int cell_of(float xm, double x0, double res, double inv_res)
 {
+    const double MAGIC = 6755399441055744.0;       // 2^52 + 2^51
     const double d = __dsub_rn((double)xm, x0);
     const double q = __dmul_rn(d, inv_res);
-    const double r = rint(q);                      // nearest integer (ties to even): one instruction
+    const double t = __dadd_rn(q, MAGIC);
+    const double r = __dsub_rn(t, MAGIC);          // nearest integer (ties to even)
     const double f = fabs(__dsub_rn(q, r));        // distance to it, exact, <= 0.5
-    if (f >= 0.5 - (fabs(q) * 1e-15 + 1e-300))     // within the multiply's error of a k + 1/2 boundary (or a tie)
+    if (!(f < 0.499999) || !(fabs(q) < 1.0e9))
         return (int)llround(__ddiv_rn(d, res));    // the reference's own arithmetic, half away from zero
-    return __double2int_rn(r);                     // away from boundaries every rounding rule agrees
+    return __double2loint(t);                      // away from boundaries every rounding rule agrees
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
                 bad = true;
         }
         const uint32_t m = __match_any_sync(0xffffffffu, tile);
-        if (tile != 0xffffffffu && lane == (uint32_t)(__ffs(m) - 1))
+        if (tile != 0xffffffffu && (m >> lane) == 1u)  // the group's highest lane adds the group size
             atomicAdd(&s_hist[tile], __popc(m));
     }
 #pragma unroll
@@ -692,7 +696,7 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
 #pragma unroll
     for (int k = 0; k < 12; ++k) Tm[k] = s_op.T[k];
     float px[PPT], py[PPT], pz[PPT];
-    uint32_t tl[PPT], cc[PPT];
+    uint32_t tl[PPT], cc[PPT], mm[PPT];
     float4 pts[PPT];
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
@@ -719,9 +723,9 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
                 cc[r] = ((cj & (BIN - 1)) << BIN_SHIFT) | (ci & (BIN - 1));
             }
         }
-        const uint32_t m = __match_any_sync(0xffffffffu, tl[r]);
-        if (tl[r] != 0xffffffffu && lane == (uint32_t)(__ffs(m) - 1))
-            my[tl[r]] += (uint16_t)__popc(m);   // row `warp` is private to this warp
+        mm[r] = __match_any_sync(0xffffffffu, tl[r]);  // kept for the placement pass below
+        if (tl[r] != 0xffffffffu && (mm[r] >> lane) == 1u)
+            my[tl[r]] += (uint16_t)__popc(mm[r]);   // row `warp` is private to this warp
         __syncwarp();
     }
     __syncthreads();
@@ -744,16 +748,14 @@ __global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD l
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
-        const uint32_t m = __match_any_sync(0xffffffffu, tl[r]);
+        const uint32_t m = mm[r];
         if (tl[r] != 0xffffffffu)
         {
-            const uint32_t leader = __ffs(m) - 1;
-            const uint32_t off = my[tl[r]];
-            const uint32_t pos = s_base[tl[r]] + off + __popc(m & ((1u << lane) - 1u));
-            b.sorted[pos] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | ((opi + b.op_base) << 8) | cc[r]));
+            const uint32_t slot = my[tl[r]] + __popc(m & ((1u << lane) - 1u));
+            b.sorted[s_base[tl[r]] + slot] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | ((opi + b.op_base) << 8) | cc[r]));
             __syncwarp(m);
-            if (lane == leader)
-                my[tl[r]] = (uint16_t)(off + __popc(m));
+            if ((m >> lane) == 1u)  // highest lane of the group: its slot + 1 is the group's end
+                my[tl[r]] = (uint16_t)(slot + 1u);
         }
         __syncwarp();
     }

@@ -123,12 +123,15 @@ struct DeviceGrid
     int r = 0, R = 0;  // classify halo, inflation halo (0 = none)
     uint64_t reallocs = 0;
 
-    ~DeviceGrid() { release(); }
-    void release()
+    ~DeviceGrid() { release(nullptr); }
+    // The planes come from the device's stream-ordered pool (release threshold raised by System): growing the
+    // window costs no device-wide synchronisation and reuses pooled memory.  st == nullptr: synchronous free.
+    void release(cudaStream_t st)
     {
-        if (v.mom) cudaFree(v.mom);
-        if (v.der) cudaFree(v.der);
-        if (v.flags) cudaFree(v.flags);
+        float *ptrs[2] = {v.mom, v.der};
+        for (float *p : ptrs)
+            if (p) { if (st) cudaFreeAsync(p, st); else cudaFree(p); }
+        if (v.flags) { if (st) cudaFreeAsync(v.flags, st); else cudaFree(v.flags); }
         v = GridView{};
     }
     static void alloc_view(GridView &n, int tx0, int ty0, int tw, int th, cudaStream_t st)
@@ -138,9 +141,9 @@ struct DeviceGrid
         n.W = tw * TILE; n.H = th * TILE;
         n.ci0 = tx0 * TILE; n.cj0 = ty0 * TILE;
         const size_t pl = n.plane();
-        CK(cudaMalloc(&n.mom, pl * REC * sizeof(float)));
-        CK(cudaMalloc(&n.der, pl * NUM_DER * sizeof(float)));
-        CK(cudaMalloc(&n.flags, pl));
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&n.mom), pl * REC * sizeof(float), st));
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&n.der), pl * NUM_DER * sizeof(float), st));
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&n.flags), pl, st));
         CK(cudaMemsetAsync(n.mom, 0xFF, pl * REC * sizeof(float), st));   // all-ones = NaN
         CK(cudaMemsetAsync(n.der, 0xFF, pl * NUM_DER * sizeof(float), st));
         CK(cudaMemsetAsync(n.flags, 0, pl, st));
@@ -190,10 +193,17 @@ struct DeviceGrid
         if (v.mom && tx0 >= v.tx0 && ty0 >= v.ty0 && tx1 <= v.tx0 + v.tw && ty1 <= v.ty0 + v.th)
             return;
         int nx0 = tx0, ny0 = ty0, nx1 = tx1, ny1 = ty1;
-        if (v.mom)
+        if (!v.mom)
+        {
+            // first allocation: spare capacity on every side (a reallocation maps fresh device memory and copies
+            // the whole window -- milliseconds -- so a moving robot should not trigger one every few metres)
+            const int pad = std::min(16, std::max(4, std::max(tx1 - tx0, ty1 - ty0) / 2));
+            nx0 -= pad; ny0 -= pad; nx1 += pad; ny1 += pad;
+        }
+        else
         {
             // grow geometrically in the direction that is needed so repeated extension amortises
-            const int gx = std::max(4, v.tw / 4), gy = std::max(4, v.th / 4);
+            const int gx = std::max(8, v.tw / 2), gy = std::max(8, v.th / 2);
             if (tx0 < v.tx0) nx0 = std::min(tx0, v.tx0 - gx); else nx0 = v.tx0;
             if (ty0 < v.ty0) ny0 = std::min(ty0, v.ty0 - gy); else ny0 = v.ty0;
             if (tx1 > v.tx0 + v.tw) nx1 = std::max(tx1, v.tx0 + v.tw + gx); else nx1 = v.tx0 + v.tw;
@@ -210,8 +220,7 @@ struct DeviceGrid
                 CK(cudaMemcpy2DAsync(n.der + k * n.plane() + oy * n.W + ox, (size_t)n.W * 4, v.der + k * v.plane(),
                                      (size_t)v.W * 4, (size_t)v.W * 4, v.H, cudaMemcpyDeviceToDevice, st));
             CK(cudaMemcpy2DAsync(n.flags + oy * n.W + ox, n.W, v.flags, v.W, v.W, v.H, cudaMemcpyDeviceToDevice, st));
-            CK(cudaStreamSynchronize(st));
-            release();
+            release(st);  // stream-ordered: freed once the copies above have run
         }
         v = n;
         ++reallocs;
@@ -698,6 +707,7 @@ class LocalMap
     }
 
     // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
+    std::chrono::steady_clock::time_point t_planned_{};
     struct Plan
     {
         BatchView b{};
@@ -919,8 +929,10 @@ class LocalMap
         const uint32_t n_ops = pl.n_ops;
         const size_t res_bytes = 64 + (size_t)n_ops * sizeof(int4);
         resH_.ensure(res_bytes + 64);
+        const auto t_launched = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
+        const auto t_synced = std::chrono::steady_clock::now();
         const uint32_t *cnt = resH_.as<uint32_t>();
         if (cnt[3])
             throw CudaError("binning consistency check failed (flags " + std::to_string(cnt[3]) + ")");
@@ -933,6 +945,13 @@ class LocalMap
                 growLogical(bb[i].x, bb[i].y, bb[i].z, bb[i].w);
 
         stats_.host_ms_batch = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        if (t_planned_ >= t_begin)  // single-GPU batches (the sharded phases are timed by their caller)
+        {
+            stats_.sum_host_ms_plan += std::chrono::duration<double, std::milli>(t_planned_ - t_begin).count();
+            stats_.sum_host_ms_launch += std::chrono::duration<double, std::milli>(t_launched - t_planned_).count();
+            stats_.sum_host_ms_wait += std::chrono::duration<double, std::milli>(t_synced - t_launched).count();
+        }
+        stats_.sum_host_ms_batch += stats_.host_ms_batch;
         stats_.batches += 1;
         stats_.points_binned += pl.total_pts;
         stats_.cells_classified += cnt[7];
@@ -951,7 +970,12 @@ class LocalMap
             cudaEventElapsedTime(&t, ev_[4], ev_[5]); stats_.ms_classify = t;
             cudaEventElapsedTime(&t, ev_[5], ev_[6]); stats_.ms_inflate = t;
             cudaEventElapsedTime(&t, ev_[0], ev_[7]); stats_.ms_total = t;
+            stats_.sum_ms_hist += stats_.ms_hist; stats_.sum_ms_scan += stats_.ms_scan; stats_.sum_ms_scatter += stats_.ms_scatter;
+            stats_.sum_ms_fold += stats_.ms_fold; stats_.sum_ms_classify += stats_.ms_classify;
+            stats_.sum_ms_inflate += stats_.ms_inflate; stats_.sum_ms_total += stats_.ms_total;
         }
+        stats_.sum_tiles += cnt[10] + cnt[11];
+        stats_.sum_cells_touched += cnt[8];
     }
 
     // ---- one device pass over a list of ops (LocalMap::recomputeKeyFrame steps 1-4) ----
@@ -961,6 +985,7 @@ class LocalMap
         CK(cudaSetDevice(P_.device));
         Plan pl = planBatch(ops, nullptr, 0);
         uploadConstants();
+        t_planned_ = std::chrono::steady_clock::now();
         CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
         g_launches += ((size_t)pl.b.btw * pl.b.bth <= 4096) ? 5 : 7;  // hist, scan kernels, scatter, fold
         if (std::getenv("TMB_EXPERIMENT_ATOMIC_FOLD"))
@@ -1047,8 +1072,10 @@ class LocalMap
         g_launches += 7;
         const size_t res_bytes = 64 + n * sizeof(int4);
         resH_.ensure(res_bytes + 64);
+        const auto t_launched = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
         CK(cudaStreamSynchronize(stream_));
+        const auto t_synced = std::chrono::steady_clock::now();
         if (resH_.as<uint32_t>()[3])
             throw CudaError("binning consistency check failed");
         const BatchView &b = shardPlan_.b;
@@ -1418,6 +1445,14 @@ class System
         kfMap_.erase(rit);
         return TMAP_OK;
     }
+    int keyFramePoints(uint64_t kfID, size_t *n_out)  // KeyFrame.hpp:85
+    {
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto it = kfs_.find(kfID);
+        if (it == kfs_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+        *n_out = it->second->hasCloud ? (size_t)it->second->n : 0;
+        return TMAP_OK;
+    }
     int updateKFMap(uint64_t kfID, uint64_t mapID)  // System.cpp:250-276
     {
         std::lock_guard<std::recursive_mutex> l(m_);
@@ -1682,6 +1717,12 @@ int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t 
 int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) *n_out = mp->numKeyFrames(); return TMAP_OK; TMAP_API_END
+}
+int tmap_keyframe_points(tmap_system *s, uint64_t kf_id, size_t *n_out)
+{
+    NEED(s)
+    if (!n_out) { tmb::g_last_error = "null n_out"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN return s->sys->keyFramePoints(kf_id, n_out); TMAP_API_END
 }
 int tmap_queue_depth(tmap_system *s, uint64_t map_id, size_t *n_out)
 {
