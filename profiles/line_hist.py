@@ -22,7 +22,7 @@ for r in rows:
         iI = hdr.index("Instructions Executed"); iT = hdr.index("Thread Instructions Executed"); iS = hdr.index("# Samples")
     except ValueError:
         continue
-    if not r[iI].isdigit(): continue
+    if not (r[iI].isdigit() and r[iS].isdigit() and r[iT].isdigit()): continue
     ln = int(r[0]); inst[ln] += int(r[iI]); samp[ln] += int(r[iS]); thrd[ln] += int(r[iT]); src[ln] = r[1].strip()
 tot = sum(inst.values()) or 1; ts = sum(samp.values()) or 1
 print("total warp inst", tot, "samples", ts)

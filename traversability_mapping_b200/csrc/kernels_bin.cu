@@ -604,7 +604,7 @@ __global__ void __launch_bounds__(256) k_tile_starts(BatchView b, GridView g, in
 
 // the three kernels above in ONE single-CTA launch, for batches whose bbox has at most 4 096 bins (a
 // stream tick): saves two dependent launches on the latency-bound path
-__global__ void __launch_bounds__(1024) k_scan_small(BatchView b, GridView g, int dc, int di)
+__global__ void __launch_bounds__(1024) k_scan_small(BatchView b)
 {
     __shared__ uint32_t s_w[33];
     const uint32_t nb = (uint32_t)(b.btw * b.bth);
@@ -657,20 +657,33 @@ __global__ void __launch_bounds__(1024) k_scan_small(BatchView b, GridView g, in
         }
         ex += cnt[k];
     }
-    __syncthreads();  // every tile_count is visible to the neighbour tests below
-    emit_lists<4>(b, g, ii, cnt, ok, dc, di);
+    // the work lists are emitted by the first CTAs of k_scatter (emit_small_lists): one bin per thread there
+    // instead of four per thread of this single CTA
 }
 
 // ---------------------------------------------------------------------------------------------
 // k_scatter: stable bucket scatter by global bin.  Per-warp counter rows are u16 (a warp slice holds
 // at most 32*PPT <= 256 points); the absolute base of a bin lives in a separate u32 row.
 // ---------------------------------------------------------------------------------------------
-template <int PPT>
-__global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD lat)
+template <int PPT, bool EMIT>
+__global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD lat, GridView g, int dc, int di)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ OpDesc s_op;
     constexpr int NW = BIN_THREADS / 32;
+    if (EMIT)
+    {
+        // small batches (k_scan_small path): the fold / gate / inflate work lists, one bin per thread, spread
+        // over this kernel's CTAs (the bin counts are final since the previous launch)
+        const uint32_t nb = (uint32_t)(b.btw * b.bth);
+        for (uint32_t base = blockIdx.x * BIN_THREADS; base < nb; base += gridDim.x * BIN_THREADS)
+        {
+            const uint32_t ii[1] = {base + threadIdx.x};
+            const bool ok[1] = {ii[0] < nb};
+            const uint32_t vv[1] = {ok[0] ? b.tile_count[ii[0]] : 0u};
+            emit_lists<1>(b, g, ii, vv, ok, dc, di);
+        }
+    }
     const uint32_t chunk = blockIdx.x;
     const uint32_t opi = b.chunk_op[chunk];
     if (threadIdx.x < sizeof(OpDesc) / 4)
@@ -852,30 +865,75 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
     __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
     __shared__ uint16_t s_cnt[FOLD_NW][BIN_CELLS];            // per-warp cell counters       4 KB
     __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_ticket;
+    __shared__ uint32_t s_next[4];  // next work item: packed item, bucket start, bucket count, valid
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_active = b.counters[10] + b.counters[11];  // heavy items (front) + light bins (back)
+    const uint32_t n_heavy = b.counters[10];
+    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front) + light bins (back)
+    // Work items are handed out by a ticket counter (heavy bins first).  Thread 0 draws the NEXT ticket while the
+    // current bin is processed and resolves it in steps placed after later barriers (ticket -> item -> bucket
+    // start / count are three dependent global accesses), so a CTA does not sit idle on them between bins.
+    __shared__ uint32_t s_nx[5];  // thread 0's prefetch state: ticket, item, start, count, stage
+    auto next_step = [&](uint32_t upto)  // thread 0 only
+    {
+        if (s_nx[4] < 1 && upto >= 1)
+        {
+            const uint32_t t = s_nx[0];
+            uint32_t item = 0xffffffffu;  // invalid
+            if (t < n_active)
+                item = t < n_heavy ? b.active_tiles[t] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (t - n_heavy)];
+            s_nx[1] = item;
+            s_nx[4] = 1;
+        }
+        if (s_nx[4] < 2 && upto >= 2)
+        {
+            const uint32_t item = s_nx[1];
+            if (item != 0xffffffffu)
+            {
+                const uint32_t gtn = item & 0x00ffffffu;
+                s_nx[2] = b.tile_start[gtn];
+                s_nx[3] = b.tile_count[gtn];
+            }
+            s_nx[4] = 2;
+        }
+    };
+    auto publish_next = [&]()  // thread 0 only
+    {
+        next_step(2);
+        s_next[0] = s_nx[1]; s_next[1] = s_nx[2]; s_next[2] = s_nx[3]; s_next[3] = s_nx[1] != 0xffffffffu;
+    };
+    if (tid == 0)
+    {
+        s_nx[0] = atomicAdd(b.counters + 4, 1u);
+        s_nx[4] = 0;
+        publish_next();
+    }
+    __syncthreads();
     for (;;)
     {
-        if (tid == 0)
-            s_ticket = atomicAdd(b.counters + 4, 1u);
-        __syncthreads();
-        const uint32_t it = s_ticket;
-        __syncthreads();
-        if (it >= n_active)
+        const uint32_t item = s_next[0], start = s_next[1], cnt = s_next[2], valid = s_next[3];
+        __syncthreads();  // everyone holds the current item: s_next may be rewritten
+        if (!valid)
             break;
-        const uint32_t n_heavy = b.counters[10];
-        const uint32_t item = it < n_heavy ? b.active_tiles[it] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (it - n_heavy)];
+        if (tid == 0)
+        {
+            s_nx[0] = atomicAdd(b.counters + 4, 1u);  // its latency is covered by the staging of this bin
+            s_nx[4] = 0;
+        }
         const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
-        const uint32_t start = b.tile_start[gt], cnt = b.tile_count[gt];
         const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
         const int col = ci - g.ci0, row = cj - g.cj0;
         if (col < 0 || col >= g.W || row < 0 || row >= g.H)
         {
-            if (tid == 0) atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
-            continue;  // uniform: a bin is inside or outside as a whole (grid is 32-aligned)
+            // uniform: a bin is inside or outside as a whole (grid is 32-aligned)
+            if (tid == 0)
+            {
+                atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
+                publish_next();
+            }
+            __syncthreads();
+            continue;
         }
         const size_t cell = (size_t)row * g.W + col;
         // the cell's 48-byte record is fetched only if this batch actually touches the cell
@@ -981,6 +1039,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 }
             }
             __syncthreads();
+            if (tid == 0) next_step(1);
             // thread = cell: exclusive prefix over the warps' counts, then over cells
             uint32_t tot = 0, wc[FOLD_NW];
 #pragma unroll
@@ -1030,6 +1089,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             // thread = cell: walk the cell's records in (op, point) order.  A new (op, cell) segment restarts the
             // sums through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly), so the
             // accumulators are updated in place and only the fold itself is a divergent block.
+            if (tid == 0) next_step(2);
             const uint32_t k0 = cstart, k1 = cstart + tot;
             const uint32_t ord_base = (uint32_t)__cvta_generic_to_shared(s_ord), rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
             for (uint32_t k = k0; k < k1; ++k)
@@ -1090,7 +1150,9 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + cell] = CUDART_NAN_F;
             }
         }
-        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);
+        if (tid == 0)
+            publish_next();
+        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);  // also publishes s_next
         if (tid == 0 && nt)
             atomicAdd(b.counters + 8, nt);
     }
@@ -1251,8 +1313,10 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     // phases: bit0 = init + hist + scans + scatter, bit1 = fold
     if (!g_attr_set)
     {
-        cudaFuncSetAttribute(k_scatter<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        cudaFuncSetAttribute(k_scatter<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
+        cudaFuncSetAttribute(k_scatter<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
+        cudaFuncSetAttribute(k_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
+        cudaFuncSetAttribute(k_scatter<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
+        cudaFuncSetAttribute(k_scatter<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
         g_attr_set = true;
     }
     const uint32_t nb = b.btw * b.bth;
@@ -1268,7 +1332,7 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     if (ev) cudaEventRecord(ev[1], st);
     k_scan_chunks<<<dim3((maxT + 31) / 32, b.n_ops), 256, 0, st>>>(b);
     if (nb <= 4096)
-        k_scan_small<<<1, 1024, 0, st>>>(b, g, dc, di);
+        k_scan_small<<<1, 1024, 0, st>>>(b);
     else
     {
         k_scan_ops<<<nblk, 256, 0, st>>>(b);
@@ -1276,10 +1340,15 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
         k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
     }
     if (ev) cudaEventRecord(ev[2], st);
-    if (ppt == 2)
-        k_scatter<2><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
+    const bool emit = nb <= 4096;
+    if (ppt == 2 && emit)
+        k_scatter<2, true><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
+    else if (ppt == 2)
+        k_scatter<2, false><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
+    else if (emit)
+        k_scatter<8, true><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
     else
-        k_scatter<8><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat);
+        k_scatter<8, false><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
     if (ev) cudaEventRecord(ev[3], st);
     }
     if (!(phases & 2))
