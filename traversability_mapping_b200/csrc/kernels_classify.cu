@@ -204,21 +204,31 @@ __global__ void __launch_bounds__(GATE_THREADS) k_gate(const __grid_constant__ C
 
 struct ClsSmem
 {
-    size_t rec_bytes, flag_bytes, stage_bytes, inv_off, flag_off, total;
+    size_t rec_bytes, flag_bytes, stage_bytes, mom_off, inv_off, total;
     __host__ __device__ explicit ClsSmem(int r)
     {
         const size_t TW = BIN + 2 * r, ncell = TW * TW;
         rec_bytes = ncell * REC * 4;
         flag_bytes = TW * FLAG_BOX_W;
         stage_bytes = ((rec_bytes + 127) & ~(size_t)127) + ((flag_bytes + 127) & ~(size_t)127);
-        inv_off = 2 * stage_bytes;
-        flag_off = inv_off + ncell * 8;
-        total = flag_off + ((ncell + 127) & ~(size_t)127);
+        mom_off = stage_bytes;                 // double [ncell][10]: N, sx, sy, sz, sxx, syy, szz, sxy, sxz, syz
+        inv_off = mom_off + ncell * 10 * 8;    // double [ncell]: 1/N of observed cells, else 0
+        total = inv_off + ncell * 8;
     }
 };
 
-// Double-buffered: while bin i is classified, the halo tile (moment records, 3-D box) and flag bytes
-// (2-D box) of bin i+1 are already in flight on the other stage's mbarrier.
+// k_classify: fit of the cells k_gate marked (F_FIT), one 16x16 bin per iteration.
+//   1. the bin's halo tile of moment records (3-D TMA box) and flag bytes (2-D box) land in shared memory;
+//   2. pre-pass, once per halo cell: the ten float32 moments are widened to fp64 and 1/N is formed
+//      (MomentLayers::read, Helpers.cpp:101-112).  The conversion unit is 4x narrower than the FP64 pipe on
+//      sm_100 (profiles/ubench/pipes.cu) and every halo cell is read by |disc| query cells, so the widening
+//      does not sit in the footprint loops;
+//   3. the float staging area is free again: the NEXT bin's boxes are requested and arrive during step 4;
+//   4. pass A fuses the footprint about the query centre (fp64 only), covariance + smallest eigenpair,
+//      pass B the spread of the barycentres along the normal.
+// (A variant that replaced pass A's per-cell multiply-adds by differences of row prefix sums was measured and
+//  dropped: it halves the fp64 work but needs 30 shared-memory doubles per footprint row and two more barriers
+//  per bin, and came out 10-20 % slower.)
 __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant__ CUtensorMap tmap,
                                                              const __grid_constant__ CUtensorMap tmap_flags, BatchView b, GridView g,
                                                           const ClassifyParams c_cp)
@@ -231,144 +241,144 @@ __global__ void __launch_bounds__(CLS_THREADS) k_classify(const __grid_constant_
     const uint32_t rec_bytes = (uint32_t)ncell * REC * 4, flag_bytes = (uint32_t)TW * FLAG_BOX_W;
     const uint32_t rec_pad = (rec_bytes + 127u) & ~127u;
     const uint32_t stage_bytes = rec_pad + ((flag_bytes + 127u) & ~127u);
-    double *s_inv = reinterpret_cast<double *>(s_raw + 2 * stage_bytes);           // [TW*TW]
-    __shared__ __align__(8) uint64_t s_bar[2];
+    const float *s_rec = reinterpret_cast<const float *>(s_raw);
+    const uint8_t *s_fraw = s_raw + rec_pad;
+    double *s_mom = reinterpret_cast<double *>(s_raw + stage_bytes);                          // [ncell][10]
+    double *s_inv = reinterpret_cast<double *>(s_raw + stage_bytes + (size_t)ncell * 80);     // [ncell]
+    __shared__ __align__(8) uint64_t s_bar;
 
     const uint32_t tid = threadIdx.x;
     const uint32_t n_cand = b.counters[12];  // bins with at least one cell to fit (listed by k_gate)
     const size_t pl = g.plane();
+    const double rs = c_cp.res;
 
-    auto issue = [&](int stage, uint32_t it)  // thread 0 only
+    auto issue = [&](uint32_t it)  // thread 0 only
     {
         const uint32_t gt = b.fit_tiles[it];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
-        unsigned char *base = s_raw + (size_t)stage * stage_bytes;
-        mbar_arrive_expect_tx(&s_bar[stage], rec_bytes + flag_bytes);
-        tma_load_3d(base, &tmap, &s_bar[stage], 0, col0 - r, row0 - r);
-        tma_load_2d(base + rec_pad, &tmap_flags, &s_bar[stage], col0 - 16, row0 - r);
+        mbar_arrive_expect_tx(&s_bar, rec_bytes + flag_bytes);
+        tma_load_3d(s_raw, &tmap, &s_bar, 0, col0 - r, row0 - r);
+        tma_load_2d(s_raw + rec_pad, &tmap_flags, &s_bar, col0 - 16, row0 - r);
     };
 
     if (tid == 0)
     {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_bar, 1);
         fence_mbar_init();
     }
     __syncthreads();
-    // static round-robin over the candidate list (its order is already arbitrary): no ticket atomics and no
-    // barrier on them in the loop; the next bin's boxes are issued one iteration ahead
+    // static round-robin over the list (its order is arbitrary): no ticket atomics in the loop
     const uint32_t stride = gridDim.x;
     uint32_t cur = blockIdx.x;
     if (tid == 0 && cur < n_cand)
-        issue(0, cur);
-    int stage = 0;
-    uint32_t parity0 = 0, parity1 = 0;
+        issue(cur);
+    uint32_t parity = 0;
+    const int x = tid & (BIN - 1), y = tid >> BIN_SHIFT;
+    const int idx = (y + r) * TW + (x + r);
+    const int nd = c_cp.n_disc;
 
     while (cur < n_cand)
     {
         const uint32_t nxt = cur + stride;
-        __syncthreads();  // previous bin fully consumed: the other stage may be refilled
-        if (tid == 0 && nxt < n_cand)
-            issue(stage ^ 1, nxt);
-
         const uint32_t gt = b.fit_tiles[cur];
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const int col0 = bx * BIN - g.ci0, row0 = by * BIN - g.cj0;
-        const float *s_rec = reinterpret_cast<const float *>(s_raw + (size_t)stage * stage_bytes);
-        const uint8_t *s_fraw = s_raw + (size_t)stage * stage_bytes + rec_pad;
-        if (stage == 0) { mbar_wait(&s_bar[0], parity0); parity0 ^= 1; }
-        else { mbar_wait(&s_bar[1], parity1); parity1 ^= 1; }
+        mbar_wait(&s_bar, parity);
+        parity ^= 1;
 
-        // pre-pass: 1/N of every observed halo cell (MomentLayers::read, Helpers.cpp:101-112)
+        // ---- pre-pass: widen once, 1/N ----
         for (int i = tid; i < ncell; i += CLS_THREADS)
         {
-            const float n = s_rec[(size_t)i * REC + R_N];
-            s_inv[i] = (!isnan(n) && n >= 1.f) ? __drcp_rn((double)rintf(n)) : 0.0;
+            const float4 *p = reinterpret_cast<const float4 *>(s_rec + (size_t)i * REC);
+            const float4 a0 = p[0], a1 = p[1], a2 = p[2];
+            double *m = s_mom + (size_t)i * 10;
+            reinterpret_cast<double2 *>(m)[0] = make_double2((double)a0.x, (double)a0.y);  // N is integral by construction
+            reinterpret_cast<double2 *>(m)[1] = make_double2((double)a0.z, (double)a0.w);
+            reinterpret_cast<double2 *>(m)[2] = make_double2((double)a1.x, (double)a1.y);
+            reinterpret_cast<double2 *>(m)[3] = make_double2((double)a1.z, (double)a1.w);
+            reinterpret_cast<double2 *>(m)[4] = make_double2((double)a2.x, (double)a2.y);
+            s_inv[i] = (!isnan(a0.x) && a0.x >= 1.f) ? __drcp_rn((double)rintf(a0.x)) : 0.0;
         }
-        __syncthreads();
+        const bool fit = (s_fraw[(y + r) * FLAG_BOX_W + (x + 16)] & F_FIT) != 0;  // marked by k_gate
+        const double nq = (double)rintf(s_rec[(size_t)idx * REC + R_N]);
+        const double szq = (double)s_rec[(size_t)idx * REC + R_SZ];
+        __syncthreads();  // fp64 tile complete, float staging area consumed
+        if (tid == 0 && nxt < n_cand)
+            issue(nxt);   // arrives while this bin is fitted
+
+        if (fit)
         {
-            const int x = tid & (BIN - 1), y = tid >> BIN_SHIFT;
-            const int idx = (y + r) * TW + (x + r);
-            const int nd = c_cp.n_disc;
-            // k_gate marked the dirty cells whose whole footprint holds >= min_points (F_FIT)
-            if (s_fraw[(y + r) * FLAG_BOX_W + (x + 16)] & F_FIT)
+            const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
+            g.flags[cell] &= (uint8_t)~F_FIT;
+            // ---- pass A: fuse the disc about the query centre ----
+            double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
+            double Sx0 = 0, Sxi = 0, Sxj = 0, Sy0 = 0, Syi = 0, Syj = 0, Sz0 = 0, Szi = 0, Szj = 0;
+            double Qxx = 0, Qyy = 0, Qzz = 0, Qxy = 0, Qxz = 0, Qyz = 0;
+            for (int o = 0; o < nd; ++o)
             {
-                const size_t cell = (size_t)(row0 + y) * g.W + (col0 + x);
-                const float *rq = s_rec + (size_t)idx * REC;
-                const double nq = (double)rintf(rq[R_N]);
-                g.flags[cell] &= (uint8_t)~F_FIT;
-                {
-                    // ---- pass A: fuse the disc about the query centre ----
-                    double Nf = 0, Nx = 0, Ny = 0, Nxx = 0, Nyy = 0, Nxy = 0;
-                    double Sx0 = 0, Sxi = 0, Sxj = 0, Sy0 = 0, Syi = 0, Syj = 0, Sz0 = 0, Szi = 0, Szj = 0;
-                    double Qxx = 0, Qyy = 0, Qzz = 0, Qxy = 0, Qxz = 0, Qyz = 0;
-                    for (int o = 0; o < nd; ++o)
-                    {
-                        const int j = idx + c_disc_off[o];
-                        const float4 *p = reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
-                        const float4 a0 = p[0], a1 = p[1], a2 = p[2];
-                        const double2 d = c_disc_d[o];
-                        const double n = (double)a0.x;  // N is integral by construction
-                        const double sx = a0.y, sy = a0.z, sz = a0.w;
-                        const double ni = n * d.x, nj = n * d.y;
-                        Nf += n; Nx += ni; Ny += nj;
-                        Nxx = fma(ni, d.x, Nxx); Nyy = fma(nj, d.y, Nyy); Nxy = fma(ni, d.y, Nxy);
-                        Sx0 += sx; Sxi = fma(sx, d.x, Sxi); Sxj = fma(sx, d.y, Sxj);
-                        Sy0 += sy; Syi = fma(sy, d.x, Syi); Syj = fma(sy, d.y, Syj);
-                        Sz0 += sz; Szi = fma(sz, d.x, Szi); Szj = fma(sz, d.y, Szj);
-                        Qxx += (double)a1.x; Qyy += (double)a1.y; Qzz += (double)a1.z;
-                        Qxy += (double)a1.w; Qxz += (double)a2.x; Qyz += (double)a2.y;
-                    }
-                    const double rs = c_cp.res, rs2 = rs * rs;
-                    const double SX = fma(rs, Nx, Sx0), SY = fma(rs, Ny, Sy0), SZ = Sz0;
-                    const double QXX = Qxx + 2.0 * rs * Sxi + rs2 * Nxx;
-                    const double QYY = Qyy + 2.0 * rs * Syj + rs2 * Nyy;
-                    const double QZZ = Qzz;
-                    const double QXY = Qxy + rs * (Sxj + Syi) + rs2 * Nxy;
-                    const double QXZ = fma(rs, Szi, Qxz);
-                    const double QYZ = fma(rs, Szj, Qyz);
-                    const double inf = 1.0 / Nf;
-                    const double mx = SX * inf, my = SY * inf, mz = SZ * inf;
-                    const double cxx = QXX * inf - mx * mx, cyy = QYY * inf - my * my, czz = QZZ * inf - mz * mz;
-                    const double cxy = QXY * inf - mx * my, cxz = QXZ * inf - mx * mz, cyz = QYZ * inf - my * mz;
-                    double nv[3];
-                    const double lam0 = eig3_min(cxx, cxy, cxz, cyy, cyz, czz, nv);
-                    if (nv[2] < 0.0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
-                    // ---- pass B: spread of the per-cell barycentres along the normal ----
-                    double dmin = CUDART_INF, dmax = -CUDART_INF;
-                    for (int o = 0; o < nd; ++o)
-                    {
-                        const int j = idx + c_disc_off[o];
-                        const float4 a0 = *reinterpret_cast<const float4 *>(s_rec + (size_t)j * REC);
-                        const double2 d = c_disc_d[o];
-                        const double iv = s_inv[j];
-                        const double bx_ = fma((double)a0.y, iv, d.x * rs) - mx;
-                        const double by_ = fma((double)a0.z, iv, d.y * rs) - my;
-                        const double bz_ = (double)a0.w * iv - mz;
-                        const double dd = bx_ * nv[0] + by_ * nv[1] + bz_ * nv[2];
-                        dmin = fmin(dmin, dd);
-                        dmax = fmax(dmax, dd);
-                    }
-                    const double slope = acos(fmin(1.0, fabs(nv[2])));
-                    const double slope_h = fmin(slope / c_cp.max_slope, 1.0);
-                    const double rough_h = fmin(sqrt(fmax(0.0, lam0)) / c_cp.ground_clearance, 1.0);
-                    const double step_h = fmin((dmax - dmin) / c_cp.ground_clearance, 1.0);
-                    const double overall = fmax(slope_h, fmax(step_h, rough_h));
-                    g.der[D_ELEVATION * pl + cell] = (float)((double)rq[R_SZ] / nq);
-                    g.der[D_HAZARD * pl + cell] = (float)overall;
-                    g.der[D_SLOPE * pl + cell] = (float)slope_h;
-                    g.der[D_STEP * pl + cell] = (float)step_h;
-                    g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
-                    g.der[D_BORDER * pl + cell] = 1.0f;  // N_q >= min_points: min(N/min_points, 1) == 1
-                    g.der[D_NX * pl + cell] = (float)nv[0];
-                    g.der[D_NY * pl + cell] = (float)nv[1];
-                    g.der[D_NZ * pl + cell] = (float)nv[2];
-                }
+                const int j = idx + c_disc_off[o];
+                const double2 *m = reinterpret_cast<const double2 *>(s_mom + (size_t)j * 10);
+                const double2 m0 = m[0], m1 = m[1], m2 = m[2], m3 = m[3], m4 = m[4];
+                const double2 d = c_disc_d[o];
+                const double n = m0.x, sx = m0.y, sy = m1.x, sz = m1.y;
+                const double ni = n * d.x, nj = n * d.y;
+                Nf += n; Nx += ni; Ny += nj;
+                Nxx = fma(ni, d.x, Nxx); Nyy = fma(nj, d.y, Nyy); Nxy = fma(ni, d.y, Nxy);
+                Sx0 += sx; Sxi = fma(sx, d.x, Sxi); Sxj = fma(sx, d.y, Sxj);
+                Sy0 += sy; Syi = fma(sy, d.x, Syi); Syj = fma(sy, d.y, Syj);
+                Sz0 += sz; Szi = fma(sz, d.x, Szi); Szj = fma(sz, d.y, Szj);
+                Qxx += m2.x; Qyy += m2.y; Qzz += m3.x;
+                Qxy += m3.y; Qxz += m4.x; Qyz += m4.y;
             }
+            const double rs2 = rs * rs;
+            const double SX = fma(rs, Nx, Sx0), SY = fma(rs, Ny, Sy0), SZ = Sz0;
+            const double QXX = Qxx + 2.0 * rs * Sxi + rs2 * Nxx;
+            const double QYY = Qyy + 2.0 * rs * Syj + rs2 * Nyy;
+            const double QZZ = Qzz;
+            const double QXY = Qxy + rs * (Sxj + Syi) + rs2 * Nxy;
+            const double QXZ = fma(rs, Szi, Qxz);
+            const double QYZ = fma(rs, Szj, Qyz);
+            const double inf = 1.0 / Nf;
+            const double mx = SX * inf, my = SY * inf, mz = SZ * inf;
+            const double cxx = QXX * inf - mx * mx, cyy = QYY * inf - my * my, czz = QZZ * inf - mz * mz;
+            const double cxy = QXY * inf - mx * my, cxz = QXZ * inf - mx * mz, cyz = QYZ * inf - my * mz;
+            double nv[3];
+            const double lam0 = eig3_min(cxx, cxy, cxz, cyy, cyz, czz, nv);
+            if (nv[2] < 0.0) { nv[0] = -nv[0]; nv[1] = -nv[1]; nv[2] = -nv[2]; }
+            // ---- pass B: spread of the per-cell barycentres along the normal.  The barycentre of cell j about the
+            // query centre is (d.x*rs + sx/N, d.y*rs + sy/N, sz/N); the footprint mean is a common offset of every
+            // projection and cancels in max - min. ----
+            double dmin = CUDART_INF, dmax = -CUDART_INF;
+            const double rnx = rs * nv[0], rny = rs * nv[1];
+            for (int o = 0; o < nd; ++o)
+            {
+                const int j = idx + c_disc_off[o];
+                const double2 *m = reinterpret_cast<const double2 *>(s_mom + (size_t)j * 10);
+                const double2 m0 = m[0], m1 = m[1];
+                const double2 d = c_disc_d[o];
+                const double within = fma(m0.y, nv[0], fma(m1.x, nv[1], m1.y * nv[2])) * s_inv[j];
+                const double dd = fma(d.x, rnx, fma(d.y, rny, within));
+                dmin = fmin(dmin, dd);
+                dmax = fmax(dmax, dd);
+            }
+            const double slope = acos(fmin(1.0, fabs(nv[2])));
+            const double slope_h = fmin(slope / c_cp.max_slope, 1.0);
+            const double rough_h = fmin(sqrt(fmax(0.0, lam0)) / c_cp.ground_clearance, 1.0);
+            const double step_h = fmin((dmax - dmin) / c_cp.ground_clearance, 1.0);
+            const double overall = fmax(slope_h, fmax(step_h, rough_h));
+            g.der[D_ELEVATION * pl + cell] = (float)(szq / nq);
+            g.der[D_HAZARD * pl + cell] = (float)overall;
+            g.der[D_SLOPE * pl + cell] = (float)slope_h;
+            g.der[D_STEP * pl + cell] = (float)step_h;
+            g.der[D_ROUGHNESS * pl + cell] = (float)rough_h;
+            g.der[D_BORDER * pl + cell] = 1.0f;  // N_q >= min_points: min(N/min_points, 1) == 1
+            g.der[D_NX * pl + cell] = (float)nv[0];
+            g.der[D_NY * pl + cell] = (float)nv[1];
+            g.der[D_NZ * pl + cell] = (float)nv[2];
         }
+        __syncthreads();  // fp64 tile consumed before the next pre-pass overwrites it
         cur = nxt;
-        stage ^= 1;
     }
 }
 
@@ -489,21 +499,27 @@ __global__ void __launch_bounds__(INF_THREADS) k_inflate(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < TILE_CELLS / INF_THREADS; ++k)
         {
-            if (!(nobs[k] >= 1.f))
-                continue;  // observed cells only (LocalMap.cpp:220-221)
             const int q = tid + k * INF_THREADS;
             const int x = q & 31, y = q >> 5;
+            // any seed inside the (2R+1)^2 box of a cell?  A warp owns one tile row (INF_THREADS == 32 x 32), so
+            // the OR of that row's KW halo-row masks is formed once per warp (two warp reductions, all lanes
+            // take part) and each cell only tests its KW-bit window of it.
+            unsigned long long seeds = ~0ull;
+            if (have_seed && use_masks)
+            {
+                const uint32_t lane = tid & 31;
+                unsigned long long rm = (int)lane < KW ? s_seedrow[y + lane] : 0ull;
+                if (KW > 32 && lane == 0) rm |= s_seedrow[y + 32];  // KW <= 33 here
+                const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)rm);
+                const uint32_t hi = __reduce_or_sync(0xffffffffu, (uint32_t)(rm >> 32));
+                const unsigned long long km = (1ull << KW) - 1ull;
+                seeds = ((((unsigned long long)hi << 32) | lo) >> x) & km;
+            }
+            if (!(nobs[k] >= 1.f))
+                continue;  // observed cells only (LocalMap.cpp:220-221)
             float best = 0.f;
             if (have_seed)
             {
-                // any seed inside the (2R+1)^2 box of this cell?  KW bits of each of the KW row masks
-                unsigned long long seeds = use_masks ? 0ull : ~0ull;
-                if (use_masks)
-                {
-                    const unsigned long long km = (1ull << KW) - 1ull;  // KW <= 33 here
-                    for (int dj = 0; dj < KW; ++dj)
-                        seeds |= (s_seedrow[y + dj] >> x) & km;
-                }
                 if (seeds != 0ull)
                 {
                     const int base = (y + R) * TW + (x + R);

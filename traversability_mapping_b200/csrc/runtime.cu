@@ -319,7 +319,7 @@ class LocalMap
                               std::to_string(MAX_DISC) + ")");
         r_ = 0;
         for (auto &o : disc_) r_ = std::max(r_, std::max(std::abs(o.first), std::abs(o.second)));
-        if (classify_smem_bytes(r_) > 200 * 1024 || r_ > 8)
+        if (classify_smem_bytes(r_) > 226 * 1024 || r_ > 8)
             throw Unsupported("footprint radius of " + std::to_string(r_) + " cells exceeds the classifier's 32-column halo-row limit (r <= 8)");
         R_ = 0;
         if (P.inflation_enabled)
