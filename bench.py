@@ -208,7 +208,7 @@ def main():
     s, m = new_system()
     for i in range(n_kf):   # insert = H2D + prune, not timed here; keyframes are NOT binned until a pose arrives
         assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]) == tm.OK
-    STAGES = ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate", "ms_total")
+    STAGES = ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_gate", "ms_classify", "ms_inflate", "ms_total")
     npts = [s.keyFramePoints(i + 1) for i in range(WINDOW + Wm, n_kf)]   # points of each timed step's new keyframe
     t_ms = 0.0
     sampler = ClockSampler(local)
@@ -239,6 +239,10 @@ def main():
     cells_classified = st1["cells_classified"] - st0["cells_classified"]
     cells_touched = st1["sum_cells_touched"] - st0["sum_cells_touched"]
     tiles = st1["sum_tiles"] - st0["sum_tiles"]
+    infl_tiles = st1["sum_infl_tiles"] - st0["sum_infl_tiles"]
+    cand_bins = st1["sum_cand_bins"] - st0["sum_cand_bins"]
+    pts_binned = st1["points_binned"] - st0["points_binned"]   # new + evicted keyframe both pass through the kernels
+    stage["ms_classify"] -= stage["ms_gate"]                    # the library's classify stage = k_gate + k_classify
     launches0 = st0["kernel_launches"]
     host = {k: (st1["sum_host_ms_" + k] - st0["sum_host_ms_" + k]) / K for k in ("plan", "launch", "wait", "batch")}
     host["grid_reallocs_in_timed_steps"] = st1["grid_reallocs"] - st0["grid_reallocs"]
@@ -335,7 +339,8 @@ def main():
             lc = {"keyframes": nk, "points": int(st["last_batch_points"]), "ms": float(min(times[1:])), "ms_all": times, "n_gpus": 1,
                   "mode": "informLoopClosure + batched worker pass (max_batch=0)",
                   "pgo_update_ms": float(min(pgo[1:])), "pgo_update_ms_all": pgo,
-                  "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]), "config": cfg}
+                  "stages_ms": {k: st[k] for k in stage}, "cells_classified": int(st["last_batch_cells_classified"]),
+                  "cells_touched": int(st["last_batch_cells_touched"]), "config": cfg}
             s.close()
         else:
             # the global map sharded over the ranks: contiguous keyframe-id blocks per rank, all-to-all point
@@ -385,35 +390,46 @@ def main():
 
     if rank == 0:
         peak, peak_src = peaks()
-        # algorithmic bytes per stage: bin = 16 B/point (float4 store) + 80 B per touched cell;
-        # classify = 76 B per recomputed cell (+8 with inflation, booked on the inflate stage)
+        # algorithmic bytes per kernel: bin = 16 B/point read (hist), 16 + 16 B/point (scatter),
+        # 16 B/record + 80 B per touched cell (fold); classify = 76 B per recomputed cell; gate = flag byte in / out
+        # of every cell of a candidate bin; inflate = step_haz in + inflated out (+ flag) of every cell of a listed tile
         stage_bytes = {
-            "ms_hist": 16.0 * (pts_total * 2),      # new + evicted keyframe both pass through the kernels
-            "ms_scatter": 32.0 * (pts_total * 2),
-            "ms_fold": 16.0 * (pts_total * 2) + 80.0 * cells_touched,
+            "ms_hist": 16.0 * pts_binned,
+            "ms_scatter": 32.0 * pts_binned,
+            "ms_fold": 16.0 * pts_binned + 80.0 * cells_touched,
+            "ms_gate": 2.0 * 256 * cand_bins,
             "ms_classify": 76.0 * cells_classified,
-            "ms_inflate": 8.0 * tiles * 1024,
+            "ms_inflate": 9.0 * infl_tiles * 1024,
         }
-        dom = max(("ms_hist", "ms_scatter", "ms_fold", "ms_classify", "ms_inflate"), key=lambda k: stage[k])
-        n_launch = 2 * K - 0  # one update batch + one eviction batch per step
+        kname = {"ms_hist": "k_hist<2>", "ms_scatter": "k_scatter<2>", "ms_fold": "k_fold", "ms_gate": "k_gate",
+                 "ms_classify": "k_classify", "ms_inflate": "k_inflate"}
+        dom = max(kname, key=lambda k: stage[k])
+        n_launch = 2 * K  # one update batch + one eviction batch per step, each launches every kernel once
         achieved = stage_bytes[dom] / (stage[dom] * 1e-3) / 1e9 if stage[dom] > 0 else 0.0
         # measured DRAM traffic per launch of that kernel, from the committed ncu capture of this same workload
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["c2_stream"]
-            key = {"ms_hist": "k_hist<2>", "ms_scatter": "k_scatter<2>", "ms_fold": "k_fold", "ms_classify": "k_classify",
-                   "ms_inflate": "k_inflate"}[dom]
-            traffic = tj[key]["dram_bytes_per_launch"]
+            traffic = tj[kname[dom]]["dram_bytes_per_launch"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": dom.replace("ms_", "k_"), "achieved": achieved, "peak": peak, "unit": "GB/s",
+        roofline = {"bound": "hbm", "kernel": kname[dom], "achieved": achieved, "peak": peak, "unit": "GB/s",
                     "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/r01_traffic.json (ncu --set full)",
                     "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": stage_bytes[dom] / n_launch, "avg_launch_ms": stage[dom] / n_launch,
+                    "note": "a 73 k-point stream tick keeps every kernel latency-bound (tens of microseconds per launch); "
+                            "the same kernels at loop-closure scale are in loop_closure.stages_frac_of_hbm",
                     "stages_ms_per_step": {k: v / K for k, v in stage.items()},
                     "host_ms_per_step": host,
                     "stages_frac_of_hbm": {k: (stage_bytes[k] / (stage[k] * 1e-3) / 1e9 / peak if stage[k] > 0 else None)
                                            for k in stage_bytes}}
+        if lc and "stages_ms" in lc:
+            # the same kernels with a full machine's worth of work: fraction of the measured copy peak per kernel
+            sm_, P_ = lc["stages_ms"], float(lc["points"])
+            lb = {"ms_hist": 16.0 * P_, "ms_scatter": 32.0 * P_, "ms_fold": 16.0 * P_ + 80.0 * lc["cells_touched"],
+                  "ms_classify": 76.0 * lc["cells_classified"]}
+            lc["stages_frac_of_hbm"] = {k: (lb[k] / ((sm_[k] - (sm_["ms_gate"] if k == "ms_classify" else 0.0)) * 1e-3) / 1e9 / peak
+                                            if sm_[k] > 0 else None) for k in lb}
         cpu = None
         if not args.no_cpu:
             sec, cpts = oracle_steps(poses, clouds, WINDOW + Wm, min(K, 3))

@@ -110,6 +110,11 @@ typedef struct tmap_stats
     /* host wall-clock per batch, summed: op descriptors + buffers + the meta upload / kernel launches /
      * waiting for the device (result copy + stream synchronize) / the whole batch */
     double sum_host_ms_plan, sum_host_ms_launch, sum_host_ms_wait, sum_host_ms_batch;
+    /* the classify stage is two kernels: ms_gate is k_gate's share of ms_classify (last batch / running sum) */
+    double sum_ms_gate;
+    float ms_gate, reserved0;
+    uint64_t sum_infl_tiles;       /* 32x32 tiles handed to k_inflate */
+    uint64_t sum_cand_bins;        /* 16x16 bins handed to k_gate */
 } tmap_stats;
 
 typedef struct tmap_system tmap_system;

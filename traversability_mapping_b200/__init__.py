@@ -58,6 +58,8 @@ class Stats(C.Structure):
         ("sum_tiles", C.c_uint64), ("sum_cells_touched", C.c_uint64),
         ("sum_host_ms_plan", C.c_double), ("sum_host_ms_launch", C.c_double), ("sum_host_ms_wait", C.c_double),
         ("sum_host_ms_batch", C.c_double),
+        ("sum_ms_gate", C.c_double), ("ms_gate", C.c_float), ("reserved0", C.c_float),
+        ("sum_infl_tiles", C.c_uint64), ("sum_cand_bins", C.c_uint64),
     ]
 
 
@@ -279,7 +281,7 @@ class LocalMap:
     def stats(self):
         st = Stats()
         _check(self._s._lib.tmap_get_stats(self._s._h, self.map_id, C.byref(st)))
-        return {f: getattr(st, f) for f, _ in Stats._fields_ if f != "reserved"}
+        return {f: getattr(st, f) for f, _ in Stats._fields_ if not f.startswith("reserved")}
 
     def setStream(self, cuda_stream_ptr):
         _check(self._s._lib.tmap_set_stream(self._s._h, self.map_id, C.c_void_p(cuda_stream_ptr or 0)))

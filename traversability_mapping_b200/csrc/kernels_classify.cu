@@ -686,7 +686,7 @@ cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d 
 }
 
 cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUtensorMap &tmap_flags, const BatchView &b, const GridView &g,
-                            const ClassifyParams &cp, int n_sm)
+                            const ClassifyParams &cp, int n_sm, cudaEvent_t ev_after_gate)
 {
     static int attr_r = -1;
     const int r = cp.r;
@@ -698,7 +698,10 @@ cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUte
     }
     const size_t nb = (size_t)b.btw * b.bth;
     // gate pass over every candidate bin (flag bytes only), then the TMA-staged fit over the bins it listed
-    k_gate<<<(int)min((size_t)(8 * n_sm), nb), GATE_THREADS, 0, st>>>(tmap_flags, b, g, cp);
+    int ggate = 6;  // measured flat between 4 and 8 CTAs per SM
+    if (const char *e = getenv("TMB_GATE_GRID")) ggate = atoi(e);
+    k_gate<<<(int)min((size_t)(ggate * n_sm), nb), GATE_THREADS, 0, st>>>(tmap_flags, b, g, cp);
+    if (ev_after_gate) cudaEventRecord(ev_after_gate, st);
     int gmul = 6;  // measured: 4-8 CTAs of work per SM level the per-bin imbalance best
     if (const char *e = getenv("TMB_CLS_GRID")) gmul = atoi(e);
     const int n_blocks = (int)min((size_t)(gmul * n_sm), nb);

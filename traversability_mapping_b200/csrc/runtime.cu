@@ -912,7 +912,7 @@ class LocalMap
         const BatchView &b = pl.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const bool prof = P_.profile != 0;
-        CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_));
+        CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_, prof ? ev_[8] : nullptr));
         g_launches += 2;  // k_gate + k_classify
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0)
@@ -968,12 +968,15 @@ class LocalMap
             cudaEventElapsedTime(&t, ev_[2], ev_[3]); stats_.ms_scatter = t;
             cudaEventElapsedTime(&t, ev_[3], ev_[4]); stats_.ms_fold = t;
             cudaEventElapsedTime(&t, ev_[4], ev_[5]); stats_.ms_classify = t;
+            cudaEventElapsedTime(&t, ev_[4], ev_[8]); stats_.ms_gate = t; stats_.sum_ms_gate += t;
             cudaEventElapsedTime(&t, ev_[5], ev_[6]); stats_.ms_inflate = t;
             cudaEventElapsedTime(&t, ev_[0], ev_[7]); stats_.ms_total = t;
             stats_.sum_ms_hist += stats_.ms_hist; stats_.sum_ms_scan += stats_.ms_scan; stats_.sum_ms_scatter += stats_.ms_scatter;
             stats_.sum_ms_fold += stats_.ms_fold; stats_.sum_ms_classify += stats_.ms_classify;
             stats_.sum_ms_inflate += stats_.ms_inflate; stats_.sum_ms_total += stats_.ms_total;
         }
+        stats_.sum_infl_tiles += cnt[2];
+        stats_.sum_cand_bins += cnt[1];
         stats_.sum_tiles += cnt[10] + cnt[11];
         stats_.sum_cells_touched += cnt[8];
     }
@@ -1212,7 +1215,7 @@ class LocalMap
     std::recursive_mutex gridMutex_;  // masterGridMapMutex_
     DeviceGrid grid_;
     cudaStream_t stream_ = nullptr, ownStream_ = nullptr;
-    cudaEvent_t ev_[8];
+    cudaEvent_t ev_[9];  // [8]: between k_gate and k_classify
     tmap_stats stats_{};
 
     std::mutex kfMutex_;  // keyFramesMapMutex_

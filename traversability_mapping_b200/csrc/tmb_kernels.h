@@ -21,7 +21,7 @@ size_t classify_smem_bytes(int r);
 size_t inflate_smem_bytes(int R, int n_taps);
 cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d, int n_disc);
 cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUtensorMap &tmap_flags, const BatchView &b, const GridView &g,
-                            const ClassifyParams &cp, int n_blocks);
+                            const ClassifyParams &cp, int n_blocks, cudaEvent_t ev_after_gate = nullptr);
 cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const GridView &g, int n_blocks);
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
                            const ClassifyParams &cp, const void *d_taps, int n_blocks);
