@@ -492,3 +492,36 @@ def test_degenerate_inputs(tmap, oracle):
         s2 = tmap.System(tmap.default_params(resolution=0.01, robot_radius=0.5))
         s2.addNewLocalMap(0)
     assert e.value.code == tmap.ERR_UNSUPPORTED
+
+
+def test_keyframe_points_and_running_stats(tmap, oracle):
+    """tmap_keyframe_points == the oracle's pruned cloud size; the running sums in tmap_stats add up the
+    per-batch values (bench.py reads them once around its timed steps)."""
+    from traversability_mapping_b200 import synth
+    P = synth.trajectory("single", 1, seed=4)[0]
+    cloud = synth.make_keyframe(4, 0, P, max_range=8.0, rings=32, azimuths=512)
+    s = tmap.System(tmap.default_params(resolution=0.1, max_range=6.0, min_range=1.0, profile=1))
+    s.addNewLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om = oracle.OracleMap(oracle.params_from(tmap.default_params(resolution=0.1, max_range=6.0, min_range=1.0)))
+    want = om.prune(cloud, synth.T_BASE_SENSOR, 6.0, 1.0)
+    assert s.addNewKeyFrameWithPCL(1, 1, 0, cloud) == tmap.OK
+    assert s.keyFramePoints(1) == len(want)
+    assert s.keyFramePoints(99) is None   # unknown id: ignored, not an error
+    m = s.getLocalMap(0)
+    tot = {k: 0.0 for k in ("ms_hist", "ms_fold", "ms_classify", "ms_gate", "ms_total")}
+    touched = 0
+    for k in range(3):
+        Pk = P.copy(); Pk[0, 3] += 0.7 * k
+        s.updateKeyFrame(1, Pk); s.flush()
+        st = m.stats()
+        for key in tot: tot[key] += st[key]
+        touched += st["last_batch_cells_touched"]
+    st = m.stats()
+    assert st["batches"] == 3 and st["points_binned"] == len(want) * 5   # add, then (subtract + add) twice
+    for key in tot:
+        assert abs(st["sum_" + key] - tot[key]) < 1e-4 * max(1.0, tot[key]), key
+    assert 0.0 < st["ms_gate"] <= st["ms_classify"]
+    assert st["sum_cells_touched"] == touched and st["sum_cand_bins"] > 0
+    assert st["sum_host_ms_batch"] >= st["sum_host_ms_wait"] > 0.0
+    s.close()

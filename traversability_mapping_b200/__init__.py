@@ -359,8 +359,8 @@ class System:
     def keyFramePoints(self, kf_id):
         """Points of the keyframe's retained, pruned base-frame cloud (KeyFrame::cloudBase().size())."""
         n = C.c_size_t(0)
-        _check(self._lib.tmap_keyframe_points(self._h, int(kf_id), C.byref(n)))
-        return int(n.value)
+        rc = _check(self._lib.tmap_keyframe_points(self._h, int(kf_id), C.byref(n)))
+        return None if rc == IGNORED_UNKNOWN_KF else int(n.value)
 
     def updateKFMap(self, kf_id, map_id):
         return _check(self._lib.tmap_update_kf_map(self._h, int(kf_id), int(map_id)))
