@@ -401,7 +401,7 @@ def main():
             "ms_classify": 76.0 * cells_classified,
             "ms_inflate": 9.0 * infl_tiles * 1024,
         }
-        kname = {"ms_hist": "k_hist<2>", "ms_scatter": "k_scatter<2>", "ms_fold": "k_fold", "ms_gate": "k_gate",
+        kname = {"ms_hist": "k_hist<2>", "ms_scatter": "k_scatter<2, 1>", "ms_fold": "k_fold", "ms_gate": "k_gate",
                  "ms_classify": "k_classify", "ms_inflate": "k_inflate"}
         dom = max(kname, key=lambda k: stage[k])
         n_launch = 2 * K  # one update batch + one eviction batch per step, each launches every kernel once
