@@ -161,6 +161,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-lc", action="store_true", help="skip the loop-closure leg")
     ap.add_argument("--lc-keyframes", type=int, default=2000)
+    ap.add_argument("--lc-extent", type=float, default=90.0, help="loop-closure trajectory inside +-extent metres")
+    ap.add_argument("--lc-resolution", type=float, default=0.1, help="loop-closure grid resolution, metres")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -289,10 +291,12 @@ def main():
     if not args.no_lc:
         nk = args.lc_keyframes
         base = 32
-        lposes = synth.trajectory("loop", nk, seed=SEED + 1, extent=90.0)
+        lposes = synth.trajectory("loop", nk, seed=SEED + 1, extent=args.lc_extent)
         drift = synth.drift_poses(lposes)
-        LCP = dict(resolution=0.1, half_size=100.0, max_range=20.0, min_range=1.0, robot_radius=0.20)
-        cfg = "C4-shaped: %d stored keyframes on a 180 m loop, 0.1 m grid, 13-cell disc, drifted -> true poses" % nk
+        LCP = dict(resolution=args.lc_resolution, half_size=args.lc_extent + 10.0, max_range=20.0, min_range=1.0,
+                   robot_radius=2.0 * args.lc_resolution)
+        cfg = "C4-shaped: %d stored keyframes on a %.0f m loop, %.2f m grid, 13-cell disc, drifted -> true poses" % (
+            nk, 2 * args.lc_extent, args.lc_resolution)
         if world == 1:
             lclouds = [synth.make_keyframe(SEED + 1, i, lposes[i], max_range=20.0) for i in range(base)]
             p = tm.default_params(device=local, max_batch=0, profile=1, **LCP)

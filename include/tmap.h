@@ -228,6 +228,9 @@ typedef struct tmap_shard_buffers
 int tmap_shard_window(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12,
                       int32_t out_bins[4]);
 int tmap_shard_blank(tmap_system *s, uint64_t map_id);
+/* blank only cell rows [cj0, cj0 + n_rows) of the window (a rank's slab + halo: rows outside it are never read
+ * until a later rebuild owns -- and blanks -- them).  Rows outside the allocated window are ignored. */
+int tmap_shard_blank_rows(tmap_system *s, uint64_t map_id, int32_t cj0, int32_t n_rows);
 int tmap_shard_bin(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12, uint32_t op_base,
                    const int32_t bbox_bins[4], tmap_shard_buffers *out);
 int tmap_shard_fold(tmap_system *s, uint64_t map_id, const void *d_recv, uint64_t n_recv, const void *d_counts_all,

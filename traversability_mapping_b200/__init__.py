@@ -108,6 +108,7 @@ _SIG = {
     "tmap_set_stream": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
     "tmap_shard_window": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
     "tmap_shard_blank": (C.c_int, [_P, C.c_uint64]),
+    "tmap_shard_blank_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "tmap_shard_bin": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32),
                                  C.POINTER(ShardBuffers)]),
     "tmap_shard_fold": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,

@@ -666,7 +666,7 @@ __global__ void __launch_bounds__(1024) k_scan_small(BatchView b)
 // at most 32*PPT <= 256 points); the absolute base of a bin lives in a separate u32 row.
 // ---------------------------------------------------------------------------------------------
 template <int PPT, bool EMIT>
-__global__ void __launch_bounds__(BIN_THREADS) k_scatter(BatchView b, LatticeD lat, GridView g, int dc, int di)
+__global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, LatticeD lat, GridView g, int dc, int di)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
     __shared__ OpDesc s_op;

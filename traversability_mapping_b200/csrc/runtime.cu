@@ -203,7 +203,8 @@ struct DeviceGrid
         else
         {
             // grow geometrically in the direction that is needed so repeated extension amortises
-            const int gx = std::max(8, v.tw / 2), gy = std::max(8, v.th / 2);
+            // (at least 8 tiles, at most 32: a 1 km map must not double its footprint for one more keyframe)
+            const int gx = std::min(32, std::max(8, v.tw / 2)), gy = std::min(32, std::max(8, v.th / 2));
             if (tx0 < v.tx0) nx0 = std::min(tx0, v.tx0 - gx); else nx0 = v.tx0;
             if (ty0 < v.ty0) ny0 = std::min(ty0, v.ty0 - gy); else ny0 = v.ty0;
             if (tx1 > v.tx0 + v.tw) nx1 = std::max(tx1, v.tx0 + v.tw + gx); else nx1 = v.tx0 + v.tw;
@@ -1061,6 +1062,20 @@ class LocalMap
         CK(cudaMemsetAsync(grid_.v.flags, 0, grid_.v.plane(), stream_));
         CK(cudaStreamSynchronize(stream_));
     }
+    void shardBlankRows(int cj0, int n_rows)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        const GridView &v = grid_.v;
+        if (!v.mom) return;
+        const long r0 = std::max<long>(0, (long)cj0 - v.cj0), r1 = std::min<long>(v.H, (long)cj0 + n_rows - v.cj0);
+        if (r1 <= r0) return;
+        const size_t off = (size_t)r0 * v.W, cnt = (size_t)(r1 - r0) * v.W;
+        CK(cudaMemsetAsync(v.mom + off * REC, 0xFF, cnt * REC * sizeof(float), stream_));
+        for (int k = 0; k < NUM_DER; ++k)
+            CK(cudaMemsetAsync(v.der + (size_t)k * v.plane() + off, 0xFF, cnt * sizeof(float), stream_));
+        CK(cudaMemsetAsync(v.flags + off, 0, cnt, stream_));
+    }
     // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
     void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out)
     {
@@ -1756,6 +1771,10 @@ int tmap_shard_window(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, s
 int tmap_shard_blank(tmap_system *s, uint64_t map_id)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardBlank(); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_blank_rows(tmap_system *s, uint64_t map_id, int32_t cj0, int32_t n_rows)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardBlankRows(cj0, n_rows); return TMAP_OK; TMAP_API_END
 }
 int tmap_shard_bin(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, uint32_t op_base,
                    const int32_t bbox_bins[4], tmap_shard_buffers *out)

@@ -63,6 +63,18 @@ def exchange_plan(counts_all, btw, slabs, rank):
     return send, recv, src_base
 
 
+def exchange_plan_rows(rows_all, slabs, rank):
+    """Same plan from per-bin-ROW totals: rows_all[s, y] = records rank s holds in bin row y.  The (world, n_bins)
+    count matrix is reduced to this (world, n_rows) one on the device, so the host never touches per-bin data
+    (1.4 M bins x 8 ranks for a 1 km map at 0.05 m)."""
+    ra = np.asarray(rows_all).astype(np.int64)
+    send = [int(ra[rank, y0:y1].sum()) for (y0, y1) in slabs]
+    y0, y1 = slabs[rank]
+    recv = [int(ra[s, y0:y1].sum()) for s in range(ra.shape[0])]
+    src_base = np.concatenate([[0], np.cumsum(recv)[:-1]]).astype(np.uint64)
+    return send, recv, src_base
+
+
 def merge_reference(recv, counts_all, starts_all, src_base, btw, slab):
     """NumPy statement of k_shard_merge (used by the CPU tests): per bin of the slab, the sources' segments
     concatenated in source-rank order.  recv: (n, width) records.  Returns (merged, bin_count, bin_start)."""
@@ -86,10 +98,14 @@ def merge_reference(recv, counts_all, starts_all, src_base, btw, slab):
     return merged, np.array(cnt), np.array(st)
 
 
-def exchange_records(records, counts_all, btw, slabs, rank, dist, width=4):
-    """The all-to-all of step 3 on a flat tensor of `width` scalars per record (CPU/gloo or CUDA/NCCL)."""
+def exchange_records(records, counts_all, btw, slabs, rank, dist, width=4, plan=None):
+    """The all-to-all of step 3 on a flat tensor of `width` scalars per record (CPU/gloo or CUDA/NCCL).
+    `plan` = (send, recv, src_base) when the caller already has it (exchange_plan_rows)."""
     import torch
-    send, recv, src_base = exchange_plan(counts_all.cpu().numpy() if hasattr(counts_all, "cpu") else counts_all, btw, slabs, rank)
+    if plan is not None:
+        send, recv, src_base = plan
+    else:
+        send, recv, src_base = exchange_plan(counts_all.cpu().numpy() if hasattr(counts_all, "cpu") else counts_all, btw, slabs, rank)
     out = torch.empty(sum(recv) * width, dtype=records.dtype, device=records.device)
     dist.all_to_all_single(out, records, [r * width for r in recv], [s * width for s in send])
     return out, send, recv, src_base
@@ -124,7 +140,9 @@ def footprint_radius_cells(robot_radius, resolution):
 class ShardedMap:
     """One rank's share of a global map (CUDA + NCCL).  Keyframes are added locally; `rebuild()` is
     collective.  Rank k must hold a contiguous block of keyframe ids (all ids on rank k smaller than
-    all ids on rank k+1) for the result to equal the single-GPU ascending-id rebuild bit for bit."""
+    all ids on rank k+1) for the result to equal the single-GPU ascending-id rebuild bit for bit.
+    After a rebuild a rank's window is valid on its own slab rows (+ the footprint halo) only: read it through
+    `export_slab` / `gather_layer`, not through whole-window queries."""
 
     def __init__(self, params, rank=None, world=None):
         import torch
@@ -180,7 +198,6 @@ class ShardedMap:
         m = meta.tolist()
         margin = max(1, (self.r + BIN - 1) // BIN)
         bbox = (C.c_int32 * 4)(m[0] - margin, m[1] - margin, -m[2] + margin, -m[3] + margin)
-        tm._check(lib.tmap_shard_blank(h, 0))
         buf = tm.ShardBuffers()
         tm._check(lib.tmap_shard_bin(h, 0, ids.ctypes.data, len(ids), poses.ctypes.data, op_base, bbox, C.byref(buf)))
         mark("bin")
@@ -191,16 +208,21 @@ class ShardedMap:
         starts_all = torch.empty((W, nb), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(counts_all, counts.contiguous())
         dist.all_gather_into_tensor(starts_all, starts.contiguous())
-        ca = counts_all.cpu().numpy()
-        row_tot = ca.astype(np.int64).sum(0).reshape(bth, btw).sum(1)
-        slabs = slab_boundaries(row_tot, W, first_global_row=buf.bty0)
+        # per-(rank, bin row) totals are formed on the device; only that small matrix goes to the host
+        rows_all = counts_all.view(W, bth, btw).sum(dim=2, dtype=torch.int64).cpu().numpy()
+        slabs = slab_boundaries(rows_all.sum(0), W, first_global_row=buf.bty0)
         y0, y1 = slabs[rank]
         # all-to-all point routing: the sorted array IS the send buffer (slab ranges are contiguous)
         records = _alias(buf.d_records, buf.n_records * 4, "<f4", torch)
-        recv, send_s, recv_s, src_base = exchange_records(records, ca, btw, slabs, rank, dist)
+        recv, send_s, recv_s, src_base = exchange_records(records, None, btw, slabs, rank, dist,
+                                                          plan=exchange_plan_rows(rows_all, slabs, rank))
         torch.cuda.synchronize()
         mark("alltoall")
         src_base = np.ascontiguousarray(src_base, dtype=np.uint64)
+        # blank this rank's slab + footprint halo only (the window spans the whole map on every rank; rows outside
+        # the slab are not read until a later rebuild owns and blanks them)
+        blank0 = (buf.bty0 + y0) * BIN - 2 * BIN
+        tm._check(lib.tmap_shard_blank_rows(h, 0, blank0, (y1 - y0) * BIN + 4 * BIN))
         tm._check(lib.tmap_shard_fold(h, 0, recv.data_ptr(), sum(recv_s), counts_all.data_ptr(), starts_all.data_ptr(),
                                       src_base.ctypes.data, W, y0, y1))
         mark("fold")
