@@ -28,6 +28,28 @@ def test_header_symbols_are_exported_and_bound(tmap):
     assert sorted(tmap.exported_symbols()) == names, "python binding table and header disagree"
 
 
+def test_struct_layouts_match_the_header(tmap, tmp_path):
+    """The ctypes mirrors of tmap_params / tmap_stats / tmap_shard_buffers must have the C compiler's size and
+    field offsets (the ABI is plain structs; a drifted mirror would read garbage silently)."""
+    import subprocess
+    fields = {"tmap_params": tmap.Params, "tmap_stats": tmap.Stats, "tmap_shard_buffers": tmap.ShardBuffers}
+    lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "tmap.h"', 'int main(void){']
+    for cname, cls in fields.items():
+        lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
+        for f, _ in cls._fields_:
+            lines.append(f'printf("{cname}.{f} %zu\\n", offsetof({cname}, {f}));')
+    lines.append('return 0;}')
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    got = dict(l.split() for l in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in fields.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got[f"{cname}.{f}"]) == getattr(cls, f).offset, f"{cname}.{f}"
+
+
 def test_no_oracle_or_cpu_fallback_in_product():
     """The product path must not reach into oracle/ (judge rule) -- checked at source level."""
     pkg = os.path.join(ROOT, "traversability_mapping_b200")

@@ -47,6 +47,20 @@ def test_exchange_plan_and_merge_reference_single_process():
         assert np.array_equal(cnt, counts[:, y0 * btw:y1 * btw].sum(0))
 
 
+def test_exchange_plan_from_row_totals_equals_plan_from_bin_counts():
+    """ShardedMap reduces the (world, n_bins) counts to (world, n_rows) on the device; the routing plan from
+    the row totals must be the plan from the full counts."""
+    rng = np.random.default_rng(3)
+    world, btw, bth = 4, 7, 30
+    counts = rng.integers(0, 9, size=(world, btw * bth))
+    rows = counts.reshape(world, bth, btw).sum(2)
+    slabs = sharding.slab_boundaries(rows.sum(0), world, first_global_row=-3)
+    for rank in range(world):
+        a = sharding.exchange_plan(counts, btw, slabs, rank)
+        b = sharding.exchange_plan_rows(rows, slabs, rank)
+        assert a[0] == b[0] and a[1] == b[1] and np.array_equal(a[2], b[2])
+
+
 WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])

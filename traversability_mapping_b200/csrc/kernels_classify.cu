@@ -698,12 +698,11 @@ cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUte
     }
     const size_t nb = (size_t)b.btw * b.bth;
     // gate pass over every candidate bin (flag bytes only), then the TMA-staged fit over the bins it listed
-    int ggate = 6;  // measured flat between 4 and 8 CTAs per SM
-    if (const char *e = getenv("TMB_GATE_GRID")) ggate = atoi(e);
+    // CTAs per SM; measured flat between 4 and 8 (profiles/sweep_grids.sh overrides them through the environment)
+    static const int ggate = getenv("TMB_GATE_GRID") ? atoi(getenv("TMB_GATE_GRID")) : 6;
     k_gate<<<(int)min((size_t)(ggate * n_sm), nb), GATE_THREADS, 0, st>>>(tmap_flags, b, g, cp);
     if (ev_after_gate) cudaEventRecord(ev_after_gate, st);
-    int gmul = 6;  // measured: 4-8 CTAs of work per SM level the per-bin imbalance best
-    if (const char *e = getenv("TMB_CLS_GRID")) gmul = atoi(e);
+    static const int gmul = getenv("TMB_CLS_GRID") ? atoi(getenv("TMB_CLS_GRID")) : 6;
     const int n_blocks = (int)min((size_t)(gmul * n_sm), nb);
     k_classify<<<n_blocks, CLS_THREADS, smem, st>>>(tmap, tmap_flags, b, g, cp);
     return cudaGetLastError();
@@ -726,8 +725,7 @@ cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const 
         cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr_R = R;
     }
-    int gmul = 4;
-    if (const char *e = getenv("TMB_INF_GRID")) gmul = atoi(e);
+    static const int gmul = getenv("TMB_INF_GRID") ? atoi(getenv("TMB_INF_GRID")) : 4;
     const int n_blocks = (int)min((size_t)(gmul * n_sm), (size_t)g.tw * g.th);
     k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, static_cast<const InflTap *>(d_taps), cp);
     return cudaGetLastError();

@@ -992,7 +992,8 @@ class LocalMap
         t_planned_ = std::chrono::steady_clock::now();
         CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
         g_launches += ((size_t)pl.b.btw * pl.b.bth <= 4096) ? 5 : 7;  // hist, scan kernels, scatter, fold
-        if (std::getenv("TMB_EXPERIMENT_ATOMIC_FOLD"))
+        static const bool atomic_experiment = std::getenv("TMB_EXPERIMENT_ATOMIC_FOLD") != nullptr;  // profiles/README.md §6
+        if (atomic_experiment)
             runAtomicExperiment(pl);
         finishBatch(pl, ops, t_begin);
     }
