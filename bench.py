@@ -310,6 +310,7 @@ def main():
                 s.updateKeyFrame(i + 1, drift[i])
             s.flush()
             times, pgo = [], []
+            kf_ids = np.arange(1, nk + 1, dtype=np.uint64)
             for rep in range(3):
                 target = lposes if rep % 2 == 0 else drift
                 # (a) the PGO batch itself: every keyframe gets a new pose; the worker subtracts each old
@@ -321,8 +322,7 @@ def main():
                     stream.synchronize()
                     e0.record(stream)
                     with m.locked():   # queue all 2000 updates before the worker starts: one batched pass
-                        for i in range(nk):
-                            s.updateKeyFrame(i + 1, target[i])
+                        s.updateKeyFrames(kf_ids, target)   # one PGO message (global_traversability_node.cpp:184-188)
                     s.flush()
                     e1.record(stream)
                     e1.synchronize()

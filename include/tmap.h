@@ -152,6 +152,10 @@ int tmap_add_keyframe_base(tmap_system *s, uint64_t kf_id, uint64_t map_id, cons
 /* System::updateKeyFrame(kfID, Affine3f pose_map_base) (System.hpp:101-105, System.cpp:195-224):
  * O(1), latest-wins, never waits on a recompute; the first call after insert triggers the bin. */
 int tmap_update_pose(tmap_system *s, uint64_t kf_id, const float T_mb[12]);
+/* GlobalTraversabilityNode::updatesCallback (traversability_mapping_ros/src/global_traversability_node.cpp:184-188):
+ * one PGO message = System::updateKeyFrame for every keyframe it lists.  Same as n tmap_update_pose calls, in
+ * order (poses12: n x 12 floats); returns the first negative code, else TMAP_OK (unknown ids are skipped). */
+int tmap_update_poses(tmap_system *s, const uint64_t *kf_ids, const float *poses12, size_t n);
 /* System::deleteKeyFrame (System.hpp:112, System.cpp:234-248): synchronous subtract+recompute */
 int tmap_delete_keyframe(tmap_system *s, uint64_t kf_id);
 /* System::updateKFMap (System.hpp:115, System.cpp:250-276) */

@@ -170,6 +170,13 @@ class System
     {
         check(tmap_update_pose(s_, kfID, pose_map_base.m));
     }
+    /// One PGO message (global_traversability_node.cpp:184-188): updateKeyFrame for every listed keyframe.
+    void updateKeyFrames(const std::vector<std::uint64_t> &kfIDs, const std::vector<Pose> &poses_map_base)
+    {
+        if (kfIDs.size() != poses_map_base.size()) throw std::invalid_argument("ids / poses size mismatch");
+        static_assert(sizeof(Pose) == 12 * sizeof(float), "Pose is 12 packed floats");
+        check(tmap_update_poses(s_, kfIDs.data(), kfIDs.empty() ? nullptr : poses_map_base[0].m, kfIDs.size()));
+    }
     void deleteKeyFrame(std::uint64_t kfID) { check(tmap_delete_keyframe(s_, kfID)); }
     void updateKFMap(std::uint64_t kfID, std::uint64_t mapID) { check(tmap_update_kf_map(s_, kfID, mapID)); }
     void informLoopClosure() { check(tmap_inform_loop_closure(s_)); }

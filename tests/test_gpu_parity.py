@@ -525,3 +525,33 @@ def test_keyframe_points_and_running_stats(tmap, oracle):
     assert st["sum_cells_touched"] == touched and st["sum_cand_bins"] > 0
     assert st["sum_host_ms_batch"] >= st["sum_host_ms_wait"] > 0.0
     s.close()
+
+
+def test_bulk_pose_update_equals_per_keyframe_calls(tmap):
+    """tmap_update_poses (one PGO message) == the same updateKeyFrame calls one by one: identical moment layers."""
+    from traversability_mapping_b200 import synth
+    poses = synth.trajectory("loop", 6, seed=9, extent=6.0)
+    clouds = [synth.make_keyframe(9, i, poses[i], max_range=8.0, rings=32, azimuths=512) for i in range(6)]
+    moved = poses.copy(); moved[:, 0, 3] += 0.37; moved[:, 1, 3] -= 0.21
+    maps = []
+    for bulk in (False, True):
+        s = tmap.System(tmap.default_params(resolution=0.1, max_range=8.0, min_range=1.0, max_batch=0))
+        s.addNewLocalMap(0)
+        s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+        m = s.getLocalMap(0)
+        for i, c in enumerate(clouds):
+            assert s.addNewKeyFrameWithPCL(i, i + 1, 0, c) == tmap.OK
+        for target in (poses, moved):
+            with m.locked():
+                if bulk:
+                    assert s.updateKeyFrames(np.arange(1, 7), target) == tmap.OK
+                else:
+                    for i in range(6):
+                        s.updateKeyFrame(i + 1, target[i])
+            s.flush()
+        kx, ky = m.gridExtent()
+        maps.append([m.exportDense(l, -kx, -ky, 2 * kx + 1, 2 * ky + 1) for l in ("N", "sz", "hazard")])
+        s.close()
+    for a, b in zip(*maps):
+        assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert np.nansum(maps[0][0]) > 0

@@ -85,6 +85,7 @@ _SIG = {
     "tmap_add_keyframe_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tmap_add_keyframe_base": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "tmap_update_pose": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float)]),
+    "tmap_update_poses": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_size_t]),
     "tmap_delete_keyframe": (C.c_int, [_P, C.c_uint64]),
     "tmap_update_kf_map": (C.c_int, [_P, C.c_uint64, C.c_uint64]),
     "tmap_inform_loop_closure": (C.c_int, [_P]),
@@ -353,6 +354,13 @@ class System:
     def updateKeyFrame(self, kf_id, pose_map_base, numConnections=0):
         a = _pose12(pose_map_base)
         return _check(self._lib.tmap_update_pose(self._h, int(kf_id), a.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def updateKeyFrames(self, kf_ids, poses_map_base):
+        """One PGO message (global_traversability_node.cpp:184-188): updateKeyFrame for every listed keyframe."""
+        ids = np.ascontiguousarray(kf_ids, dtype=np.uint64)
+        poses = np.ascontiguousarray(np.asarray(poses_map_base, dtype=np.float32).reshape(len(ids), -1)[:, :12])
+        return _check(self._lib.tmap_update_poses(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                  poses.ctypes.data_as(C.POINTER(C.c_float)), len(ids)))
 
     def deleteKeyFrame(self, kf_id):
         return _check(self._lib.tmap_delete_keyframe(self._h, int(kf_id)))

@@ -1643,6 +1643,19 @@ int tmap_update_pose(tmap_system *s, uint64_t kf_id, const float T[12])
 {
     NEED(s) TMAP_API_BEGIN return s->sys->updateKeyFrame(kf_id, T); TMAP_API_END
 }
+int tmap_update_poses(tmap_system *s, const uint64_t *kf_ids, const float *poses12, size_t n)
+{
+    NEED(s)
+    if (n && (!kf_ids || !poses12)) { tmb::g_last_error = "null ids / poses"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN
+    for (size_t i = 0; i < n; ++i)
+    {
+        const int rc = s->sys->updateKeyFrame(kf_ids[i], poses12 + 12 * i);
+        if (rc < 0) return rc;
+    }
+    return TMAP_OK;
+    TMAP_API_END
+}
 int tmap_delete_keyframe(tmap_system *s, uint64_t kf_id)
 {
     NEED(s) TMAP_API_BEGIN return s->sys->deleteKeyFrame(kf_id); TMAP_API_END
