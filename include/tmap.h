@@ -142,6 +142,13 @@ int tmap_set_current_map(tmap_system *s, uint64_t map_id);
  * until the first tmap_update_pose.  Synchronous, like the reference. */
 int tmap_add_keyframe(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id,
                       const float *xyz, size_t n, size_t stride_bytes);
+/* tmap_ros::toPCL + addNewKeyFrameWithPCL (traversability_mapping_ros/src/conversions.cpp:19-26,
+ * global_traversability_node.cpp:171-182): the raw `data` bytes of a sensor_msgs/PointCloud2 (width*height points,
+ * `point_step` apart) with the byte offsets of its FLOAT32 x / y / z fields; decoded and pruned on the device, no
+ * per-point host loop.  Offsets must be 4-byte aligned inside point_step (else TMAP_ERR_UNSUPPORTED). */
+int tmap_add_keyframe_pc2(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id, const void *data,
+                          size_t n_points, size_t point_step, uint32_t x_offset, uint32_t y_offset, uint32_t z_offset,
+                          int is_bigendian);
 /* Same, with the cloud already in DEVICE memory (float4-strided or packed). */
 int tmap_add_keyframe_device(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id,
                              const void *d_xyz, size_t n, size_t stride_bytes);

@@ -157,6 +157,19 @@ class System
                                      std::to_string(static_cast<std::int64_t>(kfID)));
         check(rc);
     }
+    /// sensor_msgs/PointCloud2 ingest (conversions.cpp:19-26 + System.cpp:159-172): raw data bytes, point_step and the
+    /// byte offsets of the FLOAT32 x / y / z fields; decoded and pruned on the device.
+    void addNewKeyFramePointCloud2(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID, const void *data,
+                                   size_t n_points, size_t point_step, std::uint32_t x_offset, std::uint32_t y_offset,
+                                   std::uint32_t z_offset, bool is_bigendian = false)
+    {
+        const int rc = tmap_add_keyframe_pc2(s_, timestamp_ns, kfID, mapID, data, n_points, point_step, x_offset, y_offset,
+                                             z_offset, is_bigendian ? 1 : 0);
+        if (rc == TMAP_ERR_NEGATIVE_ID)
+            throw std::runtime_error("The given KF ID was negative. Please make sure the keyFrame IDs are positive. KF ID: " +
+                                     std::to_string(static_cast<std::int64_t>(kfID)));
+        check(rc);
+    }
 #ifdef TMAP_HAVE_PCL
     void addNewKeyFrameWithPCL(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID,
                                std::shared_ptr<pcl::PointCloud<pcl::PointXYZ>> cloud)

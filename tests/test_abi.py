@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_symbols():
     h = open(os.path.join(ROOT, "include", "tmap.h")).read()
     h = re.sub(r"/\*.*?\*/", "", h, flags=re.S)
-    return sorted(set(re.findall(r"\b(tmap_[a-z_]+)\s*\(", h)))
+    return sorted(set(re.findall(r"\b(tmap_[a-z0-9_]+)\s*\(", h)))
 
 
 def test_header_symbols_are_exported_and_bound(tmap):

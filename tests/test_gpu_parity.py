@@ -555,3 +555,35 @@ def test_bulk_pose_update_equals_per_keyframe_calls(tmap):
     for a, b in zip(*maps):
         assert a.shape == b.shape and np.array_equal(a.view(np.uint32), b.view(np.uint32))
     assert np.nansum(maps[0][0]) > 0
+
+
+def test_pointcloud2_ingest_matches_pcl_path(tmap, oracle):
+    """tmap_add_keyframe_pc2: a PointCloud2 byte buffer (x, y, z FLOAT32 at arbitrary aligned offsets, little or
+    big endian) gives the keyframe the plain (n, 4) float cloud gives -- bit for bit, through the device prune."""
+    from traversability_mapping_b200 import synth
+    P = synth.trajectory("single", 1, seed=6)[0]
+    cloud = synth.make_keyframe(6, 0, P, max_range=8.0, rings=32, azimuths=512)
+    cloud[3] = (0.0, 0.0, 1.0, 0)
+    cloud[4] = (np.nan, 1.0, 1.0, 0)
+    n = len(cloud)
+    rng = np.random.default_rng(0)
+    buf = rng.standard_normal((n, 8)).astype(np.float32)     # point_step 32: intensity / ring / padding junk
+    buf[:, 1] = cloud[:, 0]; buf[:, 5] = cloud[:, 1]; buf[:, 2] = cloud[:, 2]   # x @4, y @20, z @8
+    s = tmap.System(tmap.default_params(resolution=0.1, max_range=6.0, min_range=1.0))
+    s.addNewLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    m = s.getLocalMap(0)
+    assert s.addNewKeyFrameWithPCL(1, 1, 0, cloud) == tmap.OK
+    want = m.getStitchedPointCloud()
+    s.deleteKeyFrame(1)
+    assert s.addNewKeyFramePointCloud2(2, 2, 0, buf, 32, 4, 20, 8) == tmap.OK
+    got = m.getStitchedPointCloud()
+    assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    s.deleteKeyFrame(2)
+    assert s.addNewKeyFramePointCloud2(3, 3, 0, buf.byteswap(), 32, 4, 20, 8, is_bigendian=True) == tmap.OK
+    got = m.getStitchedPointCloud()
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    with pytest.raises(tmap.TmapError) as e:   # a misaligned field is refused loudly
+        s.addNewKeyFramePointCloud2(4, 4, 0, buf, 32, 2, 20, 8)
+    assert e.value.code == tmap.ERR_UNSUPPORTED
+    s.close()

@@ -83,6 +83,8 @@ _SIG = {
     "tmap_set_current_map": (C.c_int, [_P, C.c_uint64]),
     "tmap_add_keyframe": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tmap_add_keyframe_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "tmap_add_keyframe_pc2": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t,
+                                        C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
     "tmap_add_keyframe_base": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "tmap_update_pose": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float)]),
     "tmap_update_poses": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_size_t]),
@@ -342,6 +344,16 @@ class System:
             raise ValueError("cloud must be (n,3) or (n,4) float32")
         return _check(self._lib.tmap_add_keyframe(self._h, int(timestamp_ns), int(kf_id) & 0xFFFFFFFFFFFFFFFF, int(map_id),
                                                   a.ctypes.data, a.shape[0], a.shape[1] * 4))
+
+    def addNewKeyFramePointCloud2(self, timestamp_ns, kf_id, map_id, data, point_step, x_offset, y_offset, z_offset,
+                                  is_bigendian=False):
+        """sensor_msgs/PointCloud2 ingest (conversions.cpp:19-26): `data` = the message's raw byte array
+        (width*height points of `point_step` bytes), FLOAT32 x / y / z at the given byte offsets."""
+        a = np.ascontiguousarray(np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data.view(np.uint8).reshape(-1))
+        n = a.size // int(point_step)
+        return _check(self._lib.tmap_add_keyframe_pc2(self._h, int(timestamp_ns), int(kf_id) & 0xFFFFFFFFFFFFFFFF, int(map_id),
+                                                      a.ctypes.data, n, int(point_step), int(x_offset), int(y_offset),
+                                                      int(z_offset), 1 if is_bigendian else 0))
 
     def addNewKeyFrameDevice(self, timestamp_ns, kf_id, map_id, dev_ptr, n, stride_bytes=16):
         return _check(self._lib.tmap_add_keyframe_device(self._h, int(timestamp_ns), int(kf_id), int(map_id),

@@ -83,7 +83,21 @@ struct PruneArgs
     size_t n, stride;
     float T[12];
     float rh, mx, mn;
+    int xo, yo, zo;            // position of x, y, z inside a point, in floats (PointCloud2 field offsets / 4)
+    int swap;                  // 1: big-endian floats (sensor_msgs/PointCloud2::is_bigendian)
 };
+
+__device__ __forceinline__ void load_xyz(const PruneArgs &a, size_t i, float &x, float &y, float &z)
+{
+    const float *p = reinterpret_cast<const float *>(a.src + i * a.stride);
+    x = p[a.xo]; y = p[a.yo]; z = p[a.zo];
+    if (a.swap)
+    {
+        x = __uint_as_float(__byte_perm(__float_as_uint(x), 0, 0x0123));
+        y = __uint_as_float(__byte_perm(__float_as_uint(y), 0, 0x0123));
+        z = __uint_as_float(__byte_perm(__float_as_uint(z), 0, 0x0123));
+    }
+}
 
 __global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
 {
@@ -100,9 +114,9 @@ __global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
         bool ok = false;
         if (i < a.n)
         {
-            const float *p = reinterpret_cast<const float *>(a.src + i * a.stride);
-            float xb, yb, zb, rg;
-            ok = prune_point(a.T, p[0], p[1], p[2], a.rh, a.mx, a.mn, xb, yb, zb, rg);
+            float x, y, z, xb, yb, zb, rg;
+            load_xyz(a, i, x, y, z);
+            ok = prune_point(a.T, x, y, z, a.rh, a.mx, a.mn, xb, yb, zb, rg);
         }
         cnt += __popc(__ballot_sync(0xffffffffu, ok));
     }
@@ -179,8 +193,9 @@ __global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_b
         float xb = 0, yb = 0, zb = 0, rg = 0;
         if (i < a.n)
         {
-            const float *p = reinterpret_cast<const float *>(a.src + i * a.stride);
-            ok = prune_point(a.T, p[0], p[1], p[2], a.rh, a.mx, a.mn, xb, yb, zb, rg);
+            float x, y, z;
+            load_xyz(a, i, x, y, z);
+            ok = prune_point(a.T, x, y, z, a.rh, a.mx, a.mn, xb, yb, zb, rg);
         }
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (ok)
@@ -1278,11 +1293,16 @@ __global__ void k_shard_merge(BatchView b, const float4 *__restrict__ recv, cons
 // host-callable launch wrappers
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
-                         float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase)
+                         float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase,
+                         const int field_floats[3], int big_endian)
 {
     PruneArgs a;
     a.src = static_cast<const unsigned char *>(d_src);
     a.n = n; a.stride = stride;
+    a.xo = field_floats ? field_floats[0] : 0;
+    a.yo = field_floats ? field_floats[1] : 1;
+    a.zo = field_floats ? field_floats[2] : 2;
+    a.swap = big_endian;
     for (int i = 0; i < 12; ++i) a.T[i] = T[i];
     a.rh = rh; a.mx = mx; a.mn = mn;
     const uint32_t n_warps = (uint32_t)((n + 32 * PRUNE_PPT - 1) / (32 * PRUNE_PPT));

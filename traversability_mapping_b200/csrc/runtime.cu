@@ -1343,7 +1343,7 @@ class System
 
     // System::prune on the device; src may be host or device memory
     std::shared_ptr<KeyFrame> pruneToKeyFrame(const void *src, bool on_device, size_t n, size_t stride, const float T[12], double mx,
-                                              double mn)
+                                              double mn, const int *field_floats = nullptr, int big_endian = 0)
     {
         std::lock_guard<std::mutex> l(ingestMutex_);
         CK(cudaSetDevice(P_.device));
@@ -1363,9 +1363,9 @@ class System
         CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), n * sizeof(float4), ingest_));
         kf->allocStream = ingest_;
         CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
-                        total_.as<uint32_t>(), kf->d_cloud, 0));
+                        total_.as<uint32_t>(), kf->d_cloud, 0, field_floats, big_endian));
         CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
-                        total_.as<uint32_t>(), kf->d_cloud, 1));
+                        total_.as<uint32_t>(), kf->d_cloud, 1, field_floats, big_endian));
         g_launches += 3;
         CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
         CK(cudaStreamSynchronize(ingest_));
@@ -1391,11 +1391,20 @@ class System
     }
     static double nsToSec(uint64_t ns) { return (double)(ns / 1000000000ULL) + (double)(ns % 1000000000ULL) * 1e-9; }
 
-    int addKeyFrame(uint64_t ts_ns, uint64_t kfID, uint64_t mapID, const void *xyz, bool on_device, size_t n, size_t stride)
+    int addKeyFrame(uint64_t ts_ns, uint64_t kfID, uint64_t mapID, const void *xyz, bool on_device, size_t n, size_t stride,
+                    const uint32_t *field_offsets = nullptr, int big_endian = 0)
     {
         if (kfID > (uint64_t)std::numeric_limits<int64_t>::max()) return TMAP_ERR_NEGATIVE_ID;  // System.cpp:163-168
         if (!xyz) return TMAP_IGNORED_NULL;
         if (stride < 12 || stride % 4) throw std::invalid_argument("stride_bytes must be a multiple of 4 and >= 12");
+        int ff[3] = {0, 1, 2};
+        if (field_offsets)
+            for (int k = 0; k < 3; ++k)
+            {
+                if (field_offsets[k] % 4 || (size_t)field_offsets[k] + 4 > stride)
+                    throw Unsupported("PointCloud2 x/y/z fields must be 4-byte aligned FLOAT32 inside point_step");
+                ff[k] = (int)(field_offsets[k] / 4);
+            }
         {
             // cheap pre-checks before spending a prune pass (same outcomes as registerKeyFrame)
             std::lock_guard<std::recursive_mutex> l(m_);
@@ -1407,7 +1416,7 @@ class System
             std::lock_guard<std::recursive_mutex> l(m_);
             std::memcpy(T, Tbv_, sizeof(T));
         }
-        auto kf = pruneToKeyFrame(xyz, on_device, n, stride, T, P_.max_range, P_.min_range);
+        auto kf = pruneToKeyFrame(xyz, on_device, n, stride, T, P_.max_range, P_.min_range, ff, big_endian);
         return registerKeyFrame(nsToSec(ts_ns), kfID, mapID, kf);
     }
     int addKeyFrameBase(uint64_t kfID, uint64_t mapID, const float *xyz, size_t n)
@@ -1634,6 +1643,15 @@ int tmap_add_keyframe(tmap_system *s, uint64_t ts, uint64_t kf_id, uint64_t map_
 int tmap_add_keyframe_device(tmap_system *s, uint64_t ts, uint64_t kf_id, uint64_t map_id, const void *d_xyz, size_t n, size_t stride)
 {
     NEED(s) TMAP_API_BEGIN return s->sys->addKeyFrame(ts, kf_id, map_id, d_xyz, true, n, stride); TMAP_API_END
+}
+int tmap_add_keyframe_pc2(tmap_system *s, uint64_t ts_ns, uint64_t kf_id, uint64_t map_id, const void *data, size_t n_points,
+                          size_t point_step, uint32_t x_offset, uint32_t y_offset, uint32_t z_offset, int is_bigendian)
+{
+    NEED(s)
+    TMAP_API_BEGIN
+    const uint32_t off[3] = {x_offset, y_offset, z_offset};
+    return s->sys->addKeyFrame(ts_ns, kf_id, map_id, data, false, n_points, point_step, off, is_bigendian ? 1 : 0);
+    TMAP_API_END
 }
 int tmap_add_keyframe_base(tmap_system *s, uint64_t kf_id, uint64_t map_id, const float *xyz, size_t n)
 {
