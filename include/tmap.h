@@ -205,6 +205,13 @@ int tmap_export_dense(tmap_system *s, uint64_t map_id, int32_t layer, int32_t ci
  * unknown; out[(cj-cj0)*w + (ci-ci0)] (nav_msgs row-major, x fastest) */
 int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t cj0, int32_t w,
                           int32_t h, int8_t *out);
+/* GlobalTraversabilityNode::publishCompleteness (traversability_mapping_ros/src/global_traversability_node.cpp:381-459):
+ * toOccupancyGrid(grid, "border_haz", 0, 1) over the w x h crop at (ci0, cj0), min-pooled to `publish_res` (0.25 m in
+ * the reference; f = lround(publish_res / float(resolution)), unobserved fine cells skipped), then mapped to the RViz
+ * costmap-palette bytes (complete -> 113, partial -> 128..254, unobserved -> -1).  out: ceil(w/f) x ceil(h/f) bytes,
+ * row-major, x fastest; out == NULL returns the dimensions only. */
+int tmap_export_completeness(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t cj0, int32_t w, int32_t h,
+                             double publish_res, int8_t *out, size_t cap_bytes, int32_t *out_w, int32_t *out_h);
 /* LocalMap::getKeyFramesMap().size() and the work-queue depth (LocalMap.cpp:339-340) */
 int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out);
 int tmap_queue_depth(tmap_system *s, uint64_t map_id, size_t *n_out);

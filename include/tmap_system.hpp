@@ -94,6 +94,16 @@ class LocalMap
         check(tmap_export_occupancy(s_, id_, -kx, -ky, width, height, out.data()));
         return out;
     }
+    /// publishCompleteness payload (global_traversability_node.cpp:381-459): whole grid, palette bytes
+    std::vector<int8_t> completeness(double publish_res, int32_t &width, int32_t &height)
+    {
+        int32_t kx, ky;
+        gridExtent(kx, ky);
+        check(tmap_export_completeness(s_, id_, -kx, -ky, 2 * kx + 1, 2 * ky + 1, publish_res, nullptr, 0, &width, &height));
+        std::vector<int8_t> out(static_cast<size_t>(width) * height);
+        check(tmap_export_completeness(s_, id_, -kx, -ky, 2 * kx + 1, 2 * ky + 1, publish_res, out.data(), out.size(), &width, &height));
+        return out;
+    }
     std::vector<float> layer(int32_t layer_id, int32_t ci0, int32_t cj0, int32_t w, int32_t h)
     {
         std::vector<float> out(static_cast<size_t>(w) * h);

@@ -76,6 +76,8 @@ def lib():
         L.tmo_grid_extent.argtypes = [P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tmo_export_dense.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P]
         L.tmo_export_occupancy.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, P]
+        L.tmo_export_completeness.argtypes = [P, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, P,
+                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tmo_cell_of.argtypes = [C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,
                                   C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         L.tmo_key.restype = C.c_uint64
@@ -210,6 +212,15 @@ class OracleMap:
         out = np.empty((h, w), dtype=np.int8)
         lib().tmo_export_occupancy(self._h, ci0, cj0, w, h, out.ctypes.data)
         return out
+
+    def export_completeness(self, publish_res=0.25, ci0=None, cj0=None, w=None, h=None):
+        if ci0 is None:
+            kx, ky = self.grid_extent()
+            ci0, cj0, w, h = -kx, -ky, 2 * kx + 1, 2 * ky + 1
+        out = np.empty(w * h, dtype=np.int8)
+        cw, ch = C.c_int32(0), C.c_int32(0)
+        lib().tmo_export_completeness(self._h, ci0, cj0, w, h, publish_res, out.ctypes.data, C.byref(cw), C.byref(ch))
+        return out[:cw.value * ch.value].reshape(ch.value, cw.value).copy()
 
 
 def cell_of(x0, y0, res, x, y):

@@ -937,6 +937,59 @@ void tmo_export_occupancy(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w,
         }
 }
 
+void tmo_export_completeness(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w, int32_t h, double publish_res,
+                             int8_t *out, int32_t *out_w, int32_t *out_h)
+{
+    /* GlobalTraversabilityNode::publishCompleteness (traversability_mapping_ros/src/global_traversability_node.cpp:381-459):
+     * toOccupancyGrid(grid, "border_haz", 0, 1) -> min-pool to publish_res (unobserved fine cells skipped) ->
+     * RViz costmap-palette bytes.  nav_msgs MapMetaData::resolution is float32. */
+    const float dataMin = 0.f, dataMax = 1.f, cellMin = 0.f, cellRange = 100.f;
+    std::vector<int8_t> fine(static_cast<size_t>(w) * h);
+    for (int j = 0; j < h; ++j)
+        for (int i = 0; i < w; ++i)
+        {
+            const int ci = ci0 + i, cj = cj0 + j;
+            float value = m->grid.inside(ci, cj) ? m->grid.L[TMO_L_BORDER][m->grid.at(ci, cj)] : kNaNf;
+            value = (value - dataMin) / (dataMax - dataMin);
+            if (std::isnan(value))
+                value = -1.f;
+            else
+                value = cellMin + std::min(std::max(0.0f, value), 1.0f) * cellRange;
+            fine[static_cast<size_t>(j) * w + i] = static_cast<int8_t>(value);
+        }
+    const float fine_res = static_cast<float>(m->P.resolution);
+    int f = static_cast<int>(std::lround(publish_res / fine_res));
+    if (f < 1)
+        f = 1;
+    const unsigned fw = w, fh = h;
+    const unsigned cw = (fw + f - 1) / f, ch = (fh + f - 1) / f;
+    *out_w = static_cast<int32_t>(cw);
+    *out_h = static_cast<int32_t>(ch);
+    for (unsigned cy = 0; cy < ch; ++cy)
+        for (unsigned cx = 0; cx < cw; ++cx)
+        {
+            int best = 101;
+            for (int dy = 0; dy < f; ++dy)
+                for (int dx = 0; dx < f; ++dx)
+                {
+                    const unsigned fx = cx * f + dx, fy = cy * f + dy;
+                    if (fx >= fw || fy >= fh)
+                        continue;
+                    const int v = fine[static_cast<size_t>(fy) * fw + fx];
+                    if (v >= 0 && v < best)
+                        best = v;
+                }
+            int8_t d = (best <= 100) ? static_cast<int8_t>(best) : static_cast<int8_t>(-1);
+            if (d >= 0)
+            {
+                const double c = static_cast<double>(d) / 100.0;
+                const int byte = (d >= 100) ? 113 : 128 + static_cast<int>(std::lround(c * (254 - 128)));
+                d = static_cast<int8_t>(byte);
+            }
+            out[static_cast<size_t>(cy) * cw + cx] = d;
+        }
+}
+
 void tmo_cell_of(double x0, double y0, double res, double x, double y, int32_t *ci, int32_t *cj)
 {
     Lattice l; l.x0 = x0; l.y0 = y0; l.res = res;

@@ -120,6 +120,10 @@ void tmo_export_dense(const tmo_map *m, int32_t layer, int32_t ci0, int32_t cj0,
  * NaN -> -1, same crop addressing as export_dense (full grid: ci0=-kx, cj0=-ky, w=2kx+1). */
 void tmo_export_occupancy(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w, int32_t h,
                           int8_t *out);
+/* publishCompleteness (global_traversability_node.cpp:381-459): border_haz occupancy, min-pooled to publish_res,
+ * RViz costmap-palette bytes; out holds ceil(w/f) x ceil(h/f) cells, f = lround(publish_res / float(resolution)) */
+void tmo_export_completeness(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w, int32_t h, double publish_res,
+                             int8_t *out, int32_t *out_w, int32_t *out_h);
 
 /* ---- stateless pieces, exposed for the known-answer tests ---- */
 /* Lattice::cellOf / key (Moments.hpp:105-133) */

@@ -587,3 +587,19 @@ def test_pointcloud2_ingest_matches_pcl_path(tmap, oracle):
         s.addNewKeyFramePointCloud2(4, 4, 0, buf, 32, 2, 20, 8)
     assert e.value.code == tmap.ERR_UNSUPPORTED
     s.close()
+
+
+def test_completeness_export_matches_oracle(tmap, oracle):
+    """tmap_export_completeness == the oracle's restatement of publishCompleteness (border_haz occupancy,
+    min-pool to the publish resolution, RViz palette bytes): integer work, so byte for byte."""
+    s, m, om, _ = run_small_scene(tmap, oracle)
+    for res in (0.25, 0.5, 0.01):
+        got, want = m.exportCompleteness(res), om.export_completeness(res)
+        assert got.shape == want.shape and np.array_equal(got, want), res
+    kx, ky = m.gridExtent()
+    got = m.exportCompleteness(0.25, -kx + 3, -ky + 1, 2 * kx - 7, 2 * ky - 2)   # crop, partial edge blocks
+    want = om.export_completeness(0.25, -kx + 3, -ky + 1, 2 * kx - 7, 2 * ky - 2)
+    assert got.shape == want.shape and np.array_equal(got, want)
+    vals = set(np.unique(want).tolist())
+    assert -1 in vals and 113 in vals and any(-128 <= v < -1 for v in vals), "unobserved, complete and partial cells all present"
+    s.close()

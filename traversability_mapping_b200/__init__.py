@@ -103,6 +103,8 @@ _SIG = {
     "tmap_grid_extent": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tmap_export_dense": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tmap_export_occupancy": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
+    "tmap_export_completeness": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_void_p,
+                                           C.c_size_t, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tmap_num_keyframes": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_queue_depth": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_keyframe_points": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
@@ -263,6 +265,19 @@ class LocalMap:
         if out is None:
             out = np.empty((h, w), dtype=np.int8)
         _check(self._s._lib.tmap_export_occupancy(self._s._h, self.map_id, ci0, cj0, w, h, out.ctypes.data))
+        return out
+
+    def exportCompleteness(self, publish_res=0.25, ci0=None, cj0=None, w=None, h=None):
+        """publishCompleteness (global_traversability_node.cpp:381-459): (rows, cols) int8 palette bytes."""
+        if ci0 is None:
+            kx, ky = self.gridExtent()
+            ci0, cj0, w, h = -kx, -ky, 2 * kx + 1, 2 * ky + 1
+        cw, ch = C.c_int32(0), C.c_int32(0)
+        lib, hnd = self._s._lib, self._s._h
+        _check(lib.tmap_export_completeness(hnd, self.map_id, ci0, cj0, w, h, publish_res, None, 0, C.byref(cw), C.byref(ch)))
+        out = np.empty((ch.value, cw.value), dtype=np.int8)
+        _check(lib.tmap_export_completeness(hnd, self.map_id, ci0, cj0, w, h, publish_res, out.ctypes.data, out.size,
+                                            C.byref(cw), C.byref(ch)))
         return out
 
     def numKeyFrames(self):

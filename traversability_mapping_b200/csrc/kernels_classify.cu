@@ -641,6 +641,45 @@ __global__ void k_export_occupancy(GridView g, int ci0, int cj0, int w, int h, i
     out[i] = (signed char)value;
 }
 
+// publishCompleteness (traversability_mapping_ros/src/global_traversability_node.cpp:381-459): per coarse cell the
+// MINIMUM of toOccupancyGrid(grid, "border_haz", 0, 1) over its f x f fine cells (unobserved ones skipped), then
+// the RViz costmap-palette byte (100 -> 113, 0..99 -> 128 + lround(c * 126), unobserved -> -1).
+__global__ void k_export_completeness(GridView g, int ci0, int cj0, int w, int h, int kx, int ky, int f, int cw, int ch,
+                                      signed char *out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)cw * ch)
+        return;
+    const int cx = (int)(i % cw), cy = (int)(i / cw);
+    int best = 101;
+    for (int dy = 0; dy < f; ++dy)
+        for (int dx = 0; dx < f; ++dx)
+        {
+            const int fx = cx * f + dx, fy = cy * f + dy;
+            if (fx >= w || fy >= h)
+                continue;  // partial edge block
+            const int ci = ci0 + fx, cj = cj0 + fy;
+            float v = CUDART_NAN_F;
+            if (abs(ci) <= kx && abs(cj) <= ky)
+                v = read_layer(g, 15, ci, cj);  // border_haz
+            float value = __fdiv_rn(__fsub_rn(v, 0.f), __fsub_rn(1.f, 0.f));
+            if (isnan(value))
+                continue;  // -1: carries no value
+            value = __fadd_rn(0.f, __fmul_rn(fminf(fmaxf(0.0f, value), 1.0f), 100.f));
+            const int iv = (int)(signed char)value;
+            if (iv >= 0 && iv < best)
+                best = iv;
+        }
+    signed char d = -1;
+    if (best <= 100)
+    {
+        const double c = (double)best / 100.0;
+        const int byte = best >= 100 ? 113 : 128 + (int)llround(c * (254 - 128));
+        d = (signed char)byte;  // 128..254 wrap to negative int8 on purpose
+    }
+    out[i] = d;
+}
+
 // clearEntireMap (LocalMap.cpp:377-383): every occupied cell becomes 'changed'; per-batch bits drop
 __global__ void k_mark_observed_changed(GridView g)
 {
@@ -765,6 +804,15 @@ cudaError_t launch_export_occupancy(cudaStream_t st, const GridView &g, int ci0,
     const size_t tot = (size_t)w * h;
     if (!tot) return cudaSuccess;
     k_export_occupancy<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, ci0, cj0, w, h, kx, ky, d_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_export_completeness(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky, int f,
+                                       int cw, int ch, signed char *d_out)
+{
+    const size_t tot = (size_t)cw * ch;
+    if (!tot) return cudaSuccess;
+    k_export_completeness<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(g, ci0, cj0, w, h, kx, ky, f, cw, ch, d_out);
     return cudaGetLastError();
 }
 

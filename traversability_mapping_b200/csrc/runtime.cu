@@ -570,6 +570,25 @@ class LocalMap
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
+    // publishCompleteness (global_traversability_node.cpp:381-459); out holds ceil(w/f) x ceil(h/f) bytes
+    void exportCompleteness(int ci0, int cj0, int w, int h, double publish_res, int8_t *out, size_t cap, int32_t *cw_out, int32_t *ch_out)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        const float fine_res = (float)P_.resolution;  // nav_msgs MapMetaData::resolution is float32
+        int f = (int)std::lround(publish_res / fine_res);
+        if (f < 1) f = 1;
+        const int cw = (w + f - 1) / f, ch = (h + f - 1) / f;
+        *cw_out = cw; *ch_out = ch;
+        const size_t tot = (size_t)cw * ch;
+        if (!out || !tot) return;
+        if (cap < tot) throw std::invalid_argument("completeness output buffer too small");
+        scratchOut_.ensure(tot);
+        CK(launch_export_completeness(stream_, grid_.v, ci0, cj0, w, h, kx_, ky_, f, cw, ch, scratchOut_.as<signed char>()));
+        CK(cudaMemcpyAsync(out, scratchOut_.p, tot, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        g_launches += 1;
+    }
     void extent(int32_t *kx, int32_t *ky)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
@@ -1763,6 +1782,13 @@ int tmap_export_occupancy(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t 
     mp->exportOccupancy(ci0, cj0, w, h, out);
     return TMAP_OK;
     TMAP_API_END
+}
+int tmap_export_completeness(tmap_system *s, uint64_t map_id, int32_t ci0, int32_t cj0, int32_t w, int32_t h, double publish_res,
+                             int8_t *out, size_t cap, int32_t *out_w, int32_t *out_h)
+{
+    NEED(s)
+    if (!out_w || !out_h || w < 0 || h < 0) { tmb::g_last_error = "bad completeness arguments"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->exportCompleteness(ci0, cj0, w, h, publish_res, out, cap, out_w, out_h); return TMAP_OK; TMAP_API_END
 }
 int tmap_num_keyframes(tmap_system *s, uint64_t map_id, size_t *n_out)
 {

@@ -35,5 +35,7 @@ cudaError_t launch_export_dense(cudaStream_t st, const GridView &g, int layer, i
 cudaError_t launch_export_occupancy(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky,
                                     signed char *d_out);
 cudaError_t launch_transform_cloud(cudaStream_t st, const float4 *d_cloud, uint32_t n, const float *d_T, float *d_out);
+cudaError_t launch_export_completeness(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky, int f,
+                                       int cw, int ch, signed char *d_out);
 cudaError_t launch_mark_observed_changed(cudaStream_t st, const GridView &g);
 }  // namespace tmb
