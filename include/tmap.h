@@ -221,6 +221,12 @@ int tmap_keyframe_points(tmap_system *s, uint64_t kf_id, size_t *n_out);
 /* LocalMap::getStitchedPointCloud without the voxel filter (LocalMap.cpp:416-437): pose * cloud
  * of every retained keyframe, packed xyz, ascending kf id.  out==NULL: count only. */
 int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t cap_points, size_t *n_out);
+/* LocalMap::getStitchedPointCloud(vx, vy, vz) with positive leaf sizes (LocalMap.cpp:416-448): the stitched cloud
+ * through pcl::VoxelGrid<pcl::PointXYZ> (PCL 1.12 filters/impl/voxel_grid.hpp, restated): one centroid per occupied
+ * voxel, ascending voxel index.  out == NULL: *n_out = an upper bound (the unfiltered size) for sizing the buffer;
+ * otherwise *n_out = the number of voxels (at most cap_points are written).  Non-positive leaves = unfiltered. */
+int tmap_stitched_cloud_voxel(tmap_system *s, uint64_t map_id, float leaf_x, float leaf_y, float leaf_z, float *out_xyz,
+                              size_t cap_points, size_t *n_out);
 
 int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out);
 /* Run the map's kernels on a caller-owned stream (cudaStream_t as void*); NULL = own stream. */

@@ -110,6 +110,16 @@ class LocalMap
         check(tmap_export_dense(s_, id_, layer_id, ci0, cj0, w, h, out.data()));
         return out;
     }
+    /// getStitchedPointCloud(vx, vy, vz) (LocalMap.cpp:416-448): packed xyz; positive leaves -> pcl::VoxelGrid centroids
+    std::vector<float> getStitchedPointCloud(float vx = 0.f, float vy = 0.f, float vz = 0.f)
+    {
+        size_t n = 0;
+        check(tmap_stitched_cloud_voxel(s_, id_, vx, vy, vz, nullptr, 0, &n));
+        std::vector<float> out(3 * n);
+        if (n) check(tmap_stitched_cloud_voxel(s_, id_, vx, vy, vz, out.data(), n, &n));
+        out.resize(3 * n);
+        return out;
+    }
     size_t numKeyFrames() { size_t n = 0; check(tmap_num_keyframes(s_, id_, &n)); return n; }
 
   private:

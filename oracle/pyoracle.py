@@ -223,6 +223,17 @@ class OracleMap:
         return out[:cw.value * ch.value].reshape(ch.value, cw.value).copy()
 
 
+def voxel_grid(xyz, lx, ly, lz):
+    """pcl::VoxelGrid centroids of a packed (n, 3) float32 cloud, ascending voxel index."""
+    a = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+    out = np.empty_like(a)
+    L = lib()
+    L.tmo_voxel_grid.restype = C.c_size_t
+    L.tmo_voxel_grid.argtypes = [C.c_void_p, C.c_size_t, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t]
+    nv = L.tmo_voxel_grid(a.ctypes.data, len(a), lx, ly, lz, out.ctypes.data, len(a))
+    return out[:nv].copy()
+
+
 def cell_of(x0, y0, res, x, y):
     ci, cj = C.c_int32(0), C.c_int32(0)
     lib().tmo_cell_of(x0, y0, res, x, y, C.byref(ci), C.byref(cj))

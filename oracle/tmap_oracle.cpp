@@ -990,6 +990,74 @@ void tmo_export_completeness(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t
         }
 }
 
+size_t tmo_voxel_grid(const float *xyz, size_t n, float lx, float ly, float lz, float *out, size_t cap)
+{
+    /* pcl::VoxelGrid<pcl::PointXYZ>::applyFilter as LocalMap::getStitchedPointCloud uses it (LocalMap.cpp:438-446;
+     * PCL 1.12 filters/impl/voxel_grid.hpp:214-426 restated, PCL itself is not in /root/reference): dense cloud, no
+     * filter field, min_points_per_voxel 0.  PCL's std::sort / spreadsort on the voxel index leaves the order INSIDE
+     * a voxel unspecified; this restatement sorts stably, so centroids are PCL's up to float summation order. */
+    if (n == 0) return 0;
+    const float leaf[3] = {lx, ly, lz};
+    float inv[3], mn[3], mx[3];
+    for (int k = 0; k < 3; ++k)
+    {
+        inv[k] = 1.0f / leaf[k];
+        mn[k] = std::numeric_limits<float>::max();
+        mx[k] = -std::numeric_limits<float>::max();
+    }
+    for (size_t i = 0; i < n; ++i)
+        for (int k = 0; k < 3; ++k)
+        {
+            mn[k] = std::min(mn[k], xyz[3 * i + k]);
+            mx[k] = std::max(mx[k], xyz[3 * i + k]);
+        }
+    const std::int64_t dx = static_cast<std::int64_t>((mx[0] - mn[0]) * inv[0]) + 1;
+    const std::int64_t dy = static_cast<std::int64_t>((mx[1] - mn[1]) * inv[1]) + 1;
+    const std::int64_t dz = static_cast<std::int64_t>((mx[2] - mn[2]) * inv[2]) + 1;
+    if ((dx * dy * dz) > static_cast<std::int64_t>(std::numeric_limits<std::int32_t>::max()))
+    {
+        for (size_t i = 0; i < std::min(n, cap) * 3; ++i) out[i] = xyz[i];  // "Leaf size is too small": output = input
+        return n;
+    }
+    int min_b[3], max_b[3], div_b[3], mul[3];
+    for (int k = 0; k < 3; ++k)
+    {
+        min_b[k] = static_cast<int>(std::floor(mn[k] * inv[k]));
+        max_b[k] = static_cast<int>(std::floor(mx[k] * inv[k]));
+        div_b[k] = max_b[k] - min_b[k] + 1;
+    }
+    mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
+    std::vector<std::pair<unsigned int, unsigned int>> index_vector;
+    index_vector.reserve(n);
+    for (size_t i = 0; i < n; ++i)
+    {
+        const int ijk0 = static_cast<int>(std::floor(xyz[3 * i] * inv[0]) - static_cast<float>(min_b[0]));
+        const int ijk1 = static_cast<int>(std::floor(xyz[3 * i + 1] * inv[1]) - static_cast<float>(min_b[1]));
+        const int ijk2 = static_cast<int>(std::floor(xyz[3 * i + 2] * inv[2]) - static_cast<float>(min_b[2]));
+        const int idx = ijk0 * mul[0] + ijk1 * mul[1] + ijk2 * mul[2];
+        index_vector.emplace_back(static_cast<unsigned int>(idx), static_cast<unsigned int>(i));
+    }
+    std::stable_sort(index_vector.begin(), index_vector.end(),
+                     [](const std::pair<unsigned int, unsigned int> &a, const std::pair<unsigned int, unsigned int> &b) { return a.first < b.first; });
+    size_t nv = 0;
+    for (size_t i = 0; i < n;)
+    {
+        size_t j = i;
+        float sx = 0.f, sy = 0.f, sz = 0.f;
+        while (j < n && index_vector[j].first == index_vector[i].first)
+        {
+            const size_t p = 3 * static_cast<size_t>(index_vector[j].second);
+            sx += xyz[p]; sy += xyz[p + 1]; sz += xyz[p + 2];
+            ++j;
+        }
+        const float c = static_cast<float>(j - i);
+        if (nv < cap) { out[3 * nv] = sx / c; out[3 * nv + 1] = sy / c; out[3 * nv + 2] = sz / c; }
+        ++nv;
+        i = j;
+    }
+    return nv;
+}
+
 void tmo_cell_of(double x0, double y0, double res, double x, double y, int32_t *ci, int32_t *cj)
 {
     Lattice l; l.x0 = x0; l.y0 = y0; l.res = res;

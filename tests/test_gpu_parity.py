@@ -466,9 +466,9 @@ def test_dropped_clouds_and_queued_deletes(tmap, oracle):
     assert m.occupiedCellKeys().tolist() == before
     compare_maps(m, om, check_changed=True)
     s.addKeyFrameBase(2, 0, [[2.0, 2.0, 0.0]]); om.add_keyframe_base(2, [[2.0, 2.0, 0.0]])
-    with m.locked():                      # keyframe 2 is queued, then deleted before the worker gets to it
-        s.updateKeyFrame(2, I34); om.update_pose(2, I34)
-    s.deleteKeyFrame(2); om.delete_keyframe(2)
+    with m.locked():                      # keyframe 2 is queued, then deleted before the worker gets to it: the
+        s.updateKeyFrame(2, I34); om.update_pose(2, I34)   # grid lock (recursive) holds the worker off until the
+        s.deleteKeyFrame(2); om.delete_keyframe(2)          # delete is in, whichever thread is faster
     s.flush(); om.process()
     s.deleteKeyFrame(1); om.delete_keyframe(1)
     assert m.occupiedCellKeys().size == 0 and m.numKeyFrames() == 0
@@ -602,4 +602,32 @@ def test_completeness_export_matches_oracle(tmap, oracle):
     assert got.shape == want.shape and np.array_equal(got, want)
     vals = set(np.unique(want).tolist())
     assert -1 in vals and 113 in vals and any(-128 <= v < -1 for v in vals), "unobserved, complete and partial cells all present"
+    s.close()
+
+
+def test_stitched_cloud_voxel_filter_matches_oracle(tmap, oracle):
+    """getStitchedPointCloud with leaf sizes: the pcl::VoxelGrid restatement of the oracle on the same stitched
+    cloud.  Voxel set and order are integer work (exact); both sides sum a voxel's points in (voxel, index) order,
+    so the centroids are bit-identical too."""
+    from traversability_mapping_b200 import synth
+    poses = synth.trajectory("loop", 4, seed=11, extent=5.0)
+    s = tmap.System(tmap.default_params(resolution=0.1, max_range=8.0, min_range=1.0))
+    s.addNewLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    m = s.getLocalMap(0)
+    for i in range(4):
+        c = synth.make_keyframe(11, i, poses[i], max_range=8.0, rings=32, azimuths=512)
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, c) == tmap.OK
+        s.updateKeyFrame(i + 1, poses[i])
+    s.flush()
+    full = m.getStitchedPointCloud()
+    assert len(full) > 10000
+    for leaf in ((0.25, 0.25, 0.25), (0.5, 0.2, 1.0)):
+        want = oracle.voxel_grid(full, *leaf)
+        got = m.getStitchedPointCloud(*leaf)
+        assert got.shape == want.shape and 0 < len(got) < len(full)
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32)), leaf
+    tiny = m.getStitchedPointCloud(1e-4, 1e-4, 1e-4)     # indices would overflow: PCL returns the input cloud
+    assert np.array_equal(tiny.view(np.uint32), full.view(np.uint32))
+    assert np.array_equal(oracle.voxel_grid(full, 1e-4, 1e-4, 1e-4).view(np.uint32), full.view(np.uint32))
     s.close()

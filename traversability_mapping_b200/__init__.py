@@ -109,6 +109,8 @@ _SIG = {
     "tmap_queue_depth": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_keyframe_points": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_size_t)]),
     "tmap_stitched_cloud": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "tmap_stitched_cloud_voxel": (C.c_int, [_P, C.c_uint64, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t,
+                                            C.POINTER(C.c_size_t)]),
     "tmap_get_stats": (C.c_int, [_P, C.c_uint64, C.POINTER(Stats)]),
     "tmap_set_stream": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
     "tmap_shard_window": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
@@ -290,7 +292,16 @@ class LocalMap:
         _check(self._s._lib.tmap_queue_depth(self._s._h, self.map_id, C.byref(n)))
         return int(n.value)
 
-    def getStitchedPointCloud(self):
+    def getStitchedPointCloud(self, voxel_size_x=0.0, voxel_size_y=0.0, voxel_size_z=0.0):
+        """LocalMap::getStitchedPointCloud (LocalMap.cpp:416-448); positive leaf sizes -> pcl::VoxelGrid centroids."""
+        if voxel_size_x > 0 and voxel_size_y > 0 and voxel_size_z > 0:
+            n = C.c_size_t(0)
+            lib, h = self._s._lib, self._s._h
+            _check(lib.tmap_stitched_cloud_voxel(h, self.map_id, voxel_size_x, voxel_size_y, voxel_size_z, None, 0, C.byref(n)))
+            out = np.zeros((max(int(n.value), 1), 3), dtype=np.float32)
+            _check(lib.tmap_stitched_cloud_voxel(h, self.map_id, voxel_size_x, voxel_size_y, voxel_size_z, out.ctypes.data,
+                                                 int(n.value), C.byref(n)))
+            return out[: int(n.value)]
         n = C.c_size_t(0)
         _check(self._s._lib.tmap_stitched_cloud(self._s._h, self.map_id, None, 0, C.byref(n)))
         out = np.zeros((max(int(n.value), 1), 3), dtype=np.float32)

@@ -17,6 +17,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 UNITS = [
     ("kernels_bin.cu", ["-fmad=false"]),
     ("kernels_classify.cu", []),
+    ("voxel.cu", ["-fmad=false"]),
     ("runtime.cu", []),
 ]
 

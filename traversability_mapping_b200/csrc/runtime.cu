@@ -625,6 +625,82 @@ class LocalMap
         }
         return total;
     }
+    // getStitchedPointCloud(vx, vy, vz) with positive leaf sizes (LocalMap.cpp:438-446): pcl::VoxelGrid centroids
+    size_t stitchedVoxel(float lx, float ly, float lz, float *out, size_t cap)
+    {
+        if (!(lx > 0.f && ly > 0.f && lz > 0.f)) return stitched(out, cap);
+        std::vector<std::shared_ptr<KeyFrame>> snap;
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            for (auto &kv : kfs_) snap.push_back(kv.second);
+        }
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        CK(cudaSetDevice(P_.device));
+        size_t total = 0;
+        for (auto &kf : snap)
+            if (kf->hasCloud) total += kf->n;
+        if (!out || total == 0) return total;  // upper bound for sizing
+        if (total >= (1ull << 31)) throw Unsupported("stitched cloud exceeds 2^31 points");
+        const uint32_t n = (uint32_t)total;
+        voxXyz_.ensure((size_t)n * 12);
+        scratchLayers_.ensure(48);
+        size_t off = 0;
+        for (auto &kf : snap)
+        {
+            if (!kf->hasCloud) continue;
+            float p[12];
+            kf->getPose(p);
+            CK(cudaMemcpyAsync(scratchLayers_.p, p, 48, cudaMemcpyHostToDevice, stream_));
+            CK(launch_transform_cloud(stream_, kf->d_cloud, kf->n, scratchLayers_.as<float>(), voxXyz_.as<float>() + off * 3));
+            CK(cudaStreamSynchronize(stream_));  // the pose staging buffer is reused by the next keyframe
+            g_launches += 1;
+            off += kf->n;
+        }
+        voxIdx_.ensure((size_t)n * 4 * 6 + 64);
+        uint32_t *keys = voxIdx_.as<uint32_t>(), *vals = keys + 2 * (size_t)n, *head = vals + 2 * (size_t)n, *ordinal = head + n;
+        uint32_t *mm = ordinal + n;
+        CK(vox_minmax(stream_, voxXyz_.as<float>(), n, mm));
+        uint32_t mmh[6];
+        CK(cudaMemcpyAsync(mmh, mm, sizeof(mmh), cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        // PCL 1.12 voxel_grid.hpp:246-291 in its own float / int arithmetic
+        const float leaf[3] = {lx, ly, lz};
+        float inv[3], mn[3], mx[3];
+        int min_b[3], max_b[3], div_b[3], mul[3];
+        int64_t d[3];
+        for (int k = 0; k < 3; ++k)
+        {
+            inv[k] = 1.0f / leaf[k];
+            mn[k] = vox_ordered_to_float(mmh[k]);
+            mx[k] = vox_ordered_to_float(mmh[3 + k]);
+            d[k] = (int64_t)((mx[k] - mn[k]) * inv[k]) + 1;
+        }
+        size_t n_out;
+        if (d[0] * d[1] * d[2] > (int64_t)std::numeric_limits<int32_t>::max())
+        {
+            // "Leaf size is too small for the input dataset. Integer indices would overflow." -> output = input
+            n_out = n;
+            CK(cudaMemcpyAsync(out, voxXyz_.p, std::min<size_t>(n, cap) * 12, cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            return n_out;
+        }
+        for (int k = 0; k < 3; ++k)
+        {
+            min_b[k] = (int)std::floor(mn[k] * inv[k]);
+            max_b[k] = (int)std::floor(mx[k] * inv[k]);
+            div_b[k] = max_b[k] - min_b[k] + 1;
+        }
+        mul[0] = 1; mul[1] = div_b[0]; mul[2] = div_b[0] * div_b[1];
+        const size_t tb = vox_temp_bytes(n);
+        voxTemp_.ensure(tb + 16);
+        voxOut_.ensure((size_t)n * 12);
+        uint32_t nv = 0;
+        CK(vox_filter(stream_, voxXyz_.as<float>(), n, inv, min_b, mul, keys, vals, head, ordinal, voxTemp_.p, tb, voxOut_.as<float>(), &nv));
+        g_launches += 5;
+        CK(cudaMemcpyAsync(out, voxOut_.p, std::min<size_t>(nv, cap) * 12, cudaMemcpyDeviceToHost, stream_));
+        CK(cudaStreamSynchronize(stream_));
+        return nv;
+    }
     void getStats(tmap_stats *s)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
@@ -1266,6 +1342,7 @@ class LocalMap
 
     PinBuf metaH_, resH_;
     DevBuf metaD_, histD_, totD_, tileD_, sortedD_, inflFlagsD_, decay_;
+    DevBuf voxXyz_, voxIdx_, voxTemp_, voxOut_;
     uint32_t epoch_ = 0;
     DevBuf scratchKeys_, scratchLayers_, scratchOut_, scratchCount_, mergedD_, srcBaseD_, expScratch_, expCount_;
     uint32_t *globD_ = nullptr;
@@ -1808,6 +1885,15 @@ int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t 
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
     const size_t n = mp->stitched(out_xyz, cap);
+    if (n_out) *n_out = n;
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_stitched_cloud_voxel(tmap_system *s, uint64_t map_id, float leaf_x, float leaf_y, float leaf_z, float *out_xyz,
+                              size_t cap, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    const size_t n = mp->stitchedVoxel(leaf_x, leaf_y, leaf_z, out_xyz, cap);
     if (n_out) *n_out = n;
     return TMAP_OK;
     TMAP_API_END

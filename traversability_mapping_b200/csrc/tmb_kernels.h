@@ -38,4 +38,11 @@ cudaError_t launch_transform_cloud(cudaStream_t st, const float4 *d_cloud, uint3
 cudaError_t launch_export_completeness(cudaStream_t st, const GridView &g, int ci0, int cj0, int w, int h, int kx, int ky, int f,
                                        int cw, int ch, signed char *d_out);
 cudaError_t launch_mark_observed_changed(cudaStream_t st, const GridView &g);
+// voxel.cu: pcl::VoxelGrid centroid filter of the stitched cloud
+cudaError_t vox_minmax(cudaStream_t st, const float *d_xyz, uint32_t n, uint32_t *d_mm6);
+float vox_ordered_to_float(uint32_t o);
+size_t vox_temp_bytes(uint32_t n);
+cudaError_t vox_filter(cudaStream_t st, const float *d_xyz, uint32_t n, const float inv[3], const int min_b[3], const int mul[3],
+                       uint32_t *d_keys, uint32_t *d_vals, uint32_t *d_head, uint32_t *d_ordinal, void *d_temp, size_t temp_bytes,
+                       float *d_out, uint32_t *n_vox_host);
 }  // namespace tmb
