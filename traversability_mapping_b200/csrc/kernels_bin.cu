@@ -235,7 +235,7 @@ __global__ void k_pack_base(const float *__restrict__ xyz, size_t n, float4 *__r
 // k_hist: transform + key + per-chunk bin histogram
 // ---------------------------------------------------------------------------------------------
 template <int PPT>
-__global__ void __launch_bounds__(BIN_THREADS) k_hist(BatchView b, LatticeD lat)
+__global__ void __launch_bounds__(BIN_THREADS, 5) k_hist(BatchView b, LatticeD lat)
 {
     extern __shared__ uint32_t s_hist[];
     __shared__ OpDesc s_op;
