@@ -1,7 +1,8 @@
 // kernels_bin.cu -- prune, transform + cell key, tile-bucket sort, per-tile segmented fold.
 //
 // Replaces (reference paths relative to traversability_mapping/):
-//   System::prune                 src/System.cpp:93-114        -> k_prune_count / k_prune_scatter
+//   System::prune                 src/System.cpp:93-114        -> k_prune_count / k_prune_scatter (also the
+//                                 PointCloud2 decode of conversions.cpp:19-26: field offsets, endianness)
 //   KeyFrame::rebin               src/KeyFrame.cpp:52-67       -> k_hist + k_scatter + k_fold
 //   Lattice::cellOf / centerOf    include/.../Moments.hpp:105-116
 //   NodeMetaData::insert          include/.../Moments.hpp:53-59
@@ -14,15 +15,16 @@
 // and sums; each keyframe's partial is cast to float32 and added to the float32 layer in op
 // order.  This file is compiled with -fmad=false and uses the _rn intrinsics on those paths.
 //
-// Pipeline for a batch of ops (op = keyframe cloud x pose x sign):
+// Pipeline for a batch of ops (op = keyframe cloud x pose x sign); buckets are 16x16-cell bins:
 //   k_hist      : per 256*PPT-point chunk, transform+key, shared-memory histogram over the op's
-//                 tile window (warp-aggregated shared atomics; integer counts are exact)
-//   k_scan_*    : exclusive prefixes over chunks, ops and tiles -> every (tile, op, chunk) slot
-//   k_scatter   : re-derive the keys, STABLE rank inside the chunk (per-warp counters +
-//                 match_any), write (x_m, y_m, z_m, op|cell) records bucketed by global tile
-//   k_fold      : one CTA per touched tile: shared-memory-staged stable LSD radix sort on the
-//                 10-bit cell key, one thread per cell walks its segment in (op, point) order
-//                 accumulating doubles, then folds float32 into the tile's 48-byte records.
+//                 bin window (warp-aggregated shared atomics; integer counts are exact)
+//   k_scan_*    : exclusive prefixes over chunks, ops and bins -> every (bin, op, chunk) slot,
+//                 plus the work lists (bins to fold / gate, tiles to inflate)
+//   k_scatter   : re-derive the keys, STABLE rank inside the chunk (per-warp counters + one
+//                 match_any per point), write (x_m, y_m, z_m, sign|op|cell) records bucketed by bin
+//   k_fold      : one CTA per touched bin: shared-memory-staged stable counting sort on the 8-bit
+//                 cell key, one thread per cell walks its run in (op, point) order accumulating
+//                 doubles, then folds float32 into the cell's 48-byte record (blank rule included).
 #include "tmb_common.cuh"
 #include <math_constants.h>
 

@@ -1,7 +1,7 @@
 // kernels_classify.cu -- halo-tile stencil classification, step inflation, exports.
 //
 // Replaces (reference paths relative to traversability_mapping/):
-//   LocalMap::recomputeCell / recomputeDirty   src/LocalMap.cpp:130-199    -> k_classify
+//   LocalMap::recomputeCell / recomputeDirty   src/LocalMap.cpp:130-199    -> k_gate + k_classify
 //   computeGoodness                            src/TraversabilityMetrics.cpp:23-124
 //   discOffsets / dilate                       src/Helpers.cpp:156-184     (disc in __constant__,
 //                                              dilation evaluated per cell from the touched bits)
@@ -10,13 +10,15 @@
 //   fillSparseUpdate                           traversability_mapping_ros/src/conversions.cpp:28-55
 //   GridMapRosConverter::toOccupancyGrid       (grid_map_ros; call site global_traversability_node.cpp:374)
 //
-// k_classify: one CTA per candidate 16x16 bin (ticket loop).  The (16+2r)^2 x 48-byte halo tile
-// of moment records arrives with ONE 3-D TMA box load (cp.async.bulk.tensor, mbarrier completion,
-// out-of-bounds cells filled with NaN = unobserved).  A pre-pass derives per-halo-cell gate bits
-// and 1/N; each thread then classifies one cell: the disc moments are fused about the query
-// centre as 21 lattice-weighted sums (the shift of Moments.cpp:49-58 expanded for offsets that
-// are integer multiples of the resolution), followed by the 3x3 covariance, the smallest
-// eigenpair (eig3.cuh) and a second pass over the disc for the step spread.  All in fp64.
+//   publishCompleteness                        traversability_mapping_ros/src/global_traversability_node.cpp:381-459
+//
+// k_gate decides, from the flag bytes alone, which cells of every candidate 16x16 bin are dirty and which of
+// those pass the footprint gate; k_classify fits the gated-in cells of the bins k_gate listed.  The (16+2r)^2 x
+// 48-byte halo tile of moment records arrives with ONE 3-D TMA box load (cp.async.bulk.tensor, mbarrier
+// completion, out-of-bounds cells filled with NaN = unobserved) and is widened to fp64 once; each thread then
+// classifies one cell: the disc moments are fused about the query centre as 21 lattice-weighted sums (the shift
+// of Moments.cpp:49-58 expanded for offsets that are integer multiples of the resolution), followed by the 3x3
+// covariance, the smallest eigenpair (eig3.cuh) and a second pass over the disc for the step spread.  All in fp64.
 #include "tmb_common.cuh"
 #include "eig3.cuh"
 #include <cuda.h>
