@@ -60,7 +60,7 @@ typedef struct tmap_params
     int32_t num_local_keyframes;/* mapping/num_local_keyframes (unused by the reference too) */
     int32_t global_adjustment_sleep; /* mapping/global_adjustment_sleep (unused: no backstop thread) */
     int32_t inflation_enabled;  /* inflation/enabled */
-    int32_t use_pointcloud_buffer; /* pointcloud/use_pointcloud_buffer (buffers are out of scope) */
+    int32_t use_pointcloud_buffer; /* pointcloud/use_pointcloud_buffer: enables tmap_push_to_buffer / tmap_add_keyframe_ts */
     int32_t use_ros_buffer;     /* pointcloud/use_ros_buffer */
     int32_t reserved0;
     double inflation_radius;    /* inflation/inflation_radius */
@@ -149,6 +149,16 @@ int tmap_add_keyframe(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uin
 int tmap_add_keyframe_pc2(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id, const void *data,
                           size_t n_points, size_t point_step, uint32_t x_offset, uint32_t y_offset, uint32_t z_offset,
                           int is_bigendian);
+/* System::pushToBuffer(timestamp, cloud) (System.hpp, System.cpp:339-344) + PointCloudBuffer::addPointCloud
+ * (PointCloudBuffer.cpp:26-32): store a sensor-frame cloud under its acquisition time (seconds).  The copy lives in
+ * DEVICE memory; when the buffered span exceeds 25 s everything older than timestamp - 5 s is dropped.  A no-op
+ * unless params.use_pointcloud_buffer (the reference creates no buffer otherwise, System.cpp:38-42). */
+int tmap_push_to_buffer(tmap_system *s, double timestamp_s, const float *xyz, size_t n, size_t stride_bytes);
+/* System::addNewKeyFrameTsDouble (System.cpp:174-186; addNewKeyFrameTsULong = the same with ns * 1e-9): the
+ * keyframe's cloud is the buffered one closest in time (the first such on a tie, PointCloudBuffer.cpp:34-46);
+ * empty / absent buffer -> TMAP_IGNORED_NULL.  Pruned on the device without another host copy. */
+int tmap_add_keyframe_ts(tmap_system *s, double timestamp_s, uint64_t kf_id, uint64_t map_id);
+int tmap_buffered_clouds(tmap_system *s, size_t *n_out);
 /* Same, with the cloud already in DEVICE memory (float4-strided or packed). */
 int tmap_add_keyframe_device(tmap_system *s, uint64_t timestamp_ns, uint64_t kf_id, uint64_t map_id,
                              const void *d_xyz, size_t n, size_t stride_bytes);

@@ -199,6 +199,20 @@ class System
                        sizeof(pcl::PointXYZ));
     }
 #endif
+    /// pushToBuffer / addNewKeyFrameTsDouble / addNewKeyFrameTsULong (System.cpp:174-191, 339-344)
+    void pushToBuffer(double timestamp_s, const float *xyz, size_t n, size_t stride_bytes)
+    {
+        check(tmap_push_to_buffer(s_, timestamp_s, xyz, n, stride_bytes));
+    }
+    void addNewKeyFrameTsDouble(double timestamp_s, std::uint64_t kfID, std::uint64_t mapID)
+    {
+        check(tmap_add_keyframe_ts(s_, timestamp_s, kfID, mapID));
+    }
+    void addNewKeyFrameTsULong(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID)
+    {
+        addNewKeyFrameTsDouble(static_cast<double>(timestamp_ns / 1000000000ULL) + static_cast<double>(timestamp_ns % 1000000000ULL) * 1e-9,
+                               kfID, mapID);
+    }
     void updateKeyFrame(std::uint64_t kfID, const Pose &pose_map_base, std::uint64_t /*numConnections*/ = 0)
     {
         check(tmap_update_pose(s_, kfID, pose_map_base.m));

@@ -631,3 +631,48 @@ def test_stitched_cloud_voxel_filter_matches_oracle(tmap, oracle):
     assert np.array_equal(tiny.view(np.uint32), full.view(np.uint32))
     assert np.array_equal(oracle.voxel_grid(full, 1e-4, 1e-4, 1e-4).view(np.uint32), full.view(np.uint32))
     s.close()
+
+
+def test_pointcloud_buffer_and_timestamped_keyframes(tmap, oracle):
+    """pushToBuffer + addNewKeyFrameTsDouble (System.cpp:174-186, 339-344; PointCloudBuffer.cpp): the keyframe's cloud
+    is the buffered one closest in time (first on a tie); a span over 25 s drops everything older than t - 5 s; without
+    use_pointcloud_buffer both calls do nothing."""
+    from traversability_mapping_b200 import synth
+    P = synth.trajectory("single", 1, seed=8)[0]
+    clouds = {t: synth.make_keyframe(8, i, P, max_range=8.0, rings=16, azimuths=256) for i, t in enumerate((1.0, 2.0, 3.0))}
+    s = tmap.System(tmap.default_params(resolution=0.1, max_range=6.0, min_range=1.0, use_pointcloud_buffer=1))
+    s.addNewLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    m = s.getLocalMap(0)
+    assert s.addNewKeyFrameTsDouble(1.0, 1, 0) == tmap.IGNORED_NULL     # empty buffer
+    for t, c in clouds.items():
+        assert s.pushToBuffer(t, c) == tmap.OK
+    assert s.bufferedClouds() == 3
+
+    def via_pcl(c):
+        assert s.addNewKeyFrameWithPCL(0, 99, 0, c) == tmap.OK
+        out = m.getStitchedPointCloud().copy()
+        s.deleteKeyFrame(99)
+        return out
+
+    for kf, (query, expect) in enumerate([(2.1, 2.0), (1.5, 1.0), (9.0, 3.0), (-4.0, 1.0)], start=1):
+        assert s.addNewKeyFrameTsDouble(query, kf, 0) == tmap.OK
+        got = m.getStitchedPointCloud().copy()
+        s.deleteKeyFrame(kf)
+        want = via_pcl(clouds[expect])
+        assert got.shape == want.shape and np.array_equal(got.view(np.uint32), want.view(np.uint32)), (query, expect)
+    assert s.addNewKeyFrameTsULong(2_900_000_000, 7, 0) == tmap.OK       # 2.9 s -> the 3.0 s cloud
+    got = m.getStitchedPointCloud().copy()
+    s.deleteKeyFrame(7)
+    assert np.array_equal(got.view(np.uint32), via_pcl(clouds[3.0]).view(np.uint32))
+    # pruning: 1, 2, 3 are buffered; 27 makes the span 26 s > 25 s -> everything older than 22 s goes
+    s.pushToBuffer(27.0, clouds[1.0])
+    assert s.bufferedClouds() == 1
+    s.pushToBuffer(30.0, clouds[2.0])
+    assert s.bufferedClouds() == 2                                        # span 3 s: nothing dropped
+    s.close()
+    s2 = tmap.System(tmap.default_params(resolution=0.1))                 # buffer not enabled
+    s2.addNewLocalMap(0)
+    assert s2.pushToBuffer(1.0, clouds[1.0]) == tmap.OK and s2.bufferedClouds() == 0
+    assert s2.addNewKeyFrameTsDouble(1.0, 1, 0) == tmap.IGNORED_NULL
+    s2.close()

@@ -85,6 +85,9 @@ _SIG = {
     "tmap_add_keyframe_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tmap_add_keyframe_pc2": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t,
                                         C.c_uint32, C.c_uint32, C.c_uint32, C.c_int]),
+    "tmap_push_to_buffer": (C.c_int, [_P, C.c_double, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "tmap_add_keyframe_ts": (C.c_int, [_P, C.c_double, C.c_uint64, C.c_uint64]),
+    "tmap_buffered_clouds": (C.c_int, [_P, C.POINTER(C.c_size_t)]),
     "tmap_add_keyframe_base": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t]),
     "tmap_update_pose": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_float)]),
     "tmap_update_poses": (C.c_int, [_P, C.POINTER(C.c_uint64), C.POINTER(C.c_float), C.c_size_t]),
@@ -380,6 +383,26 @@ class System:
         return _check(self._lib.tmap_add_keyframe_pc2(self._h, int(timestamp_ns), int(kf_id) & 0xFFFFFFFFFFFFFFFF, int(map_id),
                                                       a.ctypes.data, n, int(point_step), int(x_offset), int(y_offset),
                                                       int(z_offset), 1 if is_bigendian else 0))
+
+    def pushToBuffer(self, timestamp_s, cloud):
+        """System::pushToBuffer (System.cpp:339-344): buffer a sensor-frame cloud under its acquisition time."""
+        a = np.ascontiguousarray(cloud, dtype=np.float32)
+        if a.ndim != 2 or a.shape[1] not in (3, 4):
+            raise ValueError("cloud must be (n,3) or (n,4) float32")
+        return _check(self._lib.tmap_push_to_buffer(self._h, float(timestamp_s), a.ctypes.data, a.shape[0], a.shape[1] * 4))
+
+    def addNewKeyFrameTsDouble(self, timestamp_s, kf_id, map_id):
+        """System::addNewKeyFrameTsDouble (System.cpp:174-186): keyframe from the buffered cloud closest in time."""
+        return _check(self._lib.tmap_add_keyframe_ts(self._h, float(timestamp_s), int(kf_id) & 0xFFFFFFFFFFFFFFFF, int(map_id)))
+
+    def addNewKeyFrameTsULong(self, timestamp_ns, kf_id, map_id):
+        ns = int(timestamp_ns)
+        return self.addNewKeyFrameTsDouble((ns // 1000000000) + (ns % 1000000000) * 1e-9, kf_id, map_id)
+
+    def bufferedClouds(self):
+        n = C.c_size_t(0)
+        _check(self._lib.tmap_buffered_clouds(self._h, C.byref(n)))
+        return int(n.value)
 
     def addNewKeyFrameDevice(self, timestamp_ns, kf_id, map_id, dev_ptr, n, stride_bytes=16):
         return _check(self._lib.tmap_add_keyframe_device(self._h, int(timestamp_ns), int(kf_id), int(map_id),

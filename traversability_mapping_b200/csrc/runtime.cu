@@ -1397,6 +1397,8 @@ class System
         current_.reset();  // every owner of a KeyFrame must go before the allocation stream does
         maps_.clear();
         kfs_.clear();
+        for (auto &b : cloudBuf_) cudaFreeAsync(b.d, ingest_);
+        cloudBuf_.clear();
         cudaStreamSynchronize(ingest_);
         cudaStreamDestroy(ingest_);
     }
@@ -1514,6 +1516,63 @@ class System
         }
         auto kf = pruneToKeyFrame(xyz, on_device, n, stride, T, P_.max_range, P_.min_range, ff, big_endian);
         return registerKeyFrame(nsToSec(ts_ns), kfID, mapID, kf);
+    }
+    // System::pushToBuffer (System.cpp:339-344) + PointCloudBuffer::addPointCloud (PointCloudBuffer.cpp:26-32)
+    int pushToBuffer(double timestamp, const void *xyz, size_t n, size_t stride)
+    {
+        if (!P_.use_pointcloud_buffer) return TMAP_OK;  // no buffer was created (System.cpp:38-42): silently nothing
+        if (!xyz) return TMAP_IGNORED_NULL;
+        if (stride < 12 || stride % 4) throw std::invalid_argument("stride_bytes must be a multiple of 4 and >= 12");
+        std::lock_guard<std::recursive_mutex> l(bufMutex_);
+        Buffered b{timestamp, nullptr, n, stride};
+        {
+            std::lock_guard<std::mutex> il(ingestMutex_);
+            CK(cudaSetDevice(P_.device));
+            CK(cudaMallocAsync(&b.d, std::max<size_t>(n * stride, 16), ingest_));
+            if (n) CK(cudaMemcpyAsync(b.d, xyz, n * stride, cudaMemcpyHostToDevice, ingest_));
+            CK(cudaStreamSynchronize(ingest_));  // the caller's buffer may go away after the call returns
+        }
+        cloudBuf_.push_back(b);
+        if (std::abs(cloudBuf_.front().t - cloudBuf_.back().t) > 25.0)
+        {
+            // deletePointsBefore(timestamp - 5.0) (PointCloudBuffer.cpp:48-53)
+            std::lock_guard<std::mutex> il(ingestMutex_);
+            while (!cloudBuf_.empty() && cloudBuf_.front().t < timestamp - 5.0)
+            {
+                cudaFreeAsync(cloudBuf_.front().d, ingest_);
+                cloudBuf_.pop_front();
+            }
+        }
+        return TMAP_OK;
+    }
+    // System::addNewKeyFrameTsDouble (System.cpp:174-186) + getClosestPointCloud (PointCloudBuffer.cpp:34-46)
+    int addKeyFrameTs(double timestamp, uint64_t kfID, uint64_t mapID)
+    {
+        std::lock_guard<std::recursive_mutex> l(bufMutex_);
+        if (!P_.use_pointcloud_buffer || cloudBuf_.empty()) return TMAP_IGNORED_NULL;  // "buffer is empty" -> nullptr -> return
+        // std::min_element: the FIRST element with the smallest |t - query|
+        size_t best = 0;
+        for (size_t i = 1; i < cloudBuf_.size(); ++i)
+            if (std::abs(cloudBuf_[i].t - timestamp) < std::abs(cloudBuf_[best].t - timestamp)) best = i;
+        const Buffered &b = cloudBuf_[best];
+        if (kfID > (uint64_t)std::numeric_limits<int64_t>::max()) return TMAP_ERR_NEGATIVE_ID;
+        {
+            std::lock_guard<std::recursive_mutex> ml(m_);
+            if (kfs_.count(kfID)) return TMAP_IGNORED_DUPLICATE;
+            if (!maps_.count(mapID)) return TMAP_IGNORED_UNKNOWN_MAP;
+        }
+        float T[12];
+        {
+            std::lock_guard<std::recursive_mutex> ml(m_);
+            std::memcpy(T, Tbv_, sizeof(T));
+        }
+        auto kf = pruneToKeyFrame(b.d, true, b.n, b.stride, T, P_.max_range, P_.min_range);
+        return registerKeyFrame(timestamp, kfID, mapID, kf);
+    }
+    size_t bufferedClouds()
+    {
+        std::lock_guard<std::recursive_mutex> l(bufMutex_);
+        return cloudBuf_.size();
     }
     int addKeyFrameBase(uint64_t kfID, uint64_t mapID, const float *xyz, size_t n)
     {
@@ -1660,6 +1719,15 @@ class System
     cudaStream_t ingest_ = nullptr;
     DevBuf raw_, warpCnt_, total_;
     PinBuf totalH_;
+    // PointCloudBuffer (PointCloudBuffer.cpp): clouds by acquisition time, kept in DEVICE memory (stream-ordered pool)
+    struct Buffered
+    {
+        double t;
+        void *d;
+        size_t n, stride;
+    };
+    std::deque<Buffered> cloudBuf_;
+    std::recursive_mutex bufMutex_;
 };
 }  // namespace tmb
 
@@ -1748,6 +1816,20 @@ int tmap_add_keyframe_pc2(tmap_system *s, uint64_t ts_ns, uint64_t kf_id, uint64
     const uint32_t off[3] = {x_offset, y_offset, z_offset};
     return s->sys->addKeyFrame(ts_ns, kf_id, map_id, data, false, n_points, point_step, off, is_bigendian ? 1 : 0);
     TMAP_API_END
+}
+int tmap_push_to_buffer(tmap_system *s, double timestamp_s, const float *xyz, size_t n, size_t stride_bytes)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->pushToBuffer(timestamp_s, xyz, n, stride_bytes); TMAP_API_END
+}
+int tmap_add_keyframe_ts(tmap_system *s, double timestamp_s, uint64_t kf_id, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN return s->sys->addKeyFrameTs(timestamp_s, kf_id, map_id); TMAP_API_END
+}
+int tmap_buffered_clouds(tmap_system *s, size_t *n_out)
+{
+    NEED(s)
+    if (!n_out) { tmb::g_last_error = "null n_out"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN *n_out = s->sys->bufferedClouds(); return TMAP_OK; TMAP_API_END
 }
 int tmap_add_keyframe_base(tmap_system *s, uint64_t kf_id, uint64_t map_id, const float *xyz, size_t n)
 {
