@@ -94,3 +94,59 @@ def test_batched_vs_sequential_oracle(oracle):
             assert helpers.bits_equal(da[~gated_out, i], db[~gated_out, i])
         else:
             assert helpers.bits_equal(da[:, i], db[:, i]), l
+
+
+def test_voxel_grid_restatement_vs_independent_numpy(oracle):
+    """tmo_voxel_grid (pcl::VoxelGrid restated, PCL 1.12 voxel_grid.hpp:214-426) against an independent numpy
+    statement of the same float arithmetic: voxel ids, output order, centroids (sequential float32 sums)."""
+    rng = np.random.default_rng(5)
+    pts = (rng.standard_normal((5000, 3)) * np.array([6.0, 4.0, 1.5])).astype(np.float32)
+    for leaf in ((0.5, 0.5, 0.5), (1.0, 0.25, 2.0)):
+        got = oracle.voxel_grid(pts, *leaf)
+        inv = (np.float32(1.0) / np.asarray(leaf, dtype=np.float32)).astype(np.float32)
+        mn, mx = pts.min(0), pts.max(0)
+        min_b = np.floor(mn * inv).astype(np.int64)
+        div_b = np.floor(mx * inv).astype(np.int64) - min_b + 1
+        ijk = (np.floor(pts * inv).astype(np.float32) - min_b.astype(np.float32)).astype(np.int64)
+        idx = ijk[:, 0] + ijk[:, 1] * div_b[0] + ijk[:, 2] * div_b[0] * div_b[1]
+        order = np.argsort(idx, kind="stable")
+        sidx = idx[order]
+        starts = np.flatnonzero(np.r_[True, sidx[1:] != sidx[:-1]])
+        ends = np.r_[starts[1:], len(sidx)]
+        want = np.empty((len(starts), 3), dtype=np.float32)
+        for k, (a, b) in enumerate(zip(starts, ends)):
+            seg = pts[order[a:b]]
+            want[k] = np.cumsum(seg, axis=0, dtype=np.float32)[-1] / np.float32(b - a)   # sequential float32 sums
+        assert got.shape == want.shape
+        assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    # a leaf so small that the voxel index would overflow int32: PCL warns and returns the input
+    assert np.array_equal(oracle.voxel_grid(pts, 1e-4, 1e-4, 1e-4), pts)
+
+
+def test_completeness_restatement_vs_independent_numpy(oracle):
+    """tmo_export_completeness (publishCompleteness, global_traversability_node.cpp:381-459) against a numpy
+    statement: border_haz -> int8 occupancy, f x f min-pool skipping unobserved cells, palette bytes."""
+    import traversability_mapping_b200 as tm
+    import helpers
+    from golden.make_golden import PARAMS, scene_inputs
+    from traversability_mapping_b200 import synth
+    poses, clouds = scene_inputs()
+    om = oracle.OracleMap(oracle.params_from(tm.default_params(**PARAMS)))
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    for i, c in enumerate(clouds):
+        om.add_keyframe(i + 1, c); om.update_pose(i + 1, poses[i]); om.process()
+    kx, ky = om.grid_extent()
+    border = om.export_dense("border_haz", -kx, -ky, 2 * kx + 1, 2 * ky + 1)
+    scaled = np.nan_to_num(np.clip(border, 0, 1) * np.float32(100), nan=0.0)
+    fine = np.where(np.isnan(border), -1, scaled.astype(np.int8)).astype(np.int64)
+    for publish in (PARAMS["resolution"], 2 * PARAMS["resolution"], 3 * PARAMS["resolution"]):
+        f = max(1, int(np.floor(publish / float(np.float32(PARAMS["resolution"])) + 0.5)))
+        h, w = fine.shape
+        ch, cw = (h + f - 1) // f, (w + f - 1) // f
+        pad = np.full((ch * f, cw * f), 101, dtype=np.int64)
+        pad[:h, :w] = np.where(fine >= 0, fine, 101)
+        best = pad.reshape(ch, f, cw, f).min(axis=(1, 3))
+        want = np.where(best > 100, -1, np.where(best >= 100, 113, 128 + np.floor(best / 100.0 * 126 + 0.5).astype(np.int64)))
+        want = want.astype(np.uint8).view(np.int8)
+        got = om.export_completeness(publish)
+        assert got.shape == want.shape and np.array_equal(got, want), publish
