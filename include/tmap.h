@@ -205,6 +205,11 @@ int tmap_occupied_cell_keys(tmap_system *s, uint64_t map_id, uint64_t *out, size
  * keys outside the grid give NaN rows. */
 int tmap_read_layers(tmap_system *s, uint64_t map_id, const uint64_t *keys, size_t n,
                      const int32_t *layer_ids, size_t n_layers, float *out);
+/* tmap_ros::fillSparseUpdate (traversability_mapping_ros/src/conversions.cpp:28-55), the payload of
+ * traversability_msgs/TraversabilitySparseUpdate: keys whose cell lies outside the grid are skipped, the others keep
+ * their order; out_values[i * n_layers + l].  out_keys / out_values hold n_keys entries; *n_out = kept keys. */
+int tmap_fill_sparse_update(tmap_system *s, uint64_t map_id, const int32_t *layer_ids, size_t n_layers, const uint64_t *keys,
+                            size_t n_keys, uint64_t *out_keys, float *out_values, size_t *n_out);
 /* grid_map geometry the reference would have: cells per axis = 2*k+1 (Helpers.cpp:35-84) */
 int tmap_grid_extent(tmap_system *s, uint64_t map_id, int32_t *kx, int32_t *ky);
 /* LocalMap::getGridMap()[layer] crop: out[(cj-cj0)*w + (ci-ci0)], NaN outside the grid */

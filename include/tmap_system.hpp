@@ -82,6 +82,18 @@ class LocalMap
         check(tmap_read_layers(s_, id_, k.data(), k.size(), layers.data(), layers.size(), out.data()));
         return out;
     }
+    /// fillSparseUpdate with the in-grid filter (conversions.cpp:43-47): `k` is replaced by the kept keys
+    std::vector<float> fillSparseUpdate(std::vector<std::uint64_t> &k, const std::vector<int32_t> &layers)
+    {
+        std::vector<std::uint64_t> kept(k.size());
+        std::vector<float> vals(k.size() * layers.size());
+        size_t n = 0;
+        check(tmap_fill_sparse_update(s_, id_, layers.data(), layers.size(), k.data(), k.size(), kept.data(), vals.data(), &n));
+        kept.resize(n);
+        vals.resize(n * layers.size());
+        k.swap(kept);
+        return vals;
+    }
     void gridExtent(int32_t &kx, int32_t &ky) { check(tmap_grid_extent(s_, id_, &kx, &ky)); }
     /// toOccupancyGrid(grid, "hazard", 0, 1, og): whole grid, nav_msgs ordering
     std::vector<int8_t> occupancy(int32_t &width, int32_t &height)

@@ -213,6 +213,19 @@ class OracleMap:
         lib().tmo_export_occupancy(self._h, ci0, cj0, w, h, out.ctypes.data)
         return out
 
+    def fill_sparse_update(self, layers, keys):
+        """fillSparseUpdate (conversions.cpp:28-55) -> (kept keys, values (n, len(layers)))."""
+        import traversability_mapping_b200 as tm
+        ids = np.ascontiguousarray([tm.LAYER_ID[l] if isinstance(l, str) else int(l) for l in layers], dtype=np.int32)
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        ok = np.empty(len(k), dtype=np.uint64)
+        ov = np.empty((len(k), len(ids)), dtype=np.float32)
+        L = lib()
+        L.tmo_fill_sparse_update.restype = C.c_size_t
+        L.tmo_fill_sparse_update.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        n = L.tmo_fill_sparse_update(self._h, ids.ctypes.data, len(ids), k.ctypes.data, len(k), ok.ctypes.data, ov.ctypes.data)
+        return ok[:n].copy(), ov[:n].copy()
+
     def export_completeness(self, publish_res=0.25, ci0=None, cj0=None, w=None, h=None):
         if ci0 is None:
             kx, ky = self.grid_extent()

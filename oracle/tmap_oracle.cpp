@@ -905,6 +905,26 @@ void tmo_read_layers(const tmo_map *m, const uint64_t *keys, size_t n, const int
     }
 }
 
+size_t tmo_fill_sparse_update(const tmo_map *m, const int32_t *layer_ids, size_t n_layers, const uint64_t *keys, size_t n,
+                              uint64_t *out_keys, float *out_values)
+{
+    /* tmap_ros::fillSparseUpdate (traversability_mapping_ros/src/conversions.cpp:28-55): keys whose cell centre is
+     * outside the grid are skipped; the rest keep their order, values[i * n_layers + l]. */
+    size_t k = 0;
+    for (size_t i = 0; i < n; ++i)
+    {
+        int ci, cj;
+        Lattice::unkey(keys[i], ci, cj);
+        if (!m->grid.inside(ci, cj))
+            continue;
+        out_keys[k] = keys[i];
+        for (size_t l = 0; l < n_layers; ++l)
+            out_values[k * n_layers + l] = m->grid.L[layer_ids[l]][m->grid.at(ci, cj)];
+        ++k;
+    }
+    return k;
+}
+
 void tmo_grid_extent(const tmo_map *m, int32_t *kx, int32_t *ky) { *kx = m->grid.kx; *ky = m->grid.ky; }
 
 void tmo_export_dense(const tmo_map *m, int32_t layer, int32_t ci0, int32_t cj0, int32_t w, int32_t h, float *out)

@@ -112,6 +112,9 @@ size_t tmo_occupied_cell_keys(const tmo_map *m, uint64_t *out, size_t cap);
 void tmo_read_layers(const tmo_map *m, const uint64_t *keys, size_t n, const int32_t *layer_ids,
                      size_t n_layers, float *out);
 /* Grid geometry: cells per axis = 2*k+1, k = ceil(half/res) (Helpers.cpp:42-47). */
+/* fillSparseUpdate (conversions.cpp:28-55): keys outside the grid skipped, order kept; returns the count */
+size_t tmo_fill_sparse_update(const tmo_map *m, const int32_t *layer_ids, size_t n_layers, const uint64_t *keys, size_t n,
+                              uint64_t *out_keys, float *out_values);
 void tmo_grid_extent(const tmo_map *m, int32_t *kx, int32_t *ky);
 /* Dense crop of one layer: out[(cj-cj0)*w + (ci-ci0)], NaN outside the grid. */
 void tmo_export_dense(const tmo_map *m, int32_t layer, int32_t ci0, int32_t cj0, int32_t w,

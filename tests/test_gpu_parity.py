@@ -676,3 +676,25 @@ def test_pointcloud_buffer_and_timestamped_keyframes(tmap, oracle):
     assert s2.pushToBuffer(1.0, clouds[1.0]) == tmap.OK and s2.bufferedClouds() == 0
     assert s2.addNewKeyFrameTsDouble(1.0, 1, 0) == tmap.IGNORED_NULL
     s2.close()
+
+
+def test_sparse_update_payload_matches_oracle(tmap, oracle):
+    """tmap_fill_sparse_update == fillSparseUpdate (conversions.cpp:28-55): keys outside the grid are dropped, the
+    rest keep their order, values per (key, layer)."""
+    s, m, om, _ = run_small_scene(tmap, oracle)
+    occ = m.occupiedCellKeys()
+    assert np.array_equal(occ, om.occupied_cell_keys())
+    kx, ky = m.gridExtent()
+    far = np.array([tmap.key(kx + 5, 0), tmap.key(0, -ky - 1), tmap.key(-kx - 40, ky + 7)], dtype=np.uint64)
+    keys = np.concatenate([far[:1], occ[::3], far[1:2], occ[1::7], far[2:]])
+    layers = ["hazard", "elevation", "step_haz_inflated", "N"]
+    gk, gv = m.fillSparseUpdate(layers, keys)
+    wk, wv = om.fill_sparse_update(layers, keys)
+    assert np.array_equal(gk, wk) and len(gk) == len(keys) - 3
+    assert gv.shape == wv.shape
+    assert np.array_equal(np.isnan(gv), np.isnan(wv))
+    np.testing.assert_allclose(gv, wv, rtol=helpers.RTOL, atol=helpers.ATOL, equal_nan=True)
+    assert np.array_equal(gv[:, 3].view(np.uint32), wv[:, 3].view(np.uint32))   # counts: bit-exact
+    ek, ev = m.fillSparseUpdate(layers, np.zeros(0, dtype=np.uint64))
+    assert len(ek) == 0 and ev.shape == (0, 4)
+    s.close()

@@ -103,6 +103,8 @@ _SIG = {
     "tmap_take_changed_cells": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tmap_occupied_cell_keys": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tmap_read_layers": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "tmap_fill_sparse_update": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                          C.POINTER(C.c_size_t)]),
     "tmap_grid_extent": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "tmap_export_dense": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "tmap_export_occupancy": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
@@ -271,6 +273,17 @@ class LocalMap:
             out = np.empty((h, w), dtype=np.int8)
         _check(self._s._lib.tmap_export_occupancy(self._s._h, self.map_id, ci0, cj0, w, h, out.ctypes.data))
         return out
+
+    def fillSparseUpdate(self, layers, keys):
+        """tmap_ros::fillSparseUpdate (conversions.cpp:28-55) -> (kept keys, values (n, len(layers)))."""
+        ids = np.ascontiguousarray([LAYER_ID[l] if isinstance(l, str) else int(l) for l in layers], dtype=np.int32)
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        ok = np.empty(len(k), dtype=np.uint64)
+        ov = np.empty((len(k), len(ids)), dtype=np.float32)
+        n = C.c_size_t(0)
+        _check(self._s._lib.tmap_fill_sparse_update(self._s._h, self.map_id, ids.ctypes.data, len(ids), k.ctypes.data, len(k),
+                                                    ok.ctypes.data, ov.ctypes.data, C.byref(n)))
+        return ok[: n.value].copy(), ov[: n.value].copy()
 
     def exportCompleteness(self, publish_res=0.25, ci0=None, cj0=None, w=None, h=None):
         """publishCompleteness (global_traversability_node.cpp:381-459): (rows, cols) int8 palette bytes."""

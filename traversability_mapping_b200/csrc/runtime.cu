@@ -546,6 +546,19 @@ class LocalMap
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
+    // fillSparseUpdate (conversions.cpp:28-55): keys outside the grid are skipped (order kept), then one gather
+    size_t fillSparseUpdate(const int32_t *layers, size_t nl, const uint64_t *keys, size_t n, uint64_t *out_keys, float *out_values)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        size_t k = 0;
+        for (size_t i = 0; i < n; ++i)
+        {
+            const int ci = (int)(uint32_t)(keys[i] >> 32), cj = (int)(uint32_t)(keys[i] & 0xffffffffu);
+            if (std::abs((long)ci) <= kx_ && std::abs((long)cj) <= ky_) out_keys[k++] = keys[i];
+        }
+        readLayers(out_keys, k, layers, nl, out_values);
+        return k;
+    }
     void exportDense(int layer, int ci0, int cj0, int w, int h, float *out)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
@@ -1919,6 +1932,20 @@ int tmap_read_layers(tmap_system *s, uint64_t map_id, const uint64_t *keys, size
     for (size_t l = 0; l < n_layers; ++l)
         if (layer_ids[l] < 0 || layer_ids[l] >= TMAP_NUM_LAYERS) throw std::invalid_argument("bad layer id");
     mp->readLayers(keys, n, layer_ids, n_layers, out);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_fill_sparse_update(tmap_system *s, uint64_t map_id, const int32_t *layer_ids, size_t n_layers, const uint64_t *keys,
+                            size_t n_keys, uint64_t *out_keys, float *out_values, size_t *n_out)
+{
+    NEED(s)
+    if (!n_out || (n_keys && (!keys || !out_keys || !out_values)) || (n_layers && !layer_ids))
+    {
+        tmb::g_last_error = "null sparse-update argument";
+        return TMAP_ERR_INVALID;
+    }
+    TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    *n_out = mp->fillSparseUpdate(layer_ids, n_layers, keys, n_keys, out_keys, out_values);
     return TMAP_OK;
     TMAP_API_END
 }
