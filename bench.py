@@ -38,6 +38,10 @@ CROP = 801  # 40 m / 0.05 m + 1 cells, robot-centred
 SEED = 2
 
 
+WORKLOAD = ("C2 local map: 10 Hz stream of 131072-ray keyframes, 40x40 m rolling grid @0.05 m, window 15, "
+            "49-cell disc, inflation 0.5 m")
+
+
 def workload(n_kf):
     from traversability_mapping_b200 import synth
     poses = synth.trajectory("drive", n_kf, seed=SEED, step=0.1, curvature=0.02)  # 1 m/s sampled at 10 Hz
@@ -143,7 +147,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "points/s binned+classified", "value": v, "unit": "points/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64 moments / f32 layers", "data": "synthetic",
-        "config": {"workload": "C2 local map: 10 Hz stream of 131072-ray keyframes, 40x40 m rolling grid @0.05 m, window 15",
+        "config": {"workload": WORKLOAD,
                    "l2": "cpu run"},
         "cpu_baseline": {"value": v, "unit": "points/s", "cores": 1, "kind": "port",
                          "sample": f"{steps} stream ticks after a {WINDOW + warm}-tick fill, oracle port (reference not buildable)"},
@@ -444,8 +448,7 @@ def main():
             "metric": "points/s binned+classified", "value": pts_sum / (t_max * 1e-3), "unit": "points/s",
             "n_gpus": args.gpus, "steps": K, "warmup": Wm, "ms_per_step": t_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 moments / f32 layers", "data": "synthetic",
-            "config": {"workload": "C2 local map: 10 Hz stream of 131072-ray keyframes, 40x40 m rolling grid @0.05 m, window 15, "
-                                   "49-cell disc, inflation 0.5 m",
+            "config": {"workload": WORKLOAD,
                        "points_binned_per_step": pts_total / K, "rays_per_keyframe": RAYS, "l2": "flushed between timed steps (256 MB write)",
                        "parallelism": "replicas" if world > 1 else "single"},
             "clocks": clocks,
