@@ -8,6 +8,7 @@
 #include "tmap_oracle.cpp"  /* single TU: the KATs reach the oracle's internal types */
 
 #include <cstdio>
+#include <cstring>
 #include <functional>
 #include <random>
 
@@ -341,6 +342,19 @@ int main()
         CHECK(p.size() == 1u);
         CHECK(p.count(Lattice::key(0, 4)) == 1u);
     }
+    TEST("KeyFrame.RebinUsesPassedPoseNotLatestPose (test_keyframe.cpp:155-167)")
+    {
+        /* the oracle's rebin takes the pose as an argument by construction; a pending far-away pose on the keyframe
+         * must not leak into a rebin at identity */
+        KeyFrame kf;
+        kf.cloud = {{1.04f, -0.36f, 2.0f}};
+        translation(10.f, 0.f, 0.f, kf.pose);
+        kf.pending = true;
+        rebin(lat, kf.cloud, kIdent, kf.partials);
+        CHECK(kf.partials.size() == 1u);
+        CHECK(kf.partials.count(Lattice::key(4, -1)) == 1u);
+        CHECK(kf.partials.count(Lattice::key(44, -1)) == 0u);
+    }
     TEST("KeyFrame.RebinReplacesPreviousPartials (test_keyframe.cpp:169-182)")
     {
         float T[12];
@@ -491,7 +505,83 @@ int main()
         tmo_destroy(m);
     }
 
+    TEST("LocalMap.AddMultipleTracksAllInKeyFramesMap (test_localmap.cpp:185-193)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        addBase(m, 1, {{0.f, 0.f, 0.f}});
+        addBase(m, 2, {{1.f, 0.f, 0.f}});
+        addBase(m, 3, {{2.f, 0.f, 0.f}});
+        CHECK(tmo_num_keyframes(m) == 3u);
+        CHECK(m->kfs.count(2) == 1u);
+        tmo_destroy(m);
+    }
+    TEST("LocalMap.DetachUnknownIdReturnsNull (test_localmap.cpp:264-268)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        CHECK(tmo_delete_keyframe(m, 999) == 0);
+        tmo_destroy(m);
+    }
+    TEST("LocalMap.DeleteKeyFrameRemovesIt (test_localmap.cpp:270-280)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        addBase(m, 5, {{0.f, 0.f, 0.f}});
+        float I[12];
+        translation(0.f, 0.f, 0.f, I);
+        tmo_update_pose(m, 5, I);
+        CHECK(tmo_process(m) == 1);
+        CHECK(m->kfs.count(5) == 1u);
+        tmo_delete_keyframe(m, 5);
+        CHECK(m->kfs.count(5) == 0u);
+        CHECK(occupiedSet(m).empty());
+        tmo_destroy(m);
+    }
+    TEST("LocalMap.StitchTransformsRetainedCloudsByPose (test_localmap.cpp:305-318)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        addBase(m, 1, {{1.f, 0.f, 0.f}, {0.f, 1.f, 0.f}});
+        float T[12];
+        translation(5.f, -3.f, 2.f, T);
+        std::memcpy(m->kfs[1]->pose, T, sizeof(T));   /* KeyFrame(id, pose, cloud): the pose is set at construction */
+        float out[6];
+        CHECK(tmo_stitched_cloud(m, 0.f, 0.f, 0.f, out, 2) == 2u);
+        std::set<std::array<float, 3>> pts = {{out[0], out[1], out[2]}, {out[3], out[4], out[5]}};
+        CHECK(pts.count({6.f, -3.f, 2.f}) == 1u);
+        CHECK(pts.count({5.f, -2.f, 2.f}) == 1u);
+        tmo_destroy(m);
+    }
+    TEST("LocalMap.StitchSkipsKeyFramesWithoutCloud (test_localmap.cpp:320-327)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        addBase(m, 1, {{1.f, 1.f, 1.f}});
+        addBase(m, 2, {});
+        CHECK(tmo_stitched_cloud(m, 0.f, 0.f, 0.f, nullptr, 0) == 1u);
+        tmo_destroy(m);
+    }
+    TEST("LocalMap.StitchVoxelDownsampleReducesCount (test_localmap.cpp:329-340)")
+    {
+        tmo_map *m = tmo_create(&LP);
+        std::vector<std::array<float, 3>> pts;
+        for (int i = 0; i < 10; ++i) pts.push_back({0.001f * i, 0.f, 0.f});
+        addBase(m, 1, pts);
+        float out[30];
+        const size_t n = tmo_stitched_cloud(m, 1.f, 1.f, 1.f, out, 10);
+        CHECK(n >= 1u);
+        CHECK(n < 10u);
+        CHECK(n == 1u);                                   /* one voxel: its centroid is the mean of the ten */
+        NEAR(out[0], 0.0045f, 1e-6f);
+        tmo_destroy(m);
+    }
+
     /* ================= test_helpers.cpp ================= */
+    TEST("Helpers.CellPosIsLatticeCentre / HonoursLatticeOrigin (test_helpers.cpp:39-53)")
+    {
+        Lattice a; a.x0 = 0.0; a.y0 = 0.0; a.res = 0.25;
+        NEAR(a.cx(10), 2.5, 1e-12);
+        NEAR(a.cy(-7), -1.75, 1e-12);
+        Lattice b; b.x0 = 1.0; b.y0 = -2.0; b.res = 0.5;
+        NEAR(b.cx(2), 1.0 + 2 * 0.5, 1e-12);
+        NEAR(b.cy(4), -2.0 + 4 * 0.5, 1e-12);
+    }
     TEST("Helpers.MakeGridMapOddCellCountCentresOnLattice (test_helpers.cpp:74-84)")
     {
         Grid g;

@@ -213,6 +213,15 @@ class OracleMap:
         lib().tmo_export_occupancy(self._h, ci0, cj0, w, h, out.ctypes.data)
         return out
 
+    def stitched_cloud(self, vx=0.0, vy=0.0, vz=0.0):
+        L = lib()
+        L.tmo_stitched_cloud.restype = C.c_size_t
+        L.tmo_stitched_cloud.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t]
+        n = L.tmo_stitched_cloud(self._h, 0.0, 0.0, 0.0, None, 0)
+        out = np.zeros((max(n, 1), 3), dtype=np.float32)
+        k = L.tmo_stitched_cloud(self._h, vx, vy, vz, out.ctypes.data, n)
+        return out[:k].copy()
+
     def fill_sparse_update(self, layers, keys):
         """fillSparseUpdate (conversions.cpp:28-55) -> (kept keys, values (n, len(layers)))."""
         import traversability_mapping_b200 as tm

@@ -1010,6 +1010,35 @@ void tmo_export_completeness(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t
         }
 }
 
+size_t tmo_voxel_grid(const float *xyz, size_t n, float lx, float ly, float lz, float *out, size_t cap);
+
+size_t tmo_stitched_cloud(const tmo_map *m, float vx, float vy, float vz, float *out, size_t cap)
+{
+    /* LocalMap::getStitchedPointCloud (LocalMap.cpp:416-448): pose * retained cloud of every keyframe (ascending id
+     * here; the reference walks an unordered_map), then pcl::VoxelGrid when all three leaf sizes are positive.
+     * out == NULL: the unfiltered size. */
+    std::vector<float> all;
+    for (const auto &kv : m->kfs)
+    {
+        const KeyFrame &kf = *kv.second;
+        if (!kf.hasCloud())
+            continue;
+        for (const auto &pb : kf.cloud)
+        {
+            float pm[3];
+            xform(kf.pose, pb[0], pb[1], pb[2], pm);
+            all.insert(all.end(), pm, pm + 3);
+        }
+    }
+    const size_t n = all.size() / 3;
+    if (!out)
+        return n;
+    if (vx > 0.f && vy > 0.f && vz > 0.f && n)
+        return tmo_voxel_grid(all.data(), n, vx, vy, vz, out, cap);
+    for (size_t i = 0; i < std::min(n, cap) * 3; ++i) out[i] = all[i];
+    return n;
+}
+
 size_t tmo_voxel_grid(const float *xyz, size_t n, float lx, float ly, float lz, float *out, size_t cap)
 {
     /* pcl::VoxelGrid<pcl::PointXYZ>::applyFilter as LocalMap::getStitchedPointCloud uses it (LocalMap.cpp:438-446;

@@ -127,6 +127,9 @@ void tmo_export_occupancy(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w,
  * RViz costmap-palette bytes; out holds ceil(w/f) x ceil(h/f) cells, f = lround(publish_res / float(resolution)) */
 void tmo_export_completeness(const tmo_map *m, int32_t ci0, int32_t cj0, int32_t w, int32_t h, double publish_res,
                              int8_t *out, int32_t *out_w, int32_t *out_h);
+/* LocalMap::getStitchedPointCloud (LocalMap.cpp:416-448): pose * retained clouds, voxel-filtered when all three
+ * leaf sizes are positive; packed xyz; out == NULL returns the unfiltered size */
+size_t tmo_stitched_cloud(const tmo_map *m, float vx, float vy, float vz, float *out, size_t cap);
 /* pcl::VoxelGrid<pcl::PointXYZ> as LocalMap::getStitchedPointCloud applies it (LocalMap.cpp:438-446): packed xyz in,
  * one centroid per occupied voxel out (ascending voxel index); returns the voxel count */
 size_t tmo_voxel_grid(const float *xyz, size_t n, float lx, float ly, float lz, float *out, size_t cap);

@@ -698,3 +698,47 @@ def test_sparse_update_payload_matches_oracle(tmap, oracle):
     ek, ev = m.fillSparseUpdate(layers, np.zeros(0, dtype=np.uint64))
     assert len(ek) == 0 and ev.shape == (0, 4)
     s.close()
+
+
+def test_localmap_registry_and_stitch_kats(tmap, oracle):
+    """The remaining LocalMap tests of the reference through the C ABI: AddMultipleTracksAllInKeyFramesMap
+    (test_localmap.cpp:185-193), DetachUnknownIdReturnsNull (:264-268), DeleteKeyFrameRemovesIt (:270-280),
+    StitchTransformsRetainedCloudsByPose (:305-318), StitchSkipsKeyFramesWithoutCloud (:320-327),
+    StitchVoxelDownsampleReducesCount (:329-340) -- and the same calls on the oracle."""
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    for k, x in ((1, 0.0), (2, 1.0), (3, 2.0)):
+        s.addKeyFrameBase(k, 0, [[x, 0.0, 0.0]]); om.add_keyframe_base(k, [[x, 0.0, 0.0]])
+    assert m.numKeyFrames() == 3 == om.num_keyframes()
+    assert s.deleteKeyFrame(999) == tmap.IGNORED_UNKNOWN_KF
+    s.close()
+
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    s.addKeyFrameBase(5, 0, [[0.0, 0.0, 0.0]]); om.add_keyframe_base(5, [[0.0, 0.0, 0.0]])
+    s.updateKeyFrame(5, I34); om.update_pose(5, I34)
+    s.flush(); om.process()
+    assert m.numKeyFrames() == 1 and m.occupiedCellKeys().size == 1
+    s.deleteKeyFrame(5); om.delete_keyframe(5)
+    assert m.numKeyFrames() == 0 and m.occupiedCellKeys().size == 0 == om.occupied_cell_keys().size
+    s.close()
+
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    pts = [[1.0, 0.0, 0.0], [0.0, 1.0, 0.0]]
+    s.addKeyFrameBase(1, 0, pts); om.add_keyframe_base(1, pts)
+    s.updateKeyFrame(1, trans(5, -3, 2)); om.update_pose(1, trans(5, -3, 2))
+    s.flush(); om.process()
+    got = m.getStitchedPointCloud()
+    assert sorted(map(tuple, got.tolist())) == [(5.0, -2.0, 2.0), (6.0, -3.0, 2.0)]
+    assert np.array_equal(got.view(np.uint32), om.stitched_cloud().view(np.uint32))
+    assert s.addKeyFrameBase(2, 0, np.zeros((0, 3), dtype=np.float32)) == tmap.IGNORED_EMPTY   # no cloud: not stitched
+    assert len(m.getStitchedPointCloud()) == 2
+    s.close()
+
+    s, m, om = make_pair(tmap, oracle, **LOCALMAP)
+    ten = [[0.001 * i, 0.0, 0.0] for i in range(10)]
+    s.addKeyFrameBase(1, 0, ten); om.add_keyframe_base(1, ten)
+    got = m.getStitchedPointCloud(1.0, 1.0, 1.0)
+    want = om.stitched_cloud(1.0, 1.0, 1.0)
+    assert 1 <= len(got) < 10 and len(got) == 1
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert abs(float(got[0, 0]) - 0.0045) < 1e-6
+    s.close()
