@@ -115,6 +115,7 @@ typedef struct tmap_stats
     float ms_gate, reserved0;
     uint64_t sum_infl_tiles;       /* 32x32 tiles handed to k_inflate */
     uint64_t sum_cand_bins;        /* 16x16 bins handed to k_gate */
+    uint64_t h2d_bytes, d2h_bytes; /* bytes this library copied host->device / device->host (all maps, ingest included) */
 } tmap_stats;
 
 typedef struct tmap_system tmap_system;
@@ -135,6 +136,9 @@ int tmap_set_extrinsics(tmap_system *s, const float T_sv[12], const float T_bs[1
 int tmap_add_map(tmap_system *s, uint64_t map_id, tmap_update_cb on_update, void *user);
 /* System::setCurrentMap (System.cpp:74-82) */
 int tmap_set_current_map(tmap_system *s, uint64_t map_id);
+/* System::getLocalMap() (System.hpp:154, System.cpp:357-361): id of the ACTIVE map -- the last one created by
+ * tmap_add_map (System.cpp:71) or chosen by tmap_set_current_map; TMAP_IGNORED_UNKNOWN_MAP before any map exists. */
+int tmap_current_map(tmap_system *s, uint64_t *map_id_out);
 
 /* System::addNewKeyFrameWithPCL (System.hpp:85-87, System.cpp:159-172).  xyz: sensor-frame
  * points in HOST memory, `stride_bytes` apart (16 for pcl::PointXYZ, 12 packed).  The cloud is
@@ -197,7 +201,8 @@ int tmap_flush(tmap_system *s);
 int tmap_lock(tmap_system *s, uint64_t map_id);
 int tmap_unlock(tmap_system *s, uint64_t map_id);
 /* LocalMap::takeChangedCells (LocalMap.cpp:401-408).  out==NULL: *n_out = pending count, nothing
- * drained.  Otherwise up to cap keys (ascending) are written and the set is cleared. */
+ * drained.  Otherwise all pending keys (ascending) are written and the set is cleared; when cap is smaller than
+ * the pending count NOTHING is written or cleared and *n_out reports the count (call again with room). */
 int tmap_take_changed_cells(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out);
 /* LocalMap::occupiedCellKeys (LocalMap.cpp:410-414), ascending */
 int tmap_occupied_cell_keys(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out);
@@ -242,6 +247,12 @@ int tmap_stitched_cloud(tmap_system *s, uint64_t map_id, float *out_xyz, size_t 
  * otherwise *n_out = the number of voxels (at most cap_points are written).  Non-positive leaves = unfiltered. */
 int tmap_stitched_cloud_voxel(tmap_system *s, uint64_t map_id, float leaf_x, float leaf_y, float leaf_z, float *out_xyz,
                               size_t cap_points, size_t *n_out);
+
+/* System::getGlobalPointCloud(vx, vy, vz) (System.hpp:160-161, System.cpp:370-387): the stitched (and, for positive
+ * leaves, voxel-filtered) clouds of every map, concatenated in ascending map id.  Same sizing protocol as
+ * tmap_stitched_cloud_voxel. */
+int tmap_global_point_cloud(tmap_system *s, float leaf_x, float leaf_y, float leaf_z, float *out_xyz, size_t cap_points,
+                            size_t *n_out);
 
 int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out);
 /* Run the map's kernels on a caller-owned stream (cudaStream_t as void*); NULL = own stream. */

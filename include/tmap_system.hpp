@@ -138,14 +138,19 @@ class LocalMap
     friend class System;
     LocalMap(tmap_system *s, std::uint64_t id, const Lattice &l) : s_(s), id_(id), lat_(l) {}
     static void check(int rc) { if (rc < 0) throw std::runtime_error(tmap_last_error()); }
+    struct Guard  // the grid mutex is released on every path out of keys(), also when check() throws
+    {
+        LocalMap &m;
+        explicit Guard(LocalMap &mm) : m(mm) { m.lock(); }
+        ~Guard() { m.unlock(); }
+    };
     template <class F> std::vector<std::uint64_t> keys(F fn)
     {
         size_t n = 0;
-        lock();
+        Guard g(*this);
         check(fn(s_, id_, nullptr, 0, &n));
         std::vector<std::uint64_t> out(n);
         if (n) check(fn(s_, id_, out.data(), n, &n));
-        unlock();
         out.resize(n);
         return out;
     }
@@ -171,13 +176,17 @@ class System
     {
         check(tmap_set_obstacle_params(s_, Tb_obs.m, maxRange, minRange));
     }
+    /// System.cpp:62-72.  A duplicate id is a no-op that keeps the FIRST callback (System.cpp:65-69): the new
+    /// std::function is registered only once the library has accepted the map, so the library never holds a
+    /// pointer to a callback this object has freed.
     void addNewLocalMap(std::uint64_t mapID, std::function<void()> onUpdate = {})
     {
-        auto &slot = callbacks_[mapID];
-        slot.reset(new std::function<void()>(std::move(onUpdate)));
-        check(tmap_add_map(s_, mapID, *slot ? &System::trampoline : nullptr, slot.get()));
+        std::unique_ptr<std::function<void()>> slot(new std::function<void()>(std::move(onUpdate)));
+        const int rc = tmap_add_map(s_, mapID, *slot ? &System::trampoline : nullptr, slot.get());
+        check(rc);
+        if (rc == TMAP_OK) callbacks_[mapID] = std::move(slot);  // the new map is now the active one (System.cpp:71)
     }
-    void setCurrentMap(std::uint64_t mapID) { check(tmap_set_current_map(s_, mapID)); current_ = mapID; }
+    void setCurrentMap(std::uint64_t mapID) { check(tmap_set_current_map(s_, mapID)); }
 
     /// addNewKeyFrameWithPCL (System.cpp:159-172).  Throws std::runtime_error on a negative id.
     void addNewKeyFrame(unsigned long long timestamp_ns, std::uint64_t kfID, std::uint64_t mapID, const float *xyz, size_t n,
@@ -225,6 +234,13 @@ class System
         addNewKeyFrameTsDouble(static_cast<double>(timestamp_ns / 1000000000ULL) + static_cast<double>(timestamp_ns % 1000000000ULL) * 1e-9,
                                kfID, mapID);
     }
+    /// KeyFrame(id, ts, pose, cloud_base, mapID) + LocalMap::addAlreadyDeclaredKF (KeyFrame.hpp, LocalMap.cpp:319-328):
+    /// an already pruned BASE-frame cloud (packed xyz) registered without the prune step -- how the reference's own
+    /// LocalMap tests build their keyframes (test_localmap.cpp:118-131).
+    void addKeyFrameBase(std::uint64_t kfID, std::uint64_t mapID, const float *xyz, size_t n)
+    {
+        check(tmap_add_keyframe_base(s_, kfID, mapID, xyz, n));
+    }
     void updateKeyFrame(std::uint64_t kfID, const Pose &pose_map_base, std::uint64_t /*numConnections*/ = 0)
     {
         check(tmap_update_pose(s_, kfID, pose_map_base.m));
@@ -247,7 +263,13 @@ class System
     }
     void deleteObstacleKeyFrame(std::uint64_t kfID) { check(tmap_delete_obstacle_keyframe(s_, kfID)); }
 
-    std::shared_ptr<LocalMap> getLocalMap() { return getLocalMap(current_); }
+    /// The active map (System.cpp:357-361): the last one created or chosen by setCurrentMap; nullptr before any.
+    std::shared_ptr<LocalMap> getLocalMap()
+    {
+        std::uint64_t id = 0;
+        if (tmap_current_map(s_, &id) != TMAP_OK) return nullptr;
+        return getLocalMap(id);
+    }
     std::shared_ptr<LocalMap> getLocalMap(std::uint64_t mapID)
     {
         size_t n = 0;
@@ -255,6 +277,17 @@ class System
         Lattice l;
         l.x0 = params_.grid_center_x; l.y0 = params_.grid_center_y; l.res = params_.resolution;
         return std::shared_ptr<LocalMap>(new LocalMap(s_, mapID, l));
+    }
+    /// getGlobalPointCloud (System.hpp:160-161, System.cpp:370-387): packed xyz of every map's stitched cloud,
+    /// voxel-filtered per map when all three leaf sizes are positive.
+    std::vector<float> getGlobalPointCloud(float voxel_size_x, float voxel_size_y, float voxel_size_z)
+    {
+        size_t n = 0;
+        check(tmap_global_point_cloud(s_, voxel_size_x, voxel_size_y, voxel_size_z, nullptr, 0, &n));
+        std::vector<float> out(3 * n);
+        if (n) check(tmap_global_point_cloud(s_, voxel_size_x, voxel_size_y, voxel_size_z, out.data(), n, &n));
+        out.resize(3 * n);
+        return out;
     }
     /// Blocks until the workers have drained their queues (test hook).
     void flush() { check(tmap_flush(s_)); }
@@ -265,7 +298,6 @@ class System
     static void check(int rc) { if (rc < 0) throw std::runtime_error(tmap_last_error()); }
     tmap_params params_;
     tmap_system *s_ = nullptr;
-    std::uint64_t current_ = 0;
     std::map<std::uint64_t, std::unique_ptr<std::function<void()>>> callbacks_;
 };
 }  // namespace traversability_mapping_b200

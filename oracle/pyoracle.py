@@ -36,7 +36,7 @@ class Params(C.Structure):
 def build(force=False):
     """make -C oracle (g++ only)."""
     if force or not os.path.exists(LIB_PATH) or \
-            os.path.getmtime(LIB_PATH) < os.path.getmtime(os.path.join(_HERE, "tmap_oracle.cpp")):
+            os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("tmap_oracle.cpp", "tmap_oracle.h", "Makefile")):
         subprocess.run(["make", "-C", _HERE, "-s"], check=True)
     return LIB_PATH
 
@@ -55,6 +55,7 @@ def lib():
         L.tmo_destroy.argtypes = [P]
         L.tmo_default_params.argtypes = [C.POINTER(Params)]
         L.tmo_set_extrinsics.argtypes = [P, P]
+        L.tmo_set_threads.argtypes = [P, C.c_int32]
         L.tmo_prune.restype = C.c_size_t
         L.tmo_prune.argtypes = [P, P, C.c_size_t, C.c_size_t, P, C.c_double, C.c_double, P]
         L.tmo_add_keyframe.argtypes = [P, C.c_uint64, P, C.c_size_t, C.c_size_t]
@@ -134,6 +135,10 @@ class OracleMap:
     def set_extrinsics(self, T_bv):
         a = _f32(np.asarray(T_bv).reshape(-1)[:12])
         lib().tmo_set_extrinsics(self._h, a.ctypes.data)
+
+    def set_threads(self, n):
+        """CPU-baseline flavour 2: OpenMP over the dirty cells (archive/local_traversability_monolithic.cpp:349-362)."""
+        lib().tmo_set_threads(self._h, int(n))
 
     def prune(self, cloud, T, max_range, min_range):
         a = _f32(cloud)

@@ -19,6 +19,8 @@
 #include <set>
 #include <unordered_set>
 #include <vector>
+#include <thread>
+#include <atomic>
 
 namespace tmo_detail
 {
@@ -643,12 +645,45 @@ struct tmo_map
         }
     }
 
-    /* LocalMap.cpp:191-199 */
+    /* LocalMap.cpp:191-199.  threads > 1: the archived node's variant -- a parallel loop over the dirty cells, one cell per
+     * task, disjoint writes, flags merged serially afterwards
+     * (traversability_mapping_ros/archive/local_traversability_monolithic.cpp:349-362).  Same results either way:
+     * recomputeCell reads moment layers only and writes its own cell's derived layers. */
+    int threads = 1;
     void recomputeDirty(const std::unordered_set<std::uint64_t> &dirty)
     {
-        for (auto id : dirty)
-            if (recomputeCell(id))
-                changed.insert(id);
+        if (threads > 1)
+        {
+            const std::vector<std::uint64_t> cells(dirty.begin(), dirty.end());
+            const long n = static_cast<long>(cells.size());
+            std::vector<char> wrote(cells.size(), 0);
+            /* `#pragma omp parallel for schedule(dynamic, 64)` restated with std::thread (this image has no libgomp
+             * spec file, so -fopenmp does not link): workers draw chunks of 64 cells from a shared counter */
+            std::atomic<long> next{0};
+            auto work = [&]() {
+                for (;;)
+                {
+                    const long k0 = next.fetch_add(64);
+                    if (k0 >= n) break;
+                    const long k1 = std::min(n, k0 + 64);
+                    for (long k = k0; k < k1; ++k)
+                        wrote[k] = recomputeCell(cells[k]) ? 1 : 0;
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < threads; ++t) pool.emplace_back(work);
+            work();
+            for (auto &t : pool) t.join();
+            for (long k = 0; k < n; ++k)
+                if (wrote[k])
+                    changed.insert(cells[k]);
+        }
+        else
+        {
+            for (auto id : dirty)
+                if (recomputeCell(id))
+                    changed.insert(id);
+        }
         if (P.inflation_enabled)
             inflateDirty(dirty);
     }
@@ -709,6 +744,7 @@ tmo_map *tmo_create(const tmo_params *p) { return new tmo_map(*p); }
 void tmo_destroy(tmo_map *m) { delete m; }
 
 void tmo_set_extrinsics(tmo_map *m, const float T_bv[12]) { std::memcpy(m->Tbv, T_bv, sizeof(m->Tbv)); }
+void tmo_set_threads(tmo_map *m, int32_t n) { m->threads = n < 1 ? 1 : n; }
 
 /* System.cpp:93-114 */
 size_t tmo_prune(const tmo_map *m, const float *xyz, size_t n, size_t stride, const float T[12],

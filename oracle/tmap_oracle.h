@@ -77,6 +77,9 @@ void tmo_destroy(tmo_map *m);
 
 /* System::setExtrinsicParameters (System.cpp:45-51) with Tbv = Tbs*Tsv already composed. */
 void tmo_set_extrinsics(tmo_map *m, const float T_bv[12]);
+/* CPU-baseline flavour 2: classify the dirty cells with `n` OpenMP threads, as the archived node does
+ * (traversability_mapping_ros/archive/local_traversability_monolithic.cpp:349-362).  1 = the reference's single worker. */
+void tmo_set_threads(tmo_map *m, int32_t n);
 
 /* System::prune (System.cpp:93-114).  xyz: n points, `stride_floats` floats apart (3 packed,
  * 4 for pcl::PointXYZ).  out: up to n*3 floats.  Returns the surviving count. */

@@ -742,3 +742,200 @@ def test_localmap_registry_and_stitch_kats(tmap, oracle):
     assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
     assert abs(float(got[0, 0]) - 0.0045) < 1e-6
     s.close()
+
+
+# ---- round 2: the benchmarked configurations at their benchmarked sizes --------------------------------------
+def _torch_clouds(seed, idxs, poses, rings, az):
+    """Host clouds from the batched torch generator (bench.py's): both arms consume the same arrays."""
+    import torch
+    from traversability_mapping_b200 import synth
+    out = {}
+    idxs = list(idxs)
+    for a in range(0, len(idxs), 16):
+        part = idxs[a:a + 16]
+        t = synth.make_keyframes_torch(seed, part[0], poses[part], max_range=20.0, rings=rings, azimuths=az,
+                                       device="cuda" if torch.cuda.is_available() else "cpu")
+        h = t.cpu().numpy()
+        for k, i in enumerate(part):
+            out[i] = h[k]
+    return out
+
+
+def test_config2_at_benchmarked_size(tmap, oracle):
+    """bench.py's C2 leg exactly: 131 072-ray keyframes, 20 m range, 40 x 40 m grid @0.05 m, 49-cell disc,
+    min_points 5, inflation 0.5 m / 3.0 / 0.95, rolling window 15, max_batch = 1 -- the window is filled and
+    three more ticks (each with an eviction) are compared layer by layer with the oracle."""
+    import bench
+    from traversability_mapping_b200 import synth
+    window, extra = bench.WINDOW, 3
+    n = window + extra
+    poses = synth.trajectory("drive", n, seed=bench.SEED, step=0.1, curvature=0.02)
+    clouds = _torch_clouds(bench.SEED, range(n), poses, 128, 1024)
+    s, m, om = make_pair(tmap, oracle, max_batch=1, **bench.C2)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    om.set_threads(os.cpu_count() or 1)   # same results as 1 thread (asserted in test_oracle_kat.py); the fill takes seconds
+    st = None
+    for i in range(n):
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]); om.add_keyframe(i + 1, clouds[i])
+        s.updateKeyFrame(i + 1, poses[i]); om.update_pose(i + 1, poses[i])
+        s.flush(); om.process()
+        if i >= window:
+            s.deleteKeyFrame(i + 1 - window); om.delete_keyframe(i + 1 - window)
+        if i >= window - 1:
+            st = compare_maps(m, om, check_changed=True, label=f"C2 tick {i}")
+        else:
+            m.takeChangedCells(); om.take_changed_cells()
+    assert m.numKeyFrames() == window and st["cells"] > 200000 and st["gated_in"] > 100000, st
+    s.close()
+
+
+def test_config4_200_keyframes_against_oracle(tmap, oracle):
+    """bench.py's C4 headline at 200 of its 2 000 keyframes (262 144 rays each, 200 x 200 m map @0.1 m, 13-cell
+    disc): drifted build, then the loop closure -- every pose corrected + informLoopClosure -- in one batched pass,
+    against om.process_batched()."""
+    import bench
+    from traversability_mapping_b200 import synth
+    n = 200
+    true, drift = bench.c4_poses(bench.C4_KEYFRAMES)
+    clouds = _torch_clouds(bench.SEED + 1, range(n), true, bench.C4_RINGS, bench.C4_AZ)
+    s, m, om = make_pair(tmap, oracle, max_batch=0, **bench.C4)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    om.set_threads(os.cpu_count() or 1)
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    for i in range(n):
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]) == tmap.OK
+        om.add_keyframe(i + 1, clouds[i]); om.update_pose(i + 1, drift[i])
+    with m.locked():
+        s.updateKeyFrames(ids, drift[:n])
+    s.flush(); om.process_batched()
+    compare_maps(m, om, check_changed=True, label="C4 drifted build")
+    for i in range(n):
+        om.update_pose(i + 1, true[i])
+    with m.locked():
+        s.updateKeyFrames(ids, true[:n])
+        s.informLoopClosure()
+    om.clear_entire_map()
+    s.flush(); om.process_batched()
+    st = compare_maps(m, om, check_changed=True, label="C4 loop closure")
+    N = m.readLayers(m.occupiedCellKeys(), ["N"])[:, 0]
+    assert int(N.sum()) == m.stats()["last_batch_points"] and st["cells"] > 300000 and st["gated_in"] > 200000, st
+    s.close()
+
+
+def test_config5_geometry_reduced_extent(tmap, oracle):
+    """C5's geometry -- 0.05 m lattice with robot_radius 0.20 => the 49-cell disc -- on a reduced extent (a 60 m loop,
+    40 keyframes), one batched build + loop closure against the oracle."""
+    import bench
+    from traversability_mapping_b200 import synth
+    n = 40
+    P = dict(bench.C4, resolution=0.05, half_size=40.0)
+    true = synth.trajectory("loop", n, seed=77, extent=30.0)
+    drift = synth.drift_poses(true)
+    clouds = _torch_clouds(77, range(n), true, 128, 1024)
+    s, m, om = make_pair(tmap, oracle, max_batch=0, **P)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+    om.set_threads(os.cpu_count() or 1)
+    ids = np.arange(1, n + 1, dtype=np.uint64)
+    for i in range(n):
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i]) == tmap.OK
+        om.add_keyframe(i + 1, clouds[i]); om.update_pose(i + 1, drift[i])
+    with m.locked():
+        s.updateKeyFrames(ids, drift)
+    s.flush(); om.process_batched()
+    compare_maps(m, om, check_changed=True, label="C5 geometry, drifted")
+    for i in range(n):
+        om.update_pose(i + 1, true[i])
+    with m.locked():
+        s.updateKeyFrames(ids, true)
+        s.informLoopClosure()
+    om.clear_entire_map()
+    s.flush(); om.process_batched()
+    st = compare_maps(m, om, check_changed=True, label="C5 geometry, loop closure")
+    assert st["gated_in"] > 100000, st
+    s.close()
+
+
+def test_config4_full_size_properties(tmap):
+    """The benchmarked C4 size itself (2 000 keyframes x 262 144 rays, ~290 M points): size-independent properties --
+    per-cell counts sum to the points binned, a second loop closure at the same poses reproduces every layer bit for
+    bit, the sub-map around the first 200 keyframes is untouched by where the other 1 800 sit in the batch (checksum
+    of the count layer against a 200-keyframe build restricted to cells only they reach)."""
+    import bench
+    from traversability_mapping_b200 import synth
+    nk = bench.C4_KEYFRAMES
+    true, drift = bench.c4_poses(nk)
+    p = tmap.default_params(max_batch=0, **bench.C4)
+    s = tmap.System(p); s.addNewLocalMap(0); m = s.getLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    for i, c in bench.gen_host_clouds(bench.SEED + 1, range(nk), true, bench.C4_RINGS, bench.C4_AZ, "cuda"):
+        assert s.addNewKeyFrameWithPCL(i, i + 1, 0, c) == tmap.OK
+    ids = np.arange(1, nk + 1, dtype=np.uint64)
+    with m.locked():
+        s.updateKeyFrames(ids, drift)
+    s.flush()
+    with m.locked():
+        s.updateKeyFrames(ids, true)
+        s.informLoopClosure()
+    s.flush()
+    total = m.stats()["last_batch_points"]
+    assert total > 256e6, total
+    keys0 = m.occupiedCellKeys()
+    allL = helpers.MOMENT_LAYERS + [l for l in helpers.DERIVED_LAYERS if l != "step_haz_inflated"]
+    L0 = m.readLayers(keys0, allL)
+    assert int(L0[:, 0].astype(np.float64).sum()) == total
+    assert np.all(L0[:, 0] == np.round(L0[:, 0])) and L0[:, 0].min() >= 1
+    s.informLoopClosure(); s.flush()
+    keys1 = m.occupiedCellKeys()
+    assert np.array_equal(keys0, keys1) and helpers.bits_equal(m.readLayers(keys1, allL), L0)
+    occ = m.exportOccupancy()
+    haz = m.exportDense("hazard")
+    assert np.array_equal(occ == -1, np.isnan(haz)) and occ.max() <= 100
+    s.close()
+
+
+def test_reader_thread_against_delete_and_loop_closure(tmap):
+    """a reader that holds the grid mutex across take + read (LocalMap.hpp:102-104) must not
+    deadlock against deleteKeyFrame / informLoopClosure / updateKFMap running on another thread."""
+    import threading
+    from traversability_mapping_b200 import synth
+    p = tmap.default_params(resolution=0.1, half_size=10.0, max_range=10.0, min_range=1.0, max_batch=1)
+    s = tmap.System(p); s.addNewLocalMap(0); s.addNewLocalMap(1); m = s.getLocalMap(0)
+    s.setExtrinsicParameters(synth.IDENTITY, synth.T_BASE_SENSOR)
+    poses = synth.trajectory("drive", 40, seed=5, step=0.3)
+    clouds = [synth.make_keyframe(5, i, poses[i], max_range=10.0, rings=16, azimuths=512) for i in range(8)]
+    stop = threading.Event()
+    reads = [0]
+    err = []
+
+    def reader():
+        try:
+            while not stop.is_set():
+                with m.locked():
+                    k = m.takeChangedCells()
+                    if k.size:
+                        m.readLayers(k[:256], ["hazard", "N"])
+                    m.exportOccupancy(-20, -20, 41, 41)
+                reads[0] += 1
+        except Exception as e:  # pragma: no cover
+            err.append(e)
+
+    t = threading.Thread(target=reader, daemon=True)
+    t.start()
+    for i in range(40):
+        s.addNewKeyFrameWithPCL(i, i + 1, 0, clouds[i % 8])
+        s.updateKeyFrame(i + 1, poses[i])
+        if i >= 5:
+            s.deleteKeyFrame(i - 4)
+        if i % 7 == 3:
+            s.updateKFMap(i + 1, 1)
+        if i % 10 == 9:
+            s.informLoopClosure()
+    s.flush()
+    stop.set()
+    t.join(timeout=60)
+    assert not t.is_alive(), "reader thread is stuck: lock-order deadlock"
+    assert not err and reads[0] > 0
+    s.close()

@@ -150,3 +150,41 @@ def test_completeness_restatement_vs_independent_numpy(oracle):
         want = want.astype(np.uint8).view(np.int8)
         got = om.export_completeness(publish)
         assert got.shape == want.shape and np.array_equal(got, want), publish
+
+
+def test_threaded_classification_equals_single_thread(oracle):
+    """CPU-baseline flavour 2 (dirty cells classified in parallel, as the archived node does,
+    archive/local_traversability_monolithic.cpp:349-362) must give the single-thread oracle's map bit for bit."""
+    import helpers
+    from traversability_mapping_b200 import synth
+    n = 4
+    poses = synth.trajectory("loop", n, seed=12, extent=5.0)
+    clouds = [synth.make_keyframe(12, i, poses[i], max_range=8.0, rings=32, azimuths=512) for i in range(n)]
+    out = {}
+    for th in (1, 4):
+        om = oracle.OracleMap(oracle.default_params(resolution=0.1, half_size=10.0, max_range=8.0, min_range=1.0,
+                                                    inflation_enabled=1, inflation_radius=0.5))
+        om.set_threads(th)
+        om.set_extrinsics(helpers.compose_f32(synth.T_BASE_SENSOR, synth.IDENTITY))
+        for i in range(n):
+            om.add_keyframe(i + 1, clouds[i]); om.update_pose(i + 1, poses[i])
+            om.process()
+        om.delete_keyframe(1)
+        keys = om.occupied_cell_keys()
+        out[th] = (keys, om.read_layers(keys, helpers.MOMENT_LAYERS + helpers.DERIVED_LAYERS), om.take_changed_cells())
+        om.close()
+    assert np.array_equal(out[1][0], out[4][0]) and helpers.bits_equal(out[1][1], out[4][1]) and np.array_equal(out[1][2], out[4][2])
+
+
+def test_bench_reference_arm_prints_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the GPU arm) on a tiny sample: one JSON line
+    with the contract's keys."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--cpu-keyframes", "2", "--steps", "1",
+                        "--warmup", "0"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "points/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["config"]["workload"].startswith("C4 loop closure")

@@ -60,6 +60,7 @@ class Stats(C.Structure):
         ("sum_host_ms_batch", C.c_double),
         ("sum_ms_gate", C.c_double), ("ms_gate", C.c_float), ("reserved0", C.c_float),
         ("sum_infl_tiles", C.c_uint64), ("sum_cand_bins", C.c_uint64),
+        ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
     ]
 
 
@@ -81,6 +82,8 @@ _SIG = {
     "tmap_set_extrinsics": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "tmap_add_map": (C.c_int, [_P, C.c_uint64, UPDATE_CB, C.c_void_p]),
     "tmap_set_current_map": (C.c_int, [_P, C.c_uint64]),
+    "tmap_current_map": (C.c_int, [_P, C.POINTER(C.c_uint64)]),
+    "tmap_global_point_cloud": (C.c_int, [_P, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "tmap_add_keyframe": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tmap_add_keyframe_device": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t]),
     "tmap_add_keyframe_pc2": (C.c_int, [_P, C.c_uint64, C.c_uint64, C.c_uint64, C.c_void_p, C.c_size_t, C.c_size_t,
@@ -370,8 +373,10 @@ class System:
 
     def addNewLocalMap(self, map_id, onUpdate=None):
         cb = UPDATE_CB((lambda _u, f=onUpdate: f()) if onUpdate else 0)
-        self._cbs[int(map_id)] = cb  # keep the trampoline alive
-        return _check(self._lib.tmap_add_map(self._h, int(map_id), cb, None))
+        rc = _check(self._lib.tmap_add_map(self._h, int(map_id), cb, None))
+        if rc == OK:
+            self._cbs[int(map_id)] = cb  # keep the trampoline alive; a duplicate id keeps the FIRST one (System.cpp:65-69)
+        return rc
 
     def setCurrentMap(self, map_id):
         return _check(self._lib.tmap_set_current_map(self._h, int(map_id)))
@@ -469,5 +474,20 @@ class System:
     def flush(self):
         return _check(self._lib.tmap_flush(self._h))
 
-    def getLocalMap(self, map_id=0):
+    def getLocalMap(self, map_id=None):
+        """getLocalMap() = the active map (System.cpp:357-361; None before any map exists), getLocalMap(id) = that map."""
+        if map_id is None:
+            cur = C.c_uint64(0)
+            if _check(self._lib.tmap_current_map(self._h, C.byref(cur))) != OK:
+                return None
+            map_id = cur.value
         return LocalMap(self, map_id)
+
+    def getGlobalPointCloud(self, voxel_size_x=0.0, voxel_size_y=0.0, voxel_size_z=0.0):
+        """System::getGlobalPointCloud (System.cpp:370-387): (n, 3) float32."""
+        n = C.c_size_t(0)
+        _check(self._lib.tmap_global_point_cloud(self._h, voxel_size_x, voxel_size_y, voxel_size_z, None, 0, C.byref(n)))
+        out = np.zeros((max(int(n.value), 1), 3), dtype=np.float32)
+        _check(self._lib.tmap_global_point_cloud(self._h, voxel_size_x, voxel_size_y, voxel_size_z, out.ctypes.data,
+                                                 int(n.value), C.byref(n)))
+        return out[: int(n.value)]

@@ -5,7 +5,7 @@
 // (trigonometric) eigenvalues of the scaled, trace-shifted matrix, the eigenvector from the
 // best-conditioned cross product of rows of (A - lambda I), then one Rayleigh-quotient update of
 // lambda.  Accuracy ~1e-15*|A| on lambda and ~1e-15*|A|/gap on the vector, which is what the
-// 1e-4 parity bar needs (tests/test_eig3.py compares against the oracle's QR restatement).
+// 1e-4 parity bar needs (tests/eig3_check.cpp (run by tests/test_abi.py::test_eig3_closed_form_vs_oracle_qr) compares against the oracle's QR restatement).
 #pragma once
 #include <math.h>
 

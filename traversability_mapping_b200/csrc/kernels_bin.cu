@@ -101,7 +101,9 @@ __device__ __forceinline__ void load_xyz(const PruneArgs &a, size_t i, float &x,
     }
 }
 
-__global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
+// The count pass also forms max |p_base| of the kept points (the keyframe's window radius), so the host has both
+// the exact size of the keyframe store and the window bound after ONE round trip, before the scatter runs.
+__global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count, uint32_t *__restrict__ out_total)
 {
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -109,6 +111,7 @@ __global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
     if (base >= a.n)
         return;
     uint32_t cnt = 0;
+    float mxr = 0.f;
 #pragma unroll
     for (int r = 0; r < PRUNE_PPT; ++r)
     {
@@ -119,11 +122,18 @@ __global__ void k_prune_count(PruneArgs a, uint32_t *__restrict__ warp_count)
             float x, y, z, xb, yb, zb, rg;
             load_xyz(a, i, x, y, z);
             ok = prune_point(a.T, x, y, z, a.rh, a.mx, a.mn, xb, yb, zb, rg);
+            if (ok) mxr = fmaxf(mxr, rg);
         }
         cnt += __popc(__ballot_sync(0xffffffffu, ok));
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        mxr = fmaxf(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
     if (lane == 0)
+    {
         warp_count[gw] = cnt;
+        atomicMax(out_total + 1, __float_as_uint(mxr));  // non-negative floats order like their bit patterns
+    }
 }
 
 // single-block exclusive scan over n_warps counts; total -> out_total[0]; maxnorm slot zeroed
@@ -171,14 +181,10 @@ __global__ void k_prune_scan(uint32_t *__restrict__ warp_count, uint32_t n_warps
         __syncthreads();
     }
     if (threadIdx.x == 0)
-    {
         out_total[0] = s_run;
-        out_total[1] = 0;  // max |p_base| as float bits
-    }
 }
 
-__global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_base, float4 *__restrict__ out,
-                                uint32_t *__restrict__ out_total)
+__global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_base, float4 *__restrict__ out)
 {
     const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const uint32_t lane = threadIdx.x & 31;
@@ -186,7 +192,6 @@ __global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_b
     if (base >= a.n)
         return;
     uint32_t pos = warp_base[gw];
-    float mxr = 0.f;
 #pragma unroll
     for (int r = 0; r < PRUNE_PPT; ++r)
     {
@@ -201,17 +206,9 @@ __global__ void k_prune_scatter(PruneArgs a, const uint32_t *__restrict__ warp_b
         }
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         if (ok)
-        {
             out[pos + __popc(m & ((1u << lane) - 1u))] = make_float4(xb, yb, zb, 0.f);
-            mxr = fmaxf(mxr, rg);
-        }
         pos += __popc(m);
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1)
-        mxr = fmaxf(mxr, __shfl_xor_sync(0xffffffffu, mxr, o));
-    if (lane == 0)
-        atomicMax(out_total + 1, __float_as_uint(mxr));
 }
 
 // packed xyz (host-provided base cloud) -> float4 store + max norm
@@ -1311,11 +1308,12 @@ cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t st
     const uint32_t blocks = (n_warps + 7) / 8;
     if (phase == 0)
     {
-        k_prune_count<<<blocks, 256, 0, st>>>(a, d_warp_cnt);
+        cudaMemsetAsync(d_total, 0, 8, st);
+        k_prune_count<<<blocks, 256, 0, st>>>(a, d_warp_cnt, d_total);
         k_prune_scan<<<1, 1024, 0, st>>>(d_warp_cnt, n_warps, d_total);
     }
     else
-        k_prune_scatter<<<blocks, 256, 0, st>>>(a, d_warp_cnt, d_out, d_total);
+        k_prune_scatter<<<blocks, 256, 0, st>>>(a, d_warp_cnt, d_out);
     return cudaGetLastError();
 }
 

@@ -55,6 +55,7 @@ struct Unsupported : std::runtime_error
     } while (0)
 
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_h2d{0}, g_d2h{0};  // bytes copied across PCIe by this library
 
 struct DevBuf
 {
@@ -253,11 +254,22 @@ struct KeyFrame
     bool integrated = false;  // has a contribution in the grid (== reference partials non-empty)
     float intPose[12] = {0};
     cudaStream_t allocStream = nullptr;  // stream-ordered allocation: freed without a device-wide sync
+    cudaEvent_t ready = nullptr;         // recorded behind the prune's compaction on the ingest stream
+    std::atomic<bool> waited{false};
     ~KeyFrame()
     {
+        if (ready) cudaEventDestroy(ready);
         if (!d_cloud) return;
         if (allocStream) cudaFreeAsync(d_cloud, allocStream);
         else cudaFree(d_cloud);
+    }
+    // the first consumer orders its stream behind the compaction; later uses are ordered behind that one
+    // (every consumer of one map runs on that map's stream, and a re-parented keyframe has long been complete)
+    void waitReady(cudaStream_t consumer)
+    {
+        if (!ready || waited.load(std::memory_order_acquire)) return;
+        cudaStreamWaitEvent(consumer, ready, 0);
+        if (cudaEventQuery(ready) == cudaSuccess) waited.store(true, std::memory_order_release);
     }
 
     void setPose(const float p[12])  // KeyFrame.cpp:29-34
@@ -493,7 +505,9 @@ class LocalMap
     }
 
     // ---- queries (caller may hold gridMutex via tmap_lock; the mutex is recursive) ----
-    std::vector<uint64_t> collectKeys(int mode, bool drain)
+    // `cap`: room in the caller's buffer.  A drain that would not fit is refused whole (nothing cleared, the
+    // count is still reported), so no changed cell is ever lost to a short buffer.
+    std::vector<uint64_t> collectKeys(int mode, bool drain, size_t cap, size_t *total)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
@@ -503,14 +517,19 @@ class LocalMap
         CK(launch_collect_keys(stream_, grid_.v, mode, 0, nullptr, 0, d_count));
         uint32_t n = 0;
         CK(cudaMemcpyAsync(&n, d_count, 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(4);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
+        *total = n;
+        if (drain && cap < n)
+            return {};
         std::vector<uint64_t> keys(n);
         if (n)
         {
             scratchKeys_.ensure((size_t)n * 8);
             CK(launch_collect_keys(stream_, grid_.v, mode, drain ? 1 : 0, scratchKeys_.as<unsigned long long>(), n, d_count));
             CK(cudaMemcpyAsync(keys.data(), scratchKeys_.p, (size_t)n * 8, cudaMemcpyDeviceToHost, stream_));
+            g_d2h += (uint64_t)((size_t)n * 8);
             CK(cudaStreamSynchronize(stream_));
             g_launches += 1;
             std::sort(keys.begin(), keys.end());
@@ -526,6 +545,7 @@ class LocalMap
         CK(launch_collect_keys(stream_, grid_.v, mode, 0, nullptr, 0, d_count));
         uint32_t n = 0;
         CK(cudaMemcpyAsync(&n, d_count, 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(4);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
         return n;
@@ -539,10 +559,13 @@ class LocalMap
         scratchLayers_.ensure(nl * 4);
         scratchOut_.ensure(n * nl * 4);
         CK(cudaMemcpyAsync(scratchKeys_.p, keys, n * 8, cudaMemcpyHostToDevice, stream_));
+        g_h2d += (uint64_t)(n * 8);
         CK(cudaMemcpyAsync(scratchLayers_.p, layers, nl * 4, cudaMemcpyHostToDevice, stream_));
+        g_h2d += (uint64_t)(nl * 4);
         CK(launch_read_layers(stream_, grid_.v, scratchKeys_.as<unsigned long long>(), n, scratchLayers_.as<int>(), (int)nl, kx_, ky_,
                               scratchOut_.as<float>()));
         CK(cudaMemcpyAsync(out, scratchOut_.p, n * nl * 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(n * nl * 4);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
@@ -568,6 +591,7 @@ class LocalMap
         scratchOut_.ensure(tot * 4);
         CK(launch_export_dense(stream_, grid_.v, layer, ci0, cj0, w, h, kx_, ky_, scratchOut_.as<float>()));
         CK(cudaMemcpyAsync(out, scratchOut_.p, tot * 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(tot * 4);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
@@ -580,6 +604,7 @@ class LocalMap
         scratchOut_.ensure(tot);
         CK(launch_export_occupancy(stream_, grid_.v, ci0, cj0, w, h, kx_, ky_, scratchOut_.as<signed char>()));
         CK(cudaMemcpyAsync(out, scratchOut_.p, tot, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(tot);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
@@ -599,6 +624,7 @@ class LocalMap
         scratchOut_.ensure(tot);
         CK(launch_export_completeness(stream_, grid_.v, ci0, cj0, w, h, kx_, ky_, f, cw, ch, scratchOut_.as<signed char>()));
         CK(cudaMemcpyAsync(out, scratchOut_.p, tot, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(tot);
         CK(cudaStreamSynchronize(stream_));
         g_launches += 1;
     }
@@ -628,10 +654,13 @@ class LocalMap
             if (!kf->hasCloud || off + kf->n > cap) continue;
             float p[12];
             kf->getPose(p);
+            kf->waitReady(stream_);
             scratchOut_.ensure((size_t)kf->n * 12);
             CK(cudaMemcpyAsync(scratchLayers_.p, p, 48, cudaMemcpyHostToDevice, stream_));
+            g_h2d += (uint64_t)(48);
             CK(launch_transform_cloud(stream_, kf->d_cloud, kf->n, scratchLayers_.as<float>(), scratchOut_.as<float>()));
             CK(cudaMemcpyAsync(out + off * 3, scratchOut_.p, (size_t)kf->n * 12, cudaMemcpyDeviceToHost, stream_));
+            g_d2h += (uint64_t)kf->n * 12;
             CK(cudaStreamSynchronize(stream_));
             g_launches += 1;
             off += kf->n;
@@ -663,7 +692,9 @@ class LocalMap
             if (!kf->hasCloud) continue;
             float p[12];
             kf->getPose(p);
+            kf->waitReady(stream_);
             CK(cudaMemcpyAsync(scratchLayers_.p, p, 48, cudaMemcpyHostToDevice, stream_));
+            g_h2d += (uint64_t)(48);
             CK(launch_transform_cloud(stream_, kf->d_cloud, kf->n, scratchLayers_.as<float>(), voxXyz_.as<float>() + off * 3));
             CK(cudaStreamSynchronize(stream_));  // the pose staging buffer is reused by the next keyframe
             g_launches += 1;
@@ -675,6 +706,7 @@ class LocalMap
         CK(vox_minmax(stream_, voxXyz_.as<float>(), n, mm));
         uint32_t mmh[6];
         CK(cudaMemcpyAsync(mmh, mm, sizeof(mmh), cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(sizeof(mmh));
         CK(cudaStreamSynchronize(stream_));
         // PCL 1.12 voxel_grid.hpp:246-291 in its own float / int arithmetic
         const float leaf[3] = {lx, ly, lz};
@@ -694,6 +726,7 @@ class LocalMap
             // "Leaf size is too small for the input dataset. Integer indices would overflow." -> output = input
             n_out = n;
             CK(cudaMemcpyAsync(out, voxXyz_.p, std::min<size_t>(n, cap) * 12, cudaMemcpyDeviceToHost, stream_));
+            g_d2h += (uint64_t)(std::min<size_t>(n, cap) * 12);
             CK(cudaStreamSynchronize(stream_));
             return n_out;
         }
@@ -711,6 +744,7 @@ class LocalMap
         CK(vox_filter(stream_, voxXyz_.as<float>(), n, inv, min_b, mul, keys, vals, head, ordinal, voxTemp_.p, tb, voxOut_.as<float>(), &nv));
         g_launches += 5;
         CK(cudaMemcpyAsync(out, voxOut_.p, std::min<size_t>(nv, cap) * 12, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(std::min<size_t>(nv, cap) * 12);
         CK(cudaStreamSynchronize(stream_));
         return nv;
     }
@@ -719,6 +753,8 @@ class LocalMap
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         *s = stats_;
         s->kernel_launches = g_launches.load();
+        s->h2d_bytes = g_h2d.load();
+        s->d2h_bytes = g_d2h.load();
         s->grid_reallocs = grid_.reallocs;
     }
 
@@ -891,6 +927,7 @@ class LocalMap
             const Op &op = ops[i];
             OpDesc &d = od[i];
             std::memset(&d, 0, sizeof(d));
+            op.kf->waitReady(stream_);
             d.cloud = op.kf->d_cloud;
             d.n = op.kf->n;
             d.sign = op.sign;
@@ -989,6 +1026,7 @@ class LocalMap
         }
         {
             CK(cudaMemcpyAsync(metaD_.p, metaH_.p, meta_bytes, cudaMemcpyHostToDevice, stream_));
+            g_h2d += (uint64_t)(meta_bytes);
         }
         unsigned char *md = metaD_.as<unsigned char>();
         b.ops = reinterpret_cast<const OpDesc *>(md + off_ops);
@@ -1040,6 +1078,7 @@ class LocalMap
         resH_.ensure(res_bytes + 64);
         const auto t_launched = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(res_bytes);
         CK(cudaStreamSynchronize(stream_));
         const auto t_synced = std::chrono::steady_clock::now();
         const uint32_t *cnt = resH_.as<uint32_t>();
@@ -1121,6 +1160,7 @@ class LocalMap
         CK(cudaEventRecord(e1, stream_));
         uint32_t bad = 0;
         CK(cudaMemcpyAsync(&bad, expCount_.p, 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(4);
         CK(cudaStreamSynchronize(stream_));
         float ms = 0;
         cudaEventElapsedTime(&ms, e0, e1);
@@ -1201,6 +1241,7 @@ class LocalMap
         resH_.ensure(res_bytes + 64);
         const auto t_launched = std::chrono::steady_clock::now();
         CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)(res_bytes);
         CK(cudaStreamSynchronize(stream_));
         const auto t_synced = std::chrono::steady_clock::now();
         if (resH_.as<uint32_t>()[3])
@@ -1231,6 +1272,7 @@ class LocalMap
         mergedD_.ensure((size_t)n_recv * 16 + 16);
         srcBaseD_.ensure((size_t)world * 8);
         CK(cudaMemcpyAsync(srcBaseD_.p, src_base, (size_t)world * 8, cudaMemcpyHostToDevice, stream_));
+        g_h2d += (uint64_t)((size_t)world * 8);
         b.sorted = mergedD_.as<float4>();
         b.split_thresh = (uint32_t)std::max<uint64_t>(32768, n_recv / (uint64_t)(3 * nSM_));
         b.n_ops = 0;  // per-op bboxes were consumed by shardBin
@@ -1433,8 +1475,13 @@ class System
     {
         std::lock_guard<std::recursive_mutex> l(m_);
         if (maps_.count(id)) return TMAP_IGNORED_DUPLICATE;
-        maps_[id] = std::make_shared<LocalMap>(id, P_, cb, user);
-        current_ = maps_[id];
+        auto mp = std::make_shared<LocalMap>(id, P_, cb, user);
+        {
+            std::lock_guard<std::mutex> r(mapsM_);  // writers hold m_ AND mapsM_; map() reads under mapsM_ alone
+            maps_[id] = mp;
+        }
+        current_ = mp;
+        currentId_.store(id);
         return TMAP_OK;
     }
     int setCurrentMap(uint64_t id)  // System.cpp:74-82
@@ -1443,11 +1490,17 @@ class System
         auto it = maps_.find(id);
         if (it == maps_.end()) return TMAP_IGNORED_UNKNOWN_MAP;
         current_ = it->second;
+        currentId_.store(id);
         return TMAP_OK;
     }
+    uint64_t currentMapId() const { return currentId_.load(); }
+    // Registry lookup for the reader / query entry points.  It must NOT take m_ (localMapMutex_): a reader
+    // holds the map's grid mutex across take + read (LocalMap.hpp:102-104) while deleteKeyFrame /
+    // updateKFMap / informLoopClosure go m_ -> grid mutex; the reference's readers call LocalMap methods
+    // directly and never touch localMapMutex_ either.
     std::shared_ptr<LocalMap> map(uint64_t id)
     {
-        std::lock_guard<std::recursive_mutex> l(m_);
+        std::lock_guard<std::mutex> r(mapsM_);
         auto it = maps_.find(id);
         return it == maps_.end() ? nullptr : it->second;
     }
@@ -1456,6 +1509,7 @@ class System
     std::shared_ptr<KeyFrame> pruneToKeyFrame(const void *src, bool on_device, size_t n, size_t stride, const float T[12], double mx,
                                               double mn, const int *field_floats = nullptr, int big_endian = 0)
     {
+        if (stride < 12 || stride % 4) throw std::invalid_argument("stride_bytes must be a multiple of 4 and >= 12");
         std::lock_guard<std::mutex> l(ingestMutex_);
         CK(cudaSetDevice(P_.device));
         auto kf = std::make_shared<KeyFrame>();
@@ -1465,23 +1519,34 @@ class System
         {
             raw_.ensure(n * stride);
             CK(cudaMemcpyAsync(raw_.p, src, n * stride, cudaMemcpyHostToDevice, ingest_));
+            g_h2d += (uint64_t)(n * stride);
             d_src = raw_.p;
         }
         const size_t n_warps = (n + 255) / 256;
         warpCnt_.ensure(n_warps * 4 + 64);
         total_.ensure(16);
         totalH_.ensure(16);
-        CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), n * sizeof(float4), ingest_));
-        kf->allocStream = ingest_;
+        // Two phases around ONE host round trip: count (+ max norm) -> the store is allocated for exactly the points
+        // that survive the prune (a LiDAR frame loses 40-50 % to misses / range / height) -> compaction.  The
+        // compaction is not waited for here: the keyframe carries an event the consuming stream waits on.
         CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
-                        total_.as<uint32_t>(), kf->d_cloud, 0, field_floats, big_endian));
-        CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
-                        total_.as<uint32_t>(), kf->d_cloud, 1, field_floats, big_endian));
-        g_launches += 3;
+                        total_.as<uint32_t>(), nullptr, 0, field_floats, big_endian));
         CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
-        CK(cudaStreamSynchronize(ingest_));
+        g_d2h += (uint64_t)(8);
+        CK(cudaStreamSynchronize(ingest_));  // the caller's host buffer has been consumed by now as well
         kf->n = totalH_.as<uint32_t>()[0];
         std::memcpy(&kf->maxnorm, totalH_.as<uint32_t>() + 1, 4);
+        g_launches += 2;
+        if (kf->n == 0) return kf;
+        CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), (size_t)kf->n * sizeof(float4), ingest_));
+        kf->allocStream = ingest_;
+        CK(launch_prune(ingest_, d_src, n, stride, T, (float)P_.robot_height, (float)mx, (float)mn, warpCnt_.as<uint32_t>(),
+                        total_.as<uint32_t>(), kf->d_cloud, 1, field_floats, big_endian));
+        g_launches += 1;
+        CK(cudaEventCreateWithFlags(&kf->ready, cudaEventDisableTiming));
+        CK(cudaEventRecord(kf->ready, ingest_));
+        if (on_device)
+            CK(cudaStreamSynchronize(ingest_));  // a caller-owned device source may be reused as soon as we return
         return kf;
     }
 
@@ -1542,7 +1607,7 @@ class System
             std::lock_guard<std::mutex> il(ingestMutex_);
             CK(cudaSetDevice(P_.device));
             CK(cudaMallocAsync(&b.d, std::max<size_t>(n * stride, 16), ingest_));
-            if (n) CK(cudaMemcpyAsync(b.d, xyz, n * stride, cudaMemcpyHostToDevice, ingest_));
+            if (n) { CK(cudaMemcpyAsync(b.d, xyz, n * stride, cudaMemcpyHostToDevice, ingest_)); g_h2d += (uint64_t)(n * stride); }
             CK(cudaStreamSynchronize(ingest_));  // the caller's buffer may go away after the call returns
         }
         cloudBuf_.push_back(b);
@@ -1567,8 +1632,7 @@ class System
         size_t best = 0;
         for (size_t i = 1; i < cloudBuf_.size(); ++i)
             if (std::abs(cloudBuf_[i].t - timestamp) < std::abs(cloudBuf_[best].t - timestamp)) best = i;
-        const Buffered &b = cloudBuf_[best];
-        if (kfID > (uint64_t)std::numeric_limits<int64_t>::max()) return TMAP_ERR_NEGATIVE_ID;
+        const Buffered &b = cloudBuf_[best];  // (no id-range check here: System.cpp:174-186 has none)
         {
             std::lock_guard<std::recursive_mutex> ml(m_);
             if (kfs_.count(kfID)) return TMAP_IGNORED_DUPLICATE;
@@ -1599,11 +1663,13 @@ class System
             total_.ensure(16);
             totalH_.ensure(16);
             CK(cudaMemcpyAsync(raw_.p, xyz, n * 12, cudaMemcpyHostToDevice, ingest_));
+            g_h2d += (uint64_t)(n * 12);
             CK(cudaMallocAsync(reinterpret_cast<void **>(&kf->d_cloud), n * sizeof(float4), ingest_));
             kf->allocStream = ingest_;
             CK(launch_pack_base(ingest_, raw_.as<float>(), n, kf->d_cloud, total_.as<uint32_t>()));
             g_launches += 1;
             CK(cudaMemcpyAsync(totalH_.p, total_.p, 8, cudaMemcpyDeviceToHost, ingest_));
+            g_d2h += (uint64_t)(8);
             CK(cudaStreamSynchronize(ingest_));
             kf->n = (uint32_t)n;
             std::memcpy(&kf->maxnorm, totalH_.as<uint32_t>() + 1, 4);
@@ -1630,15 +1696,23 @@ class System
         mp->setKeyFramePose(kf, pose);
         return TMAP_OK;
     }
+    // The registry lock is dropped while the map subtracts the keyframe (grid mutex + a GPU pass) and re-taken
+    // to erase the entries: holding m_ across detachKeyFrame would order m_ -> grid mutex against any caller
+    // that holds the grid mutex and enters the library again.
     int deleteKeyFrame(uint64_t kfID)  // System.cpp:234-248
     {
+        std::shared_ptr<LocalMap> mp;
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            auto rit = kfMap_.find(kfID);
+            if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+            auto mit = maps_.find(rit->second);
+            if (mit != maps_.end()) mp = mit->second;
+        }
+        if (mp) mp->detachKeyFrame(kfID);
         std::lock_guard<std::recursive_mutex> l(m_);
-        auto rit = kfMap_.find(kfID);
-        if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
-        auto mit = maps_.find(rit->second);
-        if (mit != maps_.end()) mit->second->detachKeyFrame(kfID);
         kfs_.erase(kfID);
-        kfMap_.erase(rit);
+        kfMap_.erase(kfID);
         return TMAP_OK;
     }
     int keyFramePoints(uint64_t kfID, size_t *n_out)  // KeyFrame.hpp:85
@@ -1651,26 +1725,34 @@ class System
     }
     int updateKFMap(uint64_t kfID, uint64_t mapID)  // System.cpp:250-276
     {
-        std::lock_guard<std::recursive_mutex> l(m_);
-        auto rit = kfMap_.find(kfID);
-        if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
-        if (!maps_.count(mapID)) return TMAP_IGNORED_UNKNOWN_MAP;
-        const uint64_t old = rit->second;
-        if (old == mapID) return TMAP_OK;
-        auto kf = maps_[old]->detachKeyFrame(kfID);
+        std::shared_ptr<LocalMap> from, to;
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            auto rit = kfMap_.find(kfID);
+            if (rit == kfMap_.end()) return TMAP_IGNORED_UNKNOWN_KF;
+            auto tit = maps_.find(mapID);
+            if (tit == maps_.end()) return TMAP_IGNORED_UNKNOWN_MAP;
+            if (rit->second == mapID) return TMAP_OK;
+            auto fit = maps_.find(rit->second);
+            if (fit == maps_.end()) return TMAP_OK;
+            from = fit->second;
+            to = tit->second;
+        }
+        auto kf = from->detachKeyFrame(kfID);  // grid mutex of the old map; m_ not held
         if (!kf) return TMAP_OK;
-        maps_[mapID]->addAlreadyDeclaredKF(kf);
+        to->addAlreadyDeclaredKF(kf);
         float p[12];
         kf->getPose(p);
-        maps_[mapID]->setKeyFramePose(kf, p);
-        rit->second = mapID;
+        to->setKeyFramePose(kf, p);
+        std::lock_guard<std::recursive_mutex> l(m_);
+        auto rit = kfMap_.find(kfID);
+        if (rit != kfMap_.end()) rit->second = mapID;
         return TMAP_OK;
     }
     int informLoopClosure()  // System.cpp:278-284
     {
-        std::lock_guard<std::recursive_mutex> l(m_);
-        auto it = maps_.find(0);
-        if (it != maps_.end()) it->second->clearEntireMap();
+        auto mp = map(0);
+        if (mp) mp->clearEntireMap();
         return TMAP_OK;
     }
     int addObstacleKeyFrame(uint64_t ts_ns, const float *xyz, size_t n, size_t stride, uint64_t *id_out)  // System.cpp:300-323
@@ -1691,11 +1773,31 @@ class System
     }
     int deleteObstacleKeyFrame(uint64_t id)  // System.cpp:325-335
     {
+        {
+            std::lock_guard<std::recursive_mutex> l(m_);
+            if (!kfMap_.count(id)) return TMAP_IGNORED_UNKNOWN_KF;
+        }
+        if (deleteKeyFrame(id) != TMAP_OK) return TMAP_IGNORED_UNKNOWN_KF;  // lost a race with another delete
         std::lock_guard<std::recursive_mutex> l(m_);
-        if (!kfMap_.count(id)) return TMAP_IGNORED_UNKNOWN_KF;
-        deleteKeyFrame(id);
         freeObs_.push_back(id);
         return TMAP_OK;
+    }
+    // System::getGlobalPointCloud (System.cpp:370-387): every map's stitched (optionally voxel-filtered) cloud,
+    // concatenated.  The reference walks an unordered_map; here maps are visited in ascending id.
+    size_t globalPointCloud(float vx, float vy, float vz, float *out, size_t cap)
+    {
+        std::vector<std::shared_ptr<LocalMap>> ms;
+        {
+            std::lock_guard<std::mutex> r(mapsM_);
+            for (auto &kv : maps_) ms.push_back(kv.second);
+        }
+        size_t total = 0;
+        for (auto &mp : ms)
+        {
+            const size_t room = out && cap > total ? cap - total : 0;
+            total += mp->stitchedVoxel(vx, vy, vz, room ? out + 3 * total : nullptr, room);
+        }
+        return total;
     }
     int flush()
     {
@@ -1718,8 +1820,10 @@ class System
   private:
     tmap_params P_;
     std::recursive_mutex m_;  // localMapMutex_
+    std::mutex mapsM_;        // leaf lock of the maps_ container alone (see map())
     std::map<uint64_t, std::shared_ptr<LocalMap>> maps_;
     std::shared_ptr<LocalMap> current_;
+    std::atomic<uint64_t> currentId_{0};
     std::unordered_map<uint64_t, std::shared_ptr<KeyFrame>> kfs_;
     std::unordered_map<uint64_t, uint64_t> kfMap_;  // allKeyFramesSet_
     float Tbv_[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -1903,9 +2007,9 @@ int tmap_unlock(tmap_system *s, uint64_t map_id)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->gridMutex().unlock(); return TMAP_OK; TMAP_API_END
 }
-static int keys_out(std::vector<uint64_t> &keys, uint64_t *out, size_t cap, size_t *n_out)
+static int keys_out(std::vector<uint64_t> &keys, size_t total, uint64_t *out, size_t cap, size_t *n_out)
 {
-    if (n_out) *n_out = keys.size();
+    if (n_out) *n_out = total;
     for (size_t i = 0; i < keys.size() && i < cap; ++i) out[i] = keys[i];
     return TMAP_OK;
 }
@@ -1913,16 +2017,18 @@ int tmap_take_changed_cells(tmap_system *s, uint64_t map_id, uint64_t *out, size
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
     if (!out) { if (n_out) *n_out = mp->countKeys(0); return TMAP_OK; }
-    auto keys = mp->collectKeys(0, true);
-    return keys_out(keys, out, cap, n_out);
+    size_t total = 0;
+    auto keys = mp->collectKeys(0, true, cap, &total);  // cap < total: nothing is drained, *n_out = total
+    return keys_out(keys, total, out, cap, n_out);
     TMAP_API_END
 }
 int tmap_occupied_cell_keys(tmap_system *s, uint64_t map_id, uint64_t *out, size_t cap, size_t *n_out)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
     if (!out) { if (n_out) *n_out = mp->countKeys(1); return TMAP_OK; }
-    auto keys = mp->collectKeys(1, false);
-    return keys_out(keys, out, cap, n_out);
+    size_t total = 0;
+    auto keys = mp->collectKeys(1, false, cap, &total);
+    return keys_out(keys, total, out, cap, n_out);
     TMAP_API_END
 }
 int tmap_read_layers(tmap_system *s, uint64_t map_id, const uint64_t *keys, size_t n, const int32_t *layer_ids, size_t n_layers,
@@ -2003,6 +2109,23 @@ int tmap_stitched_cloud_voxel(tmap_system *s, uint64_t map_id, float leaf_x, flo
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
     const size_t n = mp->stitchedVoxel(leaf_x, leaf_y, leaf_z, out_xyz, cap);
+    if (n_out) *n_out = n;
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_current_map(tmap_system *s, uint64_t *map_id_out)
+{
+    NEED(s)
+    if (!map_id_out) { tmb::g_last_error = "null map_id_out"; return TMAP_ERR_INVALID; }
+    TMAP_API_BEGIN
+    *map_id_out = s->sys->currentMapId();
+    return s->sys->map(*map_id_out) ? TMAP_OK : TMAP_IGNORED_UNKNOWN_MAP;
+    TMAP_API_END
+}
+int tmap_global_point_cloud(tmap_system *s, float leaf_x, float leaf_y, float leaf_z, float *out_xyz, size_t cap, size_t *n_out)
+{
+    NEED(s) TMAP_API_BEGIN
+    const size_t n = s->sys->globalPointCloud(leaf_x, leaf_y, leaf_z, out_xyz, cap);
     if (n_out) *n_out = n;
     return TMAP_OK;
     TMAP_API_END

@@ -130,3 +130,58 @@ def drift_poses(true_poses, per_kf_forward=0.05, per_kf_yaw_deg=1.0):
         D[:2, 3] = T[:2, 3] + acc_f * heading
         out.append(D.astype(np.float32))
     return np.stack(out)
+
+
+# ---------------------------------------------------------------------------------------------
+# Batched generator (torch, CPU or CUDA): the same sensor and terrain model as make_keyframe, for the
+# workloads whose cloud count makes the numpy path too slow (2 000 keyframes x 262 144 rays).  The random
+# stream is torch's (seeded per batch), so its clouds are NOT the numpy generator's; both arms of a
+# comparison always consume the same host arrays.  Plumbing for benchmarks / tests, not part of the path.
+# ---------------------------------------------------------------------------------------------
+def _terrain_t(torch, x, y):
+    h = 0.15 * torch.sin(0.7 * x) * torch.cos(0.5 * y) + 0.05 * torch.sin(3.1 * x + 1.3 * y)
+    mx = torch.remainder(x + 40.0, 17.0)
+    h = h + 0.30 * ((mx > 8.0) & (mx < 11.0) & (torch.remainder(y + 40.0, 13.0) > 6.0)).to(h.dtype)
+    h = h + 0.20 * (torch.remainder(y + 23.0, 29.0) > 25.0).to(h.dtype)
+    md = torch.remainder(x - y + 60.0, 41.0)
+    h = h + torch.clamp(0.15 * (md - 30.0), 0.0, 0.6) * (md > 30.0).to(h.dtype)
+    return h
+
+
+def make_keyframes_torch(seed, first_index, poses, max_range=20.0, rings=128, azimuths=1024, noise=0.01, nan_frac=0.001,
+                         device="cpu"):
+    """Raycast len(poses) keyframes at once.  Returns a (K, rings*azimuths, 4) float32 tensor on `device`,
+    sensor frame, pcl::PointXYZ layout; a pure function of (seed, first_index, poses, device kind)."""
+    import torch
+    dev = torch.device(device)
+    g = torch.Generator(device=dev)
+    g.manual_seed((int(seed) * 1000003 + int(first_index) * 7919 + 12345) & 0x7FFFFFFFFFFFFFFF)
+    f64 = torch.float64
+    T = torch.as_tensor(np.asarray(poses, dtype=np.float64).reshape(-1, 3, 4), device=dev)
+    K = T.shape[0]
+    R, t = T[:, :, :3], T[:, :, 3]
+    el = torch.deg2rad(torch.linspace(-25.0, 15.0, rings, dtype=f64, device=dev))
+    az = torch.arange(azimuths, dtype=f64, device=dev) * (2.0 * math.pi / azimuths)
+    EL, AZ = torch.meshgrid(el, az, indexing="ij")
+    d_s = torch.stack([torch.cos(EL) * torch.cos(AZ), torch.cos(EL) * torch.sin(AZ), torch.sin(EL)], dim=-1).reshape(-1, 3)
+    n = d_s.shape[0]
+    o_m = R[:, :, 2] * SENSOR_HEIGHT + t                      # (K, 3)
+    d_m = torch.einsum("nj,kij->kni", d_s, R)                 # (K, n, 3)
+    down = d_m[:, :, 2] < -1e-3
+    dz = torch.where(down, d_m[:, :, 2], torch.full_like(d_m[:, :, 2], -1.0))
+    ox, oy, oz = o_m[:, 0:1], o_m[:, 1:2], o_m[:, 2:3]
+    tt = (_terrain_t(torch, ox, oy) - oz) / dz
+    for _ in range(8):
+        tt = torch.clamp(tt, 0.0, max_range * 1.2)
+        px = ox + tt * d_m[:, :, 0]
+        py = oy + tt * d_m[:, :, 1]
+        tt = 0.5 * tt + 0.5 * (_terrain_t(torch, px, py) - oz) / dz
+    found = down & (tt > 0.0)
+    rng_t = tt + noise * torch.randn((K, n), dtype=f64, device=dev, generator=g)
+    ok = found & (rng_t > 0.05) & (rng_t <= max_range * 1.05)
+    out = torch.zeros((K, n, 4), dtype=torch.float32, device=dev)
+    pts = (d_s.unsqueeze(0) * rng_t.unsqueeze(-1)).to(torch.float32)
+    out[:, :, :3] = torch.where(ok.unsqueeze(-1), pts, torch.zeros_like(pts))
+    bad = torch.rand((K, n), device=dev, generator=g) < nan_frac
+    out[:, :, :3] = torch.where(bad.unsqueeze(-1), torch.full_like(pts, float("nan")), out[:, :, :3])
+    return out
