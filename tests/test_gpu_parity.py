@@ -786,7 +786,7 @@ def test_config2_at_benchmarked_size(tmap, oracle):
             st = compare_maps(m, om, check_changed=True, label=f"C2 tick {i}")
         else:
             m.takeChangedCells(); om.take_changed_cells()
-    assert m.numKeyFrames() == window and st["cells"] > 200000 and st["gated_in"] > 100000, st
+    assert m.numKeyFrames() == window and st["cells"] > 150000 and st["gated_in"] > 15000, st
     s.close()
 
 
@@ -854,7 +854,7 @@ def test_config5_geometry_reduced_extent(tmap, oracle):
     om.clear_entire_map()
     s.flush(); om.process_batched()
     st = compare_maps(m, om, check_changed=True, label="C5 geometry, loop closure")
-    assert st["gated_in"] > 100000, st
+    assert st["cells"] > 1000000 and st["gated_in"] > 40000, st
     s.close()
 
 
@@ -880,8 +880,8 @@ def test_config4_full_size_properties(tmap):
         s.updateKeyFrames(ids, true)
         s.informLoopClosure()
     s.flush()
-    total = m.stats()["last_batch_points"]
-    assert total > 256e6, total
+    total = m.stats()["last_batch_points"]   # one pass: everything queued under the grid mutex is folded together
+    assert total > 256e6 and total == sum(s.keyFramePoints(i + 1) for i in range(0, nk, 1)), total
     keys0 = m.occupiedCellKeys()
     allL = helpers.MOMENT_LAYERS + [l for l in helpers.DERIVED_LAYERS if l != "step_haz_inflated"]
     L0 = m.readLayers(keys0, allL)

@@ -26,7 +26,10 @@
 //                 cell key, one thread per cell walks its run in (op, point) order accumulating
 //                 doubles, then folds float32 into the cell's 48-byte record (blank rule included).
 #include "tmb_common.cuh"
+#include "tmb_async.cuh"
 #include <math_constants.h>
+#include <cstdlib>
+#include <cstdio>
 
 namespace tmb
 {
@@ -231,9 +234,14 @@ __global__ void k_pack_base(const float *__restrict__ xyz, size_t n, float4 *__r
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_hist: transform + key + per-chunk bin histogram
+// k_hist: transform + key + per-chunk bin histogram.
+// A chunk is 256 * PPT * SUB consecutive points of one op, processed as SUB sub-rounds of 256 * PPT points that
+// accumulate into ONE shared-memory histogram: the per-chunk fixed costs (op descriptor fetch, zeroing and
+// writing the T-entry histogram row, the row's later trips through k_scan_chunks and k_scatter) are paid once per
+// 8 192 points at loop-closure scale (PPT 4, SUB 8) instead of once per 2 048.  The next sub-round's points are
+// requested before the current one is processed, so a CTA always has loads in flight.
 // ---------------------------------------------------------------------------------------------
-template <int PPT>
+template <int PPT, int SUB>
 __global__ void __launch_bounds__(BIN_THREADS, 5) k_hist(BatchView b, LatticeD lat)
 {
     extern __shared__ uint32_t s_hist[];
@@ -251,7 +259,7 @@ __global__ void __launch_bounds__(BIN_THREADS, 5) k_hist(BatchView b, LatticeD l
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t cl = chunk - s_op.chunk0;
-    const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
+    const uint32_t chunk_base = cl * (BIN_THREADS * PPT * SUB);
     int mnx = INT_MAX, mxx = INT_MIN, mny = INT_MAX, mxy = INT_MIN;
     bool bad = false;
     // op constants live in registers (the shared copy would be re-read around every shared atomic)
@@ -261,37 +269,56 @@ __global__ void __launch_bounds__(BIN_THREADS, 5) k_hist(BatchView b, LatticeD l
     float Tm[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) Tm[k] = s_op.T[k];
-    // all of the thread's points are requested before any is used: PPT independent 16-byte loads in flight
-    float4 pts[PPT];
+    float4 nxt[PPT];
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
-        const uint32_t i = base + r * 32 + lane;
-        pts[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t i = chunk_base + warp * (32 * PPT) + r * 32 + lane;
+        nxt[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll
-    for (int r = 0; r < PPT; ++r)
+#pragma unroll 1
+    for (int sub = 0; sub < SUB; ++sub)
     {
-        const uint32_t i = base + r * 32 + lane;
-        uint32_t tile = 0xffffffffu;
-        if (i < n_pts)
+        const uint32_t sub_base = chunk_base + sub * (BIN_THREADS * PPT);
+        if (sub_base >= n_pts)
+            break;  // uniform over the CTA
+        const uint32_t base = sub_base + warp * (32 * PPT);
+        float4 pts[PPT];
+#pragma unroll
+        for (int r = 0; r < PPT; ++r) pts[r] = nxt[r];
+        if (sub + 1 < SUB)
         {
-            const float4 p = pts[r];
-            const float xm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[0], p.x), __fmul_rn(Tm[1], p.y)), __fmul_rn(Tm[2], p.z)), Tm[3]);
-            const float ym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[4], p.x), __fmul_rn(Tm[5], p.y)), __fmul_rn(Tm[6], p.z)), Tm[7]);
-            const int ci = cell_of(xm, lat.x0, lat.res, inv_res), cj = cell_of(ym, lat.y0, lat.res, inv_res);
-            const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
-            if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
+#pragma unroll
+            for (int r = 0; r < PPT; ++r)
             {
-                tile = ty * wtw + tx;
-                mnx = min(mnx, ci); mxx = max(mxx, ci); mny = min(mny, cj); mxy = max(mxy, cj);
+                const uint32_t i = base + BIN_THREADS * PPT + r * 32 + lane;
+                nxt[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            else
-                bad = true;
         }
-        const uint32_t m = __match_any_sync(0xffffffffu, tile);
-        if (tile != 0xffffffffu && (m >> lane) == 1u)  // the group's highest lane adds the group size
-            atomicAdd(&s_hist[tile], __popc(m));
+#pragma unroll
+        for (int r = 0; r < PPT; ++r)
+        {
+            const uint32_t i = base + r * 32 + lane;
+            uint32_t tile = 0xffffffffu;
+            if (i < n_pts)
+            {
+                const float4 p = pts[r];
+                const float xm = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[0], p.x), __fmul_rn(Tm[1], p.y)), __fmul_rn(Tm[2], p.z)), Tm[3]);
+                const float ym = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(Tm[4], p.x), __fmul_rn(Tm[5], p.y)), __fmul_rn(Tm[6], p.z)), Tm[7]);
+                const int ci = cell_of(xm, lat.x0, lat.res, inv_res), cj = cell_of(ym, lat.y0, lat.res, inv_res);
+                const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
+                if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
+                {
+                    tile = ty * wtw + tx;
+                    mnx = min(mnx, ci); mxx = max(mxx, ci); mny = min(mny, cj); mxy = max(mxy, cj);
+                }
+                else
+                    bad = true;
+            }
+            const uint32_t m = __match_any_sync(0xffffffffu, tile);
+            if (tile != 0xffffffffu && (m >> lane) == 1u)  // the group's highest lane adds the group size
+                atomicAdd(&s_hist[tile], __popc(m));
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
@@ -676,10 +703,14 @@ __global__ void __launch_bounds__(1024) k_scan_small(BatchView b)
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_scatter: stable bucket scatter by global bin.  Per-warp counter rows are u16 (a warp slice holds
-// at most 32*PPT <= 256 points); the absolute base of a bin lives in a separate u32 row.
+// k_scatter: stable bucket scatter by global bin, same chunking as k_hist (SUB sub-rounds of 256 * PPT points).
+// Per sub-round: keys + per-warp u16 counter rows (ONE match.any per point, its rank and group leader kept in
+// a register for the placement), a prefix over the warps' rows per TOUCHED bin, placement.  The absolute base of
+// a bin (bin start + op offset + this chunk's prefix: three global reads) is fetched the first time a sub-round
+// touches the bin -- a chunk of consecutive LiDAR returns touches a few dozen of the op's ~800 window bins.
+// Record order inside a bucket is (op, point): sub-rounds, warps, rounds and lanes all advance with the index.
 // ---------------------------------------------------------------------------------------------
-template <int PPT, bool EMIT>
+template <int PPT, int SUB, bool EMIT>
 __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, LatticeD lat, GridView g, int dc, int di)
 {
     extern __shared__ __align__(16) unsigned char s_dyn[];
@@ -705,86 +736,134 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
     __syncthreads();
     const uint32_t T = s_op.T_tiles;
     const double inv_res = 1.0 / lat.res;
-    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn);               // [T]
+    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn);               // [T]  absolute slot of the chunk's first record per bin
     uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_base + T);           // [NW][T]
-    for (uint32_t i = threadIdx.x; i < (T * NW + 1) / 2; i += BIN_THREADS)
+    uint16_t *s_run = s_cnt + (size_t)NW * T;                             // [T]  records of this chunk already placed per bin
+    for (uint32_t i = threadIdx.x; i < (T * (NW + 1) + 1) / 2; i += BIN_THREADS)
         reinterpret_cast<uint32_t *>(s_cnt)[i] = 0;
+    for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
+        s_base[i] = 0xffffffffu;
     __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     const uint32_t cl = chunk - s_op.chunk0;
-    const uint32_t base = cl * (BIN_THREADS * PPT) + warp * (32 * PPT);
+    const uint32_t chunk_base = cl * (BIN_THREADS * PPT * SUB);
     uint16_t *my = s_cnt + warp * T;
     const uint32_t sign_bit = s_op.sign < 0.f ? META_SIGN : 0u;
     const uint32_t n_pts = s_op.n;
     const float4 *cloud = s_op.cloud;
     const int wtx0 = s_op.wtx0, wty0 = s_op.wty0, wtw = s_op.wtw, wth = s_op.wth;
+    const uint32_t meta_op = sign_bit | ((opi + b.op_base) << 8);
     float Tm[12];
 #pragma unroll
     for (int k = 0; k < 12; ++k) Tm[k] = s_op.T[k];
-    float px[PPT], py[PPT], pz[PPT];
-    uint32_t tl[PPT], cc[PPT], mm[PPT];
-    float4 pts[PPT];
+    const uint32_t *row = b.hist + s_op.hist_off + (size_t)cl * T;
+    float4 nxt[PPT];
 #pragma unroll
     for (int r = 0; r < PPT; ++r)
     {
-        const uint32_t i = base + r * 32 + lane;
-        pts[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t i = chunk_base + warp * (32 * PPT) + r * 32 + lane;
+        nxt[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-#pragma unroll
-    for (int r = 0; r < PPT; ++r)
+#pragma unroll 1
+    for (int sub = 0; sub < SUB; ++sub)
     {
-        const uint32_t i = base + r * 32 + lane;
-        tl[r] = 0xffffffffu;
-        cc[r] = 0;
-        px[r] = py[r] = pz[r] = 0.f;
-        if (i < n_pts)
+        const uint32_t sub_base = chunk_base + sub * (BIN_THREADS * PPT);
+        if (sub_base >= n_pts)
+            break;  // uniform over the CTA
+        const uint32_t base = sub_base + warp * (32 * PPT);
+        float px[PPT], py[PPT], pz[PPT];
+        uint32_t tk[PPT];  // bin in window (bits 0..15, 0xffff = none) | rank in group << 16 | leader << 31
+        uint32_t cc[PPT];
         {
-            const float4 p = pts[r];
-            xform_rn(Tm, p.x, p.y, p.z, px[r], py[r], pz[r]);
-            const int ci = cell_of(px[r], lat.x0, lat.res, inv_res), cj = cell_of(py[r], lat.y0, lat.res, inv_res);
-            const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
-            if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
+            float4 pts[PPT];
+#pragma unroll
+            for (int r = 0; r < PPT; ++r) pts[r] = nxt[r];
+            if (sub + 1 < SUB)
             {
-                tl[r] = ty * wtw + tx;
-                cc[r] = ((cj & (BIN - 1)) << BIN_SHIFT) | (ci & (BIN - 1));
+#pragma unroll
+                for (int r = 0; r < PPT; ++r)
+                {
+                    const uint32_t i = base + BIN_THREADS * PPT + r * 32 + lane;
+                    nxt[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < PPT; ++r)
+            {
+                const uint32_t i = base + r * 32 + lane;
+                uint32_t tl = 0xffffu;
+                cc[r] = 0;
+                px[r] = py[r] = pz[r] = 0.f;
+                if (i < n_pts)
+                {
+                    const float4 p = pts[r];
+                    xform_rn(Tm, p.x, p.y, p.z, px[r], py[r], pz[r]);
+                    const int ci = cell_of(px[r], lat.x0, lat.res, inv_res), cj = cell_of(py[r], lat.y0, lat.res, inv_res);
+                    const int tx = (ci >> BIN_SHIFT) - wtx0, ty = (cj >> BIN_SHIFT) - wty0;
+                    if (tx >= 0 && tx < wtw && ty >= 0 && ty < wth)
+                    {
+                        tl = ty * wtw + tx;
+                        cc[r] = ((cj & (BIN - 1)) << BIN_SHIFT) | (ci & (BIN - 1));
+                    }
+                }
+                const uint32_t m = __match_any_sync(0xffffffffu, tl);
+                const bool lead = (m >> lane) == 1u;
+                if (tl != 0xffffu && lead)
+                    my[tl] += (uint16_t)__popc(m);   // row `warp` is private to this warp
+                tk[r] = tl | ((uint32_t)__popc(m & lt) << 16) | (lead ? 0x80000000u : 0u);
+                __syncwarp();
             }
         }
-        mm[r] = __match_any_sync(0xffffffffu, tl[r]);  // kept for the placement pass below
-        if (tl[r] != 0xffffffffu && (mm[r] >> lane) == 1u)
-            my[tl[r]] += (uint16_t)__popc(mm[r]);   // row `warp` is private to this warp
-        __syncwarp();
-    }
-    __syncthreads();
-    // per bin: absolute base of this chunk's run = bin start + op offset + chunk prefix; warps' runs follow
-    const uint32_t *row = b.hist + s_op.hist_off + (size_t)cl * T;
-    for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
-    {
-        const int gx = s_op.wtx0 + (int)(t % s_op.wtw) - b.btx0, gy = s_op.wty0 + (int)(t / s_op.wtw) - b.bty0;
-        s_base[t] = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
-        uint32_t run = 0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w)
+        __syncthreads();
+        // per touched bin: base (first touch) and the warps' exclusive offsets, continuing from earlier sub-rounds
+        for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
         {
-            const uint32_t v = s_cnt[w * T + t];
-            s_cnt[w * T + t] = (uint16_t)run;
-            run += v;
-        }
-    }
-    __syncthreads();
+            uint32_t run = s_run[t];
+            const uint32_t run0 = run;
 #pragma unroll
-    for (int r = 0; r < PPT; ++r)
-    {
-        const uint32_t m = mm[r];
-        if (tl[r] != 0xffffffffu)
-        {
-            const uint32_t slot = my[tl[r]] + __popc(m & ((1u << lane) - 1u));
-            b.sorted[s_base[tl[r]] + slot] = make_float4(px[r], py[r], pz[r], __uint_as_float(sign_bit | ((opi + b.op_base) << 8) | cc[r]));
-            __syncwarp(m);
-            if ((m >> lane) == 1u)  // highest lane of the group: its slot + 1 is the group's end
-                my[tl[r]] = (uint16_t)(slot + 1u);
+            for (int w = 0; w < NW; ++w)
+            {
+                const uint32_t v = s_cnt[w * T + t];
+                if (v) s_cnt[w * T + t] = (uint16_t)run;  // untouched (warp, bin) entries stay zero for the next sub-round
+                run += v;
+            }
+            if (run != run0)
+            {
+                s_run[t] = (uint16_t)run;
+                if (s_base[t] == 0xffffffffu)
+                {
+                    const int gx = wtx0 + (int)(t % wtw) - b.btx0, gy = wty0 + (int)(t / wtw) - b.bty0;
+                    s_base[t] = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
+                }
+            }
         }
-        __syncwarp();
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < PPT; ++r)
+        {
+            const uint32_t tl = tk[r] & 0xffffu;
+            uint32_t slot = 0;
+            if (tl != 0xffffu)
+            {
+                slot = my[tl] + ((tk[r] >> 16) & 0x7fffu);
+                b.sorted[s_base[tl] + slot] = make_float4(px[r], py[r], pz[r], __uint_as_float(meta_op | cc[r]));
+            }
+            __syncwarp();
+            if (tl != 0xffffu && (tk[r] & 0x80000000u))  // highest lane of the group: its slot + 1 is the group's end
+                my[tl] = (uint16_t)(slot + 1u);
+            __syncwarp();
+        }
+        if (sub + 1 < SUB)
+        {
+            // this warp's row back to zero for the next sub-round (the row is warp-private: no CTA barrier needed here;
+            // the other warps read it again only after the next sub-round's first barrier)
+#pragma unroll
+            for (int r = 0; r < PPT; ++r)
+                if ((tk[r] & 0xffffu) != 0xffffu) my[tk[r] & 0xffffu] = 0;
+            __syncwarp();
+        }
     }
 }
 
@@ -873,7 +952,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr)
 
 constexpr int FOLD_NW = FOLD_THREADS / 32;
 
-__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView g, LatticeD lat)
+__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold_r1(BatchView b, GridView g, LatticeD lat)
 {
     __shared__ __align__(16) float4 s_rec[FOLD_CH];          // staged records            32 KB
     __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
@@ -1172,6 +1251,410 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// k_fold (round 2).  Same arithmetic and ownership as before -- one thread per cell of a 16x16 bin keeps the
+// cell's 48-byte record and its running (keyframe, cell) double sums in registers, records are walked in
+// (keyframe, point) order -- with the memory system taken off the critical path:
+//   * the bucket is streamed by the TMA unit: ONE cp.async.bulk per 2 048-record chunk lands in s_in and
+//     signals an mbarrier; chunk i+1 (or the first chunk of the NEXT bin, whose work item is resolved two bins
+//     ahead) is in flight while chunk i is sorted and walked;
+//   * every thread pulls its 8 records of the chunk into registers once (conflict-free LDS.128); the stable
+//     counting sort on the 8-bit cell key places the RECORDS (not indices) into s_sorted, so the walk reads
+//     consecutive 16-byte slots with no dependent index load;
+//   * intra-warp ranks come either from match.any (MATCH = 0; ~8 cycles per DISTINCT key on sm_100, and a LiDAR
+//     bucket puts ~20 distinct cells into 32 consecutive records) or from a per-warp shared-memory bitmap
+//     (MATCH = 1: atomicOr of the lane bit, read back = the peer mask; cost grows with EQUAL keys instead);
+//   * the walk handles two records per iteration: both loads and all float->double conversions are issued
+//     before the first dependent accumulate.
+// A part of a split heavy bin streams the whole bucket like everyone else and simply ignores the records of
+// other row groups (key 256): no compaction pass.
+// ---------------------------------------------------------------------------------------------
+constexpr int FOLD_R = FOLD_CH / FOLD_THREADS;  // records per thread and chunk
+struct FoldSmem
+{
+    static constexpr size_t in_off = 0;
+    static constexpr size_t sorted_off = (size_t)FOLD_CH * 16;
+    static constexpr size_t cnt_off = 2 * (size_t)FOLD_CH * 16;
+    static constexpr size_t total = cnt_off + (size_t)FOLD_NW * BIN_CELLS * 2;
+};
+
+template <int MATCH, bool TIMING>
+__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView g, LatticeD lat, unsigned long long *__restrict__ tim)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    float4 *s_in = reinterpret_cast<float4 *>(s_dyn + FoldSmem::in_off);
+    float4 *s_sorted = reinterpret_cast<float4 *>(s_dyn + FoldSmem::sorted_off);
+    uint16_t(*s_cnt)[BIN_CELLS] = reinterpret_cast<uint16_t(*)[BIN_CELLS]>(s_dyn + FoldSmem::cnt_off);
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_item[2][4];  // two published work items: packed item, bucket start, bucket count, valid
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_heavy = b.counters[10];
+    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front of the list) + light bins (back)
+    const uint32_t nb_total = (uint32_t)(b.btw * b.bth);
+    long long t_mark = 0;
+    unsigned long long t_acc[6] = {0, 0, 0, 0, 0, 0};  // wait, count, scan, place, walk, store (thread 0, TIMING only)
+    auto lap = [&](int k) {
+        if (TIMING && tid == 0) { const long long t = clock64(); t_acc[k] += (unsigned long long)(t - t_mark); t_mark = t; }
+    };
+
+    // ---- work items: ticket counter, heaviest bins first, resolved TWO items ahead by thread 0 -------------
+    // ticket -> list entry -> bucket start / count are three dependent global accesses; each is issued at one
+    // point of the current item's processing and consumed at a later one, so none of them is waited for.
+    uint32_t nn_ticket = 0, nn_item = 0xffffffffu, nn_start = 0, nn_cnt = 0;
+    int nn_stage = 2;
+    auto list_at = [&](uint32_t t) -> uint32_t {
+        if (t >= n_active) return 0xffffffffu;
+        return t < n_heavy ? b.active_tiles[t] : b.active_tiles[nb_total - 1 - (t - n_heavy)];
+    };
+    auto range_of = [&](uint32_t item, uint32_t &start, uint32_t &cnt) {
+        start = cnt = 0;
+        if (item == 0xffffffffu) return;
+        const uint32_t gtn = item & 0x00ffffffu;
+        start = b.tile_start[gtn];
+        cnt = b.tile_count[gtn];
+        const int bx = b.btx0 + (int)(gtn % b.btw), by = b.bty0 + (int)(gtn / b.btw);
+        const int col = bx * BIN - g.ci0, row = by * BIN - g.cj0;
+        if (col < 0 || col + BIN > g.W || row < 0 || row + BIN > g.H)
+        {
+            atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);  // reported by the host; the item is skipped
+            cnt = 0;
+        }
+    };
+    auto publish = [&](int slot, uint32_t item, uint32_t start, uint32_t cnt) {
+        s_item[slot][0] = item; s_item[slot][1] = start; s_item[slot][2] = cnt; s_item[slot][3] = item != 0xffffffffu;
+    };
+    auto issue_chunk = [&](uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0: chunk at `pos` of a bucket
+        const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+        mbar_arrive_expect_tx(&s_bar, n * 16u);
+        bulk_load(s_in, b.sorted + start + pos, n * 16u, &s_bar);
+    };
+    auto issue_first_of = [&](int slot) {  // thread 0: first chunk of a published item (if it has one)
+        if (s_item[slot][3] && s_item[slot][2])
+            issue_chunk(s_item[slot][1], 0u, s_item[slot][2]);
+    };
+    auto nn_step = [&](int upto) {  // thread 0
+        if (nn_stage < 1 && upto >= 1) { nn_item = list_at(nn_ticket); nn_stage = 1; }
+        if (nn_stage < 2 && upto >= 2) { range_of(nn_item, nn_start, nn_cnt); nn_stage = 2; }
+    };
+    if (tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        for (int slot = 0; slot < 2; ++slot)
+        {
+            const uint32_t item = list_at(atomicAdd(b.counters + 4, 1u));
+            uint32_t st, cn;
+            range_of(item, st, cn);
+            publish(slot, item, st, cn);
+        }
+        issue_first_of(0);
+        nn_ticket = atomicAdd(b.counters + 4, 1u);
+        nn_stage = 0;
+    }
+#pragma unroll
+    for (int w = 0; w < FOLD_NW; ++w)
+        s_cnt[w][tid] = 0;  // later chunks find the counters cleared by the previous chunk's walk phase
+    __syncthreads();
+    if (TIMING && tid == 0) t_mark = clock64();
+
+    uint32_t phase = 0;
+    const uint32_t sorted_base = smem_u32(s_sorted);
+    for (uint32_t it = 0;; ++it)
+    {
+        const int slot = (int)(it & 1u);
+        const uint32_t item = s_item[slot][0], start = s_item[slot][1], cnt = s_item[slot][2], valid = s_item[slot][3];
+        if (!valid)
+            break;
+        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
+        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const size_t cell = (size_t)(cj - g.cj0) * g.W + (size_t)(ci - g.ci0);       // only dereferenced when cnt > 0
+        const uint32_t nchunks = (cnt + FOLD_CH - 1) / FOLD_CH;
+        if (nchunks == 0)
+        {
+            __syncthreads();  // everyone holds this item's fields before its slot is republished below
+            if (tid == 0) issue_first_of(slot ^ 1);
+        }
+        // the cell's 48-byte record is fetched only if this batch actually touches the cell
+        float rec[REC];
+        bool loaded = false;
+        auto load_rec = [&]()
+        {
+            if (loaded) return;
+            const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
+            rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
+            rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+            rec_to_zero_form(rec);
+            loaded = true;
+        };
+        const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
+        const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
+        CellAcc acc;
+        acc.reset();
+        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
+        uint32_t fl = 0;
+        for (uint32_t c = 0; c < nchunks; ++c)
+        {
+            const uint32_t pos = c * FOLD_CH;
+            const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
+            const uint32_t SL = R * 32;                                // records per warp slice
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            lap(0);
+            // ---- this thread's records -> registers; warp w owns the contiguous slice [w*SL, (w+1)*SL) ----
+            float4 rr[FOLD_R];
+            uint32_t pk[FOLD_R];  // per record: cell key (bits 0..8, 256 = not mine) | group leader (bit 15) | rank in group << 16
+#pragma unroll
+            for (int r = 0; r < FOLD_R; ++r)
+            {
+                const uint32_t i = warp * SL + r * 32 + lane;
+                pk[r] = 256u;
+                if ((uint32_t)r < R && i < n)
+                {
+                    rr[r] = s_in[i];
+                    const uint32_t key = __float_as_uint(rr[r].w) & 255u;
+                    pk[r] = (((key >> BIN_SHIFT) & pmask) == part) ? key : 256u;  // pmask == 0: every record is mine
+                }
+            }
+            // ---- count per (warp, cell); rank inside the warp round and the group's leader are kept for the placement ----
+            const uint32_t lt = (1u << lane) - 1u;
+            if (MATCH == 0)
+            {
+#pragma unroll
+                for (int r = 0; r < FOLD_R; ++r)
+                {
+                    if ((uint32_t)r < R)
+                    {
+                        const uint32_t key = pk[r];
+                        const uint32_t m = __match_any_sync(0xffffffffu, key);
+                        const bool lead = (m >> lane) == 1u;  // the group's highest lane adds the group size
+                        if (key < 256u && lead)
+                            s_cnt[warp][key] += (uint16_t)__popc(m);
+                        pk[r] = key | (lead ? 0x8000u : 0u) | ((uint32_t)__popc(m & lt) << 16);
+                        __syncwarp();
+                    }
+                }
+            }
+            else
+            {
+                // per-warp bitmap of 256 words in a part of s_in only this warp has read (its own slice when that is
+                // at least 1 KB, else the unused tail of the staging buffer): peers of a key = lanes that OR-ed it
+                uint32_t *bm = reinterpret_cast<uint32_t *>(s_dyn + FoldSmem::in_off) +
+                               (R >= 2 ? warp * SL * 4u : 1024u + warp * 256u);
+                __syncwarp();
+                reinterpret_cast<uint4 *>(bm)[lane] = make_uint4(0u, 0u, 0u, 0u);
+                reinterpret_cast<uint4 *>(bm)[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
+                __syncwarp();
+#pragma unroll
+                for (int r = 0; r < FOLD_R; ++r)
+                {
+                    if ((uint32_t)r < R)
+                    {
+                        const uint32_t key = pk[r];
+                        if (key < 256u) atomicOr(bm + key, 1u << lane);
+                        __syncwarp();
+                        const uint32_t m = key < 256u ? bm[key] : 0u;
+                        __syncwarp();
+                        const bool lead = (m >> lane) == 1u;
+                        if (lead)
+                        {
+                            bm[key] = 0u;
+                            s_cnt[warp][key] += (uint16_t)__popc(m);
+                        }
+                        pk[r] = key | (lead ? 0x8000u : 0u) | ((uint32_t)__popc(m & lt) << 16);
+                        __syncwarp();
+                    }
+                }
+            }
+            __syncthreads();  // B1: s_in consumed, counts complete
+            lap(1);
+            if (tid == 0)
+            {
+                if (c + 1 < nchunks) issue_chunk(start, pos + FOLD_CH, cnt);  // lands while this chunk is sorted and walked
+                else issue_first_of(slot ^ 1);                                // ... or the next bin's first chunk
+                nn_step(1);
+            }
+            // ---- thread = cell: exclusive prefix over the warps' counts, then over cells ----
+            uint32_t tot = 0, wc[FOLD_NW];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+            {
+                wc[w] = tot;
+                tot += s_cnt[w][tid];
+            }
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += u;
+            }
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();  // B2
+            uint32_t cstart = inc - tot;
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                if (w < (int)warp) cstart += s_w[w];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
+            __syncthreads();  // B3
+            lap(2);
+            if (tid == 0) nn_step(2);
+            // ---- stable placement of the records themselves ----
+#pragma unroll
+            for (int r = 0; r < FOLD_R; ++r)
+            {
+                if ((uint32_t)r < R)  // uniform over the CTA
+                {
+                    const uint32_t cc = pk[r] & 0x1ffu;
+                    uint32_t sl = 0;
+                    if (cc < 256u)
+                    {
+                        sl = s_cnt[warp][cc] + (pk[r] >> 16);
+                        s_sorted[sl] = rr[r];
+                    }
+                    __syncwarp();
+                    if (cc < 256u && (pk[r] & 0x8000u))  // highest lane of the group: its slot + 1 is the group's end
+                        s_cnt[warp][cc] = (uint16_t)(sl + 1u);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();  // B4
+            lap(3);
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = 0;  // for the next chunk's count (everyone is past the placement)
+            // ---- thread = cell: walk the cell's run SEGMENT by segment ----
+            // A round takes every lane through one whole (op, cell) segment (inner loop over its records: loads one
+            // record ahead, no fold inside), then all lanes that finished a segment fold together.  The float32 fold
+            // -- ten double->float conversions on the quarter-rate conversion unit -- is what a record-major walk
+            // ends up executing on almost every step for a handful of lanes; here it runs once per round.  A cell's
+            // LAST segment of the chunk stays open (it may continue in the next chunk): it is folded at the next
+            // chunk's prelude, when the cell's first record there belongs to another op, or after the bin's last chunk.
+            {
+                uint32_t k = cstart;
+                const uint32_t k1 = cstart + tot;
+                if (k < k1 && cur != 0xffffffffu)
+                {
+                    const uint32_t so0 = __float_as_uint(lds_f4(sorted_base + 16u * k).w) >> 8;
+                    if (so0 != cur)
+                    {
+                        load_rec();
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
+                        cur = 0xffffffffu;
+                    }
+                }
+                for (;;)
+                {
+                    const bool has = k < k1;
+                    if (!__any_sync(0xffffffffu, has))
+                        break;
+                    if (has)
+                    {
+                        float4 p = lds_f4(sorted_base + 16u * k);
+                        const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
+                        double keep = (cur == so) ? 1.0 : 0.0;          // continuing the segment left open by the previous chunk?
+                        if (cur != so)
+                        {
+                            acc.n = 0;
+                            acc.zmin = CUDART_INF_F;
+                            acc.zmax = -CUDART_INF_F;
+                        }
+                        cur = so;
+                        for (;;)
+                        {
+                            // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59); a new segment restarts the sums
+                            // through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly)
+                            const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
+                            const float z = p.z;
+                            ++k;
+                            bool more = false;
+                            if (k < k1)
+                            {
+                                p = lds_f4(sorted_base + 16u * k);  // next record: in flight during this one's arithmetic
+                                more = (__float_as_uint(p.w) >> 8) == so;
+                            }
+                            acc.n += 1u;
+                            acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
+                            acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
+                            acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
+                            acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
+                            acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
+                            acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
+                            acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
+                            acc.zmin = fminf(acc.zmin, z);
+                            acc.zmax = fmaxf(acc.zmax, z);
+                            keep = 1.0;
+                            if (!more)
+                                break;
+                        }
+                    }
+                    if (has && k < k1)  // a following record exists => this segment is complete
+                    {
+                        load_rec();
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
+                        cur = 0xffffffffu;
+                    }
+                }
+            }
+            lap(4);
+            if (c + 1 < nchunks)
+                __syncthreads();  // B5: s_sorted and the counters are free again (the last chunk's B5 is the item barrier)
+        }
+        if (cur != 0xffffffffu)
+        {
+            load_rec();
+            fold_acc(rec, acc, (cur >> 23) != 0, fl);
+        }
+        if (fl & F_TOUCHED)
+        {
+            float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
+            if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
+            {
+#pragma unroll
+                for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+            }
+            dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+            // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
+            uint8_t obs = 0;
+            if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
+                obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
+            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
+            if (fl & F_BLANKED)
+            {
+                const size_t pl = g.plane();
+#pragma unroll
+                for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + cell] = CUDART_NAN_F;
+            }
+        }
+        if (tid == 0)
+        {
+            nn_step(2);                                  // whatever is still outstanding of item it + 2
+            publish(slot, nn_item, nn_start, nn_cnt);    // this item's slot becomes item it + 2
+            nn_ticket = atomicAdd(b.counters + 4, 1u);   // consumed during the next item
+            nn_stage = 0;
+        }
+        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);  // item barrier; also publishes s_item
+        if (tid == 0 && nt)
+            atomicAdd(b.counters + 8, nt);
+        lap(5);
+    }
+    if (TIMING && tid == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(tim + k, t_acc[k]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // EXPERIMENT (not on the product path; enabled by TMB_EXPERIMENT_ATOMIC_FOLD=1, see profiles/README.md):
 // the alternative the north_star asks the sort to be "chosen against" -- privatised shared-memory atomic
@@ -1324,20 +1807,76 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
     return cudaGetLastError();
 }
 
-static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 4 + (size_t)maxT * (BIN_THREADS / 32) * 2 + 16; }
+static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 4 + (size_t)maxT * (BIN_THREADS / 32 + 1) * 2 + 16; }
 
-static bool g_attr_set = false;
+// TMB_FOLD: 0 = match.any ranks, 1 = shared-memory bitmap ranks (default), 9 = the round-1 kernel (A/B runs);
+// TMB_FOLD_TIMING=1: per-phase clock64 sums of thread 0 of every CTA, printed after the launch (diagnostics only)
+static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int n_sm)
+{
+    static const int variant = getenv("TMB_FOLD") ? atoi(getenv("TMB_FOLD")) : 1;
+    static const bool timing = getenv("TMB_FOLD_TIMING") != nullptr;
+    static const int per_sm = getenv("TMB_FOLD_GRID") ? atoi(getenv("TMB_FOLD_GRID")) : 3;
+    const uint32_t nb = b.btw * b.bth;
+    const uint32_t blocks = (uint32_t)min((uint32_t)(n_sm * per_sm), nb);
+    const size_t smem = FoldSmem::total;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_done[64] = {false};
+    if (dev < 64 && !attr_done[dev])
+    {
+        cudaFuncSetAttribute(k_fold<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_fold<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_fold<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_fold<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_done[dev] = true;
+    }
+    if (variant == 9)
+    {
+        k_fold_r1<<<(uint32_t)min((uint32_t)n_sm * 4u, nb), FOLD_THREADS, 0, st>>>(b, g, lat);
+        return;
+    }
+    if (!timing)
+    {
+        if (variant == 0) k_fold<0, false><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, nullptr);
+        else k_fold<1, false><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, nullptr);
+        return;
+    }
+    static unsigned long long *d_tim = nullptr;
+    if (!d_tim) cudaMalloc(&d_tim, 64);
+    cudaMemsetAsync(d_tim, 0, 64, st);
+    if (variant == 0) k_fold<0, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
+    else k_fold<1, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
+    unsigned long long h[6];
+    cudaMemcpyAsync(h, d_tim, sizeof(h), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    double tot = 0;
+    for (int k = 0; k < 6; ++k) tot += (double)h[k];
+    if (tot > 0)
+        fprintf(stderr, "[k_fold phases, %% of thread-0 cycles over %u CTAs] wait %.1f count %.1f scan %.1f place %.1f walk %.1f store %.1f | %.0f cycles per CTA\n",
+                blocks, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / blocks);
+}
+
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
                        int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/, int phases)
 {
     // phases: bit0 = init + hist + scans + scatter, bit1 = fold
-    if (!g_attr_set)
+    // chunk tiers (planBatch picks the largest one that still gives every SM a few chunks): points per thread and chunk
+    //   2  = 256 x 2 x 1 (a stream tick), 8 = 256 x 4 x 2, 32 = 256 x 4 x 8 (loop-closure scale)
     {
-        cudaFuncSetAttribute(k_scatter<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        cudaFuncSetAttribute(k_scatter<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        cudaFuncSetAttribute(k_scatter<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        cudaFuncSetAttribute(k_scatter<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem(MAX_WINDOW_BINS));
-        g_attr_set = true;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        static bool attr_done[64] = {false};
+        if (dev < 64 && !attr_done[dev])
+        {
+            const int sm = (int)scatter_smem(MAX_WINDOW_BINS);
+            cudaFuncSetAttribute(k_scatter<2, 1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            cudaFuncSetAttribute(k_scatter<2, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            cudaFuncSetAttribute(k_scatter<4, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            cudaFuncSetAttribute(k_scatter<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            cudaFuncSetAttribute(k_scatter<4, 8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            cudaFuncSetAttribute(k_scatter<4, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm);
+            attr_done[dev] = true;
+        }
     }
     const uint32_t nb = b.btw * b.bth;
     const uint32_t nblk = (nb + 255) / 256;
@@ -1346,9 +1885,11 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     // counters and per-op bboxes arrive initialised with the batch's single host-to-device copy
     if (ev) cudaEventRecord(ev[0], st);
     if (ppt == 2)
-        k_hist<2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
+        k_hist<2, 1><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
+    else if (ppt == 8)
+        k_hist<4, 2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     else
-        k_hist<8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
+        k_hist<4, 8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
     k_scan_chunks<<<dim3((maxT + 31) / 32, b.n_ops), 256, 0, st>>>(b);
     if (nb <= 4096)
@@ -1361,20 +1902,27 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     }
     if (ev) cudaEventRecord(ev[2], st);
     const bool emit = nb <= 4096;
-    if (ppt == 2 && emit)
-        k_scatter<2, true><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
-    else if (ppt == 2)
-        k_scatter<2, false><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
-    else if (emit)
-        k_scatter<8, true><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
+    const size_t ssm = scatter_smem(maxT);
+    if (ppt == 2)
+    {
+        if (emit) k_scatter<2, 1, true><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+        else k_scatter<2, 1, false><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+    }
+    else if (ppt == 8)
+    {
+        if (emit) k_scatter<4, 2, true><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+        else k_scatter<4, 2, false><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+    }
     else
-        k_scatter<8, false><<<b.n_chunks, BIN_THREADS, scatter_smem(maxT), st>>>(b, lat, g, dc, di);
+    {
+        if (emit) k_scatter<4, 8, true><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+        else k_scatter<4, 8, false><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
+    }
     if (ev) cudaEventRecord(ev[3], st);
     }
     if (!(phases & 2))
         return cudaGetLastError();
-    const uint32_t fold_blocks = (uint32_t)min((uint32_t)n_sm * 4u, nb);
-    k_fold<<<fold_blocks, FOLD_THREADS, 0, st>>>(b, g, lat);
+    launch_fold(st, b, g, lat, n_sm);
     if (ev) cudaEventRecord(ev[4], st);
     return cudaGetLastError();
 }

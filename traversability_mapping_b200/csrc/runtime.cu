@@ -485,16 +485,14 @@ class LocalMap
     {
         for (;;)
         {
-            std::vector<std::shared_ptr<KeyFrame>> take;
             {
                 std::unique_lock<std::mutex> l(qMutex_);
                 idleCv_.wait(l, [&] { return !busy_ || !running_; });
                 if (!running_ || queue_.empty())
                     return;
-                popLocked(take);
                 busy_ = true;
             }
-            runTaken(take);
+            runClaimed();
         }
     }
     void setStream(void *s)
@@ -770,11 +768,22 @@ class LocalMap
             queued_.erase(take.back()->id);
         }
     }
-    void runTaken(const std::vector<std::shared_ptr<KeyFrame>> &take)  // busy_ already raised
+    // busy_ already raised by the caller.  The keyframes are taken from the queue only once the grid mutex is
+    // held: whatever a caller queued while it held the mutex (a PGO message, informLoopClosure's re-enqueue of
+    // every keyframe) is then folded in ONE pass instead of being split at whatever the worker had popped before
+    // it blocked on the mutex.  Same outcome as the reference's pop-then-lock (LocalMap.cpp:452-485) -- latest
+    // pose wins, every pending keyframe is recomputed once -- with fewer passes.
+    void runClaimed()
     {
         int changed = 0;
         try
         {
+            std::lock_guard<std::recursive_mutex> g(gridMutex_);
+            std::vector<std::shared_ptr<KeyFrame>> take;
+            {
+                std::lock_guard<std::mutex> l(qMutex_);
+                popLocked(take);
+            }
             changed = processTaken(take);
         }
         catch (const std::exception &e)
@@ -796,15 +805,13 @@ class LocalMap
         cudaSetDevice(P_.device);
         for (;;)
         {
-            std::vector<std::shared_ptr<KeyFrame>> take;
             {
                 std::unique_lock<std::mutex> l(qMutex_);
                 qCv_.wait(l, [&] { return (!queue_.empty() && !busy_) || !running_; });
                 if (!running_) break;
-                popLocked(take);
                 busy_ = true;
             }
-            runTaken(take);
+            runClaimed();
         }
         idleCv_.notify_all();
     }
@@ -895,10 +902,17 @@ class LocalMap
         Plan pl;
         const uint32_t n_ops = (uint32_t)ops.size();
         pl.n_ops = n_ops;
-        uint64_t total_pts = 0, chunks8 = 0;
-        for (auto &op : ops) { total_pts += op.kf->n; chunks8 += (op.kf->n + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8); }
+        uint64_t total_pts = 0, chunks8 = 0, chunks32 = 0;
+        for (auto &op : ops)
+        {
+            total_pts += op.kf->n;
+            chunks8 += (op.kf->n + BIN_THREADS * 8 - 1) / (BIN_THREADS * 8);
+            chunks32 += (op.kf->n + BIN_THREADS * 32 - 1) / (BIN_THREADS * 32);
+        }
         pl.total_pts = total_pts;
-        pl.ppt = chunks8 >= (uint64_t)2 * nSM_ ? 8 : 2;  // small batches use small chunks so the grid still fills the GPU
+        // points per thread and chunk: the largest tier that still hands every SM several chunks (small batches use
+        // small chunks so the grid fills the GPU; big ones amortise the per-chunk histogram row over 8 192 points)
+        pl.ppt = chunks32 >= (uint64_t)8 * nSM_ ? 32 : chunks8 >= (uint64_t)2 * nSM_ ? 8 : 2;
         const uint32_t CH = BIN_THREADS * pl.ppt;
         if (total_pts >= (1ull << 32))
             throw Unsupported("batch exceeds 2^32 points");
