@@ -736,20 +736,21 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
     __syncthreads();
     const uint32_t T = s_op.T_tiles;
     const double inv_res = 1.0 / lat.res;
-    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_dyn);               // [T]  absolute slot of the chunk's first record per bin
-    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_base + T);           // [NW][T]
-    uint16_t *s_run = s_cnt + (size_t)NW * T;                             // [T]  records of this chunk already placed per bin
-    for (uint32_t i = threadIdx.x; i < (T * (NW + 1) + 1) / 2; i += BIN_THREADS)
-        reinterpret_cast<uint32_t *>(s_cnt)[i] = 0;
+    static_assert(NW == 8, "a bin's eight per-warp u16 counters are read and written as one 16-byte word");
+    uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn);                // [T][NW]  per (bin, warp) counters / offsets
+    uint32_t *s_base = reinterpret_cast<uint32_t *>(s_cnt + (size_t)T * NW);  // [T]  absolute slot of the chunk's first record per bin
+    uint16_t *s_run = reinterpret_cast<uint16_t *>(s_base + T);           // [T]  records of this chunk already placed per bin
     for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
-        s_base[i] = 0xffffffffu;
-    __syncthreads();
+    {
+        reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
+        s_run[i] = 0;
+    }
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
     const uint32_t cl = chunk - s_op.chunk0;
     const uint32_t chunk_base = cl * (BIN_THREADS * PPT * SUB);
-    uint16_t *my = s_cnt + warp * T;
+    uint16_t *my = s_cnt + warp;  // this warp's counter of bin t: my[t * NW]
     const uint32_t sign_bit = s_op.sign < 0.f ? META_SIGN : 0u;
     const uint32_t n_pts = s_op.n;
     const float4 *cloud = s_op.cloud;
@@ -766,6 +767,14 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
         const uint32_t i = chunk_base + warp * (32 * PPT) + r * 32 + lane;
         nxt[r] = i < n_pts ? __ldg(cloud + i) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    // absolute base of this chunk's run in every bin of the op's window = bin start + op offset + chunk prefix: three
+    // global reads per bin, requested here (with the first points) so that none of them sits between two barriers
+    for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
+    {
+        const int gx = wtx0 + (int)(t % wtw) - b.btx0, gy = wty0 + (int)(t / wtw) - b.bty0;
+        s_base[t] = __ldg(b.tile_start + gy * b.btw + gx) + __ldg(b.op_start + s_op.tot_off + t) + __ldg(row + t);
+    }
+    __syncthreads();
 #pragma unroll 1
     for (int sub = 0; sub < SUB; ++sub)
     {
@@ -811,33 +820,33 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
                 const uint32_t m = __match_any_sync(0xffffffffu, tl);
                 const bool lead = (m >> lane) == 1u;
                 if (tl != 0xffffu && lead)
-                    my[tl] += (uint16_t)__popc(m);   // row `warp` is private to this warp
+                    my[tl * NW] += (uint16_t)__popc(m);   // column `warp` is private to this warp
                 tk[r] = tl | ((uint32_t)__popc(m & lt) << 16) | (lead ? 0x80000000u : 0u);
                 __syncwarp();
             }
         }
         __syncthreads();
-        // per touched bin: base (first touch) and the warps' exclusive offsets, continuing from earlier sub-rounds
+        // per touched bin: the warps' exclusive offsets, continuing from the earlier sub-rounds of this chunk.  The eight
+        // u16 counters of a bin are one 16-byte word; (warp, bin) pairs without points keep a zero for the next sub-round.
         for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
         {
+            uint4 v = reinterpret_cast<const uint4 *>(s_cnt)[t];
+            if ((v.x | v.y | v.z | v.w) == 0u)
+                continue;
             uint32_t run = s_run[t];
-            const uint32_t run0 = run;
+            uint32_t w32[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int w = 0; w < NW; ++w)
+            for (int q = 0; q < 4; ++q)
             {
-                const uint32_t v = s_cnt[w * T + t];
-                if (v) s_cnt[w * T + t] = (uint16_t)run;  // untouched (warp, bin) entries stay zero for the next sub-round
-                run += v;
+                const uint32_t c0 = w32[q] & 0xffffu, c1 = w32[q] >> 16;
+                const uint32_t o0 = run;
+                run += c0;
+                const uint32_t o1 = run;
+                run += c1;
+                w32[q] = (c0 ? o0 : 0u) | ((c1 ? o1 : 0u) << 16);
             }
-            if (run != run0)
-            {
-                s_run[t] = (uint16_t)run;
-                if (s_base[t] == 0xffffffffu)
-                {
-                    const int gx = wtx0 + (int)(t % wtw) - b.btx0, gy = wty0 + (int)(t / wtw) - b.bty0;
-                    s_base[t] = b.tile_start[gy * b.btw + gx] + b.op_start[s_op.tot_off + t] + row[t];
-                }
-            }
+            reinterpret_cast<uint4 *>(s_cnt)[t] = make_uint4(w32[0], w32[1], w32[2], w32[3]);
+            s_run[t] = (uint16_t)run;
         }
         __syncthreads();
 #pragma unroll
@@ -847,21 +856,21 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
             uint32_t slot = 0;
             if (tl != 0xffffu)
             {
-                slot = my[tl] + ((tk[r] >> 16) & 0x7fffu);
+                slot = my[tl * NW] + ((tk[r] >> 16) & 0x7fffu);
                 b.sorted[s_base[tl] + slot] = make_float4(px[r], py[r], pz[r], __uint_as_float(meta_op | cc[r]));
             }
             __syncwarp();
             if (tl != 0xffffu && (tk[r] & 0x80000000u))  // highest lane of the group: its slot + 1 is the group's end
-                my[tl] = (uint16_t)(slot + 1u);
+                my[tl * NW] = (uint16_t)(slot + 1u);
             __syncwarp();
         }
         if (sub + 1 < SUB)
         {
-            // this warp's row back to zero for the next sub-round (the row is warp-private: no CTA barrier needed here;
-            // the other warps read it again only after the next sub-round's first barrier)
+            // this warp's counters back to zero for the next sub-round (they are warp-private: no CTA barrier needed
+            // here; the other warps read them again only after the next sub-round's first barrier)
 #pragma unroll
             for (int r = 0; r < PPT; ++r)
-                if ((tk[r] & 0xffffu) != 0xffffu) my[tk[r] & 0xffffu] = 0;
+                if ((tk[r] & 0xffffu) != 0xffffu) my[(tk[r] & 0xffffu) * NW] = 0;
             __syncwarp();
         }
     }
@@ -1361,7 +1370,6 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
     if (TIMING && tid == 0) t_mark = clock64();
 
     uint32_t phase = 0;
-    const uint32_t sorted_base = smem_u32(s_sorted);
     for (uint32_t it = 0;; ++it)
     {
         const int slot = (int)(it & 1u);
@@ -1543,7 +1551,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                 const uint32_t k1 = cstart + tot;
                 if (k < k1 && cur != 0xffffffffu)
                 {
-                    const uint32_t so0 = __float_as_uint(lds_f4(sorted_base + 16u * k).w) >> 8;
+                    const uint32_t so0 = __float_as_uint(s_sorted[k].w) >> 8;
                     if (so0 != cur)
                     {
                         load_rec();
@@ -1558,7 +1566,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                         break;
                     if (has)
                     {
-                        float4 p = lds_f4(sorted_base + 16u * k);
+                        float4 p = s_sorted[k];
                         const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
                         double keep = (cur == so) ? 1.0 : 0.0;          // continuing the segment left open by the previous chunk?
                         if (cur != so)
@@ -1578,7 +1586,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
                             bool more = false;
                             if (k < k1)
                             {
-                                p = lds_f4(sorted_base + 16u * k);  // next record: in flight during this one's arithmetic
+                                p = s_sorted[k];  // next record: in flight during this one's arithmetic
                                 more = (__float_as_uint(p.w) >> 8) == so;
                             }
                             acc.n += 1u;
@@ -1644,6 +1652,448 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView 
             nn_stage = 0;
         }
         const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);  // item barrier; also publishes s_item
+        if (tid == 0 && nt)
+            atomicAdd(b.counters + 8, nt);
+        lap(5);
+    }
+    if (TIMING && tid == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(tim + k, t_acc[k]);
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// k_fold3: the fold with per-chunk load balancing of the walk.
+// A LiDAR bucket is very uneven over the 256 cells of a bin (cells on a ring hold tens of records per chunk, cells
+// between rings none): with one fixed thread per cell a warp walks for as long as its heaviest cell and 9 of 32
+// lanes are busy (ncu, round 2).  Here the cell state lives in shared memory -- the 48-byte record in zero form, the
+// open (keyframe, cell) segment's double sums -- so ANY thread can walk ANY cell, and after the counting sort of a
+// chunk the non-empty cells are handed to threads in descending order of their record count (a 32-class counting
+// sort of the counts): warps get cells of similar weight.  Cells are independent and a cell is walked whole by one
+// thread per chunk, in (keyframe, point) order, so the assignment does not touch the arithmetic.
+// The bucket is read straight into registers (8 coalesced 16-byte loads per thread and chunk); the next chunk -- or
+// the next bin's first chunk, whose work item is resolved two bins ahead -- is pulled into L2 by one
+// cp.async.bulk.prefetch while the current chunk is sorted and walked.
+// ---------------------------------------------------------------------------------------------
+struct Fold3Smem
+{
+    static constexpr size_t sorted_off = 0;                                   // float4 [FOLD_CH]
+    static constexpr size_t cnt_off = sorted_off + (size_t)FOLD_CH * 16;      // u16 [8][256]
+    static constexpr size_t cell_off = cnt_off + (size_t)FOLD_NW * BIN_CELLS * 2;   // float [256][12], zero form
+    static constexpr size_t cd_off = cell_off + (size_t)BIN_CELLS * REC * 4;  // double [9][256] open-segment sums
+    static constexpr size_t cm_off = cd_off + (size_t)9 * BIN_CELLS * 8;      // uint4 [256]: sign|op, n, zmin, zmax of the open segment
+    static constexpr size_t run_off = cm_off + (size_t)BIN_CELLS * 16;        // u32 [256]: run start | count << 16
+    static constexpr size_t perm_off = run_off + (size_t)BIN_CELLS * 4;       // u16 [256]: walker -> cell
+    static constexpr size_t fl_off = perm_off + (size_t)BIN_CELLS * 2;        // u8 [256]: F_TOUCHED / F_BLANKED / F_CHANGED of the item
+    static constexpr size_t class_off = fl_off + (size_t)BIN_CELLS;           // u32 [2][32]: class histogram, class cursors
+    static constexpr size_t total = class_off + 256;
+};
+static_assert(Fold3Smem::total <= 73 * 1024, "three fold CTAs per SM");
+
+__device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+template <bool TIMING>
+__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView g, LatticeD lat, unsigned long long *__restrict__ tim)
+{
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    float4 *s_sorted = reinterpret_cast<float4 *>(s_dyn + Fold3Smem::sorted_off);
+    uint16_t(*s_cnt)[BIN_CELLS] = reinterpret_cast<uint16_t(*)[BIN_CELLS]>(s_dyn + Fold3Smem::cnt_off);
+    float4 *s_cell = reinterpret_cast<float4 *>(s_dyn + Fold3Smem::cell_off);      // [256][3]
+    double(*s_cd)[BIN_CELLS] = reinterpret_cast<double(*)[BIN_CELLS]>(s_dyn + Fold3Smem::cd_off);
+    uint4 *s_cm = reinterpret_cast<uint4 *>(s_dyn + Fold3Smem::cm_off);
+    uint32_t *s_run = reinterpret_cast<uint32_t *>(s_dyn + Fold3Smem::run_off);
+    uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_dyn + Fold3Smem::perm_off);
+    uint8_t *s_fl = s_dyn + Fold3Smem::fl_off;
+    uint32_t *s_class = reinterpret_cast<uint32_t *>(s_dyn + Fold3Smem::class_off);  // [0..31] histogram, [32..63] cursors
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_item[2][4];  // two published work items: packed item, bucket start, bucket count, valid
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_heavy = b.counters[10];
+    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front of the list) + light bins (back)
+    const uint32_t nb_total = (uint32_t)(b.btw * b.bth);
+    long long t_mark = 0;
+    unsigned long long t_acc[6] = {0, 0, 0, 0, 0, 0};  // load, count, scan, place, walk, store (thread 0, TIMING only)
+    auto lap = [&](int k) {
+        if (TIMING && tid == 0) { const long long t = clock64(); t_acc[k] += (unsigned long long)(t - t_mark); t_mark = t; }
+    };
+
+    // ---- work items: ticket counter, heaviest bins first, resolved TWO items ahead by thread 0 (see k_fold) ----
+    uint32_t nn_ticket = 0, nn_item = 0xffffffffu, nn_start = 0, nn_cnt = 0;
+    int nn_stage = 2;
+    auto list_at = [&](uint32_t t) -> uint32_t {
+        if (t >= n_active) return 0xffffffffu;
+        return t < n_heavy ? b.active_tiles[t] : b.active_tiles[nb_total - 1 - (t - n_heavy)];
+    };
+    auto range_of = [&](uint32_t item, uint32_t &start, uint32_t &cnt) {
+        start = cnt = 0;
+        if (item == 0xffffffffu) return;
+        const uint32_t gtn = item & 0x00ffffffu;
+        start = b.tile_start[gtn];
+        cnt = b.tile_count[gtn];
+        const int bx = b.btx0 + (int)(gtn % b.btw), by = b.bty0 + (int)(gtn / b.btw);
+        const int col = bx * BIN - g.ci0, row = by * BIN - g.cj0;
+        if (col < 0 || col + BIN > g.W || row < 0 || row + BIN > g.H)
+        {
+            atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);  // reported by the host; the item is skipped
+            cnt = 0;
+        }
+    };
+    auto publish = [&](int slot, uint32_t item, uint32_t start, uint32_t cnt) {
+        s_item[slot][0] = item; s_item[slot][1] = start; s_item[slot][2] = cnt; s_item[slot][3] = item != 0xffffffffu;
+    };
+    auto prefetch_chunk = [&](uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0
+        const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+        l2_prefetch(b.sorted + start + pos, n * 16u);
+    };
+    auto prefetch_first_of = [&](int slot) {
+        if (s_item[slot][3] && s_item[slot][2])
+            prefetch_chunk(s_item[slot][1], 0u, s_item[slot][2]);
+    };
+    auto nn_step = [&](int upto) {  // thread 0
+        if (nn_stage < 1 && upto >= 1) { nn_item = list_at(nn_ticket); nn_stage = 1; }
+        if (nn_stage < 2 && upto >= 2) { range_of(nn_item, nn_start, nn_cnt); nn_stage = 2; }
+    };
+    if (tid == 0)
+    {
+        for (int slot = 0; slot < 2; ++slot)
+        {
+            const uint32_t item = list_at(atomicAdd(b.counters + 4, 1u));
+            uint32_t st, cn;
+            range_of(item, st, cn);
+            publish(slot, item, st, cn);
+        }
+        nn_ticket = atomicAdd(b.counters + 4, 1u);
+        nn_stage = 0;
+    }
+#pragma unroll
+    for (int w = 0; w < FOLD_NW; ++w)
+        s_cnt[w][tid] = 0;
+    if (tid < 64) s_class[tid] = 0;
+    __syncthreads();
+    if (TIMING && tid == 0) t_mark = clock64();
+
+    for (uint32_t it = 0;; ++it)
+    {
+        const int slot = (int)(it & 1u);
+        const uint32_t item = s_item[slot][0], start = s_item[slot][1], cnt = s_item[slot][2], valid = s_item[slot][3];
+        if (!valid)
+            break;
+        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
+        const uint32_t nchunks = (cnt + FOLD_CH - 1) / FOLD_CH;
+        // thread = cell for everything that is per cell and not the walk: the record's trip from / to global memory
+        const int my_ci = bx * BIN + (int)(tid & (BIN - 1)), my_cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const size_t my_cell = (size_t)(my_cj - g.cj0) * g.W + (size_t)(my_ci - g.ci0);  // dereferenced only when nchunks > 0
+        if (nchunks == 0)
+            __syncthreads();  // everyone holds this item's fields before its slot is republished below
+        else
+        {
+            // the whole bin's records arrive while the first chunk is sorted (zero form: Helpers.cpp:114-127's NaN -> 0)
+            const float4 *src = reinterpret_cast<const float4 *>(g.mom + my_cell * REC);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            float rec[REC] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+            rec_to_zero_form(rec);
+            s_cell[tid * 3 + 0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            s_cell[tid * 3 + 1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            s_cell[tid * 3 + 2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+            s_cm[tid] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+            s_fl[tid] = 0;
+        }
+        for (uint32_t c = 0; c < nchunks; ++c)
+        {
+            const uint32_t pos = c * FOLD_CH;
+            const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
+            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
+            const uint32_t SL = R * 32;                                // records per warp slice
+            // ---- this thread's records -> registers; warp w owns the contiguous slice [w*SL, (w+1)*SL) ----
+            float4 rr[FOLD_R];
+            uint32_t pk[FOLD_R];  // per record: cell key (bits 0..8, 256 = not mine) | group leader (bit 15) | rank in group << 16
+            const float4 *bucket = b.sorted + start + pos;
+#pragma unroll
+            for (int r = 0; r < FOLD_R; ++r)
+            {
+                const uint32_t i = warp * SL + r * 32 + lane;
+                pk[r] = 256u;
+                if ((uint32_t)r < R && i < n)
+                    rr[r] = bucket[i];
+            }
+            if (tid == 0)
+            {
+                if (c + 1 < nchunks) prefetch_chunk(start, pos + FOLD_CH, cnt);  // into L2 while this chunk is sorted and walked
+                else prefetch_first_of(slot ^ 1);                                // ... or the next bin's first chunk
+            }
+            const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+            for (int r = 0; r < FOLD_R; ++r)
+            {
+                const uint32_t i = warp * SL + r * 32 + lane;
+                if ((uint32_t)r < R)
+                {
+                    uint32_t key = 256u;
+                    if (i < n)
+                    {
+                        const uint32_t kk = __float_as_uint(rr[r].w) & 255u;
+                        key = (((kk >> BIN_SHIFT) & pmask) == part) ? kk : 256u;  // pmask == 0: every record is mine
+                    }
+                    const uint32_t m = __match_any_sync(0xffffffffu, key);
+                    const bool lead = (m >> lane) == 1u;  // the group's highest lane adds the group size
+                    if (key < 256u && lead)
+                        s_cnt[warp][key] += (uint16_t)__popc(m);
+                    pk[r] = key | (lead ? 0x8000u : 0u) | ((uint32_t)__popc(m & lt) << 16);
+                    __syncwarp();
+                }
+            }
+            lap(0);
+            __syncthreads();  // B1: counts complete (and, on the first chunk, the cell records are in shared memory)
+            lap(1);
+            if (tid == 0) nn_step(1);
+            // ---- thread = cell: exclusive prefix over the warps' counts, then over cells; weight class of the cell ----
+            uint32_t tot = 0, wc[FOLD_NW];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+            {
+                wc[w] = tot;
+                tot += s_cnt[w][tid];
+            }
+            // 32 weight classes of width max(1, R/2) records (R = the chunk's mean per cell), heaviest = class 31
+            const uint32_t cls = min(31u, tot / max(1u, R >> 1));
+            if (tot) atomicAdd(&s_class[cls], 1u);
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += u;
+            }
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();  // B2
+            uint32_t cstart = inc - tot;
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                if (w < (int)warp) cstart += s_w[w];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
+            s_run[tid] = cstart | (tot << 16);
+            if (tot)
+            {
+                // walkers are numbered heaviest class first; inside a class the order is whatever the cursor hands out
+                // (it only decides WHICH thread walks a cell, never what is computed)
+                uint32_t before = 0;
+                for (uint32_t q = cls + 1; q < 32u; ++q) before += s_class[q];
+                s_perm[before + atomicAdd(&s_class[32 + cls], 1u)] = (uint16_t)tid;
+            }
+            if (tid == 0) nn_step(2);
+            const uint32_t n_walk = __syncthreads_count(tot != 0);  // B3
+            lap(2);
+            // ---- stable placement of the records themselves ----
+#pragma unroll
+            for (int r = 0; r < FOLD_R; ++r)
+            {
+                if ((uint32_t)r < R)  // uniform over the CTA
+                {
+                    const uint32_t cc = pk[r] & 0x1ffu;
+                    uint32_t sl = 0;
+                    if (cc < 256u)
+                    {
+                        sl = s_cnt[warp][cc] + (pk[r] >> 16);
+                        s_sorted[sl] = rr[r];
+                    }
+                    __syncwarp();
+                    if (cc < 256u && (pk[r] & 0x8000u))  // highest lane of the group: its slot + 1 is the group's end
+                        s_cnt[warp][cc] = (uint16_t)(sl + 1u);
+                    __syncwarp();
+                }
+            }
+            __syncthreads();  // B4
+            lap(3);
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = 0;  // for the next chunk's count (everyone is past the placement)
+            if (tid < 64) s_class[tid] = 0;
+            // ---- walk: thread `tid` takes the tid-th heaviest non-empty cell, segment by segment (see k_fold) ----
+            {
+                const bool walker = tid < n_walk;
+                uint32_t cellk = 0, k = 0, k1 = 0;
+                if (walker)
+                {
+                    cellk = s_perm[tid];
+                    const uint32_t run = s_run[cellk];
+                    k = run & 0xffffu;
+                    k1 = k + (run >> 16);
+                }
+                const int ci = bx * BIN + (int)(cellk & (BIN - 1)), cj = by * BIN + (int)(cellk >> BIN_SHIFT);
+                const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
+                const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
+                CellAcc acc;
+                acc.reset();
+                uint32_t cur = 0xffffffffu, fl = 0;
+                bool had_open = false;
+                if (walker)
+                {
+                    const uint4 cm = s_cm[cellk];
+                    cur = cm.x;
+                    if (cur != 0xffffffffu)  // the segment the previous chunk left open
+                    {
+                        had_open = true;
+                        acc.n = cm.y; acc.zmin = __uint_as_float(cm.z); acc.zmax = __uint_as_float(cm.w);
+                        acc.sx = s_cd[0][cellk]; acc.sy = s_cd[1][cellk]; acc.sz = s_cd[2][cellk];
+                        acc.sx2 = s_cd[3][cellk]; acc.sy2 = s_cd[4][cellk]; acc.sz2 = s_cd[5][cellk];
+                        acc.sxy = s_cd[6][cellk]; acc.sxz = s_cd[7][cellk]; acc.syz = s_cd[8][cellk];
+                    }
+                }
+                float rec[REC];
+                bool loaded = false;
+                auto load_rec = [&]()
+                {
+                    if (loaded) return;
+                    const float4 a0 = s_cell[cellk * 3 + 0], a1 = s_cell[cellk * 3 + 1], a2 = s_cell[cellk * 3 + 2];
+                    rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
+                    rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
+                    rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+                    loaded = true;
+                };
+                if (k < k1 && cur != 0xffffffffu)
+                {
+                    const uint32_t so0 = __float_as_uint(s_sorted[k].w) >> 8;
+                    if (so0 != cur)
+                    {
+                        load_rec();
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
+                        cur = 0xffffffffu;
+                    }
+                }
+                for (;;)
+                {
+                    const bool has = k < k1;
+                    if (!__any_sync(0xffffffffu, has))
+                        break;
+                    if (has)
+                    {
+                        float4 p = s_sorted[k];
+                        const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
+                        double keep = (cur == so) ? 1.0 : 0.0;          // continuing the segment left open by the previous chunk?
+                        if (cur != so)
+                        {
+                            acc.n = 0;
+                            acc.zmin = CUDART_INF_F;
+                            acc.zmax = -CUDART_INF_F;
+                        }
+                        cur = so;
+                        for (;;)
+                        {
+                            // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59); a new segment restarts the sums
+                            // through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly)
+                            const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
+                            const float z = p.z;
+                            ++k;
+                            bool more = false;
+                            if (k < k1)
+                            {
+                                p = s_sorted[k];  // next record: in flight during this one's arithmetic
+                                more = (__float_as_uint(p.w) >> 8) == so;
+                            }
+                            acc.n += 1u;
+                            acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
+                            acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
+                            acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
+                            acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
+                            acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
+                            acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
+                            acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
+                            acc.zmin = fminf(acc.zmin, z);
+                            acc.zmax = fmaxf(acc.zmax, z);
+                            keep = 1.0;
+                            if (!more)
+                                break;
+                        }
+                    }
+                    if (has && k < k1)  // a following record exists => this segment is complete
+                    {
+                        load_rec();
+                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
+                        cur = 0xffffffffu;
+                    }
+                }
+                if (walker)
+                {
+                    if (cur != 0xffffffffu)  // the cell's last segment of this chunk stays open
+                    {
+                        s_cm[cellk] = make_uint4(cur, acc.n, __float_as_uint(acc.zmin), __float_as_uint(acc.zmax));
+                        s_cd[0][cellk] = acc.sx; s_cd[1][cellk] = acc.sy; s_cd[2][cellk] = acc.sz;
+                        s_cd[3][cellk] = acc.sx2; s_cd[4][cellk] = acc.sy2; s_cd[5][cellk] = acc.sz2;
+                        s_cd[6][cellk] = acc.sxy; s_cd[7][cellk] = acc.sxz; s_cd[8][cellk] = acc.syz;
+                    }
+                    else if (had_open)
+                        s_cm[cellk].x = 0xffffffffu;
+                    if (loaded)
+                    {
+                        s_cell[cellk * 3 + 0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+                        s_cell[cellk * 3 + 1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                        s_cell[cellk * 3 + 2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+                        s_fl[cellk] = (uint8_t)(s_fl[cellk] | fl);
+                    }
+                }
+            }
+            lap(4);
+            __syncthreads();  // B5: s_sorted, the counters and the cell state are free for the next chunk / the store below
+        }
+        // ---- thread = cell: fold the segment still open after the last chunk, then the record goes back ----
+        uint32_t touched = 0;
+        if (nchunks)
+        {
+            uint32_t fl = s_fl[tid];
+            const uint4 cm = s_cm[tid];
+            if (cm.x != 0xffffffffu || (fl & F_TOUCHED))
+            {
+                const float4 a0 = s_cell[tid * 3 + 0], a1 = s_cell[tid * 3 + 1], a2 = s_cell[tid * 3 + 2];
+                float rec[REC] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+                if (cm.x != 0xffffffffu)
+                {
+                    CellAcc acc;
+                    acc.n = cm.y; acc.zmin = __uint_as_float(cm.z); acc.zmax = __uint_as_float(cm.w);
+                    acc.sx = s_cd[0][tid]; acc.sy = s_cd[1][tid]; acc.sz = s_cd[2][tid];
+                    acc.sx2 = s_cd[3][tid]; acc.sy2 = s_cd[4][tid]; acc.sz2 = s_cd[5][tid];
+                    acc.sxy = s_cd[6][tid]; acc.sxz = s_cd[7][tid]; acc.syz = s_cd[8][tid];
+                    fold_acc(rec, acc, (cm.x >> 23) != 0, fl);
+                }
+                touched = 1;
+                float4 *dstp = reinterpret_cast<float4 *>(g.mom + my_cell * REC);
+                if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
+                {
+#pragma unroll
+                    for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+                }
+                dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+                dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+                // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
+                uint8_t obs = 0;
+                if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
+                    obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
+                g.flags[my_cell] = (uint8_t)((g.flags[my_cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
+                if (fl & F_BLANKED)
+                {
+                    const size_t pl = g.plane();
+#pragma unroll
+                    for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + my_cell] = CUDART_NAN_F;
+                }
+            }
+        }
+        if (tid == 0)
+        {
+            nn_step(2);                                  // whatever is still outstanding of item it + 2
+            publish(slot, nn_item, nn_start, nn_cnt);    // this item's slot becomes item it + 2
+            nn_ticket = atomicAdd(b.counters + 4, 1u);   // consumed during the next item
+            nn_stage = 0;
+        }
+        const uint32_t nt = __syncthreads_count(touched);  // item barrier; also publishes s_item
         if (tid == 0 && nt)
             atomicAdd(b.counters + 8, nt);
         lap(5);
@@ -1807,13 +2257,13 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
     return cudaGetLastError();
 }
 
-static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 4 + (size_t)maxT * (BIN_THREADS / 32 + 1) * 2 + 16; }
+static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 16 + (size_t)maxT * 4 + (size_t)maxT * 2 + 16; }
 
 // TMB_FOLD: 0 = match.any ranks, 1 = shared-memory bitmap ranks (default), 9 = the round-1 kernel (A/B runs);
 // TMB_FOLD_TIMING=1: per-phase clock64 sums of thread 0 of every CTA, printed after the launch (diagnostics only)
 static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int n_sm)
 {
-    static const int variant = getenv("TMB_FOLD") ? atoi(getenv("TMB_FOLD")) : 1;
+    static const int variant = getenv("TMB_FOLD") ? atoi(getenv("TMB_FOLD")) : 3;
     static const bool timing = getenv("TMB_FOLD_TIMING") != nullptr;
     static const int per_sm = getenv("TMB_FOLD_GRID") ? atoi(getenv("TMB_FOLD_GRID")) : 3;
     const uint32_t nb = b.btw * b.bth;
@@ -1828,11 +2278,18 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
         cudaFuncSetAttribute(k_fold<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_fold<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_fold<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaFuncSetAttribute(k_fold3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
+        cudaFuncSetAttribute(k_fold3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
         attr_done[dev] = true;
     }
     if (variant == 9)
     {
         k_fold_r1<<<(uint32_t)min((uint32_t)n_sm * 4u, nb), FOLD_THREADS, 0, st>>>(b, g, lat);
+        return;
+    }
+    if (variant == 3 && !timing)
+    {
+        k_fold3<false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
         return;
     }
     if (!timing)
@@ -1844,7 +2301,8 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
     static unsigned long long *d_tim = nullptr;
     if (!d_tim) cudaMalloc(&d_tim, 64);
     cudaMemsetAsync(d_tim, 0, 64, st);
-    if (variant == 0) k_fold<0, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
+    if (variant == 3) k_fold3<true><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, d_tim);
+    else if (variant == 0) k_fold<0, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
     else k_fold<1, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
     unsigned long long h[6];
     cudaMemcpyAsync(h, d_tim, sizeof(h), cudaMemcpyDeviceToHost, st);
