@@ -290,6 +290,39 @@ int tmap_shard_rows(tmap_system *s, uint64_t map_id, int32_t kind, int32_t cj, i
 int tmap_shard_classify(tmap_system *s, uint64_t map_id, const int32_t cell_bbox[4]);
 int tmap_shard_clear_flag_rows(tmap_system *s, uint64_t map_id, int32_t cj, int32_t nrows);
 
+/* ---- the sharded rebuild as ONE collective call (host code C++, NCCL issued by the library on the map's stream) ----
+ * Bootstrap as with MPI: one rank obtains a 128-byte NCCL unique id (tmap_shard_unique_id), the caller ships it to every
+ * rank over whatever channel it has, and every rank calls tmap_shard_comm_init on ITS map (one process per GPU).
+ * tmap_shard_rebuild is then collective over the job: rank k passes the contiguous block of keyframe ids it holds (all ids
+ * of rank k below those of rank k+1) with their poses.  Steps: all-gather of windows -> shared bbox and op numbering;
+ * transform + key + bucket sort of the local keyframes; all-gather of per-row totals -> slabs of bin rows balanced by
+ * record count; grouped ncclSend/ncclRecv all-to-all of the bucketed records (the bucket array is the send buffer);
+ * per-bin merge in rank order + fold; in-place halo exchange of r cell rows (48-byte moment records + flag bytes) with
+ * the neighbouring slabs; classification of the slab.  The rank's grid window covers ITS slab rows + halo over the bbox
+ * columns only.  Replaces LocalMap::clearEntireMap + re-integration (LocalMap.cpp:375-397) for a map partitioned over
+ * GPUs; the moment and derived layers are bit-identical to the single-GPU rebuild.  NCCL is loaded with dlopen at the
+ * first call (TMAP_ERR_UNSUPPORTED if libnccl.so.2 is absent). */
+typedef struct tmap_shard_info
+{
+    int32_t bbox[4];           /* btx0, bty0, btw, bth: the job-wide bbox in 16-cell bins */
+    int32_t slab_y0, slab_y1;  /* this rank's bin rows [y0, y1), bbox-local */
+    int32_t cj0, cj1;          /* the same as absolute cell rows */
+    uint64_t local_records, sent_records, recv_records;
+    uint64_t halo_bytes, grid_bytes;
+    float ms[8];               /* CUDA-event stage times: bin, plan, all-to-all, merge+fold, halo, classify, total, - */
+    int32_t n_slabs;
+    int32_t slabs[2 * 64];     /* every rank's [y0, y1) */
+} tmap_shard_info;
+int tmap_shard_unique_id(uint8_t out_id[128]);
+int tmap_shard_comm_init(tmap_system *s, uint64_t map_id, int32_t rank, int32_t world, const uint8_t id[128]);
+int tmap_shard_comm_destroy(tmap_system *s, uint64_t map_id);
+int tmap_shard_rebuild(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12,
+                       tmap_shard_info *out);
+/* the slab planner alone (pure host function; rows_all[s * n_rows + y] = records rank s holds in bin row y) */
+int tmap_shard_plan(const uint32_t *rows_all, int32_t world, int32_t n_rows, int32_t first_global_row, int32_t rank,
+                    int32_t *slabs /*[2*world]*/, uint64_t *send /*[world]*/, uint64_t *recv /*[world]*/,
+                    uint64_t *src_base /*[world]*/);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,3 +97,31 @@ def test_all_to_all_routing_world2_gloo(tmp_path):
                         "127.0.0.1", "--master-port", "29533", str(script), ROOT], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("-ok:") == 2
+
+
+def test_c_planner_equals_numpy_planner():
+    """tmap_shard_plan (the planner LocalMap::shardRebuild runs between its all-gather and its all-to-all) against
+    the numpy statement in sharding.py: slabs, per-peer send / receive counts and receive offsets, for every rank."""
+    import ctypes as C
+    import traversability_mapping_b200 as tm
+    lib = tm.load_library()
+    rng = np.random.default_rng(11)
+    for world, n_rows, first in ((2, 11, 0), (2, 40, -7), (4, 64, 5), (8, 200, -3), (8, 19, 2), (3, 33, 1)):
+        rows = rng.integers(0, 5000, size=(world, n_rows)).astype(np.uint32)
+        rows[:, : n_rows // 7] = 0
+        if world == 4:
+            rows[1:] = 0  # one rank holds everything
+        want_slabs = sharding.slab_boundaries(rows.sum(0), world, first_global_row=first)
+        for rank in range(world):
+            slabs = np.zeros(2 * world, dtype=np.int32)
+            send = np.zeros(world, dtype=np.uint64); recv = np.zeros(world, dtype=np.uint64); base = np.zeros(world, dtype=np.uint64)
+            rc = lib.tmap_shard_plan(rows.ctypes.data, world, n_rows, first, rank, slabs.ctypes.data, send.ctypes.data,
+                                     recv.ctypes.data, base.ctypes.data)
+            assert rc == tm.OK
+            assert [tuple(x) for x in slabs.reshape(world, 2)] == [tuple(x) for x in want_slabs]
+            s, r, b = sharding.exchange_plan_rows(rows, want_slabs, rank)
+            assert list(send) == s and list(recv) == r and list(base) == [int(x) for x in b]
+    # too few rows for the world size is refused, as in the numpy planner
+    rows = np.ones((4, 8), dtype=np.uint32)
+    slabs = np.zeros(8, dtype=np.int32); z = np.zeros(4, dtype=np.uint64)
+    assert lib.tmap_shard_plan(rows.ctypes.data, 4, 8, 0, 0, slabs.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data) < 0

@@ -70,6 +70,14 @@ class ShardBuffers(C.Structure):
                 ("cell_bbox", C.c_int32 * 4)]
 
 
+class ShardInfo(C.Structure):
+    """tmap_shard_info (include/tmap.h): what one rank learns from a sharded rebuild."""
+    _fields_ = [("bbox", C.c_int32 * 4), ("slab_y0", C.c_int32), ("slab_y1", C.c_int32), ("cj0", C.c_int32), ("cj1", C.c_int32),
+                ("local_records", C.c_uint64), ("sent_records", C.c_uint64), ("recv_records", C.c_uint64),
+                ("halo_bytes", C.c_uint64), ("grid_bytes", C.c_uint64), ("ms", C.c_float * 8), ("n_slabs", C.c_int32),
+                ("slabs", C.c_int32 * 128)]
+
+
 UPDATE_CB = C.CFUNCTYPE(None, C.c_void_p)
 
 # every symbol include/tmap.h declares: name -> (restype, argtypes)
@@ -131,6 +139,12 @@ _SIG = {
     "tmap_shard_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "tmap_shard_classify": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
     "tmap_shard_clear_flag_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
+    "tmap_shard_unique_id": (C.c_int, [C.c_void_p]),
+    "tmap_shard_comm_init": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
+    "tmap_shard_comm_destroy": (C.c_int, [_P, C.c_uint64]),
+    "tmap_shard_rebuild": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(ShardInfo)]),
+    "tmap_shard_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p]),
 }
 
 _lib = None

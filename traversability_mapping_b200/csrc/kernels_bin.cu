@@ -1697,7 +1697,7 @@ __device__ __forceinline__ void l2_prefetch(const void *src, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
-template <bool TIMING>
+template <bool TIMING, bool SHARD>
 __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView g, LatticeD lat, unsigned long long *__restrict__ tim)
 {
     extern __shared__ __align__(128) unsigned char s_dyn[];
@@ -1712,6 +1712,8 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
     uint32_t *s_class = reinterpret_cast<uint32_t *>(s_dyn + Fold3Smem::class_off);  // [0..31] histogram, [32..63] cursors
     __shared__ uint32_t s_w[33];
     __shared__ uint32_t s_item[2][4];  // two published work items: packed item, bucket start, bucket count, valid
+    // SHARD: per published item, the sources' segments of the bin inside the receive buffer (cumulative counts, first records)
+    __shared__ uint32_t s_segcum[2][33], s_segbase[2][32];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_heavy = b.counters[10];
@@ -1747,13 +1749,47 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
     auto publish = [&](int slot, uint32_t item, uint32_t start, uint32_t cnt) {
         s_item[slot][0] = item; s_item[slot][1] = start; s_item[slot][2] = cnt; s_item[slot][3] = item != 0xffffffffu;
     };
-    auto prefetch_chunk = [&](uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0
+    // SHARD, warp 0: lane s resolves source s's segment of bin `gtn` (two independent loads), a warp scan orders them
+    auto publish_segments = [&](int slot, uint32_t item) {
+        const uint32_t nbs = (uint32_t)(b.btw * b.bth);
+        uint32_t c = 0, base = 0;
+        if (item != 0xffffffffu && lane < (uint32_t)b.sh_world)
+        {
+            const uint32_t gtn = item & 0x00ffffffu;
+            c = b.sh_counts[(size_t)lane * nbs + gtn];
+            base = (uint32_t)b.sh_src_base[lane] + (b.sh_starts[(size_t)lane * nbs + gtn] - b.sh_starts[(size_t)lane * nbs + b.sh_first]);
+        }
+        uint32_t inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += u;
+        }
+        s_segcum[slot][lane + 1] = inc;
+        if (lane == 0) s_segcum[slot][0] = 0;
+        s_segbase[slot][lane] = base;
+    };
+    auto prefetch_chunk_of = [&](int slot, uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0
         const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
-        l2_prefetch(b.sorted + start + pos, n * 16u);
+        if (!SHARD)
+        {
+            l2_prefetch(b.sorted + start + pos, n * 16u);
+            return;
+        }
+        // the chunk [pos, pos + n) of the logical bucket, piece by piece over the sources' segments it overlaps
+        const uint32_t lo = pos, hi = pos + n;
+        for (int sg = 0; sg < b.sh_world; ++sg)
+        {
+            const uint32_t c0 = s_segcum[slot][sg], c1 = s_segcum[slot][sg + 1];
+            const uint32_t x0 = max(lo, c0), x1 = min(hi, c1);
+            if (x0 < x1)
+                l2_prefetch(b.sh_recv + s_segbase[slot][sg] + (x0 - c0), (x1 - x0) * 16u);
+        }
     };
     auto prefetch_first_of = [&](int slot) {
         if (s_item[slot][3] && s_item[slot][2])
-            prefetch_chunk(s_item[slot][1], 0u, s_item[slot][2]);
+            prefetch_chunk_of(slot, s_item[slot][1], 0u, s_item[slot][2]);
     };
     auto nn_step = [&](int upto) {  // thread 0
         if (nn_stage < 1 && upto >= 1) { nn_item = list_at(nn_ticket); nn_stage = 1; }
@@ -1775,6 +1811,15 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
     for (int w = 0; w < FOLD_NW; ++w)
         s_cnt[w][tid] = 0;
     if (tid < 64) s_class[tid] = 0;
+    if (SHARD)
+    {
+        __syncthreads();
+        if (warp == 0)
+        {
+            publish_segments(0, s_item[0][0]);
+            publish_segments(1, s_item[1][0]);
+        }
+    }
     __syncthreads();
     if (TIMING && tid == 0) t_mark = clock64();
 
@@ -1787,6 +1832,7 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
         const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
         const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
         const uint32_t nchunks = (cnt + FOLD_CH - 1) / FOLD_CH;
+        uint32_t segc = 0;  // SHARD: source segment the current chunk starts in
         // thread = cell for everything that is per cell and not the walk: the record's trip from / to global memory
         const int my_ci = bx * BIN + (int)(tid & (BIN - 1)), my_cj = by * BIN + (int)(tid >> BIN_SHIFT);
         const size_t my_cell = (size_t)(my_cj - g.cj0) * g.W + (size_t)(my_ci - g.ci0);  // dereferenced only when nchunks > 0
@@ -1815,17 +1861,45 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
             float4 rr[FOLD_R];
             uint32_t pk[FOLD_R];  // per record: cell key (bits 0..8, 256 = not mine) | group leader (bit 15) | rank in group << 16
             const float4 *bucket = b.sorted + start + pos;
-#pragma unroll
-            for (int r = 0; r < FOLD_R; ++r)
+            bool straddles = false;
+            if (SHARD)
             {
-                const uint32_t i = warp * SL + r * 32 + lane;
-                pk[r] = 256u;
-                if ((uint32_t)r < R && i < n)
-                    rr[r] = bucket[i];
+                // the source segment the chunk starts in (uniform over the CTA; segments are long, so nearly every chunk
+                // lies inside one of them and is read exactly like a single-GPU bucket)
+                while (pos >= s_segcum[slot][segc + 1]) ++segc;
+                straddles = pos + n > s_segcum[slot][segc + 1];
+                bucket = b.sh_recv + s_segbase[slot][segc] + (pos - s_segcum[slot][segc]);
+            }
+            if (!straddles)
+            {
+#pragma unroll
+                for (int r = 0; r < FOLD_R; ++r)
+                {
+                    const uint32_t i = warp * SL + r * 32 + lane;
+                    pk[r] = 256u;
+                    if ((uint32_t)r < R && i < n)
+                        rr[r] = bucket[i];
+                }
+            }
+            else
+            {
+                uint32_t seg = segc;  // source segment of the last record fetched (indices only grow with r)
+#pragma unroll
+                for (int r = 0; r < FOLD_R; ++r)
+                {
+                    const uint32_t i = warp * SL + r * 32 + lane;
+                    pk[r] = 256u;
+                    if ((uint32_t)r < R && i < n)
+                    {
+                        const uint32_t gi = pos + i;  // index inside the bin's logical bucket
+                        while (gi >= s_segcum[slot][seg + 1]) ++seg;
+                        rr[r] = b.sh_recv[s_segbase[slot][seg] + (gi - s_segcum[slot][seg])];
+                    }
+                }
             }
             if (tid == 0)
             {
-                if (c + 1 < nchunks) prefetch_chunk(start, pos + FOLD_CH, cnt);  // into L2 while this chunk is sorted and walked
+                if (c + 1 < nchunks) prefetch_chunk_of(slot, start, pos + FOLD_CH, cnt);  // into L2 while this chunk is sorted and walked
                 else prefetch_first_of(slot ^ 1);                                // ... or the next bin's first chunk
             }
             const uint32_t lt = (1u << lane) - 1u;
@@ -2086,6 +2160,498 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
                 }
             }
         }
+        if (SHARD && warp == 0)
+        {
+            if (tid == 0) nn_step(2);
+            publish_segments(slot, __shfl_sync(0xffffffffu, nn_item, 0));
+        }
+        if (tid == 0)
+        {
+            nn_step(2);                                  // whatever is still outstanding of item it + 2
+            publish(slot, nn_item, nn_start, nn_cnt);    // this item's slot becomes item it + 2
+            nn_ticket = atomicAdd(b.counters + 4, 1u);   // consumed during the next item
+            nn_stage = 0;
+        }
+        const uint32_t nt = __syncthreads_count(touched);  // item barrier; also publishes s_item
+        if (tid == 0 && nt)
+            atomicAdd(b.counters + 8, nt);
+        lap(5);
+    }
+    if (TIMING && tid == 0)
+    {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) atomicAdd(tim + k, t_acc[k]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_fold4: the fold sorts RUNS, not records.
+// A LiDAR bucket arrives in (keyframe, point) order and consecutive points mostly fall into the same cell
+// (3.1 records per run on the loop-closure workload, 10-25 in the bins under the sensor).  Here
+//   * the TMA unit lands a chunk of 3 072 records in shared memory and the records never move again;
+//   * run heads are found with one shuffle + ballot per 32 records; only the HEADS go through the stable
+//     counting sort on the 8-bit cell key (match.any over the head lanes, per-warp counters), and what is
+//     placed is a 4-byte descriptor (first record | length << 12) -- a third of the sort work of k_fold3 and no
+//     16-byte record traffic inside shared memory;
+//   * cells are handed to walker threads in EXACT descending order of their record count in the chunk (a
+//     256-class counting sort of the counts; the class scan runs in warp 0 beside the offset scan), so the
+//     lanes of a warp carry near-equal work;
+//   * a walker follows its cell's runs in (keyframe, point) order; inside a run there is no key test at all.
+// Cell state (48-byte record in zero form, the open (keyframe, cell) segment's double sums) lives in shared
+// memory between chunks as in k_fold3, so any thread can walk any cell.  Arithmetic and order of operations
+// per (keyframe, cell) and per cell are exactly k_fold's.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t FOLD4_CH_MASK = 4095u;          // keeps a speculative record address inside shared memory
+template <int FOLD4_CH>
+struct Fold4Smem
+{
+    static constexpr size_t raw_off = 0;                                           // float4 [FOLD4_CH]
+    static constexpr size_t runs_off = raw_off + (size_t)FOLD4_CH * 16;            // u32 [FOLD4_CH]: first record | length << 12, sorted by (cell, keyframe, point)
+    static constexpr size_t cnt_off = runs_off + (size_t)FOLD4_CH * 4;             // u16 [8][256]: runs per (warp, cell) -> next slot
+    static constexpr size_t tot_off = cnt_off + (size_t)FOLD_NW * BIN_CELLS * 2;   // u32 [256]: records per cell in this chunk
+    static constexpr size_t hist_off = tot_off + (size_t)BIN_CELLS * 4;            // u32 [256]: cells per count class -> walker cursors
+    static constexpr size_t cell_off = hist_off + (size_t)BIN_CELLS * 4;           // float [256][12], zero form
+    static constexpr size_t cd_off = cell_off + (size_t)BIN_CELLS * REC * 4;       // double [9][256] open-segment sums
+    static constexpr size_t cm_off = cd_off + (size_t)9 * BIN_CELLS * 8;           // uint4 [256]: sign|op, n, zmin, zmax of the open segment
+    static constexpr size_t rrun_off = cm_off + (size_t)BIN_CELLS * 16;            // u32 [256]: first run slot | runs << 16
+    static constexpr size_t perm_off = rrun_off + (size_t)BIN_CELLS * 4;           // u16 [256]: walker -> cell
+    static constexpr size_t fl_off = perm_off + (size_t)BIN_CELLS * 2;             // u8 [256]
+    static constexpr size_t total = fl_off + BIN_CELLS;
+};
+
+template <int FOLD4_CH, int PER_SM, bool TIMING>
+__global__ void __launch_bounds__(FOLD_THREADS, PER_SM) k_fold4(BatchView b, GridView g, LatticeD lat, unsigned long long *__restrict__ tim)
+{
+    constexpr int FOLD4_R = FOLD4_CH / FOLD_THREADS;  // rows of 32 records per warp slice
+    static_assert(FOLD4_CH <= 4096 && FOLD4_CH % FOLD_THREADS == 0, "run descriptors keep the first record in 12 bits");
+    using Fold4Smem = tmb::Fold4Smem<FOLD4_CH>;
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    float4 *s_raw = reinterpret_cast<float4 *>(s_dyn + Fold4Smem::raw_off);
+    uint32_t *s_runs = reinterpret_cast<uint32_t *>(s_dyn + Fold4Smem::runs_off);
+    uint16_t(*s_cnt)[BIN_CELLS] = reinterpret_cast<uint16_t(*)[BIN_CELLS]>(s_dyn + Fold4Smem::cnt_off);
+    uint32_t *s_tot = reinterpret_cast<uint32_t *>(s_dyn + Fold4Smem::tot_off);
+    uint32_t *s_hist = reinterpret_cast<uint32_t *>(s_dyn + Fold4Smem::hist_off);
+    float4 *s_cell = reinterpret_cast<float4 *>(s_dyn + Fold4Smem::cell_off);      // [256][3]
+    double(*s_cd)[BIN_CELLS] = reinterpret_cast<double(*)[BIN_CELLS]>(s_dyn + Fold4Smem::cd_off);
+    uint4 *s_cm = reinterpret_cast<uint4 *>(s_dyn + Fold4Smem::cm_off);
+    uint32_t *s_rrun = reinterpret_cast<uint32_t *>(s_dyn + Fold4Smem::rrun_off);
+    uint16_t *s_perm = reinterpret_cast<uint16_t *>(s_dyn + Fold4Smem::perm_off);
+    uint8_t *s_fl = s_dyn + Fold4Smem::fl_off;
+    __shared__ uint32_t s_w[33];
+    __shared__ uint32_t s_item[2][4];  // two published work items: packed item, bucket start, bucket count, valid
+    __shared__ __align__(8) uint64_t s_bar;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t n_heavy = b.counters[10];
+    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front of the list) + light bins (back)
+    const uint32_t nb_total = (uint32_t)(b.btw * b.bth);
+    long long t_mark = 0;
+    unsigned long long t_acc[6] = {0, 0, 0, 0, 0, 0};  // wait, heads, scan, place, walk, store (thread 0, TIMING only)
+    auto lap = [&](int k) {
+        if (TIMING && tid == 0) { const long long t = clock64(); t_acc[k] += (unsigned long long)(t - t_mark); t_mark = t; }
+    };
+
+    // ---- work items: ticket counter, heaviest bins first, resolved TWO items ahead by thread 0 (see k_fold) ----
+    uint32_t nn_ticket = 0, nn_item = 0xffffffffu, nn_start = 0, nn_cnt = 0;
+    int nn_stage = 2;
+    auto list_at = [&](uint32_t t) -> uint32_t {
+        if (t >= n_active) return 0xffffffffu;
+        return t < n_heavy ? b.active_tiles[t] : b.active_tiles[nb_total - 1 - (t - n_heavy)];
+    };
+    auto range_of = [&](uint32_t item, uint32_t &start, uint32_t &cnt) {
+        start = cnt = 0;
+        if (item == 0xffffffffu) return;
+        const uint32_t gtn = item & 0x00ffffffu;
+        start = b.tile_start[gtn];
+        cnt = b.tile_count[gtn];
+        const int bx = b.btx0 + (int)(gtn % b.btw), by = b.bty0 + (int)(gtn / b.btw);
+        const int col = bx * BIN - g.ci0, row = by * BIN - g.cj0;
+        if (col < 0 || col + BIN > g.W || row < 0 || row + BIN > g.H)
+        {
+            atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);  // reported by the host; the item is skipped
+            cnt = 0;
+        }
+    };
+    auto publish = [&](int slot, uint32_t item, uint32_t start, uint32_t cnt) {
+        s_item[slot][0] = item; s_item[slot][1] = start; s_item[slot][2] = cnt; s_item[slot][3] = item != 0xffffffffu;
+    };
+    auto issue_chunk = [&](uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0: chunk at `pos` of a bucket -> s_raw
+        const uint32_t n = min((uint32_t)FOLD4_CH, cnt - pos);
+        mbar_arrive_expect_tx(&s_bar, n * 16u);
+        bulk_load(s_raw, b.sorted + start + pos, n * 16u, &s_bar);
+    };
+    auto issue_first_of = [&](int slot) {  // thread 0: first chunk of a published item (if it has one)
+        if (s_item[slot][3] && s_item[slot][2])
+            issue_chunk(s_item[slot][1], 0u, s_item[slot][2]);
+    };
+    auto prefetch_first_of = [&](int slot) {  // thread 0: pull a published item's first chunk into L2
+        if (s_item[slot][3] && s_item[slot][2])
+            l2_prefetch(b.sorted + s_item[slot][1], min((uint32_t)FOLD4_CH, s_item[slot][2]) * 16u);
+    };
+    auto nn_step = [&](int upto) {  // thread 0
+        if (nn_stage < 1 && upto >= 1) { nn_item = list_at(nn_ticket); nn_stage = 1; }
+        if (nn_stage < 2 && upto >= 2) { range_of(nn_item, nn_start, nn_cnt); nn_stage = 2; }
+    };
+    if (tid == 0)
+    {
+        mbar_init(&s_bar, 1);
+        fence_mbar_init();
+        for (int slot = 0; slot < 2; ++slot)
+        {
+            const uint32_t item = list_at(atomicAdd(b.counters + 4, 1u));
+            uint32_t st, cn;
+            range_of(item, st, cn);
+            publish(slot, item, st, cn);
+        }
+        issue_first_of(0);
+        nn_ticket = atomicAdd(b.counters + 4, 1u);
+        nn_stage = 0;
+    }
+#pragma unroll
+    for (int w = 0; w < FOLD_NW; ++w)
+        s_cnt[w][tid] = 0;
+    s_tot[tid] = 0;
+    s_hist[tid] = 0;
+    __syncthreads();
+    if (TIMING && tid == 0) t_mark = clock64();
+
+    uint32_t phase = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t it = 0;; ++it)
+    {
+        const int slot = (int)(it & 1u);
+        const uint32_t item = s_item[slot][0], start = s_item[slot][1], cnt = s_item[slot][2], valid = s_item[slot][3];
+        if (!valid)
+            break;
+        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
+        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
+        const uint32_t nchunks = (cnt + FOLD4_CH - 1) / FOLD4_CH;
+        // thread = cell for everything that is per cell and not the walk: the record's trip from / to global memory
+        const int my_ci = bx * BIN + (int)(tid & (BIN - 1)), my_cj = by * BIN + (int)(tid >> BIN_SHIFT);
+        const size_t my_cell = (size_t)(my_cj - g.cj0) * g.W + (size_t)(my_ci - g.ci0);  // dereferenced only when nchunks > 0
+        if (nchunks == 0)
+        {
+            __syncthreads();  // everyone holds this item's fields before its slot is republished below
+            if (tid == 0) issue_first_of(slot ^ 1);
+        }
+        else
+        {
+            // the whole bin's records arrive while the first chunk lands (zero form: Helpers.cpp:114-127's NaN -> 0)
+            const float4 *src = reinterpret_cast<const float4 *>(g.mom + my_cell * REC);
+            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
+            float rec[REC] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+            rec_to_zero_form(rec);
+            s_cell[tid * 3 + 0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+            s_cell[tid * 3 + 1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+            s_cell[tid * 3 + 2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+            s_cm[tid] = make_uint4(0xffffffffu, 0u, 0u, 0u);
+            s_fl[tid] = 0;
+        }
+        for (uint32_t c = 0; c < nchunks; ++c)
+        {
+            const uint32_t pos = c * FOLD4_CH;
+            const uint32_t n = min((uint32_t)FOLD4_CH, cnt - pos);
+            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rows per warp slice
+            const uint32_t SL = R * 32;                                // records per warp slice
+            if (tid == 0)
+            {
+                // the chunk after this one (or the next bin's first) starts its trip to L2 now; the TMA copy itself
+                // is issued when s_raw is free again, after the walk
+                if (c + 1 < nchunks) l2_prefetch(b.sorted + start + pos + FOLD4_CH, min((uint32_t)FOLD4_CH, cnt - pos - FOLD4_CH) * 16u);
+                else prefetch_first_of(slot ^ 1);
+            }
+            mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+            lap(0);
+            // ---- run heads of this warp's slice [warp*SL, (warp+1)*SL): count runs per (warp, cell), records per cell ----
+            uint32_t pk[FOLD4_R];  // per record: cell (0..7) | head (8) | group leader (9) | rank in group (10..14) | run length (16..21)
+            uint32_t keys[FOLD4_R];
+#pragma unroll
+            for (int r = 0; r < FOLD4_R; ++r)
+            {
+                const uint32_t i = warp * SL + r * 32 + lane;
+                keys[r] = ((uint32_t)r < R && i < n) ? __float_as_uint(s_raw[i].w) : 0xffffffffu;
+            }
+#pragma unroll
+            for (int r = 0; r < FOLD4_R; ++r)
+            {
+                pk[r] = 0u;
+                if ((uint32_t)r < R)  // uniform over the CTA
+                {
+                    const uint32_t i = warp * SL + r * 32 + lane;
+                    const uint32_t key = keys[r];
+                    const uint32_t cellk = key & 255u;
+                    const bool mine = i < n && (((cellk >> BIN_SHIFT) & pmask) == part);  // pmask == 0: every record is mine
+                    const uint32_t prev = __shfl_up_sync(0xffffffffu, key, 1);
+                    const bool head = mine && (lane == 0 || key != prev);
+                    const uint32_t hm = __ballot_sync(0xffffffffu, head);
+                    const uint32_t stopm = hm | ~__ballot_sync(0xffffffffu, mine);
+                    if (head)
+                    {
+                        const uint32_t above = lane == 31 ? 0u : (stopm >> (lane + 1));
+                        const uint32_t len = above ? (uint32_t)__ffs(above) : 32u - lane;
+                        const uint32_t m = __match_any_sync(hm, cellk);
+                        if ((m >> lane) == 1u)  // the group's highest lane books the group's runs
+                            s_cnt[warp][cellk] += (uint16_t)__popc(m);  // row `warp` is private to this warp
+                        atomicAdd(&s_tot[cellk], len);
+                        pk[r] = cellk | 0x100u | (((m >> lane) == 1u) ? 0x200u : 0u) | ((uint32_t)__popc(m & lt) << 10) | (len << 16);
+                    }
+                    __syncwarp();
+                }
+            }
+            lap(1);
+            __syncthreads();  // B1: counts complete (and, on the first chunk, the cell records are in shared memory)
+            if (tid == 0) nn_step(1);
+            // ---- thread = cell: run offsets (exclusive over warps, then over cells) and the cell's count class ----
+            uint32_t tot = 0, wc[FOLD_NW];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+            {
+                wc[w] = tot;
+                tot += s_cnt[w][tid];
+            }
+            const uint32_t nrec = s_tot[tid];
+            const uint32_t cls = min(255u, nrec);
+            if (nrec) atomicAdd(&s_hist[cls], 1u);
+            uint32_t inc = tot;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= (uint32_t)o) inc += u;
+            }
+            if (lane == 31) s_w[warp] = inc;
+            __syncthreads();  // B2: warp totals, class histogram
+            uint32_t cstart = inc - tot;
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                if (w < (int)warp) cstart += s_w[w];
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted run list
+            s_rrun[tid] = cstart | (tot << 16);
+            s_tot[tid] = 0;  // for the next chunk
+            if (warp == 0)
+            {
+                // walkers are numbered by descending record count: s_hist[k] <- number of cells in classes above k
+                uint32_t h[8], sum = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { h[k] = s_hist[lane * 8 + k]; sum += h[k]; }
+                uint32_t suf = sum;  // inclusive suffix over lanes
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + (uint32_t)o < 32u) suf += u;
+                }
+                uint32_t run = suf - sum;  // cells in the classes of higher lanes
+#pragma unroll
+                for (int k = 7; k >= 0; --k) { s_hist[lane * 8 + k] = run; run += h[k]; }
+            }
+            if (tid == 0) nn_step(2);
+            __syncthreads();  // B3: run offsets and walker cursors
+            lap(2);
+            if (nrec)
+                s_perm[atomicAdd(&s_hist[cls], 1u)] = (uint16_t)tid;  // order inside a class only decides WHO walks a cell
+            // ---- stable placement of the run descriptors ----
+#pragma unroll
+            for (int r = 0; r < FOLD4_R; ++r)
+            {
+                if ((uint32_t)r < R)  // uniform over the CTA
+                {
+                    const uint32_t cc = pk[r] & 0xffu;
+                    const bool head = (pk[r] & 0x100u) != 0u;
+                    uint32_t sl = 0;
+                    if (head)
+                    {
+                        sl = s_cnt[warp][cc] + ((pk[r] >> 10) & 31u);
+                        s_runs[sl] = (warp * SL + r * 32 + lane) | ((pk[r] >> 16) << 12);
+                    }
+                    __syncwarp();
+                    if (head && (pk[r] & 0x200u))  // highest lane of the group: its slot + 1 is the group's end
+                        s_cnt[warp][cc] = (uint16_t)(sl + 1u);
+                    __syncwarp();
+                }
+            }
+            const uint32_t n_walk = __syncthreads_count(nrec != 0);  // B4
+            lap(3);
+#pragma unroll
+            for (int w = 0; w < FOLD_NW; ++w)
+                s_cnt[w][tid] = 0;  // for the next chunk's count (everyone is past the placement)
+            s_hist[tid] = 0;
+            // ---- walk: thread `tid` takes the tid-th heaviest cell of the chunk, run by run ----
+            {
+                const bool walker = tid < n_walk;
+                uint32_t cellk = 0, rk = 0, rend = 0;
+                if (walker)
+                {
+                    cellk = s_perm[tid];
+                    const uint32_t rr = s_rrun[cellk];
+                    rk = rr & 0xffffu;
+                    rend = rk + (rr >> 16);
+                }
+                const int ci = bx * BIN + (int)(cellk & (BIN - 1)), cj = by * BIN + (int)(cellk >> BIN_SHIFT);
+                double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
+                double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
+                asm volatile("" : "+d"(cx), "+d"(cy));  // opaque: keeps the compiler from recomputing them inside the walk loop
+                CellAcc acc;
+                acc.reset();
+                uint32_t cur = 0xffffffffu, fl = 0;
+                bool had_open = false;
+                if (walker)
+                {
+                    const uint4 cm = s_cm[cellk];
+                    cur = cm.x;
+                    if (cur != 0xffffffffu)  // the segment the previous chunk left open
+                    {
+                        had_open = true;
+                        acc.n = cm.y; acc.zmin = __uint_as_float(cm.z); acc.zmax = __uint_as_float(cm.w);
+                        acc.sx = s_cd[0][cellk]; acc.sy = s_cd[1][cellk]; acc.sz = s_cd[2][cellk];
+                        acc.sx2 = s_cd[3][cellk]; acc.sy2 = s_cd[4][cellk]; acc.sz2 = s_cd[5][cellk];
+                        acc.sxy = s_cd[6][cellk]; acc.sxz = s_cd[7][cellk]; acc.syz = s_cd[8][cellk];
+                    }
+                }
+                float rec[REC];
+                bool loaded = false;
+                auto load_rec = [&]()
+                {
+                    if (loaded) return;
+                    const float4 a0 = s_cell[cellk * 3 + 0], a1 = s_cell[cellk * 3 + 1], a2 = s_cell[cellk * 3 + 2];
+                    rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
+                    rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
+                    rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
+                    loaded = true;
+                };
+                // ONE flat loop, one record per iteration and lane: the lane's position runs through its cell's runs in
+                // (keyframe, point) order; the next record's address is known as soon as the position has advanced, so
+                // its load is in flight during this record's arithmetic, and the next run's descriptor is fetched one run
+                // ahead.  A change of keyframe folds the finished (keyframe, cell) segment into the cell's record (the only
+                // divergent block); the cell's last segment of the chunk stays open for the next chunk.
+                uint32_t pos = 0, end = 0, nd = 0;
+                float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (rk < rend)
+                {
+                    const uint32_t d = s_runs[rk];
+                    pos = d & 0xfffu;
+                    end = pos + (d >> 12);
+                    p = s_raw[pos];
+                    if (rk + 1 < rend) nd = s_runs[rk + 1];
+                }
+                while (__any_sync(0xffffffffu, rk < rend))
+                {
+                    if (rk < rend)
+                    {
+                        // advance to the following record (possibly the next run's first) and request it
+                        ++pos;
+                        if (pos == end)
+                        {
+                            ++rk;
+                            pos = nd & 0xfffu;
+                            end = pos + (nd >> 12);
+                            if (rk + 1 < rend) nd = s_runs[rk + 1];
+                        }
+                        const float4 pn = s_raw[pos & (FOLD4_CH_MASK)];  // unused after the cell's last record
+                        const uint32_t so = __float_as_uint(p.w) >> 8;   // sign | op
+                        double keep = 1.0;
+                        if (so != cur)
+                        {
+                            if (cur != 0xffffffffu)
+                            {
+                                load_rec();
+                                fold_acc(rec, acc, (cur >> 23) != 0, fl);
+                            }
+                            // a new segment restarts the sums through the fma's multiplier (acc * 0 + x == x exactly)
+                            keep = 0.0;
+                            acc.n = 0;
+                            acc.zmin = CUDART_INF_F;
+                            acc.zmax = -CUDART_INF_F;
+                            cur = so;
+                        }
+                        // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
+                        const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
+                        acc.n += 1u;
+                        acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
+                        acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
+                        acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
+                        acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
+                        acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
+                        acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
+                        acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
+                        acc.zmin = fminf(acc.zmin, p.z);
+                        acc.zmax = fmaxf(acc.zmax, p.z);
+                        p = pn;
+                    }
+                }
+                if (walker)
+                {
+                    if (cur != 0xffffffffu)  // the cell's last segment of this chunk stays open
+                    {
+                        s_cm[cellk] = make_uint4(cur, acc.n, __float_as_uint(acc.zmin), __float_as_uint(acc.zmax));
+                        s_cd[0][cellk] = acc.sx; s_cd[1][cellk] = acc.sy; s_cd[2][cellk] = acc.sz;
+                        s_cd[3][cellk] = acc.sx2; s_cd[4][cellk] = acc.sy2; s_cd[5][cellk] = acc.sz2;
+                        s_cd[6][cellk] = acc.sxy; s_cd[7][cellk] = acc.sxz; s_cd[8][cellk] = acc.syz;
+                    }
+                    else if (had_open)
+                        s_cm[cellk].x = 0xffffffffu;
+                    if (loaded)
+                    {
+                        s_cell[cellk * 3 + 0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+                        s_cell[cellk * 3 + 1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                        s_cell[cellk * 3 + 2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+                        s_fl[cellk] = (uint8_t)(s_fl[cellk] | fl);
+                    }
+                }
+            }
+            lap(4);
+            __syncthreads();  // B5: s_raw, the run list, the counters and the cell state are free
+            if (tid == 0)
+            {
+                if (c + 1 < nchunks) issue_chunk(start, pos + FOLD4_CH, cnt);
+                else issue_first_of(slot ^ 1);
+            }
+        }
+        // ---- thread = cell: fold the segment still open after the last chunk, then the record goes back ----
+        uint32_t touched = 0;
+        if (nchunks)
+        {
+            uint32_t fl = s_fl[tid];
+            const uint4 cm = s_cm[tid];
+            if (cm.x != 0xffffffffu || (fl & F_TOUCHED))
+            {
+                const float4 a0 = s_cell[tid * 3 + 0], a1 = s_cell[tid * 3 + 1], a2 = s_cell[tid * 3 + 2];
+                float rec[REC] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w, a2.x, a2.y, a2.z, a2.w};
+                if (cm.x != 0xffffffffu)
+                {
+                    CellAcc acc;
+                    acc.n = cm.y; acc.zmin = __uint_as_float(cm.z); acc.zmax = __uint_as_float(cm.w);
+                    acc.sx = s_cd[0][tid]; acc.sy = s_cd[1][tid]; acc.sz = s_cd[2][tid];
+                    acc.sx2 = s_cd[3][tid]; acc.sy2 = s_cd[4][tid]; acc.sz2 = s_cd[5][tid];
+                    acc.sxy = s_cd[6][tid]; acc.sxz = s_cd[7][tid]; acc.syz = s_cd[8][tid];
+                    fold_acc(rec, acc, (cm.x >> 23) != 0, fl);
+                }
+                touched = 1;
+                float4 *dstp = reinterpret_cast<float4 *>(g.mom + my_cell * REC);
+                if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
+                {
+#pragma unroll
+                    for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
+                }
+                dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
+                dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
+                dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
+                // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
+                uint8_t obs = 0;
+                if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
+                    obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
+                g.flags[my_cell] = (uint8_t)((g.flags[my_cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
+                if (fl & F_BLANKED)
+                {
+                    const size_t pl = g.plane();
+#pragma unroll
+                    for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + my_cell] = CUDART_NAN_F;
+                }
+            }
+        }
         if (tid == 0)
         {
             nn_step(2);                                  // whatever is still outstanding of item it + 2
@@ -2259,7 +2825,8 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
 
 static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 16 + (size_t)maxT * 4 + (size_t)maxT * 2 + 16; }
 
-// TMB_FOLD: 0 = match.any ranks, 1 = shared-memory bitmap ranks (default), 9 = the round-1 kernel (A/B runs);
+// TMB_FOLD: 3 = k_fold3 (default), 4 = k_fold4 (run sort; measured slower, kept for A/B), 0 / 1 = k_fold with match.any /
+// shared-memory bitmap ranks, 9 = the round-1 kernel;
 // TMB_FOLD_TIMING=1: per-phase clock64 sums of thread 0 of every CTA, printed after the launch (diagnostics only)
 static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int n_sm)
 {
@@ -2278,18 +2845,67 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
         cudaFuncSetAttribute(k_fold<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_fold<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_fold<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_fold3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
-        cudaFuncSetAttribute(k_fold3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
+        cudaFuncSetAttribute(k_fold3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
+        cudaFuncSetAttribute(k_fold3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
+        cudaFuncSetAttribute(k_fold3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
         attr_done[dev] = true;
+    }
+    if (b.sh_world > 0)  // sharded: the bucket is read in place from the sources' segments (k_fold3 only)
+    {
+        k_fold3<false, true><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
+        return;
     }
     if (variant == 9)
     {
         k_fold_r1<<<(uint32_t)min((uint32_t)n_sm * 4u, nb), FOLD_THREADS, 0, st>>>(b, g, lat);
         return;
     }
+    if (variant == 4)
+    {
+        // chunk size / CTAs per SM: 3072 x 2 or 1536 x 3 (TMB_FOLD_CH)
+        static const int ch = getenv("TMB_FOLD_CH") ? atoi(getenv("TMB_FOLD_CH")) : 1536;
+        static const int per_sm4 = getenv("TMB_FOLD_GRID") ? atoi(getenv("TMB_FOLD_GRID")) : (ch == 3072 ? 2 : 3);
+        const uint32_t blocks4 = (uint32_t)min((uint32_t)(n_sm * per_sm4), nb);
+        static unsigned long long *d_tim4 = nullptr;
+        if (timing)
+        {
+            if (!d_tim4) cudaMalloc(&d_tim4, 64);
+            cudaMemsetAsync(d_tim4, 0, 64, st);
+        }
+        static bool attr4[64] = {false};
+        if (dev < 64 && !attr4[dev])
+        {
+            cudaFuncSetAttribute(k_fold4<3072, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
+            cudaFuncSetAttribute(k_fold4<3072, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
+            cudaFuncSetAttribute(k_fold4<1536, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
+            cudaFuncSetAttribute(k_fold4<1536, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
+            attr4[dev] = true;
+        }
+        if (ch == 3072)
+        {
+            if (timing) k_fold4<3072, 2, true><<<blocks4, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, d_tim4);
+            else k_fold4<3072, 2, false><<<blocks4, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, nullptr);
+        }
+        else
+        {
+            if (timing) k_fold4<1536, 3, true><<<blocks4, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, d_tim4);
+            else k_fold4<1536, 3, false><<<blocks4, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, nullptr);
+        }
+        if (!timing)
+            return;
+        unsigned long long h[6];
+        cudaMemcpyAsync(h, d_tim4, sizeof(h), cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+        double tot = 0;
+        for (int k = 0; k < 6; ++k) tot += (double)h[k];
+        if (tot > 0)
+            fprintf(stderr, "[k_fold4 phases, %% of thread-0 cycles over %u CTAs] wait %.1f heads %.1f scan %.1f place %.1f walk %.1f store %.1f | %.0f cycles per CTA\n",
+                    blocks4, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / blocks4);
+        return;
+    }
     if (variant == 3 && !timing)
     {
-        k_fold3<false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
+        k_fold3<false, false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
         return;
     }
     if (!timing)
@@ -2301,7 +2917,7 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
     static unsigned long long *d_tim = nullptr;
     if (!d_tim) cudaMalloc(&d_tim, 64);
     cudaMemsetAsync(d_tim, 0, 64, st);
-    if (variant == 3) k_fold3<true><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, d_tim);
+    if (variant == 3) k_fold3<true, false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, d_tim);
     else if (variant == 0) k_fold<0, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
     else k_fold<1, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
     unsigned long long h[6];
@@ -2395,9 +3011,31 @@ cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridVi
     k_shard_counts<<<nblk, 256, 0, st>>>(b, d_counts_all, world, y0, y1, d_glob);
     k_scan_blocks<<<1, 1024, 0, st>>>(b, nblk);
     k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
-    const uint32_t nwarps = (uint32_t)((y1 - y0) * b.btw) * (uint32_t)world;
-    if (nwarps)
-        k_shard_merge<<<(nwarps + 7) / 8, 256, 0, st>>>(b, d_recv, d_counts_all, d_starts_all, d_src_base, world, y0, y1);
+    // the merge copy (k_shard_merge) is gone: the fold reads each bin's bucket in place from the sources' segments
+    (void)d_recv; (void)d_starts_all; (void)d_src_base;
+    return cudaGetLastError();
+}
+
+// per bin ROW of the batch bbox: records this process holds in it (the slab planner's input; one warp per row)
+__global__ void __launch_bounds__(256) k_row_totals(BatchView b, uint32_t *__restrict__ rows)
+{
+    const uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= (uint32_t)b.bth)
+        return;
+    uint32_t s = 0;
+    for (uint32_t x = lane; x < (uint32_t)b.btw; x += 32)
+        s += b.tile_count[(size_t)row * b.btw + x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0)
+        rows[row] = s;
+}
+
+cudaError_t launch_row_totals(cudaStream_t st, const BatchView &b, uint32_t *d_rows)
+{
+    const uint32_t warps = (uint32_t)b.bth;
+    k_row_totals<<<(warps + 7) / 8, 256, 0, st>>>(b, d_rows);
     return cudaGetLastError();
 }
 

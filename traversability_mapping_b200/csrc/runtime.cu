@@ -11,6 +11,7 @@
 // No CPU fallback exists: every arithmetic step of the path runs in the CUDA kernels.
 #include "../../include/tmap.h"
 #include "tmb_kernels.h"
+#include "tmb_nccl.h"
 
 #include <algorithm>
 #include <atomic>
@@ -392,6 +393,7 @@ class LocalMap
         qCv_.notify_all();
         if (worker_.joinable()) worker_.join();
         cudaStreamSynchronize(stream_);
+        shardCommDestroy();
         for (auto &e : ev_) cudaEventDestroy(e);
         cudaStreamDestroy(ownStream_);
     }
@@ -897,7 +899,13 @@ class LocalMap
 
     // host side of a pass: op descriptors, chunk table, scratch buffers, uploads.  `forced` (bins, inclusive,
     // already including the candidate margin) pins the per-bin arrays to a bbox shared by all ranks.
-    Plan planBatch(const std::vector<Op> &ops, const int *forced, uint32_t op_base)
+    // a bin is split across CTAs (by cell-row group) once it exceeds 1/splitDiv of a resident fold CTA's fair share
+    static int splitDiv()
+    {
+        static const int d = std::getenv("TMB_SPLIT_DIV") ? std::max(1, std::atoi(std::getenv("TMB_SPLIT_DIV"))) : 1;
+        return d;
+    }
+    Plan planBatch(const std::vector<Op> &ops, const int *forced, uint32_t op_base, bool ensure_grid = true)
     {
         Plan pl;
         const uint32_t n_ops = (uint32_t)ops.size();
@@ -985,7 +993,8 @@ class LocalMap
             b.btw = ux1 - ux0 + 1 + 2 * pl.dm; b.bth = uy1 - uy0 + 1 + 2 * pl.dm;
         }
         pl.ux0 = ux0; pl.uy0 = uy0; pl.ux1 = ux1; pl.uy1 = uy1;
-        grid_.ensure(stream_, ux0 >> 1, uy0 >> 1, (ux1 >> 1) + 1, (uy1 >> 1) + 1);  // bins -> 32x32 tiles
+        if (ensure_grid)
+            grid_.ensure(stream_, ux0 >> 1, uy0 >> 1, (ux1 >> 1) + 1, (uy1 >> 1) + 1);  // bins -> 32x32 tiles
 
         b.n_ops = n_ops;
         b.n_chunks = n_chunks;
@@ -996,7 +1005,7 @@ class LocalMap
         b.total_points = (uint32_t)total_pts;
         b.cand_y0 = 0; b.cand_y1 = b.bth;
         // a bin is split across CTAs only when it exceeds the fair share of one resident fold CTA (3 per SM)
-        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, total_pts / (uint64_t)(3 * nSM_));
+        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, total_pts / (uint64_t)(3 * nSM_ * splitDiv()));
 
         // chunk -> op table, followed by the per-32-op union windows used by the scan over ops
         std::memset(metaH_.p, 0, 64);
@@ -1240,13 +1249,14 @@ class LocalMap
         CK(cudaMemsetAsync(v.flags + off, 0, cnt, stream_));
     }
     // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
-    void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out)
+    void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out,
+                  bool ensure_grid = true)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
         shardOps_ = shardOps(ids, n, poses);
         const int forced[4] = {bbox[0], bbox[1], bbox[2], bbox[3]};
-        shardPlan_ = planBatch(shardOps_, forced, op_base);
+        shardPlan_ = planBatch(shardOps_, forced, op_base, ensure_grid);
         uploadConstants();
         CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
                       nSM_, nullptr, 1));
@@ -1277,27 +1287,33 @@ class LocalMap
     }
     // merge the records received from every rank for bin rows [y0, y1) (bbox-local) and fold them
     void shardFold(const void *d_recv, uint64_t n_recv, const void *d_counts_all, const void *d_starts_all, const uint64_t *src_base,
-                   int world, int y0, int y1)
+                   int world, int y0, int y1, bool sync = true)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
         BatchView &b = shardPlan_.b;
         if (y0 < 0 || y1 > b.bth || y0 > y1) throw std::invalid_argument("bad slab rows");
-        mergedD_.ensure((size_t)n_recv * 16 + 16);
+        if (world > 32) throw Unsupported("sharded fold: at most 32 ranks");
         srcBaseD_.ensure((size_t)world * 8);
         CK(cudaMemcpyAsync(srcBaseD_.p, src_base, (size_t)world * 8, cudaMemcpyHostToDevice, stream_));
         g_h2d += (uint64_t)((size_t)world * 8);
-        b.sorted = mergedD_.as<float4>();
-        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, n_recv / (uint64_t)(3 * nSM_));
+        b.split_thresh = (uint32_t)std::max<uint64_t>(32768, n_recv / (uint64_t)(3 * nSM_ * splitDiv()));
         b.n_ops = 0;  // per-op bboxes were consumed by shardBin
         b.nbr_count = globD_;
         b.cand_y0 = y0; b.cand_y1 = y1;
+        // a bin's bucket = the sources' segments in rank order, read in place from the receive buffer by the fold
+        b.sh_recv = static_cast<const float4 *>(d_recv);
+        b.sh_counts = static_cast<const uint32_t *>(d_counts_all);
+        b.sh_starts = static_cast<const uint32_t *>(d_starts_all);
+        b.sh_src_base = srcBaseD_.as<unsigned long long>();
+        b.sh_world = world;
+        b.sh_first = (uint32_t)y0 * (uint32_t)b.btw;
         CK(launch_shard_merge(stream_, b, grid_.v, static_cast<const float4 *>(d_recv), static_cast<const uint32_t *>(d_counts_all),
                               static_cast<const uint32_t *>(d_starts_all), srcBaseD_.as<unsigned long long>(), world, y0, y1, globD_,
                               shardPlan_.dc, shardPlan_.di));
         CK(launch_bin(stream_, b, grid_.v, lat_, shardPlan_.ppt, 1, shardPlan_.dc, shardPlan_.di, nSM_, nullptr, 2));
         g_launches += 6;
-        CK(cudaStreamSynchronize(stream_));
+        if (sync) CK(cudaStreamSynchronize(stream_));
     }
     // pointer into the grid for an in-place halo exchange: `nrows` cell rows starting at absolute row cj
     void shardRows(int kind, int32_t cj, int32_t nrows, void **ptr, size_t *bytes)
@@ -1336,6 +1352,285 @@ class LocalMap
         shardRows(1, cj, nrows, &p, &bytes);
         CK(cudaMemsetAsync(p, 0, bytes, stream_));
         CK(cudaStreamSynchronize(stream_));
+    }
+
+    // ---- the whole sharded rebuild behind ONE call, collectives issued from here (NCCL on the map's stream) ----
+    struct ShardInfo
+    {
+        int32_t bbox[4];            // btx0, bty0, btw, bth (bins) of the job-wide bbox
+        int32_t slab_y0, slab_y1;   // this rank's bin rows [y0, y1), bbox-local
+        int32_t cj0, cj1;           // the same in absolute cell rows
+        uint64_t local_records, sent_records, recv_records;
+        uint64_t halo_bytes, grid_bytes;
+        float ms[8];                // bin, plan (gathers + host), alltoall, fold, halo, classify, total, -
+        int32_t n_slabs;
+        int32_t slabs[2 * 64];
+    };
+    static void ncclCheck(ncclResult_t r, const char *what)
+    {
+        if (r != ncclSuccess)
+            throw CudaError(std::string(what) + ": " + NcclApi::get().GetErrorString(r));
+    }
+    void shardCommInit(int rank, int world, const uint8_t *id128)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        NcclApi &N = NcclApi::get();
+        if (!N.ok()) throw Unsupported(N.error);
+        if (world < 1 || world > 64 || rank < 0 || rank >= world) throw std::invalid_argument("bad rank / world size");
+        CK(cudaSetDevice(P_.device));
+        shardCommDestroy();
+        ncclUniqueId id;
+        static_assert(sizeof(id) == 128, "tmap_shard_unique_id hands out 128 bytes");
+        std::memcpy(&id, id128, sizeof(id));
+        ncclComm_t c = nullptr;
+        ncclCheck(N.CommInitRank(&c, world, id, rank), "ncclCommInitRank");
+        comm_ = c;
+        rank_ = rank;
+        world_ = world;
+        for (auto &e : shardEv_) CK(cudaEventCreate(&e));
+    }
+    void shardCommDestroy()
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        if (!comm_) return;
+        cudaStreamSynchronize(stream_);
+        NcclApi::get().CommDestroy(static_cast<ncclComm_t>(comm_));
+        comm_ = nullptr;
+        for (auto &e : shardEv_) { if (e) cudaEventDestroy(e); e = nullptr; }
+    }
+    // Slab planner (pure host function, also behind tmap_shard_plan for the CPU tests): cut n_rows bin rows into
+    // `world` contiguous slabs of ~equal record count, interior boundaries on even GLOBAL bin rows (32-cell tile
+    // rows), every slab >= 2 rows; then this rank's send / receive counts per peer and the receive offsets.
+    static void shardPlanRows(const uint32_t *rows_all /*[world][n_rows]*/, int world, int n_rows, int first_global_row, int rank,
+                              int32_t *slabs /*[2*world]*/, uint64_t *send, uint64_t *recv, uint64_t *src_base)
+    {
+        if (n_rows < 2 * world + 2)
+            throw std::invalid_argument("map too small to shard: " + std::to_string(n_rows) + " bin rows over " + std::to_string(world) +
+                                        " ranks");
+        std::vector<double> cum((size_t)n_rows + 1, 0.0);
+        for (int y = 0; y < n_rows; ++y)
+        {
+            double t = 0;
+            for (int s = 0; s < world; ++s) t += (double)rows_all[(size_t)s * n_rows + y];
+            cum[y + 1] = cum[y] + t;
+        }
+        const double total = cum[n_rows];
+        std::vector<int> cuts{0};
+        for (int k = 1; k < world; ++k)
+        {
+            const double target = total * k / world;
+            int y = (int)(std::lower_bound(cum.begin(), cum.end(), target) - cum.begin());
+            if ((first_global_row + y) % 2) ++y;
+            y = std::max(y, cuts.back() + 2);
+            y = std::min(y, n_rows - 2 * (world - k));
+            if ((first_global_row + y) % 2) --y;
+            cuts.push_back(y);
+        }
+        cuts.push_back(n_rows);
+        for (int k = 0; k < world; ++k) { slabs[2 * k] = cuts[k]; slabs[2 * k + 1] = cuts[k + 1]; }
+        for (int k = 0; k < world; ++k)
+        {
+            uint64_t t = 0;
+            for (int y = cuts[k]; y < cuts[k + 1]; ++y) t += rows_all[(size_t)rank * n_rows + y];
+            send[k] = t;
+        }
+        uint64_t run = 0;
+        for (int s = 0; s < world; ++s)
+        {
+            uint64_t t = 0;
+            for (int y = cuts[rank]; y < cuts[rank + 1]; ++y) t += rows_all[(size_t)s * n_rows + y];
+            recv[s] = t;
+            src_base[s] = run;
+            run += t;
+        }
+    }
+    void shardRebuild(const uint64_t *ids, size_t n, const float *poses, ShardInfo *info)
+    {
+        std::lock_guard<std::recursive_mutex> g(gridMutex_);
+        if (!comm_) throw std::invalid_argument("tmap_shard_comm_init has not been called on this map");
+        if (R_ > 0) throw Unsupported("step inflation is not available on a sharded map yet");
+        NcclApi &N = NcclApi::get();
+        ncclComm_t comm = static_cast<ncclComm_t>(comm_);
+        const int W = world_, rank = rank_;
+        CK(cudaSetDevice(P_.device));
+        const auto t_begin = std::chrono::steady_clock::now();
+        CK(cudaEventRecord(shardEv_[0], stream_));
+        // 1. job-wide op numbering and bbox: every rank's keyframe count and window in ONE all-gather of 8 int64
+        int32_t win[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+        if (n) shardWindow(ids, n, poses, win);
+        shardH_.ensure(4096 + (size_t)W * 64);
+        shardD_.ensure(4096 + (size_t)W * 64);
+        long long *mh = shardH_.as<long long>();
+        mh[0] = (long long)n; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3]; mh[5] = mh[6] = mh[7] = 0;
+        long long *md = shardD_.as<long long>();
+        CK(cudaMemcpyAsync(md, mh, 64, cudaMemcpyHostToDevice, stream_));
+        ncclCheck(N.AllGather(md, md + 8, 8, ncclInt64, comm, stream_), "ncclAllGather(meta)");
+        CK(cudaMemcpyAsync(mh + 8, md + 8, (size_t)W * 64, cudaMemcpyDeviceToHost, stream_));
+        g_h2d += 64; g_d2h += (uint64_t)W * 64;
+        CK(cudaStreamSynchronize(stream_));
+        uint64_t op_base = 0;
+        int32_t u[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+        for (int s = 0; s < W; ++s)
+        {
+            const long long *m = mh + 8 + 8 * s;
+            if (s < rank) op_base += (uint64_t)m[0];
+            if (m[0])
+            {
+                u[0] = std::min<long long>(u[0], m[1]); u[1] = std::min<long long>(u[1], m[2]);
+                u[2] = std::max<long long>(u[2], m[3]); u[3] = std::max<long long>(u[3], m[4]);
+            }
+        }
+        if (u[0] == INT_MAX) throw std::invalid_argument("sharded rebuild without keyframes");
+        const int margin = std::max(1, (r_ + BIN - 1) / BIN);
+        const int32_t bbox[4] = {u[0] - margin, u[1] - margin, u[2] + margin, u[3] + margin};
+        // 2. bin this rank's keyframes over the shared bbox (k_hist / scans / k_scatter); the grid is not touched yet
+        ShardBuffers buf{};
+        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false);
+        CK(cudaEventRecord(shardEv_[1], stream_));
+        const BatchView &b = shardPlan_.b;
+        const size_t nb = (size_t)b.btw * b.bth;
+        const int bth = b.bth, btw = b.btw;
+        // 3. per-row totals (+ this rank's cell bbox) of every rank -> host (slab plan); per-bin counts / starts of every
+        //    rank stay on the device (merge)
+        const size_t rw = (size_t)bth + 4;  // u32 per rank
+        rowsD_.ensure((rw + (size_t)W * rw) * 4 + 64);
+        rowsH_.ensure((size_t)W * rw * 4 + 64);
+        uint32_t *rowsMine = rowsD_.as<uint32_t>(), *rowsAll = rowsMine + rw;
+        CK(launch_row_totals(stream_, b, rowsMine));
+        g_launches += 1;
+        CK(cudaMemcpyAsync(rowsMine + bth, buf.cell_bbox, 16, cudaMemcpyHostToDevice, stream_));
+        ncclCheck(N.AllGather(rowsMine, rowsAll, rw, ncclUint32, comm, stream_), "ncclAllGather(rows)");
+        CK(cudaMemcpyAsync(rowsH_.p, rowsAll, (size_t)W * rw * 4, cudaMemcpyDeviceToHost, stream_));
+        g_d2h += (uint64_t)W * rw * 4;
+        countsAllD_.ensure((size_t)W * nb * 4 + 64);
+        startsAllD_.ensure((size_t)W * nb * 4 + 64);
+        ncclCheck(N.GroupStart(), "ncclGroupStart");
+        ncclCheck(N.AllGather(b.tile_count, countsAllD_.p, nb, ncclUint32, comm, stream_), "ncclAllGather(counts)");
+        ncclCheck(N.AllGather(b.tile_start, startsAllD_.p, nb, ncclUint32, comm, stream_), "ncclAllGather(starts)");
+        ncclCheck(N.GroupEnd(), "ncclGroupEnd");
+        CK(cudaStreamSynchronize(stream_));
+        std::vector<uint32_t> rows((size_t)W * bth);
+        int32_t cb[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        for (int s = 0; s < W; ++s)
+        {
+            const uint32_t *src = rowsH_.as<uint32_t>() + (size_t)s * rw;
+            std::memcpy(rows.data() + (size_t)s * bth, src, (size_t)bth * 4);
+            int32_t c4[4];
+            std::memcpy(c4, src + bth, 16);
+            if (c4[0] != INT_MAX)
+            {
+                cb[0] = std::min(cb[0], c4[0]); cb[1] = std::max(cb[1], c4[1]);
+                cb[2] = std::min(cb[2], c4[2]); cb[3] = std::max(cb[3], c4[3]);
+            }
+        }
+        std::vector<int32_t> slabs(2 * (size_t)W);
+        std::vector<uint64_t> send(W), recv(W), src_base(W);
+        shardPlanRows(rows.data(), W, bth, b.bty0, rank, slabs.data(), send.data(), recv.data(), src_base.data());
+        const int y0 = slabs[2 * rank], y1 = slabs[2 * rank + 1];
+        const int cj0 = (b.bty0 + y0) * BIN, cj1 = (b.bty0 + y1) * BIN;
+        uint64_t n_recv = 0, n_sent = 0;
+        for (int s = 0; s < W; ++s) { n_recv += recv[s]; if (s != rank) n_sent += send[s]; }
+        // the window of THIS rank: its slab rows + halo, the bbox columns (the other slabs never exist here)
+        {
+            const int ty0 = ((b.bty0 + y0) >> 1) - 1, ty1 = ((b.bty0 + y1 + 1) >> 1) + 1;
+            grid_.ensure(stream_, b.btx0 >> 1, ty0, ((b.btx0 + btw - 1) >> 1) + 1, ty1);
+        }
+        CK(cudaEventRecord(shardEv_[2], stream_));
+        // 4. all-to-all point routing: a slab's records are ONE contiguous range of the sender's bucket array (buckets are
+        //    row-major over the bbox), so the sorted array is the send buffer; grouped send/recv, the own share is a copy
+        recvD_.ensure((size_t)n_recv * 16 + 16);
+        {
+            const float4 *sorted = static_cast<const float4 *>(buf.d_records);
+            float4 *rb = recvD_.as<float4>();
+            uint64_t soff = 0;
+            ncclCheck(N.GroupStart(), "ncclGroupStart");
+            for (int p = 0; p < W; ++p)
+            {
+                if (p != rank)
+                {
+                    if (send[p]) ncclCheck(N.Send(sorted + soff, (size_t)send[p] * 4, ncclFloat, p, comm, stream_), "ncclSend(records)");
+                    if (recv[p]) ncclCheck(N.Recv(rb + src_base[p], (size_t)recv[p] * 4, ncclFloat, p, comm, stream_), "ncclRecv(records)");
+                }
+                else if (send[p])
+                    CK(cudaMemcpyAsync(rb + src_base[p], sorted + soff, (size_t)send[p] * 16, cudaMemcpyDeviceToDevice, stream_));
+                soff += send[p];
+            }
+            ncclCheck(N.GroupEnd(), "ncclGroupEnd");
+        }
+        CK(cudaEventRecord(shardEv_[3], stream_));
+        // 5. blank the slab + footprint halo, merge the sources' segments bin by bin in rank order, fold
+        shardBlankRows(cj0 - 2 * BIN, (y1 - y0) * BIN + 4 * BIN);
+        shardFold(recvD_.p, n_recv, countsAllD_.p, startsAllD_.p, src_base.data(), W, y0, y1, false);
+        CK(cudaEventRecord(shardEv_[4], stream_));
+        // 6. halo exchange, in place: r cell rows of moment records and flag bytes either side of each slab boundary, over
+        //    the bbox columns (row segments are contiguous in the row-major window)
+        uint64_t halo_bytes = 0;
+        if (W > 1)
+        {
+            const GridView &v = grid_.v;
+            const int col0 = b.btx0 * BIN - v.ci0, wcols = btw * BIN;
+            if (col0 < 0 || col0 + wcols > v.W) throw CudaError("sharded window does not cover the bbox columns");
+            auto mom_row = [&](int cj) { return v.mom + ((size_t)(cj - v.cj0) * v.W + col0) * REC; };
+            auto flag_row = [&](int cj) { return v.flags + (size_t)(cj - v.cj0) * v.W + col0; };
+            auto in_grid = [&](int cj) { return cj >= v.cj0 && cj < v.cj0 + v.H; };
+            ncclCheck(N.GroupStart(), "ncclGroupStart");
+            for (int k = 0; k < r_; ++k)
+            {
+                if (rank > 0)
+                {
+                    if (!in_grid(cj0 + k) || !in_grid(cj0 - r_ + k)) throw CudaError("halo rows outside the allocated window");
+                    ncclCheck(N.Send(mom_row(cj0 + k), (size_t)wcols * REC, ncclFloat, rank - 1, comm, stream_), "ncclSend(halo)");
+                    ncclCheck(N.Send(flag_row(cj0 + k), (size_t)wcols, ncclUint8, rank - 1, comm, stream_), "ncclSend(halo)");
+                    ncclCheck(N.Recv(mom_row(cj0 - r_ + k), (size_t)wcols * REC, ncclFloat, rank - 1, comm, stream_), "ncclRecv(halo)");
+                    ncclCheck(N.Recv(flag_row(cj0 - r_ + k), (size_t)wcols, ncclUint8, rank - 1, comm, stream_), "ncclRecv(halo)");
+                    halo_bytes += (uint64_t)wcols * 49;
+                }
+                if (rank < W - 1)
+                {
+                    if (!in_grid(cj1 - r_ + k) || !in_grid(cj1 + k)) throw CudaError("halo rows outside the allocated window");
+                    ncclCheck(N.Send(mom_row(cj1 - r_ + k), (size_t)wcols * REC, ncclFloat, rank + 1, comm, stream_), "ncclSend(halo)");
+                    ncclCheck(N.Send(flag_row(cj1 - r_ + k), (size_t)wcols, ncclUint8, rank + 1, comm, stream_), "ncclSend(halo)");
+                    ncclCheck(N.Recv(mom_row(cj1 + k), (size_t)wcols * REC, ncclFloat, rank + 1, comm, stream_), "ncclRecv(halo)");
+                    ncclCheck(N.Recv(flag_row(cj1 + k), (size_t)wcols, ncclUint8, rank + 1, comm, stream_), "ncclRecv(halo)");
+                    halo_bytes += (uint64_t)wcols * 49;
+                }
+            }
+            ncclCheck(N.GroupEnd(), "ncclGroupEnd");
+        }
+        CK(cudaEventRecord(shardEv_[5], stream_));
+        // 7. classify the slab; the received halo rows are not ours: drop their touched / changed bits afterwards
+        if (cb[0] != INT_MAX)
+            growLogical(cb[0], cb[1], cb[2], cb[3]);
+        {
+            std::vector<Op> none;
+            Plan pl = shardPlan_;
+            pl.n_ops = 0;
+            finishBatch(pl, none, t_begin);
+        }
+        if (W > 1)
+        {
+            const GridView &v = grid_.v;
+            const int col0 = b.btx0 * BIN - v.ci0, wcols = btw * BIN;
+            if (rank > 0)
+                CK(cudaMemset2DAsync(v.flags + (size_t)(cj0 - r_ - v.cj0) * v.W + col0, v.W, 0, wcols, r_, stream_));
+            if (rank < W - 1)
+                CK(cudaMemset2DAsync(v.flags + (size_t)(cj1 - v.cj0) * v.W + col0, v.W, 0, wcols, r_, stream_));
+        }
+        CK(cudaEventRecord(shardEv_[6], stream_));
+        CK(cudaStreamSynchronize(stream_));
+        if (info)
+        {
+            std::memset(info, 0, sizeof(*info));
+            info->bbox[0] = b.btx0; info->bbox[1] = b.bty0; info->bbox[2] = btw; info->bbox[3] = bth;
+            info->slab_y0 = y0; info->slab_y1 = y1; info->cj0 = cj0; info->cj1 = cj1;
+            info->local_records = buf.n_records; info->sent_records = n_sent; info->recv_records = n_recv;
+            info->halo_bytes = halo_bytes;
+            info->grid_bytes = (uint64_t)grid_.v.plane() * (REC * 4 + NUM_DER * 4 + 1);
+            for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&info->ms[k], shardEv_[k], shardEv_[k + 1]);
+            cudaEventElapsedTime(&info->ms[6], shardEv_[0], shardEv_[6]);
+            info->n_slabs = W;
+            for (int k = 0; k < 2 * W; ++k) info->slabs[k] = slabs[k];
+        }
     }
     int rOf() const { return r_; }
 
@@ -1417,6 +1712,11 @@ class LocalMap
     uint32_t *globD_ = nullptr;
     Plan shardPlan_;
     std::vector<Op> shardOps_;
+    void *comm_ = nullptr;  // ncclComm_t of the sharded job (tmap_shard_comm_init)
+    int rank_ = 0, world_ = 1;
+    cudaEvent_t shardEv_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    PinBuf shardH_, rowsH_;
+    DevBuf shardD_, rowsD_, countsAllD_, startsAllD_, recvD_;
 
   public:
     std::string takeWorkerError()
@@ -2194,6 +2494,44 @@ int tmap_shard_classify(tmap_system *s, uint64_t map_id, const int32_t cell_bbox
 int tmap_shard_clear_flag_rows(tmap_system *s, uint64_t map_id, int32_t cj, int32_t nrows)
 {
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardClearFlagsRows(cj, nrows); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_unique_id(uint8_t out_id[128])
+{
+    TMAP_API_BEGIN
+    tmb::NcclApi &N = tmb::NcclApi::get();
+    if (!N.ok()) throw tmb::Unsupported(N.error);
+    ncclUniqueId id;
+    ncclResult_t r = N.GetUniqueId(&id);
+    if (r != ncclSuccess) throw tmb::CudaError(std::string("ncclGetUniqueId: ") + N.GetErrorString(r));
+    std::memcpy(out_id, &id, 128);
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_shard_comm_init(tmap_system *s, uint64_t map_id, int32_t rank, int32_t world, const uint8_t id[128])
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardCommInit(rank, world, id); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_comm_destroy(tmap_system *s, uint64_t map_id)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardCommDestroy(); return TMAP_OK; TMAP_API_END
+}
+int tmap_shard_rebuild(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, tmap_shard_info *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    static_assert(sizeof(tmap_shard_info) == sizeof(tmb::LocalMap::ShardInfo), "layout");
+    mp->shardRebuild(kf_ids, n, poses, reinterpret_cast<tmb::LocalMap::ShardInfo *>(out));
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_shard_plan(const uint32_t *rows_all, int32_t world, int32_t n_rows, int32_t first_global_row, int32_t rank, int32_t *slabs,
+                    uint64_t *send, uint64_t *recv, uint64_t *src_base)
+{
+    TMAP_API_BEGIN
+    if (!rows_all || !slabs || !send || !recv || !src_base || world < 1 || rank < 0 || rank >= world)
+        throw std::invalid_argument("tmap_shard_plan: bad arguments");
+    tmb::LocalMap::shardPlanRows(rows_all, world, n_rows, first_global_row, rank, slabs, send, recv, src_base);
+    return TMAP_OK;
+    TMAP_API_END
 }
 
 }  // extern "C"

@@ -96,6 +96,14 @@ struct BatchView
     const uint32_t *nbr_count; // per-bin counts used for the candidate-list neighbour test (sharded: global totals)
     uint32_t split_thresh;     // bins with more records than this are split across CTAs by cell-row group
     int cand_y0, cand_y1;      // bbox-local bin rows [y0, y1) this process classifies / inflates (sharded: its slab)
+    // sharded fold: a bin's bucket is the concatenation, in source-rank order, of the segments the ranks sent -- read in
+    // place from the receive buffer (sh_world == 0: the bucket is b.sorted[tile_start .. + tile_count), one GPU)
+    const float4 *sh_recv;              // received records, grouped by source rank
+    const uint32_t *sh_counts;          // [world][nb] every rank's per-bin record count
+    const uint32_t *sh_starts;          // [world][nb] every rank's exclusive per-bin start in ITS bucket array
+    const unsigned long long *sh_src_base;  // [world] first record of each source inside sh_recv
+    int sh_world;
+    uint32_t sh_first;                  // first bin (bbox-local index) of this process's slab
 };
 
 struct ClassifyParams

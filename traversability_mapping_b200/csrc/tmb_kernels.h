@@ -18,6 +18,8 @@ cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridVi
                                const uint32_t *d_starts_all, const unsigned long long *d_src_base, int world, int y0, int y1,
                                uint32_t *d_glob, int dc, int di);
 
+cudaError_t launch_row_totals(cudaStream_t st, const BatchView &b, uint32_t *d_rows);
+
 size_t classify_smem_bytes(int r);
 size_t inflate_smem_bytes(int R, int n_taps);
 cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d, int n_disc);

@@ -1,7 +1,11 @@
 """Spatially sharded global map: one process per GPU (BASELINE north_star).
 
-The reference has no distributed path.  This module is the multi-GPU driver of the C ABI's tmap_shard_*
-entry points for a loop-closure style REBUILD of a global map whose keyframes are spread over the ranks:
+The reference has no distributed path.  The sharded rebuild itself is C++ behind ONE collective C-ABI call,
+tmap_shard_rebuild (csrc/runtime.cu: LocalMap::shardRebuild), which issues its NCCL collectives on the map's
+stream; this module is only the Python binding a test / bench process uses: it ships the 128-byte NCCL unique
+id to every rank (the one thing the library leaves to its host, as with MPI bootstrapping), keeps the host
+poses, and offers slab exports.  What the call does for a loop-closure style REBUILD of a global map whose
+keyframes are spread over the ranks:
 
   1. every rank transforms + keys + bucket-sorts ITS keyframes (k_hist / k_scatter) over a bbox of
      16-cell bins shared by all ranks, records ordered (bin, op, point);
@@ -17,8 +21,9 @@ entry points for a loop-closure style REBUILD of a global map whose keyframes ar
      boundary are exchanged in place with send/recv (rows are contiguous in the row-major grid);
   6. each rank classifies the bins of its slab (k_classify).
 
-The planning helpers are pure functions on CPU tensors so the N>1 logic is covered by gloo tests without
-a GPU (tests/test_sharding_gloo.py).  Step inflation is not available on a sharded map in this round.
+The planning helpers below are the numpy statement of the library's slab planner (tmap_shard_plan): the gloo tests
+(tests/test_sharding_gloo.py) check the C planner against them and run the exchange + merge on CPU tensors with
+world_size 2.  Step inflation is not available on a sharded map in this round.
 """
 import ctypes as C
 import math
@@ -111,20 +116,6 @@ def exchange_records(records, counts_all, btw, slabs, rank, dist, width=4, plan=
     return out, send, recv, src_base
 
 
-class _DevArray:
-    """Minimal __cuda_array_interface__ carrier so torch can alias library-owned device memory."""
-
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False), "version": 2}
-
-
-def _alias(ptr, n, typestr, torch):
-    if n == 0 or not ptr:
-        dt = {"<f4": torch.float32, "<i4": torch.int32, "|u1": torch.uint8}[typestr]
-        return torch.empty(0, dtype=dt, device="cuda")
-    return torch.as_tensor(_DevArray(ptr, n, typestr), device="cuda")
-
-
 def footprint_radius_cells(robot_radius, resolution):
     """Bounding radius of discOffsets (Helpers.cpp:156-169) in cells."""
     rc = max(1.0, robot_radius / resolution)
@@ -141,7 +132,7 @@ class ShardedMap:
     """One rank's share of a global map (CUDA + NCCL).  Keyframes are added locally; `rebuild()` is
     collective.  Rank k must hold a contiguous block of keyframe ids (all ids on rank k smaller than
     all ids on rank k+1) for the result to equal the single-GPU ascending-id rebuild bit for bit.
-    After a rebuild a rank's window is valid on its own slab rows (+ the footprint halo) only: read it through
+    After a rebuild a rank's window holds its own slab rows (+ the footprint halo) only: read it through
     `export_slab` / `gather_layer`, not through whole-window queries."""
 
     def __init__(self, params, rank=None, world=None):
@@ -158,8 +149,19 @@ class ShardedMap:
         self.poses = {}
         self.r = footprint_radius_cells(params.robot_radius, params.resolution)
         self.last = {}
+        # NCCL bootstrap: rank 0 draws the unique id, the process group (whatever backend it has) carries it
+        lib = self.sys._lib
+        uid = np.zeros(128, dtype=np.uint8)
+        if self.rank == 0:
+            tm._check(lib.tmap_shard_unique_id(uid.ctypes.data))
+        box = [uid.tobytes()]
+        if self.world > 1:
+            dist.broadcast_object_list(box, src=0)
+        uid = np.frombuffer(box[0], dtype=np.uint8).copy()
+        tm._check(lib.tmap_shard_comm_init(self.sys._h, 0, self.rank, self.world, uid.ctypes.data))
 
     def close(self):
+        self.sys._lib.tmap_shard_comm_destroy(self.sys._h, 0)
         self.sys.close()
 
     def add_keyframe(self, kf_id, cloud, timestamp_ns=0):
@@ -168,106 +170,34 @@ class ShardedMap:
     def set_pose(self, kf_id, pose):
         self.poses[int(kf_id)] = np.ascontiguousarray(np.asarray(pose, dtype=np.float32).reshape(-1)[:12])
 
+    def set_poses(self, kf_ids, poses):
+        """Bulk form of set_pose: the arrays are kept as they are and handed to the library at the next rebuild."""
+        self._ids = np.ascontiguousarray(kf_ids, dtype=np.uint64)
+        self._poses = np.ascontiguousarray(np.asarray(poses, dtype=np.float32).reshape(len(self._ids), -1)[:, :12])
+        self.poses = None
+
     # ------------------------------------------------------------------------------------------
     def rebuild(self, timing=None):
-        tm, torch, dist = self.tm, self.torch, self.dist
+        """Collective.  One call into the library (tmap_shard_rebuild); returns this rank's view of the result."""
+        tm = self.tm
         lib, h = self.sys._lib, self.sys._h
-        W, rank = self.world, self.rank
-        ids = np.array(sorted(self.poses), dtype=np.uint64)
-        poses = np.stack([self.poses[int(i)] for i in ids]).astype(np.float32) if len(ids) else np.zeros((0, 12), np.float32)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        ev = []
-
-        def mark(name):
-            if timing is not None:
-                e = torch.cuda.Event(enable_timing=True)
-                e.record()
-                ev.append((name, e))
-
-        mark("start")
-        # op ids unique over the job; bbox = union of every rank's keyframe windows (+1 bin candidate margin)
-        n_all = torch.zeros(W, dtype=torch.int64, device=dev)
-        n_all[rank] = len(ids)
-        win = (C.c_int32 * 4)(2 ** 31 - 1, 2 ** 31 - 1, -2 ** 31, -2 ** 31)
-        if len(ids):
-            tm._check(lib.tmap_shard_window(h, 0, ids.ctypes.data, len(ids), poses.ctypes.data, win))
-        meta = torch.tensor([win[0], win[1], -win[2], -win[3]], dtype=torch.int64, device=dev)
-        dist.all_reduce(n_all)
-        dist.all_reduce(meta, op=dist.ReduceOp.MIN)
-        op_base = int(n_all[:rank].sum())
-        m = meta.tolist()
-        margin = max(1, (self.r + BIN - 1) // BIN)
-        bbox = (C.c_int32 * 4)(m[0] - margin, m[1] - margin, -m[2] + margin, -m[3] + margin)
-        buf = tm.ShardBuffers()
-        tm._check(lib.tmap_shard_bin(h, 0, ids.ctypes.data, len(ids), poses.ctypes.data, op_base, bbox, C.byref(buf)))
-        mark("bin")
-        nb, btw, bth = buf.n_bins, buf.btw, buf.bth
-        counts = _alias(buf.d_bin_count, nb, "<i4", torch)
-        starts = _alias(buf.d_bin_start, nb, "<i4", torch)
-        counts_all = torch.empty((W, nb), dtype=torch.int32, device=dev)
-        starts_all = torch.empty((W, nb), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(counts_all, counts.contiguous())
-        dist.all_gather_into_tensor(starts_all, starts.contiguous())
-        # per-(rank, bin row) totals are formed on the device; only that small matrix goes to the host
-        rows_all = counts_all.view(W, bth, btw).sum(dim=2, dtype=torch.int64).cpu().numpy()
-        slabs = slab_boundaries(rows_all.sum(0), W, first_global_row=buf.bty0)
-        y0, y1 = slabs[rank]
-        # all-to-all point routing: the sorted array IS the send buffer (slab ranges are contiguous)
-        records = _alias(buf.d_records, buf.n_records * 4, "<f4", torch)
-        recv, send_s, recv_s, src_base = exchange_records(records, None, btw, slabs, rank, dist,
-                                                          plan=exchange_plan_rows(rows_all, slabs, rank))
-        torch.cuda.synchronize()
-        mark("alltoall")
-        src_base = np.ascontiguousarray(src_base, dtype=np.uint64)
-        # blank this rank's slab + footprint halo only (the window spans the whole map on every rank; rows outside
-        # the slab are not read until a later rebuild owns and blanks them)
-        blank0 = (buf.bty0 + y0) * BIN - 2 * BIN
-        tm._check(lib.tmap_shard_blank_rows(h, 0, blank0, (y1 - y0) * BIN + 4 * BIN))
-        tm._check(lib.tmap_shard_fold(h, 0, recv.data_ptr(), sum(recv_s), counts_all.data_ptr(), starts_all.data_ptr(),
-                                      src_base.ctypes.data, W, y0, y1))
-        mark("fold")
-        # halo exchange: r cell rows (moment records + flag bytes) across each slab boundary, in place
-        r = self.r
-        cj0, cj1 = (buf.bty0 + y0) * BIN, (buf.bty0 + y1) * BIN
-        ops, keep = [], []
-
-        def rows(kind, cj, n):
-            p, nbytes = C.c_void_p(0), C.c_size_t(0)
-            tm._check(lib.tmap_shard_rows(h, 0, kind, cj, n, C.byref(p), C.byref(nbytes)))
-            t = _alias(p.value, nbytes.value, "|u1", torch)
-            keep.append(t)
-            return t
-
-        halo_rows = []
-        if rank > 0:
-            for kind in (0, 1):
-                ops.append(dist.P2POp(dist.isend, rows(kind, cj0, r), rank - 1))
-                ops.append(dist.P2POp(dist.irecv, rows(kind, cj0 - r, r), rank - 1))
-            halo_rows.append((cj0 - r, r))
-        if rank < W - 1:
-            for kind in (0, 1):
-                ops.append(dist.P2POp(dist.isend, rows(kind, cj1 - r, r), rank + 1))
-                ops.append(dist.P2POp(dist.irecv, rows(kind, cj1, r), rank + 1))
-            halo_rows.append((cj1, r))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        torch.cuda.synchronize()
-        mark("halo")
-        cb = torch.tensor([buf.cell_bbox[0], -buf.cell_bbox[1], buf.cell_bbox[2], -buf.cell_bbox[3]], dtype=torch.int64, device=dev)
-        dist.all_reduce(cb, op=dist.ReduceOp.MIN)
-        c = cb.tolist()
-        cell_bbox = (C.c_int32 * 4)(c[0], -c[1], c[2], -c[3])
-        tm._check(lib.tmap_shard_classify(h, 0, cell_bbox))
-        for cj, n in halo_rows:  # received halo rows are not ours: drop their touched / changed bits
-            tm._check(lib.tmap_shard_clear_flag_rows(h, 0, cj, n))
-        mark("classify")
-        self.last = dict(slabs=slabs, bbox=(buf.btx0, buf.bty0, btw, bth), rows=(cj0, cj1), sent_records=sum(send_s) - send_s[rank],
-                         recv_records=sum(recv_s), local_records=int(buf.n_records), halo_bytes=len(halo_rows) * r * btw * BIN * 49)
+        if self.poses is None:
+            ids, poses = self._ids, self._poses
+        else:
+            ids = np.array(sorted(self.poses), dtype=np.uint64)
+            poses = (np.stack([self.poses[int(i)] for i in ids]).astype(np.float32) if len(ids)
+                     else np.zeros((0, 12), np.float32))
+        info = tm.ShardInfo()
+        tm._check(lib.tmap_shard_rebuild(h, 0, ids.ctypes.data, len(ids), poses.ctypes.data, C.byref(info)))
+        W = info.n_slabs
+        slabs = [(info.slabs[2 * k], info.slabs[2 * k + 1]) for k in range(W)]
+        stages = dict(zip(("bin", "plan", "alltoall", "fold", "halo", "classify", "total"), [float(x) for x in info.ms[:7]]))
         if timing is not None:
-            torch.cuda.synchronize()
-            for (_, a), (name, b_) in zip(ev[:-1], ev[1:]):
-                timing[name] = timing.get(name, 0.0) + a.elapsed_time(b_)
+            for k, v in stages.items():
+                timing[k] = timing.get(k, 0.0) + v
+        self.last = dict(slabs=slabs, bbox=tuple(info.bbox), rows=(info.cj0, info.cj1), sent_records=int(info.sent_records),
+                         recv_records=int(info.recv_records), local_records=int(info.local_records),
+                         halo_bytes=int(info.halo_bytes), grid_bytes=int(info.grid_bytes), stages_ms=stages)
         return self.last
 
     # ------------------------------------------------------------------------------------------
