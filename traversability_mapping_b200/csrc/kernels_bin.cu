@@ -740,11 +740,23 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
     uint16_t *s_cnt = reinterpret_cast<uint16_t *>(s_dyn);                // [T][NW]  per (bin, warp) counters / offsets
     uint32_t *s_base = reinterpret_cast<uint32_t *>(s_cnt + (size_t)T * NW);  // [T]  absolute slot of the chunk's first record per bin
     uint16_t *s_run = reinterpret_cast<uint16_t *>(s_base + T);           // [T]  records of this chunk already placed per bin
+    uint8_t *s_own = reinterpret_cast<uint8_t *>(s_run + T);              // [T]  rank that owns the bin (sharded scatter; else 0)
+    __shared__ unsigned long long s_rptr[32];                             // destination array per owner
+    __shared__ uint32_t s_roff[32];
+    __shared__ int s_ry1[32];
     for (uint32_t i = threadIdx.x; i < T; i += BIN_THREADS)
     {
         reinterpret_cast<uint4 *>(s_cnt)[i] = make_uint4(0u, 0u, 0u, 0u);
         s_run[i] = 0;
     }
+    if (threadIdx.x < 32)
+    {
+        const bool routed = b.rt_world > 0 && (int)threadIdx.x < b.rt_world;
+        s_rptr[threadIdx.x] = routed ? b.rt_ptr[threadIdx.x] : (unsigned long long)b.sorted;
+        s_roff[threadIdx.x] = routed ? b.rt_off[threadIdx.x] : 0u;
+        s_ry1[threadIdx.x] = routed ? b.rt_y1[threadIdx.x] : 0x7fffffff;
+    }
+    __syncthreads();
 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lt = (1u << lane) - 1u;
@@ -772,7 +784,10 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
     for (uint32_t t = threadIdx.x; t < T; t += BIN_THREADS)
     {
         const int gx = wtx0 + (int)(t % wtw) - b.btx0, gy = wty0 + (int)(t / wtw) - b.bty0;
-        s_base[t] = __ldg(b.tile_start + gy * b.btw + gx) + __ldg(b.op_start + s_op.tot_off + t) + __ldg(row + t);
+        uint32_t own = 0;
+        while (gy >= s_ry1[own]) ++own;  // slab of the bin's row (single GPU: s_ry1[0] = INT_MAX)
+        s_own[t] = (uint8_t)own;
+        s_base[t] = __ldg(b.tile_start + gy * b.btw + gx) + __ldg(b.op_start + s_op.tot_off + t) + __ldg(row + t) + s_roff[own];
     }
     __syncthreads();
 #pragma unroll 1
@@ -857,7 +872,9 @@ __global__ void __launch_bounds__(BIN_THREADS, 4) k_scatter(BatchView b, Lattice
             if (tl != 0xffffu)
             {
                 slot = my[tl * NW] + ((tk[r] >> 16) & 0x7fffu);
-                b.sorted[s_base[tl] + slot] = make_float4(px[r], py[r], pz[r], __uint_as_float(meta_op | cc[r]));
+                // single GPU: the bucket array; sharded: the owner's receive buffer (a peer-mapped pointer -> NVLink store)
+                reinterpret_cast<float4 *>(s_rptr[s_own[tl]])[s_base[tl] + slot] =
+                    make_float4(px[r], py[r], pz[r], __uint_as_float(meta_op | cc[r]));
             }
             __syncwarp();
             if (tl != 0xffffu && (tk[r] & 0x80000000u))  // highest lane of the group: its slot + 1 is the group's end
@@ -2823,7 +2840,7 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
     return cudaGetLastError();
 }
 
-static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 16 + (size_t)maxT * 4 + (size_t)maxT * 2 + 16; }
+static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 16 + (size_t)maxT * 4 + (size_t)maxT * 2 + (size_t)maxT + 32; }
 
 // TMB_FOLD: 3 = k_fold3 (default), 4 = k_fold4 (run sort; measured slower, kept for A/B), 0 / 1 = k_fold with match.any /
 // shared-memory bitmap ranks, 9 = the round-1 kernel;
@@ -2933,7 +2950,7 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,
                        int dc, int di, int n_sm, cudaEvent_t *ev /*[5] or null*/, int phases)
 {
-    // phases: bit0 = init + hist + scans + scatter, bit1 = fold
+    // phases: bit0 = hist + scans + scatter, bit1 = fold, bit2 (with bit0) = stop before the scatter, bit3 = the scatter alone
     // chunk tiers (planBatch picks the largest one that still gives every SM a few chunks): points per thread and chunk
     //   2  = 256 x 2 x 1 (a stream tick), 8 = 256 x 4 x 2, 32 = 256 x 4 x 8 (loop-closure scale)
     {
@@ -2975,6 +2992,9 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
         k_tile_starts<<<nblk, 256, 0, st>>>(b, g, dc, di);
     }
     if (ev) cudaEventRecord(ev[2], st);
+    }
+    if (((phases & 1) && !(phases & 4)) || (phases & 8))
+    {
     const bool emit = nb <= 4096;
     const size_t ssm = scatter_smem(maxT);
     if (ppt == 2)
@@ -3030,6 +3050,38 @@ __global__ void __launch_bounds__(256) k_row_totals(BatchView b, uint32_t *__res
         s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0)
         rows[row] = s;
+}
+
+// sharded rebuild: this process's cell bounding box (union of its ops' boxes) and its error flags -> out[0..4]
+__global__ void __launch_bounds__(256) k_ops_bbox(BatchView b, int32_t *__restrict__ out)
+{
+    __shared__ int s_v[4][8];
+    int v0 = INT_MAX, v1 = INT_MIN, v2 = INT_MAX, v3 = INT_MIN;
+    for (uint32_t i = threadIdx.x; i < b.n_ops; i += 256)
+    {
+        const int4 q = b.op_bbox[i];
+        if (q.x != INT_MAX) { v0 = min(v0, q.x); v1 = max(v1, q.y); v2 = min(v2, q.z); v3 = max(v3, q.w); }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        v0 = min(v0, __shfl_xor_sync(0xffffffffu, v0, o)); v1 = max(v1, __shfl_xor_sync(0xffffffffu, v1, o));
+        v2 = min(v2, __shfl_xor_sync(0xffffffffu, v2, o)); v3 = max(v3, __shfl_xor_sync(0xffffffffu, v3, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_v[0][threadIdx.x >> 5] = v0; s_v[1][threadIdx.x >> 5] = v1; s_v[2][threadIdx.x >> 5] = v2; s_v[3][threadIdx.x >> 5] = v3; }
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        for (int w = 1; w < 8; ++w) { v0 = min(v0, s_v[0][w]); v1 = max(v1, s_v[1][w]); v2 = min(v2, s_v[2][w]); v3 = max(v3, s_v[3][w]); }
+        out[0] = v0; out[1] = v1; out[2] = v2; out[3] = v3;
+        out[4] = (int32_t)b.counters[3];
+    }
+}
+
+cudaError_t launch_ops_bbox(cudaStream_t st, const BatchView &b, int32_t *d_out)
+{
+    k_ops_bbox<<<1, 256, 0, st>>>(b, d_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_row_totals(cudaStream_t st, const BatchView &b, uint32_t *d_rows)

@@ -73,6 +73,7 @@ struct DevBuf
         cap = want;
     }
     template <class T> T *as() const { return static_cast<T *>(p); }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
     ~DevBuf() { if (p) cudaFree(p); }
 };
 struct PinBuf
@@ -1250,7 +1251,7 @@ class LocalMap
     }
     // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
     void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out,
-                  bool ensure_grid = true)
+                  bool ensure_grid = true, bool counts_only = false)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
@@ -1259,8 +1260,10 @@ class LocalMap
         shardPlan_ = planBatch(shardOps_, forced, op_base, ensure_grid);
         uploadConstants();
         CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
-                      nSM_, nullptr, 1));
-        g_launches += 7;
+                      nSM_, nullptr, counts_only ? 5 : 1));
+        g_launches += counts_only ? 6 : 7;
+        if (counts_only)  // the caller routes the records itself (shardRebuild): no host round trip here
+            return;
         const size_t res_bytes = 64 + n * sizeof(int4);
         resH_.ensure(res_bytes + 64);
         const auto t_launched = std::chrono::steady_clock::now();
@@ -1394,6 +1397,12 @@ class LocalMap
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         if (!comm_) return;
         cudaStreamSynchronize(stream_);
+        for (size_t k = 0; k < peerPtr_.size(); ++k)
+            if ((int)k != rank_ && peerPtr_[k]) cudaIpcCloseMemHandle(peerPtr_[k]);
+        peerPtr_.clear();
+        peerGen_.clear();
+        for (auto &gr : recvGrave_) cudaFree(gr.second);
+        recvGrave_.clear();
         NcclApi::get().CommDestroy(static_cast<ncclComm_t>(comm_));
         comm_ = nullptr;
         for (auto &e : shardEv_) { if (e) cudaEventDestroy(e); e = nullptr; }
@@ -1452,14 +1461,19 @@ class LocalMap
         NcclApi &N = NcclApi::get();
         ncclComm_t comm = static_cast<ncclComm_t>(comm_);
         const int W = world_, rank = rank_;
+        if (W > 32) throw Unsupported("sharded rebuild: at most 32 ranks");
         CK(cudaSetDevice(P_.device));
         const auto t_begin = std::chrono::steady_clock::now();
+        static const bool dbg = std::getenv("TMB_SHARD_DEBUG") != nullptr;
+        // TMB_SHARD_ROUTE=0: bucket locally and route with grouped ncclSend / ncclRecv instead of the fused scatter (A/B runs)
+        static const bool fused = !(std::getenv("TMB_SHARD_ROUTE") && std::atoi(std::getenv("TMB_SHARD_ROUTE")) == 0);
+        auto trace = [&](const char *what) { if (dbg) { std::fprintf(stderr, "[shard %d/%d] %s\n", rank, W, what); std::fflush(stderr); } };
         CK(cudaEventRecord(shardEv_[0], stream_));
         // 1. job-wide op numbering and bbox: every rank's keyframe count and window in ONE all-gather of 8 int64
         int32_t win[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
         if (n) shardWindow(ids, n, poses, win);
-        shardH_.ensure(4096 + (size_t)W * 64);
-        shardD_.ensure(4096 + (size_t)W * 64);
+        shardH_.ensure(8192 + (size_t)W * 256);
+        shardD_.ensure(8192 + (size_t)W * 256);
         long long *mh = shardH_.as<long long>();
         mh[0] = (long long)n; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3]; mh[5] = mh[6] = mh[7] = 0;
         long long *md = shardD_.as<long long>();
@@ -1483,22 +1497,23 @@ class LocalMap
         if (u[0] == INT_MAX) throw std::invalid_argument("sharded rebuild without keyframes");
         const int margin = std::max(1, (r_ + BIN - 1) / BIN);
         const int32_t bbox[4] = {u[0] - margin, u[1] - margin, u[2] + margin, u[3] + margin};
-        // 2. bin this rank's keyframes over the shared bbox (k_hist / scans / k_scatter); the grid is not touched yet
+        // 2. key pass + scans over the shared bbox for this rank's keyframes: per-bin counts and every record's slot in
+        //    this rank's (virtual) bucket array.  The grid is not touched yet and no record has moved.
         ShardBuffers buf{};
-        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false);
-        CK(cudaEventRecord(shardEv_[1], stream_));
-        const BatchView &b = shardPlan_.b;
+        trace("meta exchanged");
+        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false, true);
+        BatchView &b = shardPlan_.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const int bth = b.bth, btw = b.btw;
-        // 3. per-row totals (+ this rank's cell bbox) of every rank -> host (slab plan); per-bin counts / starts of every
-        //    rank stay on the device (merge)
-        const size_t rw = (size_t)bth + 4;  // u32 per rank
+        // 3. per-row totals + this rank's cell bbox + its error flags of every rank -> host (slab plan); per-bin counts and
+        //    starts of every rank stay on the device (the fold's segment tables)
+        const size_t rw = (size_t)bth + 8;  // u32 per rank
         rowsD_.ensure((rw + (size_t)W * rw) * 4 + 64);
         rowsH_.ensure((size_t)W * rw * 4 + 64);
         uint32_t *rowsMine = rowsD_.as<uint32_t>(), *rowsAll = rowsMine + rw;
         CK(launch_row_totals(stream_, b, rowsMine));
-        g_launches += 1;
-        CK(cudaMemcpyAsync(rowsMine + bth, buf.cell_bbox, 16, cudaMemcpyHostToDevice, stream_));
+        CK(launch_ops_bbox(stream_, b, reinterpret_cast<int32_t *>(rowsMine + bth)));
+        g_launches += 2;
         ncclCheck(N.AllGather(rowsMine, rowsAll, rw, ncclUint32, comm, stream_), "ncclAllGather(rows)");
         CK(cudaMemcpyAsync(rowsH_.p, rowsAll, (size_t)W * rw * 4, cudaMemcpyDeviceToHost, stream_));
         g_d2h += (uint64_t)W * rw * 4;
@@ -1508,39 +1523,132 @@ class LocalMap
         ncclCheck(N.AllGather(b.tile_count, countsAllD_.p, nb, ncclUint32, comm, stream_), "ncclAllGather(counts)");
         ncclCheck(N.AllGather(b.tile_start, startsAllD_.p, nb, ncclUint32, comm, stream_), "ncclAllGather(starts)");
         ncclCheck(N.GroupEnd(), "ncclGroupEnd");
+        CK(cudaEventRecord(shardEv_[1], stream_));
         CK(cudaStreamSynchronize(stream_));
         std::vector<uint32_t> rows((size_t)W * bth);
         int32_t cb[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+        uint32_t err_flags = 0;
         for (int s = 0; s < W; ++s)
         {
             const uint32_t *src = rowsH_.as<uint32_t>() + (size_t)s * rw;
             std::memcpy(rows.data() + (size_t)s * bth, src, (size_t)bth * 4);
-            int32_t c4[4];
-            std::memcpy(c4, src + bth, 16);
-            if (c4[0] != INT_MAX)
+            int32_t c5[5];
+            std::memcpy(c5, src + bth, 20);
+            if (c5[0] != INT_MAX)
             {
-                cb[0] = std::min(cb[0], c4[0]); cb[1] = std::max(cb[1], c4[1]);
-                cb[2] = std::min(cb[2], c4[2]); cb[3] = std::max(cb[3], c4[3]);
+                cb[0] = std::min(cb[0], c5[0]); cb[1] = std::max(cb[1], c5[1]);
+                cb[2] = std::min(cb[2], c5[2]); cb[3] = std::max(cb[3], c5[3]);
             }
+            err_flags |= (uint32_t)c5[4];
         }
+        trace("rows gathered");
+        if (err_flags)
+            throw CudaError("binning consistency check failed on some rank (flags " + std::to_string(err_flags) + ")");
         std::vector<int32_t> slabs(2 * (size_t)W);
         std::vector<uint64_t> send(W), recv(W), src_base(W);
         shardPlanRows(rows.data(), W, bth, b.bty0, rank, slabs.data(), send.data(), recv.data(), src_base.data());
         const int y0 = slabs[2 * rank], y1 = slabs[2 * rank + 1];
         const int cj0 = (b.bty0 + y0) * BIN, cj1 = (b.bty0 + y1) * BIN;
-        uint64_t n_recv = 0, n_sent = 0;
-        for (int s = 0; s < W; ++s) { n_recv += recv[s]; if (s != rank) n_sent += send[s]; }
+        uint64_t n_recv = 0, n_sent = 0, n_local = 0;
+        for (int s = 0; s < W; ++s) { n_recv += recv[s]; n_local += send[s]; if (s != rank) n_sent += send[s]; }
         // the window of THIS rank: its slab rows + halo, the bbox columns (the other slabs never exist here)
         {
             const int ty0 = ((b.bty0 + y0) >> 1) - 1, ty1 = ((b.bty0 + y1 + 1) >> 1) + 1;
             grid_.ensure(stream_, b.btx0 >> 1, ty0, ((b.btx0 + btw - 1) >> 1) + 1, ty1);
         }
-        CK(cudaEventRecord(shardEv_[2], stream_));
-        // 4. all-to-all point routing: a slab's records are ONE contiguous range of the sender's bucket array (buckets are
-        //    row-major over the bbox), so the sorted array is the send buffer; grouped send/recv, the own share is a copy
-        recvD_.ensure((size_t)n_recv * 16 + 16);
+        // 4. receive buffers: one per rank, mapped into every peer (CUDA IPC); handles travel only when a buffer was
+        //    reallocated.  rt_off[k] turns a slot of my bucket array into a slot of rank k's buffer: my records of k's slab
+        //    land behind those of the lower ranks, in my bucket order.
+        for (auto it = recvGrave_.begin(); it != recvGrave_.end();)  // buffers replaced two or more rebuilds ago: unmapped everywhere
         {
-            const float4 *sorted = static_cast<const float4 *>(buf.d_records);
+            if (it->first + 2 <= shardStep_) { cudaFree(it->second); it = recvGrave_.erase(it); }
+            else ++it;
+        }
+        ++shardStep_;
+        if (recvD_.cap < (size_t)n_recv * 16 + 16)
+        {
+            if (recvD_.p) recvGrave_.emplace_back(shardStep_, recvD_.p);  // the peers still map it until they see the new handle
+            recvD_.p = nullptr;
+            recvD_.cap = 0;
+            recvD_.ensure((size_t)n_recv * 16 + (size_t)n_recv * 4 + 4096);  // 25 % spare: slab loads move a little from rebuild to rebuild
+            ++recvGen_;
+        }
+        if (fused)
+        {
+            struct HandleMsg { unsigned long long gen; cudaIpcMemHandle_t h; unsigned char pad[128 - 8 - sizeof(cudaIpcMemHandle_t)]; };
+            static_assert(sizeof(HandleMsg) == 128, "handle message");
+            HandleMsg *hm = reinterpret_cast<HandleMsg *>(shardH_.as<unsigned char>() + 4096);
+            HandleMsg *hd = reinterpret_cast<HandleMsg *>(shardD_.as<unsigned char>() + 4096);
+            std::memset(hm, 0, sizeof(HandleMsg));
+            hm[0].gen = recvGen_;
+            if (W > 1) CK(cudaIpcGetMemHandle(&hm[0].h, recvD_.p));
+            CK(cudaMemcpyAsync(hd, hm, sizeof(HandleMsg), cudaMemcpyHostToDevice, stream_));
+            ncclCheck(N.AllGather(hd, hd + 1, sizeof(HandleMsg), ncclUint8, comm, stream_), "ncclAllGather(handles)");
+            CK(cudaMemcpyAsync(hm + 1, hd + 1, (size_t)W * sizeof(HandleMsg), cudaMemcpyDeviceToHost, stream_));
+            CK(cudaStreamSynchronize(stream_));
+            trace("handles gathered");
+            peerPtr_.resize(W, nullptr);
+            peerGen_.resize(W, 0);
+            for (int k = 0; k < W; ++k)
+            {
+                if (k == rank) { peerPtr_[k] = recvD_.p; continue; }
+                const HandleMsg &m = hm[1 + k];
+                if (peerGen_[k] != m.gen || !peerPtr_[k])
+                {
+                    if (peerPtr_[k]) CK(cudaIpcCloseMemHandle(peerPtr_[k]));
+                    void *p = nullptr;
+                    CK(cudaIpcOpenMemHandle(&p, m.h, cudaIpcMemLazyEnablePeerAccess));
+                    peerPtr_[k] = p;
+                    peerGen_[k] = m.gen;
+                }
+            }
+            trace("peer buffers mapped");
+            // routing tables: [ptr u64 x W][off u32 x W][y1 i32 x W] in one small upload
+            unsigned char *th = shardH_.as<unsigned char>() + 2048;
+            unsigned long long *tp = reinterpret_cast<unsigned long long *>(th);
+            uint32_t *to = reinterpret_cast<uint32_t *>(th + 8 * W);
+            int32_t *ty = reinterpret_cast<int32_t *>(th + 12 * W);
+            // my records sent to k start, in MY bucket array, at the first slot of k's slab = sum of my rows below it
+            uint64_t my_first = 0;
+            for (int k = 0; k < W; ++k)
+            {
+                uint64_t base_at_k = 0;  // records rank k receives from the ranks below me
+                for (int s = 0; s < rank; ++s)
+                    for (int y = slabs[2 * k]; y < slabs[2 * k + 1]; ++y) base_at_k += rows[(size_t)s * bth + y];
+                tp[k] = reinterpret_cast<unsigned long long>(peerPtr_[k]);
+                to[k] = (uint32_t)(base_at_k - my_first);  // modulo 2^32: slots stay below 2^32 on both sides
+                ty[k] = slabs[2 * k + 1];
+                my_first += send[k];
+            }
+            unsigned char *td = shardD_.as<unsigned char>() + 2048;
+            CK(cudaMemcpyAsync(td, th, (size_t)16 * W, cudaMemcpyHostToDevice, stream_));
+            b.rt_ptr = reinterpret_cast<const unsigned long long *>(td);
+            b.rt_off = reinterpret_cast<const uint32_t *>(td + 8 * W);
+            b.rt_y1 = reinterpret_cast<const int *>(td + 12 * W);
+            b.rt_world = W;
+        }
+        CK(cudaEventRecord(shardEv_[2], stream_));
+        if (fused)
+        {
+            // 5. the scatter IS the all-to-all: every record is written once, straight into its owner's receive buffer
+            //    (NVLink stores through the peer mapping; the own slab's records into the own buffer).  A tiny all-gather
+            //    afterwards is the "every peer has finished writing into my buffer" barrier.
+            CK(launch_bin(stream_, b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di, nSM_,
+                          nullptr, 8));
+            g_launches += 1;
+            b.rt_world = 0;
+            uint32_t *fl = reinterpret_cast<uint32_t *>(shardD_.as<unsigned char>() + 3072);
+            CK(cudaMemcpyAsync(fl, b.counters + 3, 4, cudaMemcpyDeviceToDevice, stream_));
+            ncclCheck(N.AllGather(fl, fl + 1, 1, ncclUint32, comm, stream_), "ncclAllGather(barrier)");
+        }
+        else
+        {
+            // 5'. bucket locally, then grouped ncclSend / ncclRecv: a slab's records are one contiguous range of the sender's
+            //     bucket array
+            CK(launch_bin(stream_, b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di, nSM_,
+                          nullptr, 8));
+            g_launches += 1;
+            const float4 *sorted = b.sorted;
             float4 *rb = recvD_.as<float4>();
             uint64_t soff = 0;
             ncclCheck(N.GroupStart(), "ncclGroupStart");
@@ -1558,11 +1666,12 @@ class LocalMap
             ncclCheck(N.GroupEnd(), "ncclGroupEnd");
         }
         CK(cudaEventRecord(shardEv_[3], stream_));
-        // 5. blank the slab + footprint halo, merge the sources' segments bin by bin in rank order, fold
+        trace("records routed (enqueued)");
+        // 6. blank the slab + footprint halo; fold: a bin's bucket = the sources' segments in rank order, read in place
         shardBlankRows(cj0 - 2 * BIN, (y1 - y0) * BIN + 4 * BIN);
         shardFold(recvD_.p, n_recv, countsAllD_.p, startsAllD_.p, src_base.data(), W, y0, y1, false);
         CK(cudaEventRecord(shardEv_[4], stream_));
-        // 6. halo exchange, in place: r cell rows of moment records and flag bytes either side of each slab boundary, over
+        // 7. halo exchange, in place: r cell rows of moment records and flag bytes either side of each slab boundary, over
         //    the bbox columns (row segments are contiguous in the row-major window)
         uint64_t halo_bytes = 0;
         if (W > 1)
@@ -1598,7 +1707,7 @@ class LocalMap
             ncclCheck(N.GroupEnd(), "ncclGroupEnd");
         }
         CK(cudaEventRecord(shardEv_[5], stream_));
-        // 7. classify the slab; the received halo rows are not ours: drop their touched / changed bits afterwards
+        // 8. classify the slab; the received halo rows are not ours: drop their touched / changed bits afterwards
         if (cb[0] != INT_MAX)
             growLogical(cb[0], cb[1], cb[2], cb[3]);
         {
@@ -1618,12 +1727,13 @@ class LocalMap
         }
         CK(cudaEventRecord(shardEv_[6], stream_));
         CK(cudaStreamSynchronize(stream_));
+        trace("rebuild done");
         if (info)
         {
             std::memset(info, 0, sizeof(*info));
             info->bbox[0] = b.btx0; info->bbox[1] = b.bty0; info->bbox[2] = btw; info->bbox[3] = bth;
             info->slab_y0 = y0; info->slab_y1 = y1; info->cj0 = cj0; info->cj1 = cj1;
-            info->local_records = buf.n_records; info->sent_records = n_sent; info->recv_records = n_recv;
+            info->local_records = n_local; info->sent_records = n_sent; info->recv_records = n_recv;
             info->halo_bytes = halo_bytes;
             info->grid_bytes = (uint64_t)grid_.v.plane() * (REC * 4 + NUM_DER * 4 + 1);
             for (int k = 0; k < 6; ++k) cudaEventElapsedTime(&info->ms[k], shardEv_[k], shardEv_[k + 1]);
@@ -1717,6 +1827,11 @@ class LocalMap
     cudaEvent_t shardEv_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     PinBuf shardH_, rowsH_;
     DevBuf shardD_, rowsD_, countsAllD_, startsAllD_, recvD_;
+    std::vector<std::pair<uint64_t, void *>> recvGrave_;  // replaced receive buffers, freed once no peer can still map them
+    uint64_t shardStep_ = 0;
+    unsigned long long recvGen_ = 1;       // bumped whenever recvD_ is reallocated: peers re-open its IPC handle
+    std::vector<void *> peerPtr_;          // every rank's receive buffer as mapped into this process
+    std::vector<unsigned long long> peerGen_;
 
   public:
     std::string takeWorkerError()

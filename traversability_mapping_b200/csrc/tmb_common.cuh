@@ -104,6 +104,12 @@ struct BatchView
     const unsigned long long *sh_src_base;  // [world] first record of each source inside sh_recv
     int sh_world;
     uint32_t sh_first;                  // first bin (bbox-local index) of this process's slab
+    // sharded scatter: a record goes straight into the receive buffer of the rank that owns its bin row, through a
+    // peer-mapped pointer (NVLink store); rt_world == 0: into b.sorted
+    const unsigned long long *rt_ptr;   // [world] receive buffer of every rank as mapped into THIS process
+    const uint32_t *rt_off;             // [world] added (mod 2^32) to the local bucket slot -> slot in the owner's buffer
+    const int *rt_y1;                   // [world] exclusive last bin row (bbox-local) of every rank's slab
+    int rt_world;
 };
 
 struct ClassifyParams

@@ -19,6 +19,7 @@ cudaError_t launch_shard_merge(cudaStream_t st, const BatchView &b, const GridVi
                                uint32_t *d_glob, int dc, int di);
 
 cudaError_t launch_row_totals(cudaStream_t st, const BatchView &b, uint32_t *d_rows);
+cudaError_t launch_ops_bbox(cudaStream_t st, const BatchView &b, int32_t *d_out /*[5]: min ci, max ci, min cj, max cj, error flags*/);
 
 size_t classify_smem_bytes(int r);
 size_t inflate_smem_bytes(int R, int n_taps);
