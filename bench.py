@@ -206,7 +206,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--keyframes", type=int, default=C4_KEYFRAMES)
-    ap.add_argument("--cpu-keyframes", type=int, default=48, help="keyframes in the CPU arm's bounded sample")
+    ap.add_argument("--cpu-keyframes", type=int, default=160, help="keyframes in the CPU arm's bounded sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C2 / C3 secondary legs")
     ap.add_argument("--c2-steps", type=int, default=12)
@@ -272,8 +272,9 @@ def main():
             traffic, tsrc = None, None
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["c4_loop_closure"]
-                traffic = tj[KNAME[dom]]["dram_bytes_per_launch"]
-                tsrc = "profiles/r02_traffic.json (ncu --set full of this workload)"
+                hit = [v for k, v in tj.items() if k.startswith(KNAME[dom])]
+                traffic = hit[0]["dram_bytes_per_launch"]
+                tsrc = "profiles/r02_traffic.json (ncu --set full of this workload, same kernel)"
             except Exception:
                 pass
             bin_ms = st["ms_hist"] + st["ms_scan"] + st["ms_scatter"] + st["ms_fold"]
@@ -288,6 +289,22 @@ def main():
                     "binning_pipeline": {"algorithmic_bytes": 16.0 * P_ + 80.0 * ct, "ms": bin_ms,
                                          "frac_of_hbm": (16.0 * P_ + 80.0 * ct) / (bin_ms * 1e-3) / 1e9 / peak},
                     "host_ms_per_step": out.get("host_ms_per_step")}
+        if roof is None and "sharded" in out:
+            # N > 1: the dominant stage on rank 0 is the fold of its slab (k_fold3, HBM-bound): 16 B per received record +
+            # 80 B per touched cell over that stage's CUDA-event time (the stage also holds the slab blanking memsets)
+            sh = out["sharded"]
+            fb = 16.0 * sh["recv_records_rank0"] + 80.0 * sh["cells_touched_rank0"]
+            fms = sh["stages_ms_rank0"].get("fold", 0.0)
+            if fms > 0:
+                ach = fb / (fms * 1e-3) / 1e9
+                roof = {"bound": "hbm", "kernel": "k_fold3 (rank 0: blank + fold of its slab)", "achieved": ach, "peak": peak, "unit": "GB/s",
+                        "frac": ach / peak, "traffic": None, "traffic_source": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": fb, "avg_launch_ms": fms, "launches_per_step": 1,
+                        "stages_ms_per_step": sh["stages_ms_rank0"],
+                        "routing": {"note": "k_scatter writes records straight into the owners' receive buffers (NVLink stores through "
+                                            "CUDA-IPC peer mappings); stage 'alltoall' = that kernel + the completion barrier",
+                                    "remote_bytes_rank0": 16.0 * sh["sent_records_rank0"],
+                                    "remote_gbs_rank0": sh.get("alltoall_gbs_rank0_out")}}
         cpu = None
         if not args.no_cpu:
             cores = os.cpu_count() or 1
@@ -478,11 +495,11 @@ def bench_c4_sharded(tm, synth, torch, dist, local, rank, world, nk, true, drift
     for i, c in gen_host_clouds(SEED + 1, mine, true, C4_RINGS, C4_AZ, "cuda"):
         assert sm.add_keyframe(i + 1, c) == tm.OK
     st0 = sm.map.stats()
+    my_ids = np.array([i + 1 for i in mine], dtype=np.uint64)
     ms, info, tim_sum = [], None, {}
     for rep in range(Wm + K):
         target = true if rep % 2 == 0 else drift
-        for i in mine:
-            sm.set_pose(i + 1, target[i])
+        sm.set_poses(my_ids, target[mine])
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -510,6 +527,9 @@ def bench_c4_sharded(tm, synth, torch, dist, local, rank, world, nk, true, drift
            "gpu_launches": int(pts[2]), "parallelism": "sharded%d: slabs of bin rows, all-to-all point routing, halo exchange" % world,
            "shard_parity": parity,
            "sharded": {"routed_points": int(pts[1]), "stages_ms_rank0": tim_sum, "slabs": info["slabs"],
+                       "recv_records_rank0": int(info["recv_records"]), "sent_records_rank0": int(info["sent_records"]),
+                       "cells_touched_rank0": int(st1["last_batch_cells_touched"]), "grid_bytes_rank0": int(info["grid_bytes"]),
+                       "host_code": "C++ (tmap_shard_rebuild): NCCL all-gathers + CUDA-IPC peer-mapped receive buffers, one call per rank",
                        "alltoall_gbs_rank0_out": (sent_bytes_rank0 / (a2a_ms * 1e-3) / 1e9) if a2a_ms > 0 else None,
                        "parity_check": {"keyframes": parity_kf, "cells": parity_cells, "bit_identical_to_1_gpu": parity}},
            # end to end for the sharded job: the step already starts from host poses (set_pose takes host arrays; they ride the op
@@ -520,8 +540,7 @@ def bench_c4_sharded(tm, synth, torch, dist, local, rank, world, nk, true, drift
     d2h = 0
     for rep in range(1 + K):
         target = true if rep % 2 == 1 else drift
-        for i in mine:
-            sm.set_pose(i + 1, target[i])
+        sm.set_poses(my_ids, target[mine])
         barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
