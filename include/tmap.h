@@ -318,6 +318,14 @@ int tmap_shard_comm_init(tmap_system *s, uint64_t map_id, int32_t rank, int32_t 
 int tmap_shard_comm_destroy(tmap_system *s, uint64_t map_id);
 int tmap_shard_rebuild(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12,
                        tmap_shard_info *out);
+/* Collective pose update on a sharded map: the listed keyframes of this rank (ascending ids; n may be 0) move to new poses.
+ * One batch over the job = System::updateKeyFrame for each of them (System.cpp:216-232 -> LocalMap::recomputeKeyFrame,
+ * LocalMap.cpp:245-315): each keyframe is subtracted at the pose it is integrated at and added at the new one, records are
+ * routed to the owners of the LAST rebuild's slabs (cells keep their owners), nothing is blanked and only the dirty cells
+ * (touched, dilated by the footprint, across slab boundaries through the halo rows) are re-classified.  Bit-identical to the
+ * same batch on one GPU (max_batch = 0). */
+int tmap_shard_update(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12,
+                      tmap_shard_info *out);
 /* the slab planner alone (pure host function; rows_all[s * n_rows + y] = records rank s holds in bin row y) */
 int tmap_shard_plan(const uint32_t *rows_all, int32_t world, int32_t n_rows, int32_t first_global_row, int32_t rank,
                     int32_t *slabs /*[2*world]*/, uint64_t *send /*[world]*/, uint64_t *recv /*[world]*/,

@@ -65,6 +65,30 @@ if rank == 0:
             ok = False
     occ = int(np.sum(~np.isnan(got["N"])))
     print(f"world={world} keyframes={n_kf} occupied={occ} slabs={info['slabs']} bit-identical={ok} timing_ms={ {k: round(v, 3) for k, v in timing.items()} }")
+
+# ---- incremental pose update on the sharded map (tmap_shard_update) vs the same batch on one GPU -------------------
+# every third keyframe moves (a PGO message); one rank may own none of them.  Subtract + add on the slabs of the rebuild.
+moved = [i for i in range(n_kf) if i % 3 == 1]
+new_poses = synth.drift_poses(poses)
+mine_moved = [i for i in moved if i // per == rank]
+uinfo = sm.update([i + 1 for i in mine_moved], new_poses[mine_moved] if mine_moved else np.zeros((0, 3, 4), np.float32))
+got2 = {}
+for l in layers:
+    got2[l], origin2 = sm.gather_layer(l)
+if rank == 0:
+    with m.locked():            # ONE batch, ascending ids: subtract at the integrated pose, add at the new one
+        s.updateKeyFrames(np.array([i + 1 for i in moved], dtype=np.uint64), new_poses[moved])
+    s.flush()
+    h2, w2 = got2[layers[0]].shape
+    ok2 = True
+    for l in layers:
+        ref = m.exportDense(l, origin2[0], origin2[1], w2, h2)
+        if not helpers.bits_equal(got2[l], ref):
+            bad = (np.isnan(got2[l]) != np.isnan(ref)) | (~np.isnan(ref) & (got2[l] != ref))
+            print(f"after update, layer {l}: {int(bad.sum())} cells differ")
+            ok2 = False
+    print(f"pose update of {len(moved)} keyframes on the sharded map: bit-identical={ok2} slabs={uinfo['slabs']}")
+    ok = ok and ok2
     s.close()
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.broadcast(flag, 0)

@@ -143,6 +143,7 @@ _SIG = {
     "tmap_shard_comm_init": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "tmap_shard_comm_destroy": (C.c_int, [_P, C.c_uint64]),
     "tmap_shard_rebuild": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(ShardInfo)]),
+    "tmap_shard_update": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(ShardInfo)]),
     "tmap_shard_plan": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p,
                                   C.c_void_p]),
 }

@@ -2975,14 +2975,17 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     {
     // counters and per-op bboxes arrive initialised with the batch's single host-to-device copy
     if (ev) cudaEventRecord(ev[0], st);
-    if (ppt == 2)
+    // (a rank of a sharded pass may hold no keyframe at all: nothing to key, but its per-bin counts must still be zeroed)
+    if (b.n_chunks == 0) { }
+    else if (ppt == 2)
         k_hist<2, 1><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     else if (ppt == 8)
         k_hist<4, 2><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     else
         k_hist<4, 8><<<b.n_chunks, BIN_THREADS, maxT * 4, st>>>(b, lat);
     if (ev) cudaEventRecord(ev[1], st);
-    k_scan_chunks<<<dim3((maxT + 31) / 32, b.n_ops), 256, 0, st>>>(b);
+    if (b.n_ops)
+        k_scan_chunks<<<dim3((maxT + 31) / 32, b.n_ops), 256, 0, st>>>(b);
     if (nb <= 4096)
         k_scan_small<<<1, 1024, 0, st>>>(b);
     else
@@ -2997,7 +3000,8 @@ cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, c
     {
     const bool emit = nb <= 4096;
     const size_t ssm = scatter_smem(maxT);
-    if (ppt == 2)
+    if (b.n_chunks == 0) { }
+    else if (ppt == 2)
     {
         if (emit) k_scatter<2, 1, true><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);
         else k_scatter<2, 1, false><<<b.n_chunks, BIN_THREADS, ssm, st>>>(b, lat, g, dc, di);

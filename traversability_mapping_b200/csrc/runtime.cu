@@ -1251,11 +1251,11 @@ class LocalMap
     }
     // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
     void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out,
-                  bool ensure_grid = true, bool counts_only = false)
+                  bool ensure_grid = true, bool counts_only = false, const std::vector<Op> *prebuilt = nullptr)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
-        shardOps_ = shardOps(ids, n, poses);
+        shardOps_ = prebuilt ? *prebuilt : shardOps(ids, n, poses);
         const int forced[4] = {bbox[0], bbox[1], bbox[2], bbox[3]};
         shardPlan_ = planBatch(shardOps_, forced, op_base, ensure_grid);
         uploadConstants();
@@ -1453,7 +1453,11 @@ class LocalMap
             run += t;
         }
     }
-    void shardRebuild(const uint64_t *ids, size_t n, const float *poses, ShardInfo *info)
+    // update == false: rebuild from blank (LocalMap::clearEntireMap + re-integration, LocalMap.cpp:375-397), slabs re-planned.
+    // update == true : the listed keyframes move (LocalMap::recomputeKeyFrame for each of them, LocalMap.cpp:245-315, as ONE
+    //                  batch): subtract at the pose each is integrated at, add at the new one; the slabs of the last rebuild
+    //                  stay (cells keep their owners), nothing is blanked, only dirty cells are re-classified.
+    void shardRebuild(const uint64_t *ids, size_t n, const float *poses, ShardInfo *info, bool update = false)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         if (!comm_) throw std::invalid_argument("tmap_shard_comm_init has not been called on this map");
@@ -1470,12 +1474,46 @@ class LocalMap
         auto trace = [&](const char *what) { if (dbg) { std::fprintf(stderr, "[shard %d/%d] %s\n", rank, W, what); std::fflush(stderr); } };
         CK(cudaEventRecord(shardEv_[0], stream_));
         // 1. job-wide op numbering and bbox: every rank's keyframe count and window in ONE all-gather of 8 int64
+        if (update && shardCuts_.size() != (size_t)W + 1)
+            throw std::invalid_argument("tmap_shard_update needs a map built by tmap_shard_rebuild");
+        std::vector<Op> ops;
+        std::vector<std::shared_ptr<KeyFrame>> moved;
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            for (size_t i = 0; i < n; ++i)
+            {
+                auto it = kfs_.find(ids[i]);
+                if (it == kfs_.end()) throw std::invalid_argument("unknown keyframe id in shard op list");
+                if (update && it->second->integrated)
+                {
+                    Op sub;
+                    sub.kf = it->second;
+                    std::memcpy(sub.pose, it->second->intPose, sizeof(sub.pose));
+                    sub.sign = -1.f;
+                    ops.push_back(sub);
+                }
+                Op add;
+                add.kf = it->second;
+                std::memcpy(add.pose, poses + 12 * i, sizeof(add.pose));
+                add.sign = +1.f;
+                ops.push_back(add);
+                moved.push_back(it->second);
+            }
+            if (!update)  // a rebuild drops every contribution: keyframes not listed are no longer integrated
+                for (auto &kv : kfs_) kv.second->integrated = false;
+        }
+        const size_t n_ops_local = ops.size();
         int32_t win[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
-        if (n) shardWindow(ids, n, poses, win);
+        for (auto &op : ops)
+        {
+            int x0, y0w, x1, y1w;
+            opWindow(op, x0, y0w, x1, y1w);
+            win[0] = std::min(win[0], x0); win[1] = std::min(win[1], y0w); win[2] = std::max(win[2], x1); win[3] = std::max(win[3], y1w);
+        }
         shardH_.ensure(8192 + (size_t)W * 256);
         shardD_.ensure(8192 + (size_t)W * 256);
         long long *mh = shardH_.as<long long>();
-        mh[0] = (long long)n; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3]; mh[5] = mh[6] = mh[7] = 0;
+        mh[0] = (long long)n_ops_local; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3]; mh[5] = mh[6] = mh[7] = 0;
         long long *md = shardD_.as<long long>();
         CK(cudaMemcpyAsync(md, mh, 64, cudaMemcpyHostToDevice, stream_));
         ncclCheck(N.AllGather(md, md + 8, 8, ncclInt64, comm, stream_), "ncclAllGather(meta)");
@@ -1496,12 +1534,18 @@ class LocalMap
         }
         if (u[0] == INT_MAX) throw std::invalid_argument("sharded rebuild without keyframes");
         const int margin = std::max(1, (r_ + BIN - 1) / BIN);
-        const int32_t bbox[4] = {u[0] - margin, u[1] - margin, u[2] + margin, u[3] + margin};
+        int32_t bbox[4] = {u[0] - margin, u[1] - margin, u[2] + margin, u[3] + margin};
+        if (update)
+        {
+            // keep every slab boundary of the last rebuild inside the bbox so that each rank has rows to own
+            bbox[1] = std::min(bbox[1], shardCuts_[0]);
+            bbox[3] = std::max(bbox[3], shardCuts_[W] - 1);
+        }
         // 2. key pass + scans over the shared bbox for this rank's keyframes: per-bin counts and every record's slot in
         //    this rank's (virtual) bucket array.  The grid is not touched yet and no record has moved.
         ShardBuffers buf{};
         trace("meta exchanged");
-        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false, true);
+        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false, true, &ops);
         BatchView &b = shardPlan_.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const int bth = b.bth, btw = b.btw;
@@ -1546,7 +1590,40 @@ class LocalMap
             throw CudaError("binning consistency check failed on some rank (flags " + std::to_string(err_flags) + ")");
         std::vector<int32_t> slabs(2 * (size_t)W);
         std::vector<uint64_t> send(W), recv(W), src_base(W);
-        shardPlanRows(rows.data(), W, bth, b.bty0, rank, slabs.data(), send.data(), recv.data(), src_base.data());
+        if (!update)
+        {
+            shardPlanRows(rows.data(), W, bth, b.bty0, rank, slabs.data(), send.data(), recv.data(), src_base.data());
+            shardCuts_.assign((size_t)W + 1, 0);  // slab boundaries as GLOBAL bin rows: they survive a change of bbox
+            for (int kq = 0; kq < W; ++kq) shardCuts_[kq] = b.bty0 + slabs[2 * kq];
+            shardCuts_[W] = b.bty0 + bth;
+        }
+        else
+        {
+            // the owners stay: the cuts of the last rebuild, clamped into this pass's bbox rows (the first / last rank own
+            // whatever lies beyond the old extent)
+            for (int kq = 0; kq < W; ++kq)
+            {
+                const int lo = kq == 0 ? 0 : std::min(std::max(shardCuts_[kq] - b.bty0, 0), bth);
+                const int hi = kq == W - 1 ? bth : std::min(std::max(shardCuts_[kq + 1] - b.bty0, 0), bth);
+                slabs[2 * kq] = lo;
+                slabs[2 * kq + 1] = std::max(hi, lo);
+            }
+            uint64_t run = 0;
+            for (int kq = 0; kq < W; ++kq)
+            {
+                uint64_t t = 0;
+                for (int y = slabs[2 * kq]; y < slabs[2 * kq + 1]; ++y) t += rows[(size_t)rank * bth + y];
+                send[kq] = t;
+            }
+            for (int sq = 0; sq < W; ++sq)
+            {
+                uint64_t t = 0;
+                for (int y = slabs[2 * rank]; y < slabs[2 * rank + 1]; ++y) t += rows[(size_t)sq * bth + y];
+                recv[sq] = t;
+                src_base[sq] = run;
+                run += t;
+            }
+        }
         const int y0 = slabs[2 * rank], y1 = slabs[2 * rank + 1];
         const int cj0 = (b.bty0 + y0) * BIN, cj1 = (b.bty0 + y1) * BIN;
         uint64_t n_recv = 0, n_sent = 0, n_local = 0;
@@ -1668,7 +1745,8 @@ class LocalMap
         CK(cudaEventRecord(shardEv_[3], stream_));
         trace("records routed (enqueued)");
         // 6. blank the slab + footprint halo; fold: a bin's bucket = the sources' segments in rank order, read in place
-        shardBlankRows(cj0 - 2 * BIN, (y1 - y0) * BIN + 4 * BIN);
+        if (!update)
+            shardBlankRows(cj0 - 2 * BIN, (y1 - y0) * BIN + 4 * BIN);
         shardFold(recvD_.p, n_recv, countsAllD_.p, startsAllD_.p, src_base.data(), W, y0, y1, false);
         CK(cudaEventRecord(shardEv_[4], stream_));
         // 7. halo exchange, in place: r cell rows of moment records and flag bytes either side of each slab boundary, over
@@ -1727,6 +1805,11 @@ class LocalMap
         }
         CK(cudaEventRecord(shardEv_[6], stream_));
         CK(cudaStreamSynchronize(stream_));
+        for (size_t i = 0; i < moved.size(); ++i)
+        {
+            moved[i]->integrated = true;
+            std::memcpy(moved[i]->intPose, poses + 12 * i, sizeof(moved[i]->intPose));
+        }
         trace("rebuild done");
         if (info)
         {
@@ -1829,6 +1912,7 @@ class LocalMap
     DevBuf shardD_, rowsD_, countsAllD_, startsAllD_, recvD_;
     std::vector<std::pair<uint64_t, void *>> recvGrave_;  // replaced receive buffers, freed once no peer can still map them
     uint64_t shardStep_ = 0;
+    std::vector<int> shardCuts_;  // slab boundaries of the last sharded rebuild, global bin rows, world + 1 entries
     unsigned long long recvGen_ = 1;       // bumped whenever recvD_ is reallocated: peers re-open its IPC handle
     std::vector<void *> peerPtr_;          // every rank's receive buffer as mapped into this process
     std::vector<unsigned long long> peerGen_;
@@ -2635,6 +2719,13 @@ int tmap_shard_rebuild(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, 
     NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
     static_assert(sizeof(tmap_shard_info) == sizeof(tmb::LocalMap::ShardInfo), "layout");
     mp->shardRebuild(kf_ids, n, poses, reinterpret_cast<tmb::LocalMap::ShardInfo *>(out));
+    return TMAP_OK;
+    TMAP_API_END
+}
+int tmap_shard_update(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, tmap_shard_info *out)
+{
+    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
+    mp->shardRebuild(kf_ids, n, poses, reinterpret_cast<tmb::LocalMap::ShardInfo *>(out), true);
     return TMAP_OK;
     TMAP_API_END
 }

@@ -23,7 +23,8 @@ keyframes are spread over the ranks:
 
 The planning helpers below are the numpy statement of the library's slab planner (tmap_shard_plan): the gloo tests
 (tests/test_sharding_gloo.py) check the C planner against them and run the exchange + merge on CPU tensors with
-world_size 2.  Step inflation is not available on a sharded map in this round.
+world_size 2.  Pose updates of a sharded map are tmap_shard_update (same pipeline, subtract + add, slabs kept).  Step inflation is not
+available on a sharded map in this round.
 """
 import ctypes as C
 import math
@@ -198,6 +199,28 @@ class ShardedMap:
         self.last = dict(slabs=slabs, bbox=tuple(info.bbox), rows=(info.cj0, info.cj1), sent_records=int(info.sent_records),
                          recv_records=int(info.recv_records), local_records=int(info.local_records),
                          halo_bytes=int(info.halo_bytes), grid_bytes=int(info.grid_bytes), stages_ms=stages)
+        return self.last
+
+    def update(self, kf_ids, poses, timing=None):
+        """Collective.  The listed keyframes of THIS rank (ascending ids, possibly none) move to `poses`: one subtract + add
+        batch over the job on the slabs of the last rebuild (tmap_shard_update)."""
+        tm = self.tm
+        ids = np.ascontiguousarray(kf_ids, dtype=np.uint64)
+        ps = np.ascontiguousarray(np.asarray(poses, dtype=np.float32).reshape(len(ids), -1)[:, :12]) if len(ids) else np.zeros((0, 12), np.float32)
+        info = tm.ShardInfo()
+        tm._check(self.sys._lib.tmap_shard_update(self.sys._h, 0, ids.ctypes.data, len(ids), ps.ctypes.data, C.byref(info)))
+        stages = dict(zip(("bin", "plan", "alltoall", "fold", "halo", "classify", "total"), [float(x) for x in info.ms[:7]]))
+        if timing is not None:
+            for k, v in stages.items():
+                timing[k] = timing.get(k, 0.0) + v
+        W = info.n_slabs
+        self.last = dict(slabs=[(info.slabs[2 * k], info.slabs[2 * k + 1]) for k in range(W)], bbox=tuple(info.bbox),
+                         rows=(info.cj0, info.cj1), sent_records=int(info.sent_records), recv_records=int(info.recv_records),
+                         local_records=int(info.local_records), halo_bytes=int(info.halo_bytes), grid_bytes=int(info.grid_bytes),
+                         stages_ms=stages)
+        if self.poses is not None:
+            for i, p in zip(ids, ps):
+                self.poses[int(i)] = p
         return self.last
 
     # ------------------------------------------------------------------------------------------
