@@ -22,6 +22,9 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 rank, world = dist.get_rank(), dist.get_world_size()
 n_kf = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 P = dict(resolution=0.1, half_size=20.0, max_range=10.0, min_range=1.0, robot_radius=0.20, min_points_per_grid=3)
+INFLATE = len(sys.argv) > 2 and sys.argv[2] == "inflate"
+if INFLATE:   # step inflation on (LocalMap::inflateDirty): the step layer's halo rows travel between the slabs too
+    P.update(inflation_enabled=1, inflation_radius=0.5, cost_scaling_factor=3.0, lethal_step_threshold=0.3)
 poses = synth.trajectory("loop", n_kf, seed=9, extent=14.0)
 clouds = [synth.make_keyframe(9, i, poses[i], max_range=10.0, rings=64, azimuths=1024) for i in range(n_kf)]
 
@@ -35,7 +38,7 @@ for i in range(n_kf):
 timing = {}
 info = sm.rebuild(timing)
 info2 = sm.rebuild()          # idempotent: a second rebuild gives the same map
-layers = helpers.MOMENT_LAYERS + [l for l in helpers.DERIVED_LAYERS if l != "step_haz_inflated"]
+layers = helpers.MOMENT_LAYERS + [l for l in helpers.DERIVED_LAYERS if INFLATE or l != "step_haz_inflated"]
 got = {}
 for l in layers:
     got[l], origin = sm.gather_layer(l)
@@ -61,7 +64,8 @@ if rank == 0:
         same = helpers.bits_equal(got[l], ref)
         if not same:
             bad = (np.isnan(got[l]) != np.isnan(ref)) | (~np.isnan(ref) & (got[l] != ref))
-            print(f"layer {l}: {int(bad.sum())} cells differ")
+            print(f"layer {l}: {int(bad.sum())} cells differ (sharded: {int(np.sum(~np.isnan(got[l])))} numeric cells, "
+                  f"one GPU: {int(np.sum(~np.isnan(ref)))}; inflation tiles listed so far: {sm.map.stats()['sum_infl_tiles']} / {m.stats()['sum_infl_tiles']})")
             ok = False
     occ = int(np.sum(~np.isnan(got["N"])))
     print(f"world={world} keyframes={n_kf} occupied={occ} slabs={info['slabs']} bit-identical={ok} timing_ms={ {k: round(v, 3) for k, v in timing.items()} }")

@@ -308,12 +308,13 @@ def test_cpp_mirror_replays_localmap_kat(tmap):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
-def _run_shard_check(nproc, n_kf, port):
+def _run_shard_check(nproc, n_kf, port, *extra):
     import subprocess, sys
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(nproc), "--master-addr",
-                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_gpu_check.py"), str(n_kf)],
+                        "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tests", "shard_gpu_check.py"), str(n_kf), *extra],
                        capture_output=True, text=True, timeout=600)
-    assert r.returncode == 0 and "bit-identical=True" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert r.returncode == 0 and "bit-identical=True" in r.stdout and "bit-identical=False" not in r.stdout, \
+        r.stdout[-3000:] + r.stderr[-3000:]
 
 
 def test_sharded_rebuild_world1_matches_plain_rebuild(tmap):
@@ -328,6 +329,20 @@ def test_sharded_rebuild_world2_bit_identical(tmap):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     _run_shard_check(2, 24, 29562)
+
+
+def test_sharded_map_with_inflation_world1(tmap):
+    """tmap_shard_rebuild + tmap_shard_update with step inflation on (one rank): every layer including
+    step_haz_inflated equals the ordinary single-GPU sequence bit for bit."""
+    _run_shard_check(1, 12, 29563, "inflate")
+
+
+def test_sharded_map_with_inflation_world2(tmap):
+    """Two ranks: the step layer's halo rows are exchanged between classification and inflation."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    _run_shard_check(2, 24, 29564, "inflate")
 
 
 def test_heavy_bins_split_across_ctas(tmap, oracle):

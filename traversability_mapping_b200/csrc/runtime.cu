@@ -1078,7 +1078,8 @@ class LocalMap
     }
 
     // classify + inflate + clear of the bins listed by the bin phase, statistics, logical growth
-    void finishBatch(const Plan &pl, const std::vector<Op> &ops, const std::chrono::steady_clock::time_point &t_begin)
+    void finishBatch(const Plan &pl, const std::vector<Op> &ops, const std::chrono::steady_clock::time_point &t_begin,
+                     const std::function<void()> &before_inflate = nullptr)
     {
         const BatchView &b = pl.b;
         const size_t nb = (size_t)b.btw * b.bth;
@@ -1086,6 +1087,8 @@ class LocalMap
         CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_, prof ? ev_[8] : nullptr));
         g_launches += 2;  // k_gate + k_classify
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
+        if (R_ > 0 && before_inflate)
+            before_inflate();  // sharded map: the neighbours' step values R cells beyond the slab arrive here
         if (R_ > 0)
         {
             CK(launch_inflate(stream_, grid_.tmap_step, b, grid_.v, cp_, decay_.p, nSM_));
@@ -1311,6 +1314,17 @@ class LocalMap
         b.sh_src_base = srcBaseD_.as<unsigned long long>();
         b.sh_world = world;
         b.sh_first = (uint32_t)y0 * (uint32_t)b.btw;
+        if (R_ > 0)
+        {
+            // the key pass / scatter of this pass may already have stamped inflation tiles with the batch's epoch (their
+            // work lists are discarded): the merged counts below list the tiles afresh
+            if (++epoch_ == 0)
+            {
+                CK(cudaMemsetAsync(inflFlagsD_.p, 0, inflFlagsD_.cap, stream_));
+                epoch_ = 1;
+            }
+            b.epoch = epoch_;
+        }
         CK(launch_shard_merge(stream_, b, grid_.v, static_cast<const float4 *>(d_recv), static_cast<const uint32_t *>(d_counts_all),
                               static_cast<const uint32_t *>(d_starts_all), srcBaseD_.as<unsigned long long>(), world, y0, y1, globD_,
                               shardPlan_.dc, shardPlan_.di));
@@ -1461,7 +1475,6 @@ class LocalMap
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         if (!comm_) throw std::invalid_argument("tmap_shard_comm_init has not been called on this map");
-        if (R_ > 0) throw Unsupported("step inflation is not available on a sharded map yet");
         NcclApi &N = NcclApi::get();
         ncclComm_t comm = static_cast<ncclComm_t>(comm_);
         const int W = world_, rank = rank_;
@@ -1630,8 +1643,30 @@ class LocalMap
         for (int s = 0; s < W; ++s) { n_recv += recv[s]; n_local += send[s]; if (s != rank) n_sent += send[s]; }
         // the window of THIS rank: its slab rows + halo, the bbox columns (the other slabs never exist here)
         {
-            const int ty0 = ((b.bty0 + y0) >> 1) - 1, ty1 = ((b.bty0 + y1 + 1) >> 1) + 1;
+            const int mt = (std::max(r_, R_) + r_ + TILE - 1) / TILE;  // footprint (+ inflation) halo, in 32-cell tiles
+            const int ty0 = ((b.bty0 + y0) >> 1) - mt, ty1 = ((b.bty0 + y1 + 1) >> 1) + mt;
             grid_.ensure(stream_, b.btx0 >> 1, ty0, ((b.btx0 + btw - 1) >> 1) + 1, ty1);
+        }
+        if (R_ > 0)
+        {
+            // the inflation work list and its dedup stamps are sized by the window, which has only just been fixed
+            const size_t n_t32 = (size_t)grid_.v.tw * grid_.v.th;
+            const size_t need = n_t32 * 4 + 64;
+            if (need > inflFlagsD_.cap)
+            {
+                inflFlagsD_.ensure(need);
+                CK(cudaMemsetAsync(inflFlagsD_.p, 0, inflFlagsD_.cap, stream_));
+                epoch_ = 0;
+            }
+            if (++epoch_ == 0)
+            {
+                CK(cudaMemsetAsync(inflFlagsD_.p, 0, inflFlagsD_.cap, stream_));
+                epoch_ = 1;
+            }
+            shardInflD_.ensure(need);
+            b.infl_flags = inflFlagsD_.as<uint32_t>();
+            b.epoch = epoch_;
+            b.infl_tiles = shardInflD_.as<uint32_t>();
         }
         // 4. receive buffers: one per rank, mapped into every peer (CUDA IPC); handles travel only when a buffer was
         //    reallocated.  rt_off[k] turns a slot of my bucket array into a slot of rank k's buffer: my records of k's slab
@@ -1792,7 +1827,37 @@ class LocalMap
             std::vector<Op> none;
             Plan pl = shardPlan_;
             pl.n_ops = 0;
-            finishBatch(pl, none, t_begin);
+            // step inflation (LocalMap::inflateDirty, LocalMap.cpp:201-241) reads the step layer R cells around a cell: the R
+            // rows of it either side of each slab boundary are exchanged after the classification, before the inflation
+            auto step_halo = [&]()
+            {
+                if (W == 1) return;
+                const GridView &v = grid_.v;
+                const int col0 = b.btx0 * BIN - v.ci0, wcols = btw * BIN;
+                float *step = v.der + (size_t)D_STEP * v.plane();
+                auto row = [&](int cj) { return step + (size_t)(cj - v.cj0) * v.W + col0; };
+                auto in_grid = [&](int cj) { return cj >= v.cj0 && cj < v.cj0 + v.H; };
+                ncclCheck(N.GroupStart(), "ncclGroupStart");
+                for (int q = 0; q < R_; ++q)
+                {
+                    if (rank > 0)
+                    {
+                        if (!in_grid(cj0 + q) || !in_grid(cj0 - R_ + q)) throw CudaError("inflation halo rows outside the allocated window");
+                        ncclCheck(N.Send(row(cj0 + q), (size_t)wcols, ncclFloat, rank - 1, comm, stream_), "ncclSend(step halo)");
+                        ncclCheck(N.Recv(row(cj0 - R_ + q), (size_t)wcols, ncclFloat, rank - 1, comm, stream_), "ncclRecv(step halo)");
+                        halo_bytes += (uint64_t)wcols * 4;
+                    }
+                    if (rank < W - 1)
+                    {
+                        if (!in_grid(cj1 - R_ + q) || !in_grid(cj1 + q)) throw CudaError("inflation halo rows outside the allocated window");
+                        ncclCheck(N.Send(row(cj1 - R_ + q), (size_t)wcols, ncclFloat, rank + 1, comm, stream_), "ncclSend(step halo)");
+                        ncclCheck(N.Recv(row(cj1 + q), (size_t)wcols, ncclFloat, rank + 1, comm, stream_), "ncclRecv(step halo)");
+                        halo_bytes += (uint64_t)wcols * 4;
+                    }
+                }
+                ncclCheck(N.GroupEnd(), "ncclGroupEnd");
+            };
+            finishBatch(pl, none, t_begin, step_halo);
         }
         if (W > 1)
         {
@@ -1909,7 +1974,7 @@ class LocalMap
     int rank_ = 0, world_ = 1;
     cudaEvent_t shardEv_[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     PinBuf shardH_, rowsH_;
-    DevBuf shardD_, rowsD_, countsAllD_, startsAllD_, recvD_;
+    DevBuf shardD_, rowsD_, countsAllD_, startsAllD_, recvD_, shardInflD_;
     std::vector<std::pair<uint64_t, void *>> recvGrave_;  // replaced receive buffers, freed once no peer can still map them
     uint64_t shardStep_ = 0;
     std::vector<int> shardCuts_;  // slab boundaries of the last sharded rebuild, global bin rows, world + 1 entries
