@@ -210,7 +210,17 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-secondary", action="store_true", help="skip the C1 / C2 / C3 secondary legs")
     ap.add_argument("--c2-steps", type=int, default=12)
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"],
+                    help="c5 = BASELINE config[4]: the same 2 000-keyframe loop closure on a 1 x 1 km map at 0.05 m (49-cell disc), "
+                         "meant for N > 1 (the map is tiled across the ranks)")
     args = ap.parse_args()
+    if args.workload == "c5":
+        global C4, C4_EXTENT, WORKLOAD
+        C4 = dict(C4, resolution=0.05, half_size=500.0)
+        C4_EXTENT = 480.0
+        WORKLOAD = ("C5 loop closure: %d stored keyframes x %d rays on a 960 m loop, 1 x 1 km map @0.05 m tiled across the ranks "
+                    "(slabs of bin rows, records routed by the scatter kernel over NVLink, halo exchange), 49-cell disc"
+                    % (C4_KEYFRAMES, C4_RINGS * C4_AZ))
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <math_constants.h>
 #include <cstdlib>
+#include <mutex>
 
 namespace tmb
 {
@@ -680,17 +681,29 @@ cudaError_t upload_classify_constants(const int *disc_off, const double *disc_d 
     return cudaMemcpyToSymbol(c_disc_d, disc_d, sizeof(double) * 2 * n_disc);
 }
 
+// The dynamic shared-memory limit of a kernel is a per-device attribute and several maps (threads, devices, footprint
+// radii) share this process: the limit only ever grows, per device, under a lock.
+static void raise_smem_limit(const void *fn, int which, size_t bytes)
+{
+    static std::mutex m;
+    static size_t limit[2][64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes); return; }
+    std::lock_guard<std::mutex> l(m);
+    if (bytes > limit[which][dev])
+    {
+        cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        limit[which][dev] = bytes;
+    }
+}
+
 cudaError_t launch_classify(cudaStream_t st, const CUtensorMap &tmap, const CUtensorMap &tmap_flags, const BatchView &b, const GridView &g,
                             const ClassifyParams &cp, int n_sm, cudaEvent_t ev_after_gate)
 {
-    static int attr_r = -1;
     const int r = cp.r;
     const size_t smem = classify_smem_bytes(r);
-    if (attr_r != r)
-    {
-        cudaFuncSetAttribute(k_classify, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_r = r;
-    }
+    raise_smem_limit(reinterpret_cast<const void *>(k_classify), 0, smem);
     const size_t nb = (size_t)b.btw * b.bth;
     // gate pass over every candidate bin (flag bytes only), then the TMA-staged fit over the bins it listed
     // CTAs per SM; measured flat between 4 and 8 (profiles/sweep_grids.sh overrides them through the environment)
@@ -712,14 +725,9 @@ cudaError_t launch_clear_touched(cudaStream_t st, const BatchView &b, const Grid
 cudaError_t launch_inflate(cudaStream_t st, const CUtensorMap &tmap_step, const BatchView &b, const GridView &g,
                            const ClassifyParams &cp, const void *d_taps, int n_sm)
 {
-    static int attr_R = -1;
     const int R = cp.infl_r;
     const size_t smem = inflate_smem_bytes(R, cp.n_infl);
-    if (attr_R != R)
-    {
-        cudaFuncSetAttribute(k_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr_R = R;
-    }
+    raise_smem_limit(reinterpret_cast<const void *>(k_inflate), 1, smem);
     static const int gmul = getenv("TMB_INF_GRID") ? atoi(getenv("TMB_INF_GRID")) : 4;
     const int n_blocks = (int)min((size_t)(gmul * n_sm), (size_t)g.tw * g.th);
     k_inflate<<<n_blocks, INF_THREADS, smem, st>>>(tmap_step, b, g, static_cast<const InflTap *>(d_taps), cp);
