@@ -258,39 +258,10 @@ int tmap_get_stats(tmap_system *s, uint64_t map_id, tmap_stats *out);
 /* Run the map's kernels on a caller-owned stream (cudaStream_t as void*); NULL = own stream. */
 int tmap_set_stream(tmap_system *s, uint64_t map_id, void *cuda_stream);
 
-/* ---- sharded global map: one process per GPU, bins owned in slabs of rows ----------
- * The reference has no distributed path; these entry points are what a multi-GPU caller drives (see
- * traversability_mapping_b200/sharding.py): every rank bins ITS keyframes over a bbox shared by all
- * ranks, the per-bin record ranges are exchanged with one all-to-all over NVLink (NCCL, by the
- * caller), each rank merges + folds the bins of its slab, moment-record halo rows are exchanged in
- * place, then each rank classifies its slab.  Rebuild-from-blank only in this round. */
-typedef struct tmap_shard_buffers
-{
-    void *d_records;        /* device: float4 records bucketed by bin (row-major over the bbox) */
-    uint64_t n_records;
-    void *d_bin_count;      /* device: uint32[n_bins] records per bin */
-    void *d_bin_start;      /* device: uint32[n_bins] exclusive scan of d_bin_count */
-    uint32_t n_bins;
-    int32_t btx0, bty0, btw, bth;  /* bbox in 16-cell bins */
-    int32_t cell_bbox[4];   /* min ci, max ci, min cj, max cj of this rank's points (INT_MAX if none) */
-} tmap_shard_buffers;
-/* union window of the listed keyframes at the given poses, in bins: x0, y0, x1, y1 (inclusive) */
-int tmap_shard_window(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12,
-                      int32_t out_bins[4]);
-int tmap_shard_blank(tmap_system *s, uint64_t map_id);
-/* blank only cell rows [cj0, cj0 + n_rows) of the window (a rank's slab + halo: rows outside it are never read
- * until a later rebuild owns -- and blanks -- them).  Rows outside the allocated window are ignored. */
-int tmap_shard_blank_rows(tmap_system *s, uint64_t map_id, int32_t cj0, int32_t n_rows);
-int tmap_shard_bin(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses12, uint32_t op_base,
-                   const int32_t bbox_bins[4], tmap_shard_buffers *out);
-int tmap_shard_fold(tmap_system *s, uint64_t map_id, const void *d_recv, uint64_t n_recv, const void *d_counts_all,
-                    const void *d_starts_all, const uint64_t *src_base, int32_t world, int32_t y0, int32_t y1);
-/* kind 0: moment records (48 B/cell), 1: flag bytes; pointer to `nrows` whole cell rows starting at row cj */
-int tmap_shard_rows(tmap_system *s, uint64_t map_id, int32_t kind, int32_t cj, int32_t nrows, void **d_ptr, size_t *bytes);
-int tmap_shard_classify(tmap_system *s, uint64_t map_id, const int32_t cell_bbox[4]);
-int tmap_shard_clear_flag_rows(tmap_system *s, uint64_t map_id, int32_t cj, int32_t nrows);
+/* ---- sharded global map: one process per GPU, bins owned in slabs of bin rows ----------
+ * The reference has no distributed path.  A multi-GPU host drives the three collective entry points below: */
 
-/* ---- the sharded rebuild as ONE collective call (host code C++, NCCL issued by the library on the map's stream) ----
+/* ---- the sharded rebuild as ONE collective call (host code C++, collectives issued by the library on the map's stream) ----
  * Bootstrap as with MPI: one rank obtains a 128-byte NCCL unique id (tmap_shard_unique_id), the caller ships it to every
  * rank over whatever channel it has, and every rank calls tmap_shard_comm_init on ITS map (one process per GPU).
  * tmap_shard_rebuild is then collective over the job: rank k passes the contiguous block of keyframe ids it holds (all ids

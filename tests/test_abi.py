@@ -29,10 +29,10 @@ def test_header_symbols_are_exported_and_bound(tmap):
 
 
 def test_struct_layouts_match_the_header(tmap, tmp_path):
-    """The ctypes mirrors of tmap_params / tmap_stats / tmap_shard_buffers must have the C compiler's size and
+    """The ctypes mirrors of tmap_params / tmap_stats / tmap_shard_info must have the C compiler's size and
     field offsets (the ABI is plain structs; a drifted mirror would read garbage silently)."""
     import subprocess
-    fields = {"tmap_params": tmap.Params, "tmap_stats": tmap.Stats, "tmap_shard_buffers": tmap.ShardBuffers}
+    fields = {"tmap_params": tmap.Params, "tmap_stats": tmap.Stats, "tmap_shard_info": tmap.ShardInfo}
     lines = ['#include <stddef.h>', '#include <stdio.h>', '#include "tmap.h"', 'int main(void){']
     for cname, cls in fields.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

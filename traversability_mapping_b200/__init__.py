@@ -64,12 +64,6 @@ class Stats(C.Structure):
     ]
 
 
-class ShardBuffers(C.Structure):
-    _fields_ = [("d_records", C.c_void_p), ("n_records", C.c_uint64), ("d_bin_count", C.c_void_p), ("d_bin_start", C.c_void_p),
-                ("n_bins", C.c_uint32), ("btx0", C.c_int32), ("bty0", C.c_int32), ("btw", C.c_int32), ("bth", C.c_int32),
-                ("cell_bbox", C.c_int32 * 4)]
-
-
 class ShardInfo(C.Structure):
     """tmap_shard_info (include/tmap.h): what one rank learns from a sharded rebuild."""
     _fields_ = [("bbox", C.c_int32 * 4), ("slab_y0", C.c_int32), ("slab_y1", C.c_int32), ("cj0", C.c_int32), ("cj1", C.c_int32),
@@ -129,16 +123,6 @@ _SIG = {
                                             C.POINTER(C.c_size_t)]),
     "tmap_get_stats": (C.c_int, [_P, C.c_uint64, C.POINTER(Stats)]),
     "tmap_set_stream": (C.c_int, [_P, C.c_uint64, C.c_void_p]),
-    "tmap_shard_window": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_int32)]),
-    "tmap_shard_blank": (C.c_int, [_P, C.c_uint64]),
-    "tmap_shard_blank_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
-    "tmap_shard_bin": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_size_t, C.c_void_p, C.c_uint32, C.POINTER(C.c_int32),
-                                 C.POINTER(ShardBuffers)]),
-    "tmap_shard_fold": (C.c_int, [_P, C.c_uint64, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
-                                  C.c_int32, C.c_int32]),
-    "tmap_shard_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
-    "tmap_shard_classify": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_int32)]),
-    "tmap_shard_clear_flag_rows": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32]),
     "tmap_shard_unique_id": (C.c_int, [C.c_void_p]),
     "tmap_shard_comm_init": (C.c_int, [_P, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p]),
     "tmap_shard_comm_destroy": (C.c_int, [_P, C.c_uint64]),

@@ -2754,9 +2754,8 @@ __global__ void __launch_bounds__(FOLD_THREADS) k_fold_atomic_experiment(BatchVi
 //   counts_all / starts_all : [world][nb] every rank's per-bin record count and exclusive start
 //   k_shard_counts : my bins' merged count (sum over sources inside my slab, 0 outside), the global
 //                    total per bin (candidate-list neighbour test) and the 256-bin block sums
-//   k_shard_merge  : warp per (source, bin of my slab): copy that source's segment behind the earlier
-//                    sources' segments -> per-bin buckets ordered (source rank, op, point) = global op
-//                    order, because ranks hold contiguous keyframe-id blocks
+//   (no merge copy: k_fold3<.., SHARD> reads a bin's bucket in place as the sources' segments in rank order
+//    = global op order, because ranks hold contiguous keyframe-id blocks)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_shard_counts(BatchView b, const uint32_t *__restrict__ counts_all, int world, int y0, int y1,
                                                       uint32_t *__restrict__ glob)
@@ -2779,29 +2778,6 @@ __global__ void __launch_bounds__(256) k_shard_counts(BatchView b, const uint32_
     block_excl_scan(mine, s_w, tot);
     if (threadIdx.x == 0)
         b.block_sums[blockIdx.x] = tot;
-}
-
-__global__ void k_shard_merge(BatchView b, const float4 *__restrict__ recv, const uint32_t *__restrict__ counts_all,
-                              const uint32_t *__restrict__ starts_all, const unsigned long long *__restrict__ src_base, int world,
-                              int y0, int y1)
-{
-    const uint32_t nb = (uint32_t)(b.btw * b.bth);
-    const uint32_t nslab = (uint32_t)((y1 - y0) * b.btw);
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= nslab * (uint32_t)world)
-        return;
-    const int s = warp / nslab;
-    const uint32_t bin = (uint32_t)y0 * b.btw + warp % nslab;
-    const uint32_t cnt = counts_all[(size_t)s * nb + bin];
-    if (!cnt)
-        return;
-    const uint32_t first = (uint32_t)y0 * b.btw;
-    const unsigned long long src = src_base[s] + (starts_all[(size_t)s * nb + bin] - starts_all[(size_t)s * nb + first]);
-    uint32_t dst = b.tile_start[bin];
-    for (int q = 0; q < s; ++q)
-        dst += counts_all[(size_t)q * nb + bin];
-    for (uint32_t k = lane; k < cnt; k += 32)
-        b.sorted[dst + k] = recv[src + k];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1199,45 +1199,6 @@ class LocalMap
 
   public:
     // ---- sharded rebuild: this process owns a slab of bin rows of a global map -------------
-    struct ShardBuffers
-    {
-        void *d_records; uint64_t n_records; void *d_bin_count; void *d_bin_start;
-        uint32_t n_bins; int32_t btx0, bty0, btw, bth; int32_t cell_bbox[4];
-    };
-    std::vector<Op> shardOps(const uint64_t *ids, size_t n, const float *poses)
-    {
-        std::vector<Op> ops(n);
-        std::lock_guard<std::mutex> l(kfMutex_);
-        for (size_t i = 0; i < n; ++i)
-        {
-            auto it = kfs_.find(ids[i]);
-            if (it == kfs_.end()) throw std::invalid_argument("unknown keyframe id in shard op list");
-            ops[i].kf = it->second;
-            std::memcpy(ops[i].pose, poses + 12 * i, sizeof(ops[i].pose));
-            ops[i].sign = +1.f;
-        }
-        return ops;
-    }
-    void shardWindow(const uint64_t *ids, size_t n, const float *poses, int32_t out[4])
-    {
-        auto ops = shardOps(ids, n, poses);
-        int x0 = INT_MAX, y0 = INT_MAX, x1 = INT_MIN, y1 = INT_MIN;
-        for (auto &op : ops)
-        {
-            int a, b, c, d;
-            opWindow(op, a, b, c, d);
-            x0 = std::min(x0, a); y0 = std::min(y0, b); x1 = std::max(x1, c); y1 = std::max(y1, d);
-        }
-        out[0] = x0; out[1] = y0; out[2] = x1; out[3] = y1;
-    }
-    void shardBlank()
-    {
-        std::lock_guard<std::recursive_mutex> g(gridMutex_);
-        CK(cudaSetDevice(P_.device));
-        grid_.blank_all(stream_);
-        CK(cudaMemsetAsync(grid_.v.flags, 0, grid_.v.plane(), stream_));
-        CK(cudaStreamSynchronize(stream_));
-    }
     void shardBlankRows(int cj0, int n_rows)
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
@@ -1252,46 +1213,21 @@ class LocalMap
             CK(cudaMemsetAsync(v.der + (size_t)k * v.plane() + off, 0xFF, cnt * sizeof(float), stream_));
         CK(cudaMemsetAsync(v.flags + off, 0, cnt, stream_));
     }
-    // phase A on this rank's keyframes: records bucketed by bin over the shared bbox
-    void shardBin(const uint64_t *ids, size_t n, const float *poses, uint32_t op_base, const int32_t bbox[4], ShardBuffers *out,
-                  bool ensure_grid = true, bool counts_only = false, const std::vector<Op> *prebuilt = nullptr)
+    // key pass + scans of this rank's ops over the shared bbox: per-bin counts and every record's slot in this rank's
+    // (virtual) bucket array; nothing is written yet and the grid is not touched
+    void shardKeyPass(const std::vector<Op> &ops, uint32_t op_base, const int32_t bbox[4])
     {
         std::lock_guard<std::recursive_mutex> g(gridMutex_);
         CK(cudaSetDevice(P_.device));
-        shardOps_ = prebuilt ? *prebuilt : shardOps(ids, n, poses);
+        shardOps_ = ops;
         const int forced[4] = {bbox[0], bbox[1], bbox[2], bbox[3]};
-        shardPlan_ = planBatch(shardOps_, forced, op_base, ensure_grid);
+        shardPlan_ = planBatch(shardOps_, forced, op_base, false);
         uploadConstants();
         CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
-                      nSM_, nullptr, counts_only ? 5 : 1));
-        g_launches += counts_only ? 6 : 7;
-        if (counts_only)  // the caller routes the records itself (shardRebuild): no host round trip here
-            return;
-        const size_t res_bytes = 64 + n * sizeof(int4);
-        resH_.ensure(res_bytes + 64);
-        const auto t_launched = std::chrono::steady_clock::now();
-        CK(cudaMemcpyAsync(resH_.p, metaD_.p, res_bytes, cudaMemcpyDeviceToHost, stream_));
-        g_d2h += (uint64_t)(res_bytes);
-        CK(cudaStreamSynchronize(stream_));
-        const auto t_synced = std::chrono::steady_clock::now();
-        if (resH_.as<uint32_t>()[3])
-            throw CudaError("binning consistency check failed");
-        const BatchView &b = shardPlan_.b;
-        out->d_records = b.sorted; out->n_records = shardPlan_.total_pts;
-        out->d_bin_count = b.tile_count; out->d_bin_start = b.tile_start;
-        out->n_bins = (uint32_t)(b.btw * b.bth);
-        out->btx0 = b.btx0; out->bty0 = b.bty0; out->btw = b.btw; out->bth = b.bth;
-        int bb4[4] = {INT_MAX, INT_MIN, INT_MAX, INT_MIN};
-        const int4 *bb = reinterpret_cast<const int4 *>(resH_.as<unsigned char>() + 64);
-        for (size_t i = 0; i < n; ++i)
-            if (bb[i].x != INT_MAX)
-            {
-                bb4[0] = std::min(bb4[0], bb[i].x); bb4[1] = std::max(bb4[1], bb[i].y);
-                bb4[2] = std::min(bb4[2], bb[i].z); bb4[3] = std::max(bb4[3], bb[i].w);
-            }
-        for (int k = 0; k < 4; ++k) out->cell_bbox[k] = bb4[k];
+                      nSM_, nullptr, 5));
+        g_launches += 6;
     }
-    // merge the records received from every rank for bin rows [y0, y1) (bbox-local) and fold them
+    // fold the records received from every rank for bin rows [y0, y1) (bbox-local): per bin, the sources' segments in rank order
     void shardFold(const void *d_recv, uint64_t n_recv, const void *d_counts_all, const void *d_starts_all, const uint64_t *src_base,
                    int world, int y0, int y1, bool sync = true)
     {
@@ -1304,7 +1240,7 @@ class LocalMap
         CK(cudaMemcpyAsync(srcBaseD_.p, src_base, (size_t)world * 8, cudaMemcpyHostToDevice, stream_));
         g_h2d += (uint64_t)((size_t)world * 8);
         b.split_thresh = (uint32_t)std::max<uint64_t>(32768, n_recv / (uint64_t)(3 * nSM_ * splitDiv()));
-        b.n_ops = 0;  // per-op bboxes were consumed by shardBin
+        b.n_ops = 0;  // per-op bboxes were consumed after the key pass
         b.nbr_count = globD_;
         b.cand_y0 = y0; b.cand_y1 = y1;
         // a bin's bucket = the sources' segments in rank order, read in place from the receive buffer by the fold
@@ -1332,45 +1268,6 @@ class LocalMap
         g_launches += 6;
         if (sync) CK(cudaStreamSynchronize(stream_));
     }
-    // pointer into the grid for an in-place halo exchange: `nrows` cell rows starting at absolute row cj
-    void shardRows(int kind, int32_t cj, int32_t nrows, void **ptr, size_t *bytes)
-    {
-        std::lock_guard<std::recursive_mutex> g(gridMutex_);
-        const int row = cj - grid_.v.cj0;
-        if (row < 0 || row + nrows > grid_.v.H) throw std::invalid_argument("halo rows outside the allocated grid");
-        if (kind == 0)
-        {
-            *ptr = grid_.v.mom + (size_t)row * grid_.v.W * REC;
-            *bytes = (size_t)nrows * grid_.v.W * REC * 4;
-        }
-        else
-        {
-            *ptr = grid_.v.flags + (size_t)row * grid_.v.W;
-            *bytes = (size_t)nrows * grid_.v.W;
-        }
-    }
-    void shardClassify(const int32_t cell_bbox[4])
-    {
-        std::lock_guard<std::recursive_mutex> g(gridMutex_);
-        CK(cudaSetDevice(P_.device));
-        if (R_ > 0) throw Unsupported("step inflation is not available on a sharded map yet");
-        const auto t_begin = std::chrono::steady_clock::now();
-        if (cell_bbox[0] != INT_MAX)
-            growLogical(cell_bbox[0], cell_bbox[1], cell_bbox[2], cell_bbox[3]);
-        std::vector<Op> none;
-        Plan pl = shardPlan_;
-        pl.n_ops = 0;
-        finishBatch(pl, none, t_begin);
-    }
-    void shardClearFlagsRows(int32_t cj, int32_t nrows)
-    {
-        std::lock_guard<std::recursive_mutex> g(gridMutex_);
-        void *p; size_t bytes;
-        shardRows(1, cj, nrows, &p, &bytes);
-        CK(cudaMemsetAsync(p, 0, bytes, stream_));
-        CK(cudaStreamSynchronize(stream_));
-    }
-
     // ---- the whole sharded rebuild behind ONE call, collectives issued from here (NCCL on the map's stream) ----
     struct ShardInfo
     {
@@ -1487,16 +1384,23 @@ class LocalMap
         auto trace = [&](const char *what) { if (dbg) { std::fprintf(stderr, "[shard %d/%d] %s\n", rank, W, what); std::fflush(stderr); } };
         CK(cudaEventRecord(shardEv_[0], stream_));
         // 1. job-wide op numbering and bbox: every rank's keyframe count and window in ONE all-gather of 8 int64
+        // A rank that finds its own arguments invalid must not leave the others waiting in a collective: the verdict
+        // travels with the first all-gather and every rank throws together.
+        std::string local_error;
         if (update && shardCuts_.size() != (size_t)W + 1)
-            throw std::invalid_argument("tmap_shard_update needs a map built by tmap_shard_rebuild");
+            local_error = "tmap_shard_update needs a map built by tmap_shard_rebuild";
         std::vector<Op> ops;
         std::vector<std::shared_ptr<KeyFrame>> moved;
         {
             std::lock_guard<std::mutex> l(kfMutex_);
-            for (size_t i = 0; i < n; ++i)
+            for (size_t i = 0; i < n && local_error.empty(); ++i)
             {
                 auto it = kfs_.find(ids[i]);
-                if (it == kfs_.end()) throw std::invalid_argument("unknown keyframe id in shard op list");
+                if (it == kfs_.end()) { local_error = "unknown keyframe id in shard op list"; break; }
+                if (i && ids[i] <= ids[i - 1]) { local_error = "keyframe ids must be ascending"; break; }
+                for (int q = 0; q < 12; ++q)
+                    if (!std::isfinite(poses[12 * i + q])) local_error = "non-finite pose";
+                if (!local_error.empty()) break;
                 if (update && it->second->integrated)
                 {
                     Op sub;
@@ -1512,7 +1416,8 @@ class LocalMap
                 ops.push_back(add);
                 moved.push_back(it->second);
             }
-            if (!update)  // a rebuild drops every contribution: keyframes not listed are no longer integrated
+            if (!local_error.empty()) { ops.clear(); moved.clear(); }
+            else if (!update)  // a rebuild drops every contribution: keyframes not listed are no longer integrated
                 for (auto &kv : kfs_) kv.second->integrated = false;
         }
         const size_t n_ops_local = ops.size();
@@ -1526,7 +1431,8 @@ class LocalMap
         shardH_.ensure(8192 + (size_t)W * 256);
         shardD_.ensure(8192 + (size_t)W * 256);
         long long *mh = shardH_.as<long long>();
-        mh[0] = (long long)n_ops_local; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3]; mh[5] = mh[6] = mh[7] = 0;
+        mh[0] = (long long)n_ops_local; mh[1] = win[0]; mh[2] = win[1]; mh[3] = win[2]; mh[4] = win[3];
+        mh[5] = local_error.empty() ? 0 : 1; mh[6] = mh[7] = 0;
         long long *md = shardD_.as<long long>();
         CK(cudaMemcpyAsync(md, mh, 64, cudaMemcpyHostToDevice, stream_));
         ncclCheck(N.AllGather(md, md + 8, 8, ncclInt64, comm, stream_), "ncclAllGather(meta)");
@@ -1535,6 +1441,10 @@ class LocalMap
         CK(cudaStreamSynchronize(stream_));
         uint64_t op_base = 0;
         int32_t u[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
+        for (int s = 0; s < W; ++s)
+            if (mh[8 + 8 * s + 5])
+                throw std::invalid_argument(local_error.empty() ? "sharded pass refused: rank " + std::to_string(s) + " reported invalid arguments"
+                                                                : local_error);
         for (int s = 0; s < W; ++s)
         {
             const long long *m = mh + 8 + 8 * s;
@@ -1556,9 +1466,8 @@ class LocalMap
         }
         // 2. key pass + scans over the shared bbox for this rank's keyframes: per-bin counts and every record's slot in
         //    this rank's (virtual) bucket array.  The grid is not touched yet and no record has moved.
-        ShardBuffers buf{};
         trace("meta exchanged");
-        shardBin(ids, n, poses, (uint32_t)op_base, bbox, &buf, false, true, &ops);
+        shardKeyPass(ops, (uint32_t)op_base, bbox);
         BatchView &b = shardPlan_.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const int bth = b.bth, btw = b.btw;
@@ -2718,47 +2627,6 @@ int tmap_set_stream(tmap_system *s, uint64_t map_id, void *stream)
 }
 
 /* ---- sharded global map ---- */
-int tmap_shard_window(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, int32_t out_bins[4])
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardWindow(kf_ids, n, poses, out_bins); return TMAP_OK; TMAP_API_END
-}
-int tmap_shard_blank(tmap_system *s, uint64_t map_id)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardBlank(); return TMAP_OK; TMAP_API_END
-}
-int tmap_shard_blank_rows(tmap_system *s, uint64_t map_id, int32_t cj0, int32_t n_rows)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardBlankRows(cj0, n_rows); return TMAP_OK; TMAP_API_END
-}
-int tmap_shard_bin(tmap_system *s, uint64_t map_id, const uint64_t *kf_ids, size_t n, const float *poses, uint32_t op_base,
-                   const int32_t bbox_bins[4], tmap_shard_buffers *out)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
-    static_assert(sizeof(tmap_shard_buffers) == sizeof(tmb::LocalMap::ShardBuffers), "layout");
-    mp->shardBin(kf_ids, n, poses, op_base, bbox_bins, reinterpret_cast<tmb::LocalMap::ShardBuffers *>(out));
-    return TMAP_OK;
-    TMAP_API_END
-}
-int tmap_shard_fold(tmap_system *s, uint64_t map_id, const void *d_recv, uint64_t n_recv, const void *d_counts_all,
-                    const void *d_starts_all, const uint64_t *src_base, int32_t world, int32_t y0, int32_t y1)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id)
-    mp->shardFold(d_recv, n_recv, d_counts_all, d_starts_all, src_base, world, y0, y1);
-    return TMAP_OK;
-    TMAP_API_END
-}
-int tmap_shard_rows(tmap_system *s, uint64_t map_id, int32_t kind, int32_t cj, int32_t nrows, void **d_ptr, size_t *bytes)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardRows(kind, cj, nrows, d_ptr, bytes); return TMAP_OK; TMAP_API_END
-}
-int tmap_shard_classify(tmap_system *s, uint64_t map_id, const int32_t cell_bbox[4])
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardClassify(cell_bbox); return TMAP_OK; TMAP_API_END
-}
-int tmap_shard_clear_flag_rows(tmap_system *s, uint64_t map_id, int32_t cj, int32_t nrows)
-{
-    NEED(s) TMAP_API_BEGIN NEED_MAP(mp, s, map_id) mp->shardClearFlagsRows(cj, nrows); return TMAP_OK; TMAP_API_END
-}
 int tmap_shard_unique_id(uint8_t out_id[128])
 {
     TMAP_API_BEGIN
