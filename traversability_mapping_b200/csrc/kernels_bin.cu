@@ -3,10 +3,10 @@
 // Replaces (reference paths relative to traversability_mapping/):
 //   System::prune                 src/System.cpp:93-114        -> k_prune_count / k_prune_scatter (also the
 //                                 PointCloud2 decode of conversions.cpp:19-26: field offsets, endianness)
-//   KeyFrame::rebin               src/KeyFrame.cpp:52-67       -> k_hist + k_scatter + k_fold
+//   KeyFrame::rebin               src/KeyFrame.cpp:52-67       -> k_hist + k_scatter + k_fold3
 //   Lattice::cellOf / centerOf    include/.../Moments.hpp:105-116
 //   NodeMetaData::insert          include/.../Moments.hpp:53-59
-//   MomentLayers::add             src/Helpers.cpp:114-127      -> k_fold (float32 fold, blank rule
+//   MomentLayers::add             src/Helpers.cpp:114-127      -> k_fold3 (float32 fold, blank rule
 //   LocalMap::addPartialToGrid    src/LocalMap.cpp:110-126        of LocalMap.cpp:121-125)
 //
 // Bit-exactness contract: the transform is r_i = ((R_i0 x + R_i1 y) + R_i2 z) + t_i
@@ -16,15 +16,19 @@
 // order.  This file is compiled with -fmad=false and uses the _rn intrinsics on those paths.
 //
 // Pipeline for a batch of ops (op = keyframe cloud x pose x sign); buckets are 16x16-cell bins:
-//   k_hist      : per 256*PPT-point chunk, transform+key, shared-memory histogram over the op's
-//                 bin window (warp-aggregated shared atomics; integer counts are exact)
+//   k_hist      : per chunk of 256*PPT*SUB points (512 .. 8 192), transform+key, shared-memory histogram over
+//                 the op's bin window (warp-aggregated shared atomics; integer counts are exact)
 //   k_scan_*    : exclusive prefixes over chunks, ops and bins -> every (bin, op, chunk) slot,
 //                 plus the work lists (bins to fold / gate, tiles to inflate)
-//   k_scatter   : re-derive the keys, STABLE rank inside the chunk (per-warp counters + one
-//                 match_any per point), write (x_m, y_m, z_m, sign|op|cell) records bucketed by bin
-//   k_fold      : one CTA per touched bin: shared-memory-staged stable counting sort on the 8-bit
-//                 cell key, one thread per cell walks its run in (op, point) order accumulating
-//                 doubles, then folds float32 into the cell's 48-byte record (blank rule included).
+//   k_scatter   : re-derive the keys, STABLE rank inside the chunk (per-(bin, warp) counters + one
+//                 match_any per point), write (x_m, y_m, z_m, sign|op|cell) records bucketed by bin --
+//                 on a sharded map straight into the owning rank's receive buffer (peer-mapped pointer)
+//   k_fold3     : one CTA per touched bin: stable counting sort of a 2 048-record chunk on the 8-bit cell key
+//                 into shared memory, cells handed to walker threads by descending record count, each
+//                 walker follows its cell's run in (op, point) order accumulating doubles and folds float32
+//                 into the cell's 48-byte record (blank rule included); cell state lives in shared memory
+//   k_fold4     : experiment (TMB_FOLD=4): sorts run heads instead of records; parity-green, slower
+//   k_fold_atomic_experiment : the shared-atomic alternative the sort is "chosen against" (profiles/README.md 6)
 #include "tmb_common.cuh"
 #include "tmb_async.cuh"
 #include <math_constants.h>
@@ -963,723 +967,9 @@ __device__ __forceinline__ void fold_acc(float *rec, const CellAcc &a, bool subt
     }
 }
 
-__device__ __forceinline__ uint32_t lds_u16(uint32_t addr)
-{
-    uint16_t v;
-    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
-    return v;
-}
-__device__ __forceinline__ float4 lds_f4(uint32_t addr)
-{
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
-    return v;
-}
-
 constexpr int FOLD_NW = FOLD_THREADS / 32;
 
-__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold_r1(BatchView b, GridView g, LatticeD lat)
-{
-    __shared__ __align__(16) float4 s_rec[FOLD_CH];          // staged records            32 KB
-    __shared__ uint16_t s_ord[FOLD_CH];                       // record order sorted by cell 4 KB
-    __shared__ uint16_t s_cnt[FOLD_NW][BIN_CELLS];            // per-warp cell counters       4 KB
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_next[4];  // next work item: packed item, bucket start, bucket count, valid
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_heavy = b.counters[10];
-    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front) + light bins (back)
-    // Work items are handed out by a ticket counter (heavy bins first).  Thread 0 draws the NEXT ticket while the
-    // current bin is processed and resolves it in steps placed after later barriers (ticket -> item -> bucket
-    // start / count are three dependent global accesses), so a CTA does not sit idle on them between bins.
-    __shared__ uint32_t s_nx[5];  // thread 0's prefetch state: ticket, item, start, count, stage
-    auto next_step = [&](uint32_t upto)  // thread 0 only
-    {
-        if (s_nx[4] < 1 && upto >= 1)
-        {
-            const uint32_t t = s_nx[0];
-            uint32_t item = 0xffffffffu;  // invalid
-            if (t < n_active)
-                item = t < n_heavy ? b.active_tiles[t] : b.active_tiles[(uint32_t)(b.btw * b.bth) - 1 - (t - n_heavy)];
-            s_nx[1] = item;
-            s_nx[4] = 1;
-        }
-        if (s_nx[4] < 2 && upto >= 2)
-        {
-            const uint32_t item = s_nx[1];
-            if (item != 0xffffffffu)
-            {
-                const uint32_t gtn = item & 0x00ffffffu;
-                s_nx[2] = b.tile_start[gtn];
-                s_nx[3] = b.tile_count[gtn];
-            }
-            s_nx[4] = 2;
-        }
-    };
-    auto publish_next = [&]()  // thread 0 only
-    {
-        next_step(2);
-        s_next[0] = s_nx[1]; s_next[1] = s_nx[2]; s_next[2] = s_nx[3]; s_next[3] = s_nx[1] != 0xffffffffu;
-    };
-    if (tid == 0)
-    {
-        s_nx[0] = atomicAdd(b.counters + 4, 1u);
-        s_nx[4] = 0;
-        publish_next();
-    }
-    __syncthreads();
-    for (;;)
-    {
-        const uint32_t item = s_next[0], start = s_next[1], cnt = s_next[2], valid = s_next[3];
-        __syncthreads();  // everyone holds the current item: s_next may be rewritten
-        if (!valid)
-            break;
-        if (tid == 0)
-        {
-            s_nx[0] = atomicAdd(b.counters + 4, 1u);  // its latency is covered by the staging of this bin
-            s_nx[4] = 0;
-        }
-        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
-        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
-        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
-        const int col = ci - g.ci0, row = cj - g.cj0;
-        if (col < 0 || col >= g.W || row < 0 || row >= g.H)
-        {
-            // uniform: a bin is inside or outside as a whole (grid is 32-aligned)
-            if (tid == 0)
-            {
-                atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);
-                publish_next();
-            }
-            __syncthreads();
-            continue;
-        }
-        const size_t cell = (size_t)row * g.W + col;
-        // the cell's 48-byte record is fetched only if this batch actually touches the cell
-        float rec[REC];
-        bool loaded = false;
-        auto load_rec = [&]()
-        {
-            if (loaded) return;
-            const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
-            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
-            rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
-            rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
-            rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
-            rec_to_zero_form(rec);
-            loaded = true;
-        };
-        const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
-        const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
-        CellAcc acc;
-        acc.reset();
-        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
-        uint32_t fl = 0;
-
-        for (uint32_t pos = 0; pos < cnt;)
-        {
-            uint32_t n;
-            if (pmask == 0u)
-            {
-                n = min((uint32_t)FOLD_CH, cnt - pos);
-                for (uint32_t i = tid; i < n; i += FOLD_THREADS)
-                    s_rec[i] = b.sorted[start + pos + i];
-                pos += n;
-            }
-            else
-            {
-                // part of a split heavy bin: stream the bucket, keep (order-preserving) the records of my rows
-                n = 0;
-                while (n + 4 * FOLD_THREADS <= (uint32_t)FOLD_CH && pos < cnt)
-                {
-                    const uint32_t nin = min(4u * FOLD_THREADS, cnt - pos);
-                    uint32_t keep = 0, kc = 0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                    {
-                        const uint32_t j = 4 * tid + q;
-                        if (j < nin)
-                        {
-                            const uint32_t meta = __float_as_uint(reinterpret_cast<const float *>(b.sorted + start + pos + j)[3]);
-                            if ((((meta & 255u) >> BIN_SHIFT) & pmask) == part) { keep |= 1u << q; ++kc; }
-                        }
-                    }
-                    uint32_t inc = kc;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1)
-                    {
-                        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= (uint32_t)o) inc += u;
-                    }
-                    if (lane == 31) s_w[warp] = inc;
-                    __syncthreads();
-                    uint32_t wbase = 0, total = 0;
-#pragma unroll
-                    for (int w = 0; w < FOLD_NW; ++w)
-                    {
-                        const uint32_t v = s_w[w];
-                        if (w < (int)warp) wbase += v;
-                        total += v;
-                    }
-                    uint32_t dst = n + wbase + inc - kc;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        if (keep & (1u << q))
-                            s_rec[dst++] = b.sorted[start + pos + 4 * tid + q];
-                    __syncthreads();
-                    n += total;
-                    pos += nin;
-                }
-            }
-            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
-            const uint32_t SL = R * 32;                                // records per warp slice
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                s_cnt[w][tid] = 0;
-            __syncthreads();
-            // count: warp w owns the contiguous slice [w*SL, (w+1)*SL).  The peer masks are kept in registers for
-            // the placement pass: match.any costs ~8 cycles per distinct value (profiles/ubench/pipes.cu)
-            constexpr int MAX_R = FOLD_CH / FOLD_THREADS;
-            uint32_t cm[MAX_R], mm[MAX_R];
-#pragma unroll
-            for (int r = 0; r < MAX_R; ++r)
-            {
-                cm[r] = 256u;
-                mm[r] = 0u;
-                if ((uint32_t)r < R)
-                {
-                    const uint32_t i = warp * SL + r * 32 + lane;
-                    cm[r] = i < n ? (__float_as_uint(s_rec[i].w) & 255u) : 256u;
-                    mm[r] = __match_any_sync(0xffffffffu, cm[r]);
-                    // the group's highest lane adds the group size: no leader search
-                    if (cm[r] < 256u && (mm[r] >> lane) == 1u)
-                        s_cnt[warp][cm[r]] += (uint16_t)__popc(mm[r]);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            if (tid == 0) next_step(1);
-            // thread = cell: exclusive prefix over the warps' counts, then over cells
-            uint32_t tot = 0, wc[FOLD_NW];
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-            {
-                wc[w] = tot;
-                tot += s_cnt[w][tid];
-            }
-            // exclusive prefix of the cell counts: warp scan, one barrier, then the earlier warps' totals
-            uint32_t inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (uint32_t)o) inc += u;
-            }
-            if (lane == 31) s_w[warp] = inc;
-            __syncthreads();
-            uint32_t cstart = inc - tot;
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                if (w < (int)warp) cstart += s_w[w];
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
-            __syncthreads();
-            // stable placement: position = next slot of (warp, cell) + rank inside the warp round
-#pragma unroll
-            for (int r = 0; r < MAX_R; ++r)
-            {
-                if ((uint32_t)r < R)
-                {
-                    const uint32_t i = warp * SL + r * 32 + lane;
-                    const uint32_t c = cm[r], m = mm[r];
-                    if (c < 256u)
-                    {
-                        const uint32_t slot = s_cnt[warp][c] + __popc(m & ((1u << lane) - 1u));
-                        s_ord[slot] = (uint16_t)i;
-                        __syncwarp(m);
-                        if ((m >> lane) == 1u)  // highest lane of the group: its slot + 1 is the group's end
-                            s_cnt[warp][c] = (uint16_t)(slot + 1u);
-                    }
-                    __syncwarp();
-                }
-            }
-            __syncthreads();
-            // thread = cell: walk the cell's records in (op, point) order.  A new (op, cell) segment restarts the
-            // sums through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly), so the
-            // accumulators are updated in place and only the fold itself is a divergent block.
-            if (tid == 0) next_step(2);
-            const uint32_t k0 = cstart, k1 = cstart + tot;
-            const uint32_t ord_base = (uint32_t)__cvta_generic_to_shared(s_ord), rec_base = (uint32_t)__cvta_generic_to_shared(s_rec);
-            for (uint32_t k = k0; k < k1; ++k)
-            {
-                const float4 p = lds_f4(rec_base + 16u * lds_u16(ord_base + 2u * k));
-                const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
-                const bool fresh = so != cur;
-                if (fresh)
-                {
-                    if (cur != 0xffffffffu)
-                    {
-                        load_rec();
-                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
-                    }
-                    cur = so;
-                }
-                const double keep = fresh ? 0.0 : 1.0;
-                // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59)
-                const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
-                acc.n = fresh ? 1u : acc.n + 1u;
-                acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
-                acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
-                acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
-                acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
-                acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
-                acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
-                acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
-                acc.zmin = fminf(fresh ? CUDART_INF_F : acc.zmin, p.z);
-                acc.zmax = fmaxf(fresh ? -CUDART_INF_F : acc.zmax, p.z);
-            }
-            __syncthreads();
-        }
-        if (cur != 0xffffffffu)
-        {
-            load_rec();
-            fold_acc(rec, acc, (cur >> 23) != 0, fl);
-        }
-        if (fl & F_TOUCHED)
-        {
-            float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
-            if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
-            {
-#pragma unroll
-                for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
-            }
-            dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-            dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-            dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-            // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
-            uint8_t obs = 0;
-            if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
-                obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
-            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
-            if (fl & F_BLANKED)
-            {
-                const size_t pl = g.plane();
-#pragma unroll
-                for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + cell] = CUDART_NAN_F;
-            }
-        }
-        if (tid == 0)
-            publish_next();
-        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);  // also publishes s_next
-        if (tid == 0 && nt)
-            atomicAdd(b.counters + 8, nt);
-    }
-}
-
-
-// ---------------------------------------------------------------------------------------------
-// k_fold (round 2).  Same arithmetic and ownership as before -- one thread per cell of a 16x16 bin keeps the
-// cell's 48-byte record and its running (keyframe, cell) double sums in registers, records are walked in
-// (keyframe, point) order -- with the memory system taken off the critical path:
-//   * the bucket is streamed by the TMA unit: ONE cp.async.bulk per 2 048-record chunk lands in s_in and
-//     signals an mbarrier; chunk i+1 (or the first chunk of the NEXT bin, whose work item is resolved two bins
-//     ahead) is in flight while chunk i is sorted and walked;
-//   * every thread pulls its 8 records of the chunk into registers once (conflict-free LDS.128); the stable
-//     counting sort on the 8-bit cell key places the RECORDS (not indices) into s_sorted, so the walk reads
-//     consecutive 16-byte slots with no dependent index load;
-//   * intra-warp ranks come either from match.any (MATCH = 0; ~8 cycles per DISTINCT key on sm_100, and a LiDAR
-//     bucket puts ~20 distinct cells into 32 consecutive records) or from a per-warp shared-memory bitmap
-//     (MATCH = 1: atomicOr of the lane bit, read back = the peer mask; cost grows with EQUAL keys instead);
-//   * the walk handles two records per iteration: both loads and all float->double conversions are issued
-//     before the first dependent accumulate.
-// A part of a split heavy bin streams the whole bucket like everyone else and simply ignores the records of
-// other row groups (key 256): no compaction pass.
-// ---------------------------------------------------------------------------------------------
 constexpr int FOLD_R = FOLD_CH / FOLD_THREADS;  // records per thread and chunk
-struct FoldSmem
-{
-    static constexpr size_t in_off = 0;
-    static constexpr size_t sorted_off = (size_t)FOLD_CH * 16;
-    static constexpr size_t cnt_off = 2 * (size_t)FOLD_CH * 16;
-    static constexpr size_t total = cnt_off + (size_t)FOLD_NW * BIN_CELLS * 2;
-};
-
-template <int MATCH, bool TIMING>
-__global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold(BatchView b, GridView g, LatticeD lat, unsigned long long *__restrict__ tim)
-{
-    extern __shared__ __align__(128) unsigned char s_dyn[];
-    float4 *s_in = reinterpret_cast<float4 *>(s_dyn + FoldSmem::in_off);
-    float4 *s_sorted = reinterpret_cast<float4 *>(s_dyn + FoldSmem::sorted_off);
-    uint16_t(*s_cnt)[BIN_CELLS] = reinterpret_cast<uint16_t(*)[BIN_CELLS]>(s_dyn + FoldSmem::cnt_off);
-    __shared__ uint32_t s_w[33];
-    __shared__ uint32_t s_item[2][4];  // two published work items: packed item, bucket start, bucket count, valid
-    __shared__ __align__(8) uint64_t s_bar;
-
-    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t n_heavy = b.counters[10];
-    const uint32_t n_active = n_heavy + b.counters[11];  // heavy items (front of the list) + light bins (back)
-    const uint32_t nb_total = (uint32_t)(b.btw * b.bth);
-    long long t_mark = 0;
-    unsigned long long t_acc[6] = {0, 0, 0, 0, 0, 0};  // wait, count, scan, place, walk, store (thread 0, TIMING only)
-    auto lap = [&](int k) {
-        if (TIMING && tid == 0) { const long long t = clock64(); t_acc[k] += (unsigned long long)(t - t_mark); t_mark = t; }
-    };
-
-    // ---- work items: ticket counter, heaviest bins first, resolved TWO items ahead by thread 0 -------------
-    // ticket -> list entry -> bucket start / count are three dependent global accesses; each is issued at one
-    // point of the current item's processing and consumed at a later one, so none of them is waited for.
-    uint32_t nn_ticket = 0, nn_item = 0xffffffffu, nn_start = 0, nn_cnt = 0;
-    int nn_stage = 2;
-    auto list_at = [&](uint32_t t) -> uint32_t {
-        if (t >= n_active) return 0xffffffffu;
-        return t < n_heavy ? b.active_tiles[t] : b.active_tiles[nb_total - 1 - (t - n_heavy)];
-    };
-    auto range_of = [&](uint32_t item, uint32_t &start, uint32_t &cnt) {
-        start = cnt = 0;
-        if (item == 0xffffffffu) return;
-        const uint32_t gtn = item & 0x00ffffffu;
-        start = b.tile_start[gtn];
-        cnt = b.tile_count[gtn];
-        const int bx = b.btx0 + (int)(gtn % b.btw), by = b.bty0 + (int)(gtn / b.btw);
-        const int col = bx * BIN - g.ci0, row = by * BIN - g.cj0;
-        if (col < 0 || col + BIN > g.W || row < 0 || row + BIN > g.H)
-        {
-            atomicOr(b.counters + 3, (uint32_t)ERR_OUT_OF_GRID);  // reported by the host; the item is skipped
-            cnt = 0;
-        }
-    };
-    auto publish = [&](int slot, uint32_t item, uint32_t start, uint32_t cnt) {
-        s_item[slot][0] = item; s_item[slot][1] = start; s_item[slot][2] = cnt; s_item[slot][3] = item != 0xffffffffu;
-    };
-    auto issue_chunk = [&](uint32_t start, uint32_t pos, uint32_t cnt) {  // thread 0: chunk at `pos` of a bucket
-        const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
-        mbar_arrive_expect_tx(&s_bar, n * 16u);
-        bulk_load(s_in, b.sorted + start + pos, n * 16u, &s_bar);
-    };
-    auto issue_first_of = [&](int slot) {  // thread 0: first chunk of a published item (if it has one)
-        if (s_item[slot][3] && s_item[slot][2])
-            issue_chunk(s_item[slot][1], 0u, s_item[slot][2]);
-    };
-    auto nn_step = [&](int upto) {  // thread 0
-        if (nn_stage < 1 && upto >= 1) { nn_item = list_at(nn_ticket); nn_stage = 1; }
-        if (nn_stage < 2 && upto >= 2) { range_of(nn_item, nn_start, nn_cnt); nn_stage = 2; }
-    };
-    if (tid == 0)
-    {
-        mbar_init(&s_bar, 1);
-        fence_mbar_init();
-        for (int slot = 0; slot < 2; ++slot)
-        {
-            const uint32_t item = list_at(atomicAdd(b.counters + 4, 1u));
-            uint32_t st, cn;
-            range_of(item, st, cn);
-            publish(slot, item, st, cn);
-        }
-        issue_first_of(0);
-        nn_ticket = atomicAdd(b.counters + 4, 1u);
-        nn_stage = 0;
-    }
-#pragma unroll
-    for (int w = 0; w < FOLD_NW; ++w)
-        s_cnt[w][tid] = 0;  // later chunks find the counters cleared by the previous chunk's walk phase
-    __syncthreads();
-    if (TIMING && tid == 0) t_mark = clock64();
-
-    uint32_t phase = 0;
-    for (uint32_t it = 0;; ++it)
-    {
-        const int slot = (int)(it & 1u);
-        const uint32_t item = s_item[slot][0], start = s_item[slot][1], cnt = s_item[slot][2], valid = s_item[slot][3];
-        if (!valid)
-            break;
-        const uint32_t gt = item & 0x00ffffffu, part = (item >> 24) & 15u, pmask = (1u << (item >> 28)) - 1u;
-        const int bx = b.btx0 + (int)(gt % b.btw), by = b.bty0 + (int)(gt / b.btw);  // global bin
-        const int ci = bx * BIN + (int)(tid & (BIN - 1)), cj = by * BIN + (int)(tid >> BIN_SHIFT);
-        const size_t cell = (size_t)(cj - g.cj0) * g.W + (size_t)(ci - g.ci0);       // only dereferenced when cnt > 0
-        const uint32_t nchunks = (cnt + FOLD_CH - 1) / FOLD_CH;
-        if (nchunks == 0)
-        {
-            __syncthreads();  // everyone holds this item's fields before its slot is republished below
-            if (tid == 0) issue_first_of(slot ^ 1);
-        }
-        // the cell's 48-byte record is fetched only if this batch actually touches the cell
-        float rec[REC];
-        bool loaded = false;
-        auto load_rec = [&]()
-        {
-            if (loaded) return;
-            const float4 *src = reinterpret_cast<const float4 *>(g.mom + cell * REC);
-            const float4 a0 = src[0], a1 = src[1], a2 = src[2];
-            rec[0] = a0.x; rec[1] = a0.y; rec[2] = a0.z; rec[3] = a0.w;
-            rec[4] = a1.x; rec[5] = a1.y; rec[6] = a1.z; rec[7] = a1.w;
-            rec[8] = a2.x; rec[9] = a2.y; rec[10] = a2.z; rec[11] = a2.w;
-            rec_to_zero_form(rec);
-            loaded = true;
-        };
-        const double cx = __dadd_rn(lat.x0, __dmul_rn((double)ci, lat.res));  // Lattice::centerOf
-        const double cy = __dadd_rn(lat.y0, __dmul_rn((double)cj, lat.res));
-        CellAcc acc;
-        acc.reset();
-        uint32_t cur = 0xffffffffu;  // (sign | op) of the segment being accumulated
-        uint32_t fl = 0;
-        for (uint32_t c = 0; c < nchunks; ++c)
-        {
-            const uint32_t pos = c * FOLD_CH;
-            const uint32_t n = min((uint32_t)FOLD_CH, cnt - pos);
-            const uint32_t R = (n + FOLD_THREADS - 1) / FOLD_THREADS;  // rounds per thread
-            const uint32_t SL = R * 32;                                // records per warp slice
-            mbar_wait(&s_bar, phase);
-            phase ^= 1u;
-            lap(0);
-            // ---- this thread's records -> registers; warp w owns the contiguous slice [w*SL, (w+1)*SL) ----
-            float4 rr[FOLD_R];
-            uint32_t pk[FOLD_R];  // per record: cell key (bits 0..8, 256 = not mine) | group leader (bit 15) | rank in group << 16
-#pragma unroll
-            for (int r = 0; r < FOLD_R; ++r)
-            {
-                const uint32_t i = warp * SL + r * 32 + lane;
-                pk[r] = 256u;
-                if ((uint32_t)r < R && i < n)
-                {
-                    rr[r] = s_in[i];
-                    const uint32_t key = __float_as_uint(rr[r].w) & 255u;
-                    pk[r] = (((key >> BIN_SHIFT) & pmask) == part) ? key : 256u;  // pmask == 0: every record is mine
-                }
-            }
-            // ---- count per (warp, cell); rank inside the warp round and the group's leader are kept for the placement ----
-            const uint32_t lt = (1u << lane) - 1u;
-            if (MATCH == 0)
-            {
-#pragma unroll
-                for (int r = 0; r < FOLD_R; ++r)
-                {
-                    if ((uint32_t)r < R)
-                    {
-                        const uint32_t key = pk[r];
-                        const uint32_t m = __match_any_sync(0xffffffffu, key);
-                        const bool lead = (m >> lane) == 1u;  // the group's highest lane adds the group size
-                        if (key < 256u && lead)
-                            s_cnt[warp][key] += (uint16_t)__popc(m);
-                        pk[r] = key | (lead ? 0x8000u : 0u) | ((uint32_t)__popc(m & lt) << 16);
-                        __syncwarp();
-                    }
-                }
-            }
-            else
-            {
-                // per-warp bitmap of 256 words in a part of s_in only this warp has read (its own slice when that is
-                // at least 1 KB, else the unused tail of the staging buffer): peers of a key = lanes that OR-ed it
-                uint32_t *bm = reinterpret_cast<uint32_t *>(s_dyn + FoldSmem::in_off) +
-                               (R >= 2 ? warp * SL * 4u : 1024u + warp * 256u);
-                __syncwarp();
-                reinterpret_cast<uint4 *>(bm)[lane] = make_uint4(0u, 0u, 0u, 0u);
-                reinterpret_cast<uint4 *>(bm)[lane + 32] = make_uint4(0u, 0u, 0u, 0u);
-                __syncwarp();
-#pragma unroll
-                for (int r = 0; r < FOLD_R; ++r)
-                {
-                    if ((uint32_t)r < R)
-                    {
-                        const uint32_t key = pk[r];
-                        if (key < 256u) atomicOr(bm + key, 1u << lane);
-                        __syncwarp();
-                        const uint32_t m = key < 256u ? bm[key] : 0u;
-                        __syncwarp();
-                        const bool lead = (m >> lane) == 1u;
-                        if (lead)
-                        {
-                            bm[key] = 0u;
-                            s_cnt[warp][key] += (uint16_t)__popc(m);
-                        }
-                        pk[r] = key | (lead ? 0x8000u : 0u) | ((uint32_t)__popc(m & lt) << 16);
-                        __syncwarp();
-                    }
-                }
-            }
-            __syncthreads();  // B1: s_in consumed, counts complete
-            lap(1);
-            if (tid == 0)
-            {
-                if (c + 1 < nchunks) issue_chunk(start, pos + FOLD_CH, cnt);  // lands while this chunk is sorted and walked
-                else issue_first_of(slot ^ 1);                                // ... or the next bin's first chunk
-                nn_step(1);
-            }
-            // ---- thread = cell: exclusive prefix over the warps' counts, then over cells ----
-            uint32_t tot = 0, wc[FOLD_NW];
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-            {
-                wc[w] = tot;
-                tot += s_cnt[w][tid];
-            }
-            uint32_t inc = tot;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= (uint32_t)o) inc += u;
-            }
-            if (lane == 31) s_w[warp] = inc;
-            __syncthreads();  // B2
-            uint32_t cstart = inc - tot;
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                if (w < (int)warp) cstart += s_w[w];
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
-            __syncthreads();  // B3
-            lap(2);
-            if (tid == 0) nn_step(2);
-            // ---- stable placement of the records themselves ----
-#pragma unroll
-            for (int r = 0; r < FOLD_R; ++r)
-            {
-                if ((uint32_t)r < R)  // uniform over the CTA
-                {
-                    const uint32_t cc = pk[r] & 0x1ffu;
-                    uint32_t sl = 0;
-                    if (cc < 256u)
-                    {
-                        sl = s_cnt[warp][cc] + (pk[r] >> 16);
-                        s_sorted[sl] = rr[r];
-                    }
-                    __syncwarp();
-                    if (cc < 256u && (pk[r] & 0x8000u))  // highest lane of the group: its slot + 1 is the group's end
-                        s_cnt[warp][cc] = (uint16_t)(sl + 1u);
-                    __syncwarp();
-                }
-            }
-            __syncthreads();  // B4
-            lap(3);
-#pragma unroll
-            for (int w = 0; w < FOLD_NW; ++w)
-                s_cnt[w][tid] = 0;  // for the next chunk's count (everyone is past the placement)
-            // ---- thread = cell: walk the cell's run SEGMENT by segment ----
-            // A round takes every lane through one whole (op, cell) segment (inner loop over its records: loads one
-            // record ahead, no fold inside), then all lanes that finished a segment fold together.  The float32 fold
-            // -- ten double->float conversions on the quarter-rate conversion unit -- is what a record-major walk
-            // ends up executing on almost every step for a handful of lanes; here it runs once per round.  A cell's
-            // LAST segment of the chunk stays open (it may continue in the next chunk): it is folded at the next
-            // chunk's prelude, when the cell's first record there belongs to another op, or after the bin's last chunk.
-            {
-                uint32_t k = cstart;
-                const uint32_t k1 = cstart + tot;
-                if (k < k1 && cur != 0xffffffffu)
-                {
-                    const uint32_t so0 = __float_as_uint(s_sorted[k].w) >> 8;
-                    if (so0 != cur)
-                    {
-                        load_rec();
-                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
-                        cur = 0xffffffffu;
-                    }
-                }
-                for (;;)
-                {
-                    const bool has = k < k1;
-                    if (!__any_sync(0xffffffffu, has))
-                        break;
-                    if (has)
-                    {
-                        float4 p = s_sorted[k];
-                        const uint32_t so = __float_as_uint(p.w) >> 8;  // sign | op
-                        double keep = (cur == so) ? 1.0 : 0.0;          // continuing the segment left open by the previous chunk?
-                        if (cur != so)
-                        {
-                            acc.n = 0;
-                            acc.zmin = CUDART_INF_F;
-                            acc.zmax = -CUDART_INF_F;
-                        }
-                        cur = so;
-                        for (;;)
-                        {
-                            // KeyFrame.cpp:62-65 + NodeMetaData::insert (Moments.hpp:53-59); a new segment restarts the sums
-                            // through the fma's multiplier (acc * 0 + x == x, acc * 1 + x == acc + x, both exactly)
-                            const double lx = __dsub_rn((double)p.x, cx), ly = __dsub_rn((double)p.y, cy), lz = (double)p.z;
-                            const float z = p.z;
-                            ++k;
-                            bool more = false;
-                            if (k < k1)
-                            {
-                                p = s_sorted[k];  // next record: in flight during this one's arithmetic
-                                more = (__float_as_uint(p.w) >> 8) == so;
-                            }
-                            acc.n += 1u;
-                            acc.sx = __fma_rn(acc.sx, keep, lx); acc.sy = __fma_rn(acc.sy, keep, ly); acc.sz = __fma_rn(acc.sz, keep, lz);
-                            acc.sx2 = __fma_rn(acc.sx2, keep, __dmul_rn(lx, lx));
-                            acc.sy2 = __fma_rn(acc.sy2, keep, __dmul_rn(ly, ly));
-                            acc.sz2 = __fma_rn(acc.sz2, keep, __dmul_rn(lz, lz));
-                            acc.sxy = __fma_rn(acc.sxy, keep, __dmul_rn(lx, ly));
-                            acc.sxz = __fma_rn(acc.sxz, keep, __dmul_rn(lx, lz));
-                            acc.syz = __fma_rn(acc.syz, keep, __dmul_rn(ly, lz));
-                            acc.zmin = fminf(acc.zmin, z);
-                            acc.zmax = fmaxf(acc.zmax, z);
-                            keep = 1.0;
-                            if (!more)
-                                break;
-                        }
-                    }
-                    if (has && k < k1)  // a following record exists => this segment is complete
-                    {
-                        load_rec();
-                        fold_acc(rec, acc, (cur >> 23) != 0, fl);
-                        cur = 0xffffffffu;
-                    }
-                }
-            }
-            lap(4);
-            if (c + 1 < nchunks)
-                __syncthreads();  // B5: s_sorted and the counters are free again (the last chunk's B5 is the item barrier)
-        }
-        if (cur != 0xffffffffu)
-        {
-            load_rec();
-            fold_acc(rec, acc, (cur >> 23) != 0, fl);
-        }
-        if (fl & F_TOUCHED)
-        {
-            float4 *dstp = reinterpret_cast<float4 *>(g.mom + cell * REC);
-            if (rec[R_N] == 0.f)  // zero form of a blank cell -> NaN layers
-            {
-#pragma unroll
-                for (int k = 0; k < REC; ++k) rec[k] = CUDART_NAN_F;
-            }
-            dstp[0] = make_float4(rec[0], rec[1], rec[2], rec[3]);
-            dstp[1] = make_float4(rec[4], rec[5], rec[6], rec[7]);
-            dstp[2] = make_float4(rec[8], rec[9], rec[10], rec[11]);
-            // the flag byte also mirrors "observed" (N >= 1) so the inflation kernel need not touch the records
-            uint8_t obs = 0;
-            if (!isnan(rec[R_N]) && rec[R_N] >= 1.f)
-                obs = (uint8_t)(F_OBSERVED | (lroundf(rec[R_N]) >= (long)b.min_points ? F_ENOUGH : 0));
-            g.flags[cell] = (uint8_t)((g.flags[cell] & ~(F_OBSERVED | F_ENOUGH)) | fl | obs);
-            if (fl & F_BLANKED)
-            {
-                const size_t pl = g.plane();
-#pragma unroll
-                for (int k = 0; k < NUM_DER; ++k) g.der[k * pl + cell] = CUDART_NAN_F;
-            }
-        }
-        if (tid == 0)
-        {
-            nn_step(2);                                  // whatever is still outstanding of item it + 2
-            publish(slot, nn_item, nn_start, nn_cnt);    // this item's slot becomes item it + 2
-            nn_ticket = atomicAdd(b.counters + 4, 1u);   // consumed during the next item
-            nn_stage = 0;
-        }
-        const uint32_t nt = __syncthreads_count((fl & F_TOUCHED) != 0);  // item barrier; also publishes s_item
-        if (tid == 0 && nt)
-            atomicAdd(b.counters + 8, nt);
-        lap(5);
-    }
-    if (TIMING && tid == 0)
-    {
-#pragma unroll
-        for (int k = 0; k < 6; ++k) atomicAdd(tim + k, t_acc[k]);
-    }
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // k_fold3: the fold with per-chunk load balancing of the walk.
@@ -2818,8 +2108,7 @@ cudaError_t launch_pack_base(cudaStream_t st, const float *d_xyz, size_t n, floa
 
 static size_t scatter_smem(uint32_t maxT) { return (size_t)maxT * 16 + (size_t)maxT * 4 + (size_t)maxT * 2 + (size_t)maxT + 32; }
 
-// TMB_FOLD: 3 = k_fold3 (default), 4 = k_fold4 (run sort; measured slower, kept for A/B), 0 / 1 = k_fold with match.any /
-// shared-memory bitmap ranks, 9 = the round-1 kernel;
+// TMB_FOLD: 3 = k_fold3 (default), 4 = k_fold4 (run sort; measured slower, kept for A/B runs: profiles/README.md R2.4);
 // TMB_FOLD_TIMING=1: per-phase clock64 sums of thread 0 of every CTA, printed after the launch (diagnostics only)
 static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int n_sm)
 {
@@ -2828,19 +2117,18 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
     static const int per_sm = getenv("TMB_FOLD_GRID") ? atoi(getenv("TMB_FOLD_GRID")) : 3;
     const uint32_t nb = b.btw * b.bth;
     const uint32_t blocks = (uint32_t)min((uint32_t)(n_sm * per_sm), nb);
-    const size_t smem = FoldSmem::total;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_done[64] = {false};
     if (dev < 64 && !attr_done[dev])
     {
-        cudaFuncSetAttribute(k_fold<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_fold<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_fold<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaFuncSetAttribute(k_fold<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         cudaFuncSetAttribute(k_fold3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
         cudaFuncSetAttribute(k_fold3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
         cudaFuncSetAttribute(k_fold3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold3Smem::total);
+        cudaFuncSetAttribute(k_fold4<3072, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
+        cudaFuncSetAttribute(k_fold4<3072, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
+        cudaFuncSetAttribute(k_fold4<1536, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
+        cudaFuncSetAttribute(k_fold4<1536, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
         attr_done[dev] = true;
     }
     if (b.sh_world > 0)  // sharded: the bucket is read in place from the sources' segments (k_fold3 only)
@@ -2848,79 +2136,44 @@ static void launch_fold(cudaStream_t st, const BatchView &b, const GridView &g, 
         k_fold3<false, true><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
         return;
     }
-    if (variant == 9)
+    static unsigned long long *d_tim = nullptr;
+    if (timing)
     {
-        k_fold_r1<<<(uint32_t)min((uint32_t)n_sm * 4u, nb), FOLD_THREADS, 0, st>>>(b, g, lat);
-        return;
+        if (!d_tim) cudaMalloc(&d_tim, 64);
+        cudaMemsetAsync(d_tim, 0, 64, st);
     }
+    uint32_t launched = blocks;
     if (variant == 4)
     {
         // chunk size / CTAs per SM: 3072 x 2 or 1536 x 3 (TMB_FOLD_CH)
         static const int ch = getenv("TMB_FOLD_CH") ? atoi(getenv("TMB_FOLD_CH")) : 1536;
         static const int per_sm4 = getenv("TMB_FOLD_GRID") ? atoi(getenv("TMB_FOLD_GRID")) : (ch == 3072 ? 2 : 3);
-        const uint32_t blocks4 = (uint32_t)min((uint32_t)(n_sm * per_sm4), nb);
-        static unsigned long long *d_tim4 = nullptr;
-        if (timing)
-        {
-            if (!d_tim4) cudaMalloc(&d_tim4, 64);
-            cudaMemsetAsync(d_tim4, 0, 64, st);
-        }
-        static bool attr4[64] = {false};
-        if (dev < 64 && !attr4[dev])
-        {
-            cudaFuncSetAttribute(k_fold4<3072, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
-            cudaFuncSetAttribute(k_fold4<3072, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<3072>::total);
-            cudaFuncSetAttribute(k_fold4<1536, 3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
-            cudaFuncSetAttribute(k_fold4<1536, 3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Fold4Smem<1536>::total);
-            attr4[dev] = true;
-        }
+        launched = (uint32_t)min((uint32_t)(n_sm * per_sm4), nb);
         if (ch == 3072)
         {
-            if (timing) k_fold4<3072, 2, true><<<blocks4, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, d_tim4);
-            else k_fold4<3072, 2, false><<<blocks4, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, nullptr);
+            if (timing) k_fold4<3072, 2, true><<<launched, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, d_tim);
+            else k_fold4<3072, 2, false><<<launched, FOLD_THREADS, Fold4Smem<3072>::total, st>>>(b, g, lat, nullptr);
         }
         else
         {
-            if (timing) k_fold4<1536, 3, true><<<blocks4, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, d_tim4);
-            else k_fold4<1536, 3, false><<<blocks4, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, nullptr);
+            if (timing) k_fold4<1536, 3, true><<<launched, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, d_tim);
+            else k_fold4<1536, 3, false><<<launched, FOLD_THREADS, Fold4Smem<1536>::total, st>>>(b, g, lat, nullptr);
         }
-        if (!timing)
-            return;
-        unsigned long long h[6];
-        cudaMemcpyAsync(h, d_tim4, sizeof(h), cudaMemcpyDeviceToHost, st);
-        cudaStreamSynchronize(st);
-        double tot = 0;
-        for (int k = 0; k < 6; ++k) tot += (double)h[k];
-        if (tot > 0)
-            fprintf(stderr, "[k_fold4 phases, %% of thread-0 cycles over %u CTAs] wait %.1f heads %.1f scan %.1f place %.1f walk %.1f store %.1f | %.0f cycles per CTA\n",
-                    blocks4, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / blocks4);
-        return;
     }
-    if (variant == 3 && !timing)
-    {
+    else if (timing)
+        k_fold3<true, false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, d_tim);
+    else
         k_fold3<false, false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, nullptr);
-        return;
-    }
     if (!timing)
-    {
-        if (variant == 0) k_fold<0, false><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, nullptr);
-        else k_fold<1, false><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, nullptr);
         return;
-    }
-    static unsigned long long *d_tim = nullptr;
-    if (!d_tim) cudaMalloc(&d_tim, 64);
-    cudaMemsetAsync(d_tim, 0, 64, st);
-    if (variant == 3) k_fold3<true, false><<<blocks, FOLD_THREADS, Fold3Smem::total, st>>>(b, g, lat, d_tim);
-    else if (variant == 0) k_fold<0, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
-    else k_fold<1, true><<<blocks, FOLD_THREADS, smem, st>>>(b, g, lat, d_tim);
     unsigned long long h[6];
     cudaMemcpyAsync(h, d_tim, sizeof(h), cudaMemcpyDeviceToHost, st);
     cudaStreamSynchronize(st);
     double tot = 0;
     for (int k = 0; k < 6; ++k) tot += (double)h[k];
     if (tot > 0)
-        fprintf(stderr, "[k_fold phases, %% of thread-0 cycles over %u CTAs] wait %.1f count %.1f scan %.1f place %.1f walk %.1f store %.1f | %.0f cycles per CTA\n",
-                blocks, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / blocks);
+        fprintf(stderr, "[fold phases, %% of thread-0 cycles over %u CTAs] load/wait %.1f count/heads %.1f scan %.1f place %.1f walk %.1f store %.1f | %.0f cycles per CTA\n",
+                launched, 100 * h[0] / tot, 100 * h[1] / tot, 100 * h[2] / tot, 100 * h[3] / tot, 100 * h[4] / tot, 100 * h[5] / tot, tot / launched);
 }
 
 cudaError_t launch_bin(cudaStream_t st, const BatchView &b, const GridView &g, const LatticeD &lat, int ppt, uint32_t maxT,

@@ -5,7 +5,6 @@
 
 namespace tmb
 {
-size_t fold_smem_bytes();
 cudaError_t launch_prune(cudaStream_t st, const void *d_src, size_t n, size_t stride, const float T[12], float rh,
                          float mx, float mn, uint32_t *d_warp_cnt, uint32_t *d_total, float4 *d_out, int phase,
                          const int field_floats[3] = nullptr, int big_endian = 0);
