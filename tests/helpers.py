@@ -84,3 +84,55 @@ def compose_f32(A, B):
             out[i, j] = np.float32(np.float32(A[i, 0] * B[0, j]) + np.float32(A[i, 1] * B[1, j])) + np.float32(A[i, 2] * B[2, j])
         out[i, 3] = np.float32(np.float32(np.float32(A[i, 0] * B[0, 3]) + np.float32(A[i, 1] * B[1, 3])) + np.float32(A[i, 2] * B[2, 3])) + A[i, 3]
     return out
+
+
+class OracleSystem:
+    """The reference's System-level calls the ROS nodes make, on top of one OracleMap (test infrastructure): lets the
+    ros_shim drivers run against the oracle with the method names they use on the product.  Obstacle ids follow
+    System.cpp:288-335 (INT64_MAX downward, freed ids reused last-in first-out); an obstacle cloud is pruned with the
+    obstacle extrinsic and ranges (System::prune, System.cpp:93-114) and registered as a base-frame keyframe.
+    The reference's worker is asynchronous; here every pose update is processed at once, which is the order a node that
+    waits for `onMapUpdated` observes."""
+
+    def __init__(self, om):
+        self.om = om
+        self.obst = None
+        self.next_obst = 2 ** 63 - 1
+        self.free = []
+        self.known = set()
+
+    def addNewKeyFrameWithPCL(self, ts_ns, kf_id, map_id, cloud):
+        self.om.add_keyframe(kf_id, cloud)
+        self.known.add(kf_id)
+
+    def updateKeyFrame(self, kf_id, T):
+        self.om.update_pose(kf_id, T)
+        self.om.process()
+
+    def deleteKeyFrame(self, kf_id):
+        self.om.delete_keyframe(kf_id)
+        self.known.discard(kf_id)
+
+    def setObstacleParameters(self, T_base_obs, max_range, min_range):
+        self.obst = (np.asarray(T_base_obs, dtype=np.float32).reshape(-1)[:12].copy(), float(max_range), float(min_range))
+
+    def addObstacleKeyFrame(self, ts_ns, cloud):
+        if self.obst is None or cloud is None:
+            return 0
+        base = self.om.prune(cloud, self.obst[0], self.obst[1], self.obst[2])
+        if base.shape[0] == 0:
+            return 0
+        if self.free:
+            oid = self.free.pop()
+        else:
+            oid = self.next_obst
+            self.next_obst -= 1
+        self.om.add_keyframe_base(oid, base)
+        self.known.add(oid)
+        return oid
+
+    def deleteObstacleKeyFrame(self, kf_id):
+        if kf_id not in self.known:
+            return
+        self.deleteKeyFrame(kf_id)
+        self.free.append(kf_id)
