@@ -56,7 +56,7 @@ C2 = dict(resolution=0.05, half_size=20.0, extend_length=30.0, robot_radius=0.20
           cost_scaling_factor=3.0, lethal_step_threshold=0.95, robot_height=3.5, max_range=20.0, min_range=1.0)
 CROP = 801  # 40 m / 0.05 m + 1 cells, robot-centred
 STAGES = ("ms_hist", "ms_scan", "ms_scatter", "ms_fold", "ms_gate", "ms_classify", "ms_inflate", "ms_total")
-KNAME = {"ms_hist": "k_hist", "ms_scatter": "k_scatter", "ms_fold": "k_fold", "ms_gate": "k_gate",
+KNAME = {"ms_hist": "k_hist", "ms_scatter": "k_scatter", "ms_fold": "k_fold3", "ms_gate": "k_gate",
          "ms_classify": "k_classify", "ms_inflate": "k_inflate"}
 
 

@@ -1084,7 +1084,14 @@ class LocalMap
         const BatchView &b = pl.b;
         const size_t nb = (size_t)b.btw * b.bth;
         const bool prof = P_.profile != 0;
-        CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_, prof ? ev_[8] : nullptr));
+        {
+            // the footprint tables live in __constant__ memory (one copy per device, shared by every map of the process):
+            // the check / upload and the enqueue of the kernels that read them are one critical section, so another map
+            // with a different footprint cannot slip its tables in between (its upload first waits for the device)
+            std::lock_guard<std::mutex> cl(constMutex());
+            uploadConstantsLocked();
+            CK(launch_classify(stream_, grid_.tmap_mom, grid_.tmap_flags, b, grid_.v, cp_, nSM_, prof ? ev_[8] : nullptr));
+        }
         g_launches += 2;  // k_gate + k_classify
         if (prof) CK(cudaEventRecord(ev_[5], stream_));
         if (R_ > 0 && before_inflate)
@@ -1162,7 +1169,6 @@ class LocalMap
         const auto t_begin = std::chrono::steady_clock::now();
         CK(cudaSetDevice(P_.device));
         Plan pl = planBatch(ops, nullptr, 0);
-        uploadConstants();
         t_planned_ = std::chrono::steady_clock::now();
         CK(launch_bin(stream_, pl.b, grid_.v, lat_, pl.ppt, pl.maxT, pl.dc, pl.di, nSM_, P_.profile ? ev_ : nullptr, 3));
         g_launches += ((size_t)pl.b.btw * pl.b.bth <= 4096) ? 5 : 7;  // hist, scan kernels, scatter, fold
@@ -1222,7 +1228,6 @@ class LocalMap
         shardOps_ = ops;
         const int forced[4] = {bbox[0], bbox[1], bbox[2], bbox[3]};
         shardPlan_ = planBatch(shardOps_, forced, op_base, false);
-        uploadConstants();
         CK(launch_bin(stream_, shardPlan_.b, grid_.v, lat_, shardPlan_.ppt, std::max(shardPlan_.maxT, 1u), shardPlan_.dc, shardPlan_.di,
                       nSM_, nullptr, 5));
         g_launches += 6;
@@ -1820,14 +1825,18 @@ class LocalMap
         ky_ = static_cast<int>(std::ceil(newHalfY / res));
     }
 
-    void uploadConstants()
+    static std::mutex &constMutex()
     {
-        // The footprint tables live in __constant__ memory, one copy per process: re-upload whenever a
-        // different map instance (identified by a never-reused serial) used them last.
         static std::mutex m;
+        return m;
+    }
+    void uploadConstantsLocked()  // caller holds constMutex()
+    {
+        // re-upload whenever a different map instance (identified by a never-reused serial) or another device used the
+        // tables last
         static uint64_t owner = 0;
-        std::lock_guard<std::mutex> l(m);
-        if (owner == serial_) return;
+        static int owner_dev = -1;
+        if (owner == serial_ && owner_dev == P_.device) return;
         const int TW = BIN + 2 * r_;
         std::vector<int> off(disc_.size());
         std::vector<double> dd(disc_.size() * 2);
@@ -1840,6 +1849,7 @@ class LocalMap
         CK(cudaDeviceSynchronize());
         CK(upload_classify_constants(off.data(), dd.data(), (int)disc_.size()));
         owner = serial_;
+        owner_dev = P_.device;
     }
 
     uint64_t mapID_;
