@@ -1,3 +1,5 @@
+# The round-2 capture run (through gpurun): default bench, the CPU arm, one ncu --set full pass over the step kernels of
+# profiles/c4_probe.py and the ncu launch list of a short bench run (step kernels only).
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
 RX='regex:k_hist|k_scan|k_tile|k_scatter|k_fold|k_gate|k_classify|k_clear|k_inflate'
