@@ -1262,13 +1262,21 @@ __global__ void __launch_bounds__(FOLD_THREADS, 3) k_fold3(BatchView b, GridView
             for (int w = 0; w < FOLD_NW; ++w)
                 s_cnt[w][tid] = (uint16_t)(cstart + wc[w]);  // next slot of (warp, cell) in the sorted order
             s_run[tid] = cstart | (tot << 16);
-            if (tot)
             {
                 // walkers are numbered heaviest class first; inside a class the order is whatever the cursor hands out
-                // (it only decides WHICH thread walks a cell, never what is computed)
-                uint32_t before = 0;
-                for (uint32_t q = cls + 1; q < 32u; ++q) before += s_class[q];
-                s_perm[before + atomicAdd(&s_class[32 + cls], 1u)] = (uint16_t)tid;
+                // (it only decides WHICH thread walks a cell, never what is computed).  Cells in heavier classes = an
+                // exclusive suffix sum over the 32 class counts, formed once per warp with shuffles (lane = class).
+                uint32_t suf = s_class[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t u = __shfl_down_sync(0xffffffffu, suf, o);
+                    if (lane + (uint32_t)o < 32u) suf += u;
+                }
+                const uint32_t heavier = __shfl_sync(0xffffffffu, suf, (cls + 1u) & 31u);  // inclusive suffix of class cls + 1
+                const uint32_t before = cls == 31u ? 0u : heavier;
+                if (tot)
+                    s_perm[before + atomicAdd(&s_class[32 + cls], 1u)] = (uint16_t)tid;
             }
             if (tid == 0) nn_step(2);
             const uint32_t n_walk = __syncthreads_count(tot != 0);  // B3
