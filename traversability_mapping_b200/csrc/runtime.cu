@@ -1421,18 +1421,25 @@ class LocalMap
                 ops.push_back(add);
                 moved.push_back(it->second);
             }
-            if (!local_error.empty()) { ops.clear(); moved.clear(); }
-            else if (!update)  // a rebuild drops every contribution: keyframes not listed are no longer integrated
-                for (auto &kv : kfs_) kv.second->integrated = false;
         }
-        const size_t n_ops_local = ops.size();
+        // the limits planBatch enforces, checked here so that a rank-local refusal is agreed on before the data collectives
         int32_t win[4] = {INT_MAX, INT_MAX, INT_MIN, INT_MIN};
-        for (auto &op : ops)
         {
-            int x0, y0w, x1, y1w;
-            opWindow(op, x0, y0w, x1, y1w);
-            win[0] = std::min(win[0], x0); win[1] = std::min(win[1], y0w); win[2] = std::max(win[2], x1); win[3] = std::max(win[3], y1w);
+            uint64_t pts = 0;
+            for (auto &op : ops)
+            {
+                int x0, y0w, x1, y1w;
+                opWindow(op, x0, y0w, x1, y1w);
+                if ((uint64_t)(x1 - x0 + 1) * (uint64_t)(y1w - y0w + 1) > MAX_WINDOW_BINS)
+                    local_error = "a keyframe spans more than " + std::to_string(MAX_WINDOW_BINS) + " bins of 16x16 cells";
+                win[0] = std::min(win[0], x0); win[1] = std::min(win[1], y0w); win[2] = std::max(win[2], x1); win[3] = std::max(win[3], y1w);
+                pts += op.kf->n;
+            }
+            if (pts >= (1ull << 32)) local_error = "batch exceeds 2^32 points";
+            if (ops.size() > 65535) local_error = "batch exceeds 65535 ops";
         }
+        if (!local_error.empty()) { ops.clear(); moved.clear(); }
+        const size_t n_ops_local = ops.size();
         shardH_.ensure(8192 + (size_t)W * 256);
         shardD_.ensure(8192 + (size_t)W * 256);
         long long *mh = shardH_.as<long long>();
@@ -1461,6 +1468,16 @@ class LocalMap
             }
         }
         if (u[0] == INT_MAX) throw std::invalid_argument("sharded rebuild without keyframes");
+        {
+            uint64_t all_ops = 0;
+            for (int s = 0; s < W; ++s) all_ops += (uint64_t)mh[8 + 8 * s];
+            if (all_ops >= (1u << 23)) throw Unsupported("sharded pass exceeds 2^23 ops over the job");
+        }
+        if (!update)  // a rebuild drops every contribution: keyframes not listed are no longer integrated
+        {
+            std::lock_guard<std::mutex> l(kfMutex_);
+            for (auto &kv : kfs_) kv.second->integrated = false;
+        }
         const int margin = std::max(1, (r_ + BIN - 1) / BIN);
         int32_t bbox[4] = {u[0] - margin, u[1] - margin, u[2] + margin, u[3] + margin};
         if (update)
