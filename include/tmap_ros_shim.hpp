@@ -21,7 +21,7 @@ class RollingWindowDriver
 {
   public:
     RollingWindowDriver(System &system, std::uint64_t window_size, double keyframe_min_displacement_m = 0.0, std::uint64_t map_id = 0)
-        : system_(system), window_(window_size), min_disp_(keyframe_min_displacement_m), map_(map_id)
+        : system_(system), window_(window_size), map_(map_id), min_disp_(keyframe_min_displacement_m)
     {
     }
     // One synced (cloud, pose) pair -> at most one keyframe.  cloud_xyz4: n points, 4 floats each (pcl::PointXYZ); pose: map <- base.

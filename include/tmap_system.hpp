@@ -11,6 +11,7 @@
 #include "tmap.h"
 
 #include <cstdint>
+#include <array>
 #include <functional>
 #include <limits>
 #include <map>
@@ -292,6 +293,39 @@ class System
     /// Blocks until the workers have drained their queues (test hook).
     void flush() { check(tmap_flush(s_)); }
     tmap_system *handle() { return s_; }
+
+    // ---- a global map tiled over the GPUs of one box (no reference counterpart) ----
+    /// Rank 0 draws the 128-byte job id and ships it to the other ranks over whatever channel the host has.
+    static std::array<std::uint8_t, 128> shardUniqueId()
+    {
+        std::array<std::uint8_t, 128> id{};
+        check(tmap_shard_unique_id(id.data()));
+        return id;
+    }
+    void shardCommInit(std::uint64_t mapID, int rank, int world, const std::array<std::uint8_t, 128> &id)
+    {
+        check(tmap_shard_comm_init(s_, mapID, rank, world, id.data()));
+    }
+    void shardCommDestroy(std::uint64_t mapID) { check(tmap_shard_comm_destroy(s_, mapID)); }
+    /// Collective loop-closure rebuild (LocalMap::clearEntireMap + re-integration, LocalMap.cpp:375-397): this rank's
+    /// keyframes (ascending ids) at their corrected poses.
+    tmap_shard_info shardRebuild(std::uint64_t mapID, const std::vector<std::uint64_t> &kfIDs, const std::vector<Pose> &poses_map_base)
+    {
+        if (kfIDs.size() != poses_map_base.size()) throw std::invalid_argument("kfIDs / poses size mismatch");
+        tmap_shard_info info;
+        check(tmap_shard_rebuild(s_, mapID, kfIDs.data(), kfIDs.size(),
+                                 poses_map_base.empty() ? nullptr : poses_map_base.front().m, &info));
+        return info;
+    }
+    /// Collective pose update of some keyframes of this rank (possibly none): one subtract + add batch over the job.
+    tmap_shard_info shardUpdate(std::uint64_t mapID, const std::vector<std::uint64_t> &kfIDs, const std::vector<Pose> &poses_map_base)
+    {
+        if (kfIDs.size() != poses_map_base.size()) throw std::invalid_argument("kfIDs / poses size mismatch");
+        tmap_shard_info info;
+        check(tmap_shard_update(s_, mapID, kfIDs.data(), kfIDs.size(),
+                                poses_map_base.empty() ? nullptr : poses_map_base.front().m, &info));
+        return info;
+    }
 
   private:
     static void trampoline(void *user) { (*static_cast<std::function<void()> *>(user))(); }
