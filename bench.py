@@ -299,6 +299,14 @@ def main():
                     "binning_pipeline": {"algorithmic_bytes": 16.0 * P_ + 80.0 * ct, "ms": bin_ms,
                                          "frac_of_hbm": (16.0 * P_ + 80.0 * ct) / (bin_ms * 1e-3) / 1e9 / peak},
                     "host_ms_per_step": out.get("host_ms_per_step")}
+            try:
+                # the classifier is FP64-pipe bound, not HBM bound: its pipe utilisation from the committed
+                # ncu capture rides along so that its small HBM fraction is read against the right ceiling
+                fp = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))["fp64_pipe"]
+                roof["fp64_bound_kernels"] = {"k_classify": dict(fp["k_classify"], peak_lane_inst_per_s=fp["peak_lane_inst_per_s"],
+                                                                 source="profiles/r02_ncu_c4.md, profiles/ubench/pipes.cu")}
+            except Exception:
+                pass
         if roof is None and "sharded" in out:
             # N > 1: the dominant stage on rank 0 is the fold of its slab (k_fold3, HBM-bound): 16 B per received record +
             # 80 B per touched cell over that stage's CUDA-event time (the stage also holds the slab blanking memsets)
