@@ -324,7 +324,7 @@ def main():
                                     "remote_bytes_rank0": 16.0 * sh["sent_records_rank0"],
                                     "remote_gbs_rank0": sh.get("alltoall_gbs_rank0_out")}}
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # the CPU arm is timed at N = 1 only (rank 0); N > 1 lines carry null
             cores = os.cpu_count() or 1
             sec1, pts1, _ = oracle_c4(args.cpu_keyframes, 2, 1, 1)
             cpu = {"value": pts1 / sec1, "unit": "points/s", "cores": 1, "kind": "port",
