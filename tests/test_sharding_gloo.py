@@ -125,3 +125,64 @@ def test_c_planner_equals_numpy_planner():
     rows = np.ones((4, 8), dtype=np.uint32)
     slabs = np.zeros(8, dtype=np.int32); z = np.zeros(4, dtype=np.uint64)
     assert lib.tmap_shard_plan(rows.ctypes.data, 4, 8, 0, 0, slabs.ctypes.data, z.ctypes.data, z.ctypes.data, z.ctypes.data) < 0
+
+
+WORKER_C_PLAN = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import traversability_mapping_b200 as tm
+from traversability_mapping_b200 import sharding
+lib = tm.load_library()
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+rng = np.random.default_rng(13)
+btw, bth, first = 5, 24, -3
+nb = btw * bth
+counts = rng.integers(0, 6, size=(world, nb))
+starts = np.concatenate([np.zeros((world, 1), int), np.cumsum(counts, 1)[:, :-1]], 1)
+mine = np.array([(b, rank, k, 0) for b in range(nb) for k in range(counts[rank, b])], dtype=np.float32).reshape(-1, 4)
+# what LocalMap::shardRebuild gathers: every rank's per-bin-row totals
+rows_mine = torch.from_numpy(counts[rank].reshape(bth, btw).sum(1).astype(np.int32))
+ra = [torch.zeros(bth, dtype=torch.int32) for _ in range(world)]
+dist.all_gather(ra, rows_mine)
+rows_all = np.ascontiguousarray(torch.stack(ra).numpy().astype(np.uint32))
+slabs = np.zeros(2 * world, dtype=np.int32)
+send = np.zeros(world, dtype=np.uint64); recv = np.zeros(world, dtype=np.uint64); base = np.zeros(world, dtype=np.uint64)
+assert lib.tmap_shard_plan(rows_all.ctypes.data, world, bth, first, rank, slabs.ctypes.data, send.ctypes.data, recv.ctypes.data,
+                           base.ctypes.data) == tm.OK
+sl = [tuple(int(v) for v in x) for x in slabs.reshape(world, 2)]
+# route with the library's counts: a slab's records are one contiguous range of the sender's bin-major array
+out = torch.empty(int(recv.sum()) * 4, dtype=torch.float32)
+dist.all_to_all_single(out, torch.from_numpy(mine).reshape(-1), [int(r) * 4 for r in recv], [int(s) * 4 for s in send])
+got = out.numpy().reshape(-1, 4)
+# the fused scatter's destination rule (runtime.cu, routing tables): my record at bucket slot s that belongs to rank k lands at
+# s + (records k receives from the ranks below me) - (my first slot of k's slab); check it against the exchanged layout
+mine_first = np.concatenate([[0], np.cumsum(send)[:-1]]).astype(np.int64)
+all_recv = [torch.zeros(world, dtype=torch.int64) for _ in range(world)]
+dist.all_gather(all_recv, torch.from_numpy(recv.astype(np.int64)))
+recv_matrix = torch.stack(all_recv).numpy()          # recv_matrix[k][s] = records rank k receives from rank s
+for k in range(world):
+    base_at_k = int(recv_matrix[k][:rank].sum())
+    lo, n_k = int(mine_first[k]), int(send[k])
+    dest = np.arange(lo, lo + n_k) + (base_at_k - lo)
+    assert np.array_equal(dest, np.arange(base_at_k, base_at_k + n_k))
+y0, y1 = sl[rank]
+merged, cnt, st = sharding.merge_reference(got, counts, starts, base, btw, (y0, y1))
+want = np.array([(b, s, k, 0) for b in range(y0 * btw, y1 * btw) for s in range(world) for k in range(counts[s, b])], dtype=np.float32).reshape(-1, 4)
+assert np.array_equal(merged, want), (rank, merged.shape, want.shape)
+for (a, b_), (c, d) in zip(sl[:-1], sl[1:]):
+    assert b_ == c and (first + b_) % 2 == 0
+sys.stdout.write(f"[rank{rank}-ok:{len(merged)}]\n"); sys.stdout.flush()
+dist.destroy_process_group()
+'''
+
+
+def test_library_planner_routes_world2_gloo(tmp_path):
+    """world_size 2 over gloo with the LIBRARY's planner (tmap_shard_plan) between the all-gather of row totals and the
+    exchange: counts, offsets and the per-bin merge order come out as the single-process fold order."""
+    script = tmp_path / "worker_c.py"
+    script.write_text(WORKER_C_PLAN)
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29534", str(script), ROOT], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("-ok:") == 2
